@@ -1,0 +1,442 @@
+#!/usr/bin/env python3
+"""
+bench.py -- reads/s pseudo-aligned (k=31, 150 bp) on B200, with the reference-build k-mers/s beside it.
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation (one rank per GPU, weak scaling)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port on all host cores
+
+A step = one pass of the hot path over one batch of synthetic reads: K4 (align) + K8 (summary reduction) per
+rank, plus one NCCL all-reduce of the per-genome summary when N > 1.  Workload = BASELINE.json configs[1]
+("1xB200: 100 synthetic bacterial genomes (~5 Mb each), 10M 150-bp reads, k=31, plain pseudo-alignment");
+`--extquality` switches to configs[2].  Inputs are synthetic (seeded, generated on the device) and far larger
+than L2 (1.5 GB of reads against a multi-GB table), so no explicit L2 flush is needed between iterations.
+
+Prints ONE JSON line (see the keys at the bottom).  Only the `cpu_baseline` leg and `--impl reference` touch
+oracle/ (the CPU checker); the timed GPU path goes through the C ABI of libpa_b200.so only.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG_DIR = os.path.join(ROOT, "bioinformatics-project-for-shotgun-metagenomics-pseudo-alignment-shotgun-_b200")
+for p in (ROOT, PKG_DIR):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+ALG_BYTES_PLAIN = 3998      # per 150-bp read at k=31: 150 bases + 32 B x 120 lookups + 8 B result
+ALG_BYTES_QUAL = 4148       # + 150 quality bytes
+BUILD_BYTES_PER_KMER = 17   # 1 base in + 16 B record out
+RANDOM_SECTOR_PEAK_GBS = 1393.6   # measured: profiles/r01_gather_roofline.jsonl, 16 GiB table, one 256-bit load per lookup
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genomes", type=int, default=100)
+    ap.add_argument("--genome-len", type=int, default=5_000_000)
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("-k", type=int, default=31)
+    ap.add_argument("--extquality", action="store_true", help="configs[2]: min-read-quality 62, min-kmer-quality 60, max-genomes 3")
+    ap.add_argument("--sample-genomes", type=int, default=4, help="CPU baseline / parity sample: genomes")
+    ap.add_argument("--sample-reads", type=int, default=1_000_000, help="CPU baseline / parity sample: reads")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------
+# synthetic workload on the device (torch is plumbing: allocation, RNG, streams, NCCL)
+# ---------------------------------------------------------------------------
+def device_genomes(torch, dev, n_genomes, length, seed, cluster=4, shared_frac=0.3, sub=0.01, n_every=1_000_000, n_run=40):
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=dev)
+    bases = torch.empty(n_genomes * length, dtype=torch.uint8, device=dev)
+    blk = int(length * shared_frac)
+    anc = None
+    for g in range(n_genomes):
+        seq = lut[torch.randint(0, 4, (length,), generator=gen, device=dev)]
+        if blk > 0 and cluster > 1:
+            if g % cluster == 0 or anc is None:
+                anc = lut[torch.randint(0, 4, (blk,), generator=gen, device=dev)]
+            shared = anc.clone()
+            hit = torch.rand(blk, generator=gen, device=dev) < sub
+            shared[hit] = lut[torch.randint(0, 4, (int(hit.sum().item()),), generator=gen, device=dev)]
+            start = int(torch.randint(0, length - blk + 1, (1,), generator=gen, device=dev).item())
+            seq[start:start + blk] = shared
+        if n_every > 0:
+            for at in range(n_every // 2, length - n_run, n_every):
+                seq[at:at + n_run] = 78  # 'N'
+        bases[g * length:(g + 1) * length] = seq
+    return bases
+
+
+def device_reads(torch, dev, bases, n_genomes, length, n_reads, read_len, seed, sub=0.01, random_frac=0.02, chunk=1_000_000):
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=dev)
+    out = torch.empty(n_reads * read_len, dtype=torch.uint8, device=dev)
+    quals = torch.empty(n_reads * read_len, dtype=torch.uint8, device=dev)
+    ar = torch.arange(read_len, device=dev)
+    for lo in range(0, n_reads, chunk):
+        n = min(chunk, n_reads - lo)
+        which = torch.randint(0, n_genomes, (n,), generator=gen, device=dev)
+        start = (torch.rand(n, generator=gen, device=dev, dtype=torch.float64) * (length - read_len + 1)).long()
+        idx = (which * length + start)[:, None] + ar[None, :]
+        r = bases[idx]
+        r[r == 78] = 65
+        hit = torch.rand(n, read_len, generator=gen, device=dev) < sub
+        r[hit] = lut[torch.randint(0, 4, (int(hit.sum().item()),), generator=gen, device=dev)]
+        rnd = torch.rand(n, generator=gen, device=dev) < random_frac
+        nr = int(rnd.sum().item())
+        if nr:
+            r[rnd] = lut[torch.randint(0, 4, (nr, read_len), generator=gen, device=dev)]
+        out[lo * read_len:(lo + n) * read_len] = r.reshape(-1)
+        q = torch.clamp(torch.round(torch.randn(n * read_len, generator=gen, device=dev) * 8.0 + 30.0), 2, 41) + 33
+        quals[lo * read_len:(lo + n) * read_len] = q.to(torch.uint8)
+    off = torch.arange(n_reads + 1, device=dev, dtype=torch.int64) * read_len
+    return out, quals, off
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) >= 6 and s[2 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm (oracle port) -- also the parity checker of the GPU arm's sample
+# ---------------------------------------------------------------------------
+def cpu_sample_workload(args):
+    """The bounded sample: `sample_genomes` genomes of the workload's shape and `sample_reads` reads from them."""
+    import synth
+    genomes = synth.make_genomes(args.sample_genomes, args.genome_len, seed=4242, cluster_size=4, shared_frac=0.3,
+                                 sub_rate=0.01, n_every=1_000_000, n_run=40)
+    b, q, off = synth.make_reads(genomes, args.sample_reads, args.read_len, seed=4243, sub_rate=0.01, random_frac=0.02)
+    return genomes, b, q, off
+
+
+def filters(args):
+    return (62, 60, 3) if args.extquality else (None, None, None)
+
+
+def run_cpu_oracle(args, genomes, b, q, off, steps=1, warmup=0):
+    from oracle import oracle as orc
+    import synth
+    nthreads = orc.max_threads()
+    t0 = time.perf_counter()
+    o = orc.OracleReference(args.k, synth.genomes_as_pairs(genomes))
+    t_build = time.perf_counter() - t0
+    mrq, mkq, mg = filters(args)
+    ids = None
+    times = []
+    al = None
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        al = o.align_packed(ids or [], b, q, off, 1, 1, mrq, mkq, mg, nthreads=nthreads)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    n_occ = o.sizes()[2]
+    return o, al, {"build_s": t_build, "build_kmers_per_s": n_occ / t_build if t_build > 0 else None,
+                   "align_s": float(np.mean(times)), "reads_per_s": (len(off) - 1) / float(np.mean(times)), "threads": nthreads}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    genomes, b, q, off = cpu_sample_workload(args)
+    _, _, r = run_cpu_oracle(args, genomes, b, q, off, steps=args.steps, warmup=args.warmup)
+    sample = (f"{args.sample_genomes} genomes x {args.genome_len} bp index, {args.sample_reads} x {args.read_len} bp reads of "
+              f"the same generator; oracle/pa_oracle.c (C port of kmer.py), OpenMP over reads")
+    line = {
+        "impl": "reference", "metric": "reads/s pseudo-aligned (k=31,150bp)", "value": r["reads_per_s"], "unit": "reads/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["align_s"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": r["reads_per_s"], "unit": "reads/s", "cores": r["threads"], "kind": "port", "sample": sample,
+                         "build_kmers_per_s": r["build_kmers_per_s"]},
+        "e2e": {"value": r["reads_per_s"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    name = "configs[2]: configs[1] + EXTQUALITY (mrq=62,mkq=60,mg=3)" if args.extquality else \
+        "configs[1]: 100 genomes x 5 Mb, 10M x 150 bp reads, k=31, plain"
+    return {"workload": name, "genomes": args.genomes, "genome_len": args.genome_len, "reads_per_gpu": args.reads,
+            "read_len": args.read_len, "k": args.k, "m": 1, "p": 1, "l2": "inputs larger than L2 (no flush needed)",
+            "parallelism": f"reads sharded over {args.gpus} GPU(s), index replicated"}
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import _native as nat
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nat.require_device()
+    L = nat.lib()
+    G, GL, NR, RL, k = args.genomes, args.genome_len, args.reads, args.read_len, args.k
+    mrq, mkq, mg = filters(args)
+    params = nat.make_params(1, 1, mrq, mkq, mg)
+    need_q = args.extquality
+    stream = torch.cuda.current_stream()
+    sptr = ctypes.c_void_p(stream.cuda_stream)
+
+    # ---- index build (replicated on every rank), device-resident input ----
+    bases = device_genomes(torch, dev, G, GL, seed=1000)
+    goff = (np.arange(G + 1, dtype=np.uint64) * np.uint64(GL)).astype(np.uint64)
+    torch.cuda.synchronize()
+    build_times = []
+    ix = None
+    for _ in range(2):
+        if ix is not None:
+            ix.close()
+        t0 = time.perf_counter()
+        ix = nat.NativeIndex.build_device(bases.data_ptr(), goff, k, device=local)
+        build_times.append(time.perf_counter() - t0)
+    inf = ix.info()
+    build_kernel_ms = inf.build_encode_ms + inf.build_sort_ms + inf.build_rle_ms + inf.build_table_ms
+
+    # ---- reads of this rank (weak scaling: every rank aligns its own `reads` reads) ----
+    rbases, rquals, roff = device_reads(torch, dev, bases, G, GL, NR, RL, seed=2000 + rank)
+    words = torch.empty(NR, dtype=torch.int64, device=dev)
+    list_cap = max(NR // 2, 1024)
+    lst = torch.empty(list_cap, dtype=torch.int32, device=dev)
+    state = torch.zeros(5, dtype=torch.int64, device=dev)
+    acc = torch.zeros(4 + 2 * G, dtype=torch.int64, device=dev)        # stats[4], unique[G], ambiguous[G]  (SUM)
+    first_seen = torch.full((G,), -1, dtype=torch.int64, device=dev)    # uint64 max                            (MIN)
+    n_launch = ctypes.c_int32(0)
+    launches = {"n": 0}
+
+    def step():
+        state.zero_()
+        acc.zero_()
+        first_seen.fill_(-1)
+        nat.check(L.pa_align_batch_device(ix.handle, ctypes.c_void_p(rbases.data_ptr()),
+                                          ctypes.c_void_p(rquals.data_ptr()) if need_q else None,
+                                          ctypes.c_void_p(roff.data_ptr()), NR, RL, ctypes.byref(params),
+                                          ctypes.c_void_p(words.data_ptr()), ctypes.c_void_p(lst.data_ptr()), list_cap,
+                                          ctypes.c_void_p(state.data_ptr()), sptr, ctypes.byref(n_launch)))
+        launches["n"] += n_launch.value
+        nat.check(L.pa_summary_reduce_device(ctypes.c_void_p(words.data_ptr()), ctypes.c_void_p(lst.data_ptr()), NR,
+                                             rank * NR, G, ctypes.c_void_p(acc.data_ptr()),
+                                             ctypes.c_void_p(acc.data_ptr() + 32), ctypes.c_void_p(acc.data_ptr() + 32 + 8 * G),
+                                             ctypes.c_void_p(first_seen.data_ptr()), sptr))
+        launches["n"] += 1
+        if world > 1:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+            # first_seen holds uint64 order keys < 2^63 or the all-ones "never" marker (-1 as int64): MIN over
+            # the unsigned order = MIN over int64 after mapping -1 to int64 max
+            fs = torch.where(first_seen < 0, torch.full_like(first_seen, 2 ** 63 - 1), first_seen)
+            dist.all_reduce(fs, op=dist.ReduceOp.MIN)
+            first_seen.copy_(fs)
+
+    def kernel_only_ms(reps):
+        # CUDA events around the K4 launch alone, on the stream it is launched on
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        total = 0.0
+        for _ in range(reps):
+            state.zero_()
+            e0.record(stream)
+            nat.check(L.pa_align_batch_device(ix.handle, ctypes.c_void_p(rbases.data_ptr()),
+                                              ctypes.c_void_p(rquals.data_ptr()) if need_q else None,
+                                              ctypes.c_void_p(roff.data_ptr()), NR, RL, ctypes.byref(params),
+                                              ctypes.c_void_p(words.data_ptr()), ctypes.c_void_p(lst.data_ptr()), list_cap,
+                                              ctypes.c_void_p(state.data_ptr()), sptr, ctypes.byref(n_launch)))
+            e1.record(stream)
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        return total / reps
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if int(state[1].item()) != 0:
+        raise RuntimeError("list buffer overflow in the benchmark step")
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches["n"] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    k4_ms = kernel_only_ms(3)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * NR / (ms_step * 1e-3)
+    stats_host = acc[:4].cpu().tolist()
+
+    # ---- end-to-end through the host-buffer C ABI call (pinned host inputs, H2D + D2H inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        hb = torch.empty(NR * RL, dtype=torch.uint8).pin_memory()
+        hb.copy_(rbases)
+        hq = None
+        if need_q:
+            hq = torch.empty(NR * RL, dtype=torch.uint8).pin_memory()
+            hq.copy_(rquals)
+        hoff = torch.empty(NR + 1, dtype=torch.int64).pin_memory()
+        hoff.copy_(roff)
+        hwords = torch.empty(NR, dtype=torch.int64).pin_memory()
+        hlist = torch.empty(list_cap, dtype=torch.int32).pin_memory()
+        need = ctypes.c_uint64(0)
+        counters = np.zeros(3, dtype=np.uint64)
+        e2e_times = []
+        for it in range(2 + max(2, min(args.steps, 5))):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            nat.check(L.pa_align_batch(ix.handle, ctypes.c_void_p(hb.data_ptr()), ctypes.c_void_p(hq.data_ptr()) if need_q else None,
+                                       ctypes.c_void_p(hoff.data_ptr()), NR, ctypes.byref(params), ctypes.c_void_p(hwords.data_ptr()),
+                                       ctypes.c_void_p(hlist.data_ptr()), list_cap, ctypes.byref(need),
+                                       counters.ctypes.data_as(ctypes.c_void_p)))
+            dt = time.perf_counter() - t0
+            if it >= 2:
+                e2e_times.append(dt)
+        te = torch.tensor([float(np.mean(e2e_times))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        assert torch.equal(hwords.to(dev), words), "host-buffer call disagrees with the device-resident call"
+        h2d = NR * RL * (2 if need_q else 1) + (NR + 1) * 8
+        d2h = NR * 8 + int(need.value) * 4 + 40
+        e2e = {"value": world * NR / float(te.item()), "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": float(te.item()) * 1e3}
+
+    # ---- CPU baseline + parity of the GPU path on the same bounded sample (rank 0, N = 1) ----
+    cpu_baseline, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import synth
+        genomes, b, q, off = cpu_sample_workload(args)
+        o, al, r = run_cpu_oracle(args, genomes, b, q, off, steps=1, warmup=0)
+        data, sgoff = nat.pack_strings([g.tobytes().decode("ascii") for g in genomes])
+        six = nat.NativeIndex.build(data, sgoff, k, device=local)
+        sinf = six.info()
+        w2, l2, c2 = six.align(b, q, off, params)
+        types, lens, payload = nat.decode_words(w2)
+        ok = (sinf.n_keys, sinf.n_runs, sinf.n_occ) == o.sizes() and np.array_equal(types, al.types)
+        want_len = np.diff(al.list_off.astype(np.int64))
+        ok = ok and np.array_equal(lens, want_len)
+        if ok:
+            single = lens == 1
+            ok = np.array_equal(payload[single], al.genomes[al.list_off[:-1][single].astype(np.int64)].astype(np.int64))
+            for i in np.nonzero(lens > 1)[0]:
+                ok = ok and np.array_equal(l2[payload[i]:payload[i] + lens[i]], al.genomes[int(al.list_off[i]):int(al.list_off[i + 1])])
+            ok = ok and [int(x) for x in c2] == [al.filtered_quality_reads, al.filtered_quality_kmers if mkq is not None else 0,
+                                                al.filtered_hr_kmers if mg is not None else 0]
+        parity = "bit-exact vs oracle on the sample" if ok else "MISMATCH vs oracle on the sample"
+        six.close()
+        cpu_baseline = {"value": r["reads_per_s"], "unit": "reads/s", "cores": r["threads"], "kind": "port",
+                        "sample": f"{args.sample_genomes} genomes x {GL} bp index, {args.sample_reads} x {RL} bp reads; "
+                                  f"oracle/pa_oracle.c with OpenMP over reads",
+                        "build_kmers_per_s": r["build_kmers_per_s"]}
+
+    if rank == 0:
+        alg = ALG_BYTES_QUAL if need_q else ALG_BYTES_PLAIN
+        if RL != 150 or k != 31:
+            alg = RL * (2 if need_q else 1) + 32 * max(RL - k + 1, 0) + 8
+        achieved = NR * alg / (k4_ms * 1e-3) / 1e9
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        line = {
+            "metric": "reads/s pseudo-aligned (k=31,150bp)", "value": value, "unit": "reads/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args),
+            "e2e": e2e, "gpu_launches": launches["n"],
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "kernel": "align_kernel (K4)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                         "traffic": None, "kernel_ms": k4_ms, "algorithmic_bytes_per_read": alg,
+                         "random_access": {"peak": RANDOM_SECTOR_PEAK_GBS, "unit": "GB/s of 32-B sectors",
+                                           "achieved": NR * 32 * max(RL - k + 1, 0) / (k4_ms * 1e-3) / 1e9,
+                                           "frac": NR * 32 * max(RL - k + 1, 0) / (k4_ms * 1e-3) / 1e9 / RANDOM_SECTOR_PEAK_GBS,
+                                           "source": "profiles/r01_gather_roofline.jsonl"}},
+            "cpu_baseline": cpu_baseline, "parity": parity,
+            "build": {"kmers_per_s_kernels": inf.n_occ / (build_kernel_ms * 1e-3) if build_kernel_ms > 0 else None,
+                      "kmers_per_s_call": inf.n_occ / min(build_times), "kmer_occurrences": int(inf.n_occ),
+                      "distinct_kmers": int(inf.n_keys), "encode_ms": inf.build_encode_ms, "sort_ms": inf.build_sort_ms,
+                      "rle_ms": inf.build_rle_ms, "table_ms": inf.build_table_ms, "index_bytes": int(inf.device_bytes),
+                      "stash_count": int(inf.stash_count), "bucket_bits": int(inf.bucket_bits),
+                      "roofline_frac_17B": (inf.n_occ * BUILD_BYTES_PER_KMER / (build_kernel_ms * 1e-3) / 1e9 / hbm_peak) if build_kernel_ms > 0 else None},
+            "result": {"unique": stats_host[0], "ambiguous": stats_host[1], "unmapped": stats_host[2], "dropped": stats_host[3]},
+        }
+        print(json.dumps(line))
+    ix.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

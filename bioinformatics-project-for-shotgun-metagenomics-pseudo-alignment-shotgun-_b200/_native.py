@@ -1,0 +1,352 @@
+"""
+_native.py -- ctypes binding of libpa_b200.so (the C ABI in include/pa_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or no CUDA device is
+usable, every entry point raises.  Build the library with
+`python -c "import __graft_entry__ as g; g.build()"` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpa_b200.so")
+
+PA_OK = 0
+PA_ERR_INVALID_ARG = -1
+PA_ERR_BAD_BASE = -2
+PA_ERR_CUDA = -3
+PA_ERR_NOMEM = -4
+PA_ERR_CAPACITY = -5
+PA_ERR_UNSUPPORTED = -6
+RANK_MISS = 0xFFFFFFFFFFFFFFFF
+
+EXPORTED_SYMBOLS = [
+    "pa_abi_version", "pa_last_error", "pa_device_count", "pa_index_build", "pa_index_build_device", "pa_index_import",
+    "pa_index_free", "pa_index_info_get", "pa_index_export", "pa_decode_kmers", "pa_encode_kmers", "pa_index_lookup",
+    "pa_extsim_stats", "pa_extsim_pairwise", "pa_index_drop_genomes", "pa_align_batch", "pa_align_batch_device",
+    "pa_summary_reduce_device", "pa_summary_reduce", "pa_debug_sort_pairs", "pa_debug_table_lookup",
+]
+
+
+class NativeLibraryMissing(ImportError):
+    pass
+
+
+class IndexInfo(ctypes.Structure):
+    _fields_ = [
+        ("k", ctypes.c_int32), ("device", ctypes.c_int32), ("n_genomes", ctypes.c_uint32),
+        ("bucket_bits", ctypes.c_uint32), ("tag_bits", ctypes.c_uint32), ("stash_count", ctypes.c_uint32),
+        ("n_keys", ctypes.c_uint64), ("n_runs", ctypes.c_uint64), ("n_occ", ctypes.c_uint64),
+        ("total_bases", ctypes.c_uint64), ("n_list_sectors", ctypes.c_uint64), ("device_bytes", ctypes.c_uint64),
+        ("build_encode_ms", ctypes.c_float), ("build_sort_ms", ctypes.c_float), ("build_rle_ms", ctypes.c_float),
+        ("build_table_ms", ctypes.c_float),
+    ]
+
+
+class AlignParams(ctypes.Structure):
+    _fields_ = [
+        ("m", ctypes.c_int64), ("p", ctypes.c_int64), ("min_read_quality", ctypes.c_int64),
+        ("min_kmer_quality", ctypes.c_int64), ("max_genomes", ctypes.c_int64),
+        ("has_min_read_quality", ctypes.c_int32), ("has_min_kmer_quality", ctypes.c_int32),
+        ("has_max_genomes", ctypes.c_int32), ("reserved", ctypes.c_int32),
+    ]
+
+
+def _clamp64(v: int) -> int:
+    return max(-(1 << 62), min(1 << 62, int(v)))
+
+
+def make_params(m: int, p: int, mrq: Optional[int], mkq: Optional[int], mg: Optional[int]) -> AlignParams:
+    return AlignParams(_clamp64(m), _clamp64(p), _clamp64(mrq or 0), _clamp64(mkq or 0), _clamp64(mg or 0),
+                       int(mrq is not None), int(mkq is not None), int(mg is not None), 0)
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Loads libpa_b200.so; raises NativeLibraryMissing when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryMissing(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built (run __graft_entry__.build()). "
+            "This package has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, u64, u32, i32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int32
+    sig = {
+        "pa_abi_version": (i32, []),
+        "pa_last_error": (i32, [ctypes.c_char_p, ctypes.c_size_t]),
+        "pa_device_count": (i32, [vp]),
+        "pa_index_build": (i32, [vp, vp, u32, i32, i32, vp]),
+        "pa_index_build_device": (i32, [vp, vp, u32, i32, i32, vp]),
+        "pa_index_import": (i32, [i32, u32, vp, u64, u64, u64, vp, vp, vp, vp, vp, vp, i32, vp]),
+        "pa_index_free": (i32, [vp]),
+        "pa_index_info_get": (i32, [vp, vp]),
+        "pa_index_export": (i32, [vp, vp, vp, vp, vp, vp, vp, vp]),
+        "pa_decode_kmers": (i32, [i32, vp, u64, vp]),
+        "pa_encode_kmers": (i32, [i32, vp, u64, vp]),
+        "pa_index_lookup": (i32, [vp, vp, u64, vp]),
+        "pa_extsim_stats": (i32, [vp, vp, u32, vp, vp]),
+        "pa_extsim_pairwise": (i32, [vp, vp, u32, vp]),
+        "pa_index_drop_genomes": (i32, [vp, vp]),
+        "pa_align_batch": (i32, [vp, vp, vp, vp, u64, vp, vp, vp, u64, vp, vp]),
+        "pa_align_batch_device": (i32, [vp, vp, vp, vp, u64, u64, vp, vp, vp, u64, vp, vp, vp]),
+        "pa_summary_reduce_device": (i32, [vp, vp, u64, u64, u32, vp, vp, vp, vp, vp]),
+        "pa_summary_reduce": (i32, [vp, vp, vp, u64, u64, u64, vp, vp, vp, vp]),
+        "pa_debug_sort_pairs": (i32, [vp, vp, u64, i32, i32]),
+        "pa_debug_table_lookup": (i32, [vp, vp, u64, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    buf = ctypes.create_string_buffer(512)
+    lib().pa_last_error(buf, 512)
+    return buf.value.decode("utf-8", "replace")
+
+
+def check(status: int) -> None:
+    """Maps the C status codes onto the exception types the reference raises."""
+    if status == PA_OK:
+        return
+    msg = last_error()
+    if status in (PA_ERR_INVALID_ARG, PA_ERR_BAD_BASE, PA_ERR_UNSUPPORTED):
+        raise ValueError(msg)
+    if status == PA_ERR_NOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError(f"pa_b200 error {status}: {msg}")
+
+
+def device_count() -> int:
+    n = ctypes.c_int32(0)
+    st = lib().pa_device_count(ctypes.byref(n))
+    return n.value if st == PA_OK else 0
+
+
+def require_device() -> None:
+    if device_count() < 1:
+        raise RuntimeError("pa_b200: no CUDA device available; this package has no CPU fallback (" + last_error() + ")")
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _u8(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def pack_strings(strings: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
+    """Concatenates str objects into (uint8 bytes, uint64 offsets).  latin-1: one byte per character."""
+    off = np.zeros(len(strings) + 1, dtype=np.uint64)
+    if len(strings):
+        off[1:] = np.cumsum(np.fromiter((len(s) for s in strings), dtype=np.uint64, count=len(strings)))
+    data = np.frombuffer("".join(strings).encode("latin-1"), dtype=np.uint8)
+    if data.size == 0:
+        data = np.zeros(1, dtype=np.uint8)
+    return np.ascontiguousarray(data), off
+
+
+def decode_words(words: np.ndarray):
+    """Result words -> (type uint8, list length, payload)."""
+    types = (words >> np.uint64(62)).astype(np.uint8)
+    lens = ((words >> np.uint64(40)) & np.uint64(0x3FFFFF)).astype(np.int64)
+    payload = (words & np.uint64(0xFFFFFFFFFF)).astype(np.int64)
+    return types, lens, payload
+
+
+class NativeIndex:
+    """Owns one pa_index handle."""
+
+    def __init__(self, handle: int):
+        self._h = ctypes.c_void_p(handle)
+
+    # -- construction --------------------------------------------------------
+    @classmethod
+    def build(cls, bases: np.ndarray, genome_off: np.ndarray, k: int, device: int = 0) -> "NativeIndex":
+        require_device()
+        bases = _u8(bases)
+        genome_off = np.ascontiguousarray(genome_off, dtype=np.uint64)
+        h = ctypes.c_void_p()
+        check(lib().pa_index_build(_p(bases), _p(genome_off), len(genome_off) - 1, int(k), device, ctypes.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def build_device(cls, d_bases_ptr: int, genome_off: np.ndarray, k: int, device: int = 0) -> "NativeIndex":
+        require_device()
+        genome_off = np.ascontiguousarray(genome_off, dtype=np.uint64)
+        h = ctypes.c_void_p()
+        check(lib().pa_index_build_device(ctypes.c_void_p(d_bases_ptr), _p(genome_off), len(genome_off) - 1, int(k),
+                                          device, ctypes.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def import_csr(cls, k: int, genome_off: np.ndarray, keys, run_off, run_genome, pos_off, pos, first_occ=None,
+                   device: int = 0) -> "NativeIndex":
+        require_device()
+        genome_off = np.ascontiguousarray(genome_off, dtype=np.uint64)
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        run_off = np.ascontiguousarray(run_off, dtype=np.uint64)
+        run_genome = np.ascontiguousarray(run_genome, dtype=np.uint32)
+        pos_off = np.ascontiguousarray(pos_off, dtype=np.uint64)
+        pos = np.ascontiguousarray(pos, dtype=np.uint32)
+        if first_occ is not None:
+            first_occ = np.ascontiguousarray(first_occ, dtype=np.uint64)
+        h = ctypes.c_void_p()
+        check(lib().pa_index_import(int(k), len(genome_off) - 1, _p(genome_off), len(keys), len(run_genome), len(pos),
+                                    _p(keys), _p(run_off), _p(run_genome), _p(pos_off), _p(pos), _p(first_occ), device,
+                                    ctypes.byref(h)))
+        return cls(h.value)
+
+    def close(self) -> None:
+        if self._h is not None and self._h.value and _lib is not None:
+            _lib.pa_index_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self) -> ctypes.c_void_p:
+        if self._h is None:
+            raise RuntimeError("index handle already freed")
+        return self._h
+
+    # -- queries ---------------------------------------------------------------
+    def info(self) -> IndexInfo:
+        inf = IndexInfo()
+        check(lib().pa_index_info_get(self.handle, ctypes.byref(inf)))
+        return inf
+
+    def export(self, with_positions: bool = True, with_order: bool = True):
+        inf = self.info()
+        keys = np.zeros(max(inf.n_keys, 1), dtype=np.uint64)
+        run_off = np.zeros(inf.n_keys + 1, dtype=np.uint64)
+        run_genome = np.zeros(max(inf.n_runs, 1), dtype=np.uint32)
+        pos_off = np.zeros(inf.n_runs + 1, dtype=np.uint64)
+        pos = np.zeros(max(inf.n_occ, 1), dtype=np.uint32) if with_positions else None
+        order = np.zeros(max(inf.n_keys, 1), dtype=np.uint32) if with_order else None
+        first = np.zeros(max(inf.n_keys, 1), dtype=np.uint64)
+        check(lib().pa_index_export(self.handle, _p(keys), _p(run_off), _p(run_genome), _p(pos_off), _p(pos), _p(order),
+                                    _p(first)))
+        return {"keys": keys[:inf.n_keys], "run_off": run_off, "run_genome": run_genome[:inf.n_runs], "pos_off": pos_off,
+                "pos": None if pos is None else pos[:inf.n_occ], "order": None if order is None else order[:inf.n_keys],
+                "first_occ": first[:inf.n_keys]}
+
+    def lookup(self, kmers: Sequence[str]) -> np.ndarray:
+        k = self.info().k
+        n = len(kmers)
+        rank = np.full(max(n, 1), RANK_MISS, dtype=np.uint64)
+        good = [i for i, s in enumerate(kmers) if len(s) == k and k >= 1]
+        if good:
+            try:
+                flat = np.frombuffer("".join(kmers[i] for i in good).encode("latin-1"), dtype=np.uint8)
+            except UnicodeEncodeError:
+                good = [i for i in good if all(ord(c) < 256 for c in kmers[i])]
+                flat = np.frombuffer("".join(kmers[i] for i in good).encode("latin-1"), dtype=np.uint8)
+            if good:
+                sub = np.zeros(len(good), dtype=np.uint64)
+                flat = np.ascontiguousarray(flat)
+                check(lib().pa_index_lookup(self.handle, _p(flat), len(good), _p(sub)))
+                rank[np.asarray(good, dtype=np.int64)] = sub
+        return rank[:n]
+
+    def table_lookup(self, kmers: Sequence[str]):
+        k = self.info().k
+        n = len(kmers)
+        assert all(len(s) == k for s in kmers)
+        flat = np.ascontiguousarray(np.frombuffer("".join(kmers).encode("latin-1"), dtype=np.uint8)) if n else np.zeros(1, np.uint8)
+        ng = np.zeros(max(n, 1), dtype=np.uint32)
+        g0 = np.zeros(max(n, 1), dtype=np.uint32)
+        check(lib().pa_debug_table_lookup(self.handle, _p(flat), n, _p(ng), _p(g0)))
+        return ng[:n], g0[:n]
+
+    # -- EXTSIM ------------------------------------------------------------------
+    def extsim_stats(self, group: np.ndarray, n_groups: int):
+        group = np.ascontiguousarray(group, dtype=np.uint32)
+        total = np.zeros(max(n_groups, 1), dtype=np.uint64)
+        uniq = np.zeros(max(n_groups, 1), dtype=np.uint64)
+        check(lib().pa_extsim_stats(self.handle, _p(group), n_groups, _p(total), _p(uniq)))
+        return total[:n_groups], uniq[:n_groups]
+
+    def extsim_pairwise(self, group: np.ndarray, n_groups: int) -> np.ndarray:
+        group = np.ascontiguousarray(group, dtype=np.uint32)
+        inter = np.zeros(max(n_groups * n_groups, 1), dtype=np.uint64)
+        check(lib().pa_extsim_pairwise(self.handle, _p(group), n_groups, _p(inter)))
+        return inter[:n_groups * n_groups].reshape(n_groups, n_groups)
+
+    def drop_genomes(self, keep: np.ndarray) -> None:
+        keep = np.ascontiguousarray(keep, dtype=np.uint8)
+        if keep.size == 0:
+            keep = np.zeros(1, dtype=np.uint8)
+        check(lib().pa_index_drop_genomes(self.handle, _p(keep)))
+
+    # -- alignment ----------------------------------------------------------------
+    def align(self, bases: np.ndarray, quals: Optional[np.ndarray], read_off: np.ndarray, params: AlignParams):
+        """Host-buffer batch alignment.  Returns (words, list, counters[3])."""
+        bases = _u8(bases)
+        quals = None if quals is None else _u8(quals)
+        read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
+        n = len(read_off) - 1
+        words = np.zeros(max(n, 1), dtype=np.uint64)
+        counters = np.zeros(3, dtype=np.uint64)
+        cap = max(n // 4, 1024)
+        while True:
+            lst = np.zeros(cap, dtype=np.uint32)
+            need = ctypes.c_uint64(0)
+            st = lib().pa_align_batch(self.handle, _p(bases), _p(quals), _p(read_off), n, ctypes.byref(params), _p(words),
+                                      _p(lst), cap, ctypes.byref(need), _p(counters))
+            if st == PA_ERR_CAPACITY:
+                cap = int(need.value) + 16
+                counters[:] = 0
+                continue
+            check(st)
+            return words[:n], lst[:need.value], counters
+
+    def summary(self, words: np.ndarray, lst: np.ndarray, read_index_base: int = 0):
+        """K8 on host buffers.  Returns (stats[4], unique_reads[G], ambiguous_reads[G], first_seen[G])."""
+        G = self.info().n_genomes
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        lst = np.ascontiguousarray(lst, dtype=np.uint32)
+        stats = np.zeros(4, dtype=np.uint64)
+        uniq = np.zeros(max(G, 1), dtype=np.uint64)
+        amb = np.zeros(max(G, 1), dtype=np.uint64)
+        first = np.zeros(max(G, 1), dtype=np.uint64)
+        check(lib().pa_summary_reduce(self.handle, _p(words if len(words) else np.zeros(1, np.uint64)),
+                                      _p(lst if len(lst) else np.zeros(1, np.uint32)), len(words), len(lst),
+                                      int(read_index_base), _p(stats), _p(uniq), _p(amb), _p(first)))
+        return stats, uniq[:G], amb[:G], first[:G]
+
+
+def decode_kmers(k: int, keys: np.ndarray) -> List[str]:
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    n = len(keys)
+    if n == 0 or k <= 0:
+        return ["" for _ in range(n)]
+    out = np.zeros(n * k, dtype=np.uint8)
+    check(lib().pa_decode_kmers(k, _p(keys), n, _p(out)))
+    raw = out.tobytes().decode("ascii")
+    return [raw[i * k:(i + 1) * k] for i in range(n)]
+
+
+def debug_sort_pairs(keys: np.ndarray, vals: np.ndarray, end_bit: int = 64, device: int = 0):
+    require_device()
+    keys = np.ascontiguousarray(keys, dtype=np.uint64).copy()
+    vals = np.ascontiguousarray(vals, dtype=np.uint32).copy()
+    check(lib().pa_debug_sort_pairs(_p(keys), _p(vals), len(keys), end_bit, device))
+    return keys, vals

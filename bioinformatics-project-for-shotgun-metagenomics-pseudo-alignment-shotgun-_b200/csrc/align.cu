@@ -1,0 +1,535 @@
+// align.cu -- K4 (warp-per-read pseudo-alignment with the EXTQUALITY filters
+// fused in) and K8 (summary reduction).
+//
+// Reference being replaced, per read: Read.mean_quality / kmer_quality /
+// extract_kmer_references / generate_genome_counts / try_to_align_specific /
+// validate_unique_mappings / pseudo_align (/root/reference/src/kmer.py:394-526)
+// and the per-read part of PseudoAlignment.add_read_from_read_record
+// (kmer.py:586-598); K8 replaces PseudoAlignment.get_summary (kmer.py:622-657).
+//
+// Bound: random 32-byte sector requests into the bucket table (one per k-mer
+// window; measured roofline in profiles/r01_gather_roofline.jsonl).  All
+// arithmetic is integer; the reference's float means are compared as
+// sum < threshold * length, which is exact.
+#include "align.cuh"
+
+namespace pa {
+
+namespace {
+
+constexpr int AL_THREADS = 256;
+constexpr int AL_WARPS = AL_THREADS / 32;
+constexpr int AL_ROUNDS = 4;                 // windows per lane per super-round
+constexpr int AL_SUPER = 32 * AL_ROUNDS;     // 128 windows per super-round
+constexpr uint32_t NOPOS = 0xFFFFFFFFu;
+
+struct WarpScratch {
+  uint32_t* gtab;        // [G][4] = {S count, T count, first specific pos, first pos}
+  uint32_t* touched;     // [G]
+  unsigned long long* kset_key;  // [kset_cap]
+  uint32_t* kset_pos;            // [kset_cap]
+  uint32_t kset_mask;
+};
+
+__device__ __forceinline__ uint32_t vld(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ void vst(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+__device__ __forceinline__ void vst64(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
+__device__ __forceinline__ void reset_entry(uint32_t* e) { vst(e, 0u); vst(e + 1, 0u); vst(e + 2, 0xFFFFFFFFu); vst(e + 3, 0xFFFFFFFFu); }
+
+// walk an mlist entry: count the ids (needed by the max-genomes filter, kmer.py:425)
+__device__ __forceinline__ uint32_t mlist_count(const uint32_t* __restrict__ mlist, uint64_t sector) {
+  uint32_t c = 0;
+  for (;;) {
+    uint32_t ids[8];
+    ld_sector_u32_nc(mlist + sector * MLIST_SECTOR, ids);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      ++c;
+      if (ids[i] & LIST_END) return c;
+    }
+    ++sector;
+  }
+}
+
+// generate_genome_counts (kmer.py:431-442) for one kept, de-duplicated k-mer at window `pos`
+__device__ __forceinline__ void count_genome(const WarpScratch& ws, uint32_t* n_touched, uint32_t g, uint32_t pos, bool specific) {
+  uint32_t* e = ws.gtab + (size_t)g * 4;
+  uint32_t old = atomicAdd(e + 1, 1u);
+  if (old == 0) vst(ws.touched + atomicAdd(n_touched, 1u), g);
+  atomicMin(e + 3, pos);
+  if (specific) { atomicAdd(e + 0, 1u); atomicMin(e + 2, pos); }
+}
+
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { uint64_t t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { uint32_t t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+  return v;
+}
+
+struct Emit {
+  uint64_t* out_word;
+  uint32_t* out_list;
+  uint64_t out_cap;
+  unsigned long long* cursor;  // [0] list cursor, [1] overflow flag
+};
+
+__device__ __forceinline__ uint64_t make_word(uint32_t type, uint64_t len, uint64_t payload) {
+  return ((uint64_t)type << 62) | (len << 40) | payload;
+}
+
+// try_to_align_specific (kmer.py:444-462) + validate_unique_mappings (kmer.py:464-480) on the
+// per-genome table of one read; writes the result word and, for lists longer than one, the list.
+__device__ void decide_and_emit(const WarpScratch& ws, uint32_t nT, const AlignParams& prm, const Emit& em, uint64_t read,
+                                uint32_t lane) {
+  // pass 1: nS, top specific count (ties -> earliest first specific position), max total
+  uint32_t nS = 0, maxT = 0;
+  uint64_t best = 0;
+  for (uint32_t i = lane; i < nT; i += 32) {
+    uint32_t g = vld(ws.touched + i);
+    const uint32_t* e = ws.gtab + (size_t)g * 4;
+    uint32_t S = vld(e), T = vld(e + 1), fS = vld(e + 2);
+    if (S) { ++nS; uint64_t key = ((uint64_t)S << 32) | (uint32_t)(NOPOS - fS); best = key > best ? key : best; }
+    maxT = T > maxT ? T : maxT;
+  }
+  nS = warp_sum(nS);
+  maxT = warp_max_u32(maxT);
+  best = warp_max_u64(best);
+  if (nS == 0) {  // kept k-mers but none specific: ambiguous with an empty list (kmer.py:461)
+    if (lane == 0) em.out_word[read] = make_word(3, 0, 0);
+    return;
+  }
+  const uint32_t topS = (uint32_t)(best >> 32), top_fS = NOPOS - (uint32_t)best;
+  // pass 2: identify the top genome and the runner-up count
+  uint32_t top_g = 0, second = 0;
+  for (uint32_t i = lane; i < nT; i += 32) {
+    uint32_t g = vld(ws.touched + i);
+    const uint32_t* e = ws.gtab + (size_t)g * 4;
+    uint32_t S = vld(e), fS = vld(e + 2);
+    if (S == topS && fS == top_fS) top_g = g + 1;
+    else if (S > second) second = S;
+  }
+  top_g = warp_max_u32(top_g) - 1;
+  second = warp_max_u32(second);
+  const bool unique = (nS == 1) || ((int64_t)topS >= (int64_t)second + prm.m);
+  uint32_t Tm = 0;
+  bool flip = false;
+  if (unique && prm.p >= 0) {
+    Tm = vld(ws.gtab + (size_t)top_g * 4 + 1);
+    flip = (int64_t)maxT - (int64_t)Tm > prm.p;
+  }
+  if (unique && !flip) {
+    if (lane == 0) em.out_word[read] = make_word(2, 1, top_g);
+    return;
+  }
+  // ambiguous: ordered list.  not unique -> genomes with S>0 by first specific position (dict order of
+  // kmer.py:461); flipped -> [mapped] + genomes with T >= T[mapped] by (first position, genome) (kmer.py:476-479).
+  uint32_t n = 0;
+  for (uint32_t i = lane; i < nT; i += 32) {
+    uint32_t g = vld(ws.touched + i);
+    const uint32_t* e = ws.gtab + (size_t)g * 4;
+    n += flip ? (vld(e + 1) >= Tm) : (vld(e) > 0);
+  }
+  n = warp_sum(n);
+  const uint32_t len = n + (flip ? 1u : 0u);
+  unsigned long long off = 0;
+  if (lane == 0) off = atomicAdd(em.cursor, (unsigned long long)len);
+  off = __shfl_sync(0xffffffffu, off, 0);
+  if (lane == 0) em.out_word[read] = make_word(3, len, off);
+  if (off + len > em.out_cap) {
+    if (lane == 0) atomicExch(em.cursor + 1, 1ULL);
+    return;
+  }
+  uint32_t* dst = em.out_list + off;
+  if (flip && lane == 0) dst[0] = top_g;
+  if (flip) ++dst;
+  for (uint32_t i = lane; i < nT; i += 32) {
+    uint32_t g = vld(ws.touched + i);
+    const uint32_t* e = ws.gtab + (size_t)g * 4;
+    bool in = flip ? (vld(e + 1) >= Tm) : (vld(e) > 0);
+    if (!in) continue;
+    uint64_t key = flip ? (((uint64_t)vld(e + 3) << 32) | g) : (uint64_t)vld(e + 2);
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < nT; ++j) {
+      uint32_t gj = vld(ws.touched + j);
+      const uint32_t* ej = ws.gtab + (size_t)gj * 4;
+      bool inj = flip ? (vld(ej + 1) >= Tm) : (vld(ej) > 0);
+      uint64_t kj = flip ? (((uint64_t)vld(ej + 3) << 32) | gj) : (uint64_t)vld(ej + 2);
+      rank += (inj && kj < key);
+    }
+    dst[rank] = g;
+  }
+}
+
+template <bool QUAL>
+__global__ void __launch_bounds__(AL_THREADS)
+align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals,
+             const uint64_t* __restrict__ read_off, uint64_t n_reads, AlignParams prm, Emit em,
+             unsigned long long* __restrict__ counters, unsigned char* __restrict__ scratch, uint64_t scratch_stride,
+             uint32_t G, uint32_t kset_cap, int gtab_in_smem, int kset_in_smem) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ uint32_t s_ntouched[AL_WARPS];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t warp_global = (uint64_t)blockIdx.x * AL_WARPS + warp;
+  const uint64_t n_warps = (uint64_t)gridDim.x * AL_WARPS;
+  const int k = (int)t.k;
+  const uint32_t kmask = (k >= 1 && k < 32) ? ((1u << k) - 1) : 0u;
+
+  // carve the per-warp scratch (shared memory when it fits, else this warp's slice of the global scratch)
+  WarpScratch ws;
+  {
+    unsigned char* gp = scratch + warp_global * scratch_stride;
+    size_t kset_bytes = (size_t)kset_cap * 12, gtab_bytes = (size_t)G * 20;
+    size_t per_warp_smem = (kset_in_smem ? kset_bytes : 0) + (gtab_in_smem ? gtab_bytes : 0);
+    per_warp_smem = (per_warp_smem + 15) & ~(size_t)15;
+    unsigned char* sp = dyn_smem + warp * per_warp_smem;
+    if (kset_in_smem) { ws.kset_key = (unsigned long long*)sp; ws.kset_pos = (uint32_t*)(sp + (size_t)kset_cap * 8); sp += kset_bytes; }
+    else { ws.kset_key = (unsigned long long*)gp; ws.kset_pos = (uint32_t*)(gp + (size_t)kset_cap * 8); gp += (kset_bytes + 15) & ~(size_t)15; }
+    if (gtab_in_smem) { ws.gtab = (uint32_t*)sp; ws.touched = (uint32_t*)(sp + (size_t)G * 16); }
+    else { ws.gtab = (uint32_t*)gp; ws.touched = (uint32_t*)(gp + (size_t)G * 16); }
+    ws.kset_mask = kset_cap - 1;
+    if (kset_in_smem) for (uint32_t i = lane; i < kset_cap; i += 32) { ws.kset_key[i] = EMPTY64; ws.kset_pos[i] = NOPOS; }
+    if (gtab_in_smem) for (uint32_t i = lane; i < G; i += 32) { ws.gtab[i * 4] = 0; ws.gtab[i * 4 + 1] = 0; ws.gtab[i * 4 + 2] = NOPOS; ws.gtab[i * 4 + 3] = NOPOS; }
+    if (lane == 0) s_ntouched[warp] = 0;
+    __syncwarp();
+  }
+  uint32_t* n_touched = &s_ntouched[warp];
+
+  unsigned long long c_drop = 0, c_nq = 0, c_nr = 0;  // per-lane partial counters
+
+  for (uint64_t read = warp_global; read < n_reads; read += n_warps) {
+    const uint64_t beg = read_off[read];
+    const uint64_t L = read_off[read + 1] - beg;
+    const uint8_t* rb = bases + beg;
+    const uint8_t* rq = QUAL ? quals + beg : nullptr;
+
+    if (QUAL && prm.has_mrq) {  // Read.mean_quality() < min_read_quality  (kmer.py:587)
+      uint64_t s = 0;
+      for (uint64_t i = lane; i < L; i += 32) s += rq[i];
+      s = warp_sum(s);
+      if ((int64_t)s < prm.mrq * (int64_t)L) {
+        if (lane == 0) { em.out_word[read] = 0; ++c_drop; }
+        continue;
+      }
+    }
+    const uint64_t W = (k >= 1 && L >= (uint64_t)k) ? L - k + 1 : 0;  // kmer.py:91-92
+    const bool single = W <= AL_SUPER;
+    bool slow_used = false;
+    uint32_t read_nq = 0, read_nr = 0;
+    bool done = false;
+
+    for (uint64_t wbase = 0; wbase < W; wbase += AL_SUPER) {
+      // ---- encode AL_ROUNDS+1 chunks of 32 bases into bit planes with ballots ----
+      uint32_t lo[AL_ROUNDS + 1], hi[AL_ROUNDS + 1], inv[AL_ROUNDS + 1];
+      uint32_t qex[AL_ROUNDS + 1];  // exclusive quality prefix at this lane's base, relative to wbase
+      uint32_t carry = 0;
+#pragma unroll
+      for (int c = 0; c <= AL_ROUNDS; ++c) {
+        uint64_t bi = wbase + 32 * c + lane;
+        uint32_t ch = bi < L ? rb[bi] : 0;
+        bool ok = is_acgt(ch);
+        uint32_t code = base_code(ch);
+        lo[c] = __ballot_sync(0xffffffffu, code & 1u);
+        hi[c] = __ballot_sync(0xffffffffu, code >> 1);
+        inv[c] = __ballot_sync(0xffffffffu, !ok);
+        if (QUAL && prm.has_mkq) {
+          uint32_t q = bi < L ? rq[bi] : 0, incl = q;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+          qex[c] = carry + incl - q;
+          carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+      }
+      // ---- per window: quality filter, key, bucket load ----
+      uint64_t h[AL_ROUNDS];
+      uint64_t bucket[AL_ROUNDS][4];
+      bool look[AL_ROUNDS];
+#pragma unroll
+      for (int r = 0; r < AL_ROUNDS; ++r) {
+        const uint64_t s = wbase + 32 * r + lane;
+        bool exists = s < W;
+        bool qf = false;
+        if (QUAL && prm.has_mkq) {  // kmer_quality(start, k) < min_kmer_quality, before the lookup (kmer.py:420-422)
+          uint32_t tl = lane + k;   // prefix at base s + k lives in chunk r (tl < 32) or r + 1
+          uint32_t p_a = __shfl_sync(0xffffffffu, qex[r], tl & 31);
+          uint32_t p_b = __shfl_sync(0xffffffffu, qex[r + 1], tl & 31);
+          uint32_t end = tl < 32 ? p_a : p_b;
+          qf = exists && ((int64_t)(end - qex[r]) < prm.mkq * (int64_t)k);
+          read_nq += qf;
+        }
+        uint32_t wl = __funnelshift_r(lo[r], lo[r + 1], lane) & kmask;
+        uint32_t wh = __funnelshift_r(hi[r], hi[r + 1], lane) & kmask;
+        uint32_t wi = __funnelshift_r(inv[r], inv[r + 1], lane) & kmask;
+        look[r] = exists && !qf && wi == 0;
+        h[r] = mix_key(((uint64_t)wh << k) | wl, t.mix);
+        if (look[r]) ld_sector_nc(t.buckets + (h[r] >> t.tag_bits) * 4, bucket[r]);
+      }
+      // ---- resolve ----
+      uint64_t val[AL_ROUNDS];
+      bool any_multi = false, any_found = false;
+#pragma unroll
+      for (int r = 0; r < AL_ROUNDS; ++r) {
+        val[r] = look[r] ? bucket_resolve(t, bucket[r], h[r]) : LOOKUP_MISS;
+        if (val[r] != LOOKUP_MISS) { any_found = true; any_multi |= !value_is_specific(t, val[r]); }
+      }
+      const bool w_multi = __any_sync(0xffffffffu, any_multi);
+      const bool w_found = __any_sync(0xffffffffu, any_found);
+      const bool spec_kept = !(prm.has_mg && prm.mg < 1);  // a specific k-mer has one genome (kmer.py:425)
+
+      // ---- fast path: one super-round, nothing multi-genome, every kept k-mer names the same genome.
+      // Then S == T == {g: n}: unique whatever m and p are, and duplicates cannot change that.
+      if (single && !w_multi) {
+        if (!w_found) { if (lane == 0) em.out_word[read] = make_word(1, 0, 0); done = true; break; }
+        if (!spec_kept) {
+          uint32_t f = 0;
+#pragma unroll
+          for (int r = 0; r < AL_ROUNDS; ++r) f += val[r] != LOOKUP_MISS;
+          read_nr += f;
+          if (lane == 0) em.out_word[read] = make_word(1, 0, 0);
+          done = true; break;
+        }
+        uint32_t mine = 0xFFFFFFFFu;
+        bool same = true;
+#pragma unroll
+        for (int r = 0; r < AL_ROUNDS; ++r)
+          if (val[r] != LOOKUP_MISS) {
+            uint32_t g = (uint32_t)value_payload(t, val[r]);
+            if (mine == 0xFFFFFFFFu) mine = g; else same &= (g == mine);
+          }
+        uint32_t have = __ballot_sync(0xffffffffu, mine != 0xFFFFFFFFu);
+        uint32_t g0 = __shfl_sync(0xffffffffu, mine, __ffs(have) - 1);
+        same &= (mine == 0xFFFFFFFFu) || (mine == g0);
+        if (__all_sync(0xffffffffu, same)) {
+          if (lane == 0) em.out_word[read] = make_word(2, 1, g0);
+          done = true; break;
+        }
+      }
+
+      // ---- general path: max-genomes filter, in-read de-duplication, per-genome counting ----
+      slow_used = true;
+      uint32_t slot[AL_ROUNDS];
+      bool kept[AL_ROUNDS];
+#pragma unroll
+      for (int r = 0; r < AL_ROUNDS; ++r) {
+        kept[r] = false;
+        if (val[r] == LOOKUP_MISS) continue;
+        bool specific = value_is_specific(t, val[r]);
+        if (prm.has_mg) {
+          uint32_t c = specific ? 1u : mlist_count(t.mlist, value_payload(t, val[r]));
+          if ((int64_t)c > prm.mg) { ++read_nr; continue; }
+        }
+        kept[r] = true;
+        // self.kmers[kmer] = ...: a repeated k-mer keeps the position of its first kept occurrence (kmer.py:429)
+        const uint32_t pos = (uint32_t)(wbase + 32 * r + lane);
+        uint32_t sl = (uint32_t)(h[r] ^ (h[r] >> 29)) & ws.kset_mask;
+        for (;;) {
+          unsigned long long old = atomicCAS(ws.kset_key + sl, (unsigned long long)EMPTY64, (unsigned long long)h[r]);
+          if (old == EMPTY64 || old == h[r]) break;
+          sl = (sl + 1) & ws.kset_mask;
+        }
+        atomicMin(ws.kset_pos + sl, pos);
+        slot[r] = sl;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < AL_ROUNDS; ++r) {
+        if (!kept[r]) continue;
+        const uint32_t pos = (uint32_t)(wbase + 32 * r + lane);
+        if (vld(ws.kset_pos + slot[r]) != pos) continue;  // an earlier occurrence represents this k-mer
+        if (value_is_specific(t, val[r])) {
+          count_genome(ws, n_touched, (uint32_t)value_payload(t, val[r]), pos, true);
+        } else {
+          uint64_t sector = value_payload(t, val[r]);
+          for (bool more = true; more; ++sector) {
+            uint32_t ids[8];
+            ld_sector_u32_nc(t.mlist + sector * MLIST_SECTOR, ids);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (!more) break;
+              count_genome(ws, n_touched, ids[i] & ~LIST_END, pos, false);
+              if (ids[i] & LIST_END) more = false;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (single) {
+        // one super-round: decide now, while slot[] is still in scope for a targeted cleanup
+        uint32_t nT = vld(n_touched);
+        if (nT == 0) { if (lane == 0) em.out_word[read] = make_word(1, 0, 0); }
+        else decide_and_emit(ws, nT, prm, em, read, lane);
+        __syncwarp();
+        for (uint32_t i = lane; i < nT; i += 32) reset_entry(ws.gtab + (size_t)vld(ws.touched + i) * 4);
+#pragma unroll
+        for (int r = 0; r < AL_ROUNDS; ++r)
+          if (kept[r]) { vst64(ws.kset_key + slot[r], EMPTY64); vst(ws.kset_pos + slot[r], NOPOS); }
+        if (lane == 0) vst(n_touched, 0u);
+        __threadfence_block();
+        __syncwarp();
+        done = true;
+      }
+    }
+
+    if (!done) {
+      // reads longer than one super-round (or without any window)
+      uint32_t nT = vld(n_touched);
+      if (nT == 0) { if (lane == 0) em.out_word[read] = make_word(1, 0, 0); }
+      else decide_and_emit(ws, nT, prm, em, read, lane);
+      __syncwarp();
+      if (slow_used) {
+        for (uint32_t i = lane; i < nT; i += 32) reset_entry(ws.gtab + (size_t)vld(ws.touched + i) * 4);
+        for (uint32_t i = lane; i < kset_cap; i += 32) { vst64(ws.kset_key + i, EMPTY64); vst(ws.kset_pos + i, NOPOS); }
+        if (lane == 0) vst(n_touched, 0u);
+        __threadfence_block();
+        __syncwarp();
+      }
+    }
+    c_nq += read_nq;
+    c_nr += read_nr;
+  }
+
+  c_drop = warp_sum(c_drop); c_nq = warp_sum(c_nq); c_nr = warp_sum(c_nr);
+  if (lane == 0) {
+    if (c_drop) atomicAdd(counters + 0, c_drop);
+    if (c_nq) atomicAdd(counters + 1, c_nq);
+    if (c_nr) atomicAdd(counters + 2, c_nr);
+  }
+}
+
+__global__ void scratch_init(unsigned char* scratch, uint64_t n_warps, uint64_t stride, uint32_t G, uint32_t kset_cap,
+                             int gtab_in_smem, int kset_in_smem) {
+  uint64_t w = blockIdx.x;
+  if (w >= n_warps) return;
+  unsigned char* gp = scratch + w * stride;
+  if (!kset_in_smem) {
+    unsigned long long* kk = (unsigned long long*)gp;
+    uint32_t* kp = (uint32_t*)(gp + (size_t)kset_cap * 8);
+    for (uint32_t i = threadIdx.x; i < kset_cap; i += blockDim.x) { kk[i] = EMPTY64; kp[i] = NOPOS; }
+    gp += ((size_t)kset_cap * 12 + 15) & ~(size_t)15;
+  }
+  if (!gtab_in_smem) {
+    uint32_t* gt = (uint32_t*)gp;
+    for (uint32_t i = threadIdx.x; i < G; i += blockDim.x) { gt[i * 4] = 0; gt[i * 4 + 1] = 0; gt[i * 4 + 2] = NOPOS; gt[i * 4 + 3] = NOPOS; }
+  }
+}
+
+// ===========================================================================
+// K8: PseudoAlignment.get_summary (kmer.py:622-657) over the result words.
+// stats = {unique, ambiguous, unmapped, dropped}; per genome one count per LIST
+// ELEMENT; first_seen[g] = min over (global read index << 22 | list position),
+// which orders the "Summary" keys by first appearance.
+// ===========================================================================
+constexpr int SUM_THREADS = 256;
+
+__global__ void __launch_bounds__(SUM_THREADS)
+summary_kernel(const uint64_t* __restrict__ words, const uint32_t* __restrict__ list, uint64_t n_reads, uint64_t read_index_base,
+               uint32_t G, unsigned long long* __restrict__ stats, unsigned long long* __restrict__ unique_reads,
+               unsigned long long* __restrict__ ambiguous_reads, unsigned long long* __restrict__ first_seen) {
+  unsigned long long st[4] = {0, 0, 0, 0};
+  const uint64_t stride = (uint64_t)gridDim.x * SUM_THREADS;
+  for (uint64_t i = blockIdx.x * (uint64_t)SUM_THREADS + threadIdx.x; i < n_reads; i += stride) {
+    uint64_t w = words[i];
+    uint32_t type = (uint32_t)(w >> 62);
+    uint64_t len = (w >> 40) & 0x3FFFFF, payload = w & 0xFFFFFFFFFFULL;
+    if (type == 0) { ++st[3]; continue; }
+    if (type == 1) { ++st[2]; continue; }
+    ++st[type == 2 ? 0 : 1];
+    unsigned long long* cnt = type == 2 ? unique_reads : ambiguous_reads;
+    const uint64_t order_base = (read_index_base + i) << 22;
+    if (len == 1) {
+      atomicAdd(&cnt[payload], 1ULL);
+      atomicMin(&first_seen[payload], (unsigned long long)order_base);
+    } else {
+      for (uint64_t j = 0; j < len; ++j) {
+        uint32_t g = list[payload + j];
+        atomicAdd(&cnt[g], 1ULL);
+        atomicMin(&first_seen[g], (unsigned long long)(order_base | j));
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    unsigned long long v = warp_sum(st[c]);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&stats[c], v);
+  }
+}
+
+}  // namespace
+
+int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_quals, const uint64_t* d_read_off,
+                           uint64_t n_reads, uint64_t max_read_len, const AlignParams& prm_in, uint64_t* d_words,
+                           uint32_t* d_list, uint64_t list_cap, unsigned long long* d_cursor /*[2]*/,
+                           unsigned long long* d_counters /*[3]*/, cudaStream_t s, int32_t* launches) {
+  if (launches) *launches = 0;
+  if (n_reads == 0) return ST_OK;
+  AlignParams prm = prm_in;
+  const int k = ix.k;
+  const bool qual = (prm.has_mrq || prm.has_mkq);
+  if (qual && !d_quals) { set_error("align: quality filters requested without quality data"); return ST_INVALID_ARG; }
+  int dev = 0, sms = 148;
+  PA_CUDA(cudaGetDevice(&dev));
+  PA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+
+  const uint32_t G = std::max<uint32_t>(ix.n_genomes, 1);
+  const uint64_t Wmax = (k >= 1 && max_read_len >= (uint64_t)k) ? max_read_len - k + 1 : 0;
+  uint32_t kset_cap = 256;
+  const int kset_in_smem = Wmax <= AL_SUPER;
+  if (!kset_in_smem) { uint64_t c = 256; while (c < 2 * Wmax) c <<= 1; if (c > 0x40000000ull) { set_error("align: read too long"); return ST_UNSUPPORTED; } kset_cap = (uint32_t)c; }
+  const int gtab_in_smem = G <= 256;
+  size_t per_warp_smem = (kset_in_smem ? (size_t)kset_cap * 12 : 0) + (gtab_in_smem ? (size_t)G * 20 : 0);
+  per_warp_smem = (per_warp_smem + 15) & ~(size_t)15;
+  const size_t dyn_smem = per_warp_smem * AL_WARPS;
+
+  auto kern = qual ? align_kernel<true> : align_kernel<false>;
+  PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(dyn_smem, 1024)));
+  int occ = 1;
+  PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, AL_THREADS, dyn_smem));
+  if (occ < 1) occ = 1;
+  uint64_t grid = (uint64_t)sms * occ;
+  grid = std::min<uint64_t>(grid, (n_reads + AL_WARPS - 1) / AL_WARPS);
+  grid = std::max<uint64_t>(grid, 1);
+  const uint64_t n_warps = grid * AL_WARPS;
+
+  uint64_t stride = 0;
+  if (!kset_in_smem) stride += ((uint64_t)kset_cap * 12 + 15) & ~15ull;
+  if (!gtab_in_smem) stride += ((uint64_t)G * 20 + 15) & ~15ull;
+  if (stride) {
+    uint64_t key = stride * 1000003ull + kset_cap * 7ull + G;
+    if (ix.align_scratch_warps < n_warps || ix.align_scratch_stride != key) {
+      PA_TRY(ix.align_scratch.alloc(n_warps * stride));
+      scratch_init<<<(unsigned)n_warps, 128, 0, s>>>(ix.align_scratch.as<unsigned char>(), n_warps, stride, G, kset_cap,
+                                                     gtab_in_smem, kset_in_smem);
+      PA_CUDA(cudaGetLastError());
+      ix.align_scratch_warps = n_warps; ix.align_scratch_stride = key;
+      if (launches) ++*launches;
+    }
+  }
+  TableView tv = ix.view();  // k <= 0: the kernel sees no windows (kmer.py:91-92) and only applies the read-quality drop
+  Emit em{d_words, d_list, list_cap, d_cursor};
+  kern<<<(unsigned)grid, AL_THREADS, dyn_smem, s>>>(tv, d_bases, d_quals, d_read_off, n_reads, prm, em, d_counters,
+                                                    ix.align_scratch.as<unsigned char>(), stride, G, kset_cap,
+                                                    gtab_in_smem, kset_in_smem);
+  PA_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  return ST_OK;
+}
+
+int32_t summary_reduce_device(const uint64_t* d_words, const uint32_t* d_list, uint64_t n_reads, uint64_t read_index_base,
+                              uint32_t G, unsigned long long* d_stats, unsigned long long* d_unique,
+                              unsigned long long* d_ambiguous, unsigned long long* d_first_seen, cudaStream_t s) {
+  if (n_reads == 0) return ST_OK;
+  int dev = 0, sms = 148;
+  PA_CUDA(cudaGetDevice(&dev));
+  PA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  uint64_t grid = std::min<uint64_t>((n_reads + SUM_THREADS - 1) / SUM_THREADS, (uint64_t)sms * 8);
+  summary_kernel<<<(unsigned)grid, SUM_THREADS, 0, s>>>(d_words, d_list, n_reads, read_index_base, G, d_stats, d_unique,
+                                                         d_ambiguous, d_first_seen);
+  PA_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+}  // namespace pa

@@ -1,0 +1,809 @@
+// build.cu -- K1 (2-bit window encoder), K3 (run-length / CSR pass), lookup-table
+// construction, and the CSR consumers (rank lookup, insertion order, EXTSIM
+// statistics K5/K6, genome removal K7).
+//
+// Reference being replaced: KmerReference._build_kmer_mapping
+// (/root/reference/src/kmer.py:135-150), get_kmer_references (kmer.py:292-298),
+// _compute_genome_stats (kmer.py:152-177), the intersections of
+// _apply_greedy_filter (kmer.py:206-207) and _remove_filtered_genomes_from_kmers
+// (kmer.py:232-243).  All kernels are integer, HBM-bound streaming passes.
+#include "index.cuh"
+#include "scan.cuh"
+#include "sort.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace pa {
+
+// ===========================================================================
+// generic scans
+// ===========================================================================
+namespace {
+
+__global__ void __launch_bounds__(SCAN_THREADS) tile_sum_u32(const uint32_t* __restrict__ in, uint64_t n,
+                                                             uint64_t* __restrict__ tile_sums) {
+  __shared__ uint64_t ws[SCAN_THREADS / 32];
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+  uint64_t acc = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    uint64_t i = base + (uint64_t)j * SCAN_THREADS + threadIdx.x;
+    if (i < n) acc += in[i];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t t = 0;
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) t += ws[w];
+    tile_sums[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) tile_scan_apply_u32(const uint32_t* __restrict__ in,
+                                                                    uint64_t* __restrict__ out, uint64_t n,
+                                                                    const uint64_t* __restrict__ tile_excl) {
+  __shared__ uint64_t ws[SCAN_THREADS / 32];
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  uint64_t local = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    v[j] = (base + j < n) ? in[base + j] : 0;
+    local += v[j];
+  }
+  uint64_t total;
+  uint64_t excl = block_exclusive_scan<SCAN_THREADS, uint64_t>(local, total, ws) + tile_excl[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    if (base + j < n) out[base + j] = excl;
+    excl += v[j];
+  }
+}
+
+}  // namespace
+
+__global__ void scan_u64_single_block(uint64_t* data, uint64_t n, uint64_t* d_total) {
+  __shared__ uint64_t ws[1024 / 32];
+  __shared__ uint64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint64_t base = 0; base < n; base += blockDim.x) {
+    uint64_t i = base + threadIdx.x;
+    uint64_t v = i < n ? data[i] : 0;
+    uint64_t total;
+    uint64_t excl = block_exclusive_scan<1024, uint64_t>(v, total, ws);
+    uint64_t c = carry;
+    if (i < n) data[i] = c + excl;
+    __syncthreads();
+    if (threadIdx.x == 0) carry = c + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && d_total) *d_total = carry;
+}
+
+int32_t exclusive_scan_u32(const uint32_t* d_in, uint64_t* d_out, uint64_t n, uint64_t* d_tile_sums, uint64_t* d_total,
+                           cudaStream_t s) {
+  if (n == 0) { PA_CUDA(cudaMemsetAsync(d_total, 0, 8, s)); return ST_OK; }
+  uint64_t tiles = scan_tiles(n);
+  tile_sum_u32<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(d_in, n, d_tile_sums);
+  scan_u64_single_block<<<1, 1024, 0, s>>>(d_tile_sums, tiles, d_total);
+  tile_scan_apply_u32<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(d_in, d_out, n, d_tile_sums);
+  PA_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+namespace {
+
+// ===========================================================================
+// K1: window encoder.  One tile = ENC_TILE window starts.  Phase 1 packs the
+// tile's bases into bit planes (low code bit, high code bit, "not ACGT",
+// "last base of a genome") with coalesced 16-byte loads; phase 2 extracts each
+// window with funnel shifts and writes key / position fully coalesced.
+// A window is valid iff it has k ACGT bases inside one genome (kmer.py:93-94
+// bounds the window to the genome, kmer.py:145 drops windows containing N).
+// ===========================================================================
+constexpr int ENC_THREADS = 256;
+constexpr int ENC_TILE = 4096;
+constexpr int ENC_WORDS = ENC_TILE / 32 + 2;
+
+__global__ void __launch_bounds__(ENC_THREADS)
+encode_windows(const uint8_t* __restrict__ bases, uint64_t total, const uint64_t* __restrict__ genome_off, uint32_t G,
+               int k, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned long long* __restrict__ n_valid,
+               unsigned int* __restrict__ bad_flag) {
+  __shared__ uint32_t s_lo[ENC_WORDS], s_hi[ENC_WORDS], s_inv[ENC_WORDS], s_brk[ENC_WORDS];
+  __shared__ uint32_t s_cnt[ENC_THREADS / 32];
+  const uint64_t tile_base = (uint64_t)blockIdx.x * ENC_TILE;
+  const int tid = threadIdx.x;
+  bool bad = false;
+  for (int w = tid; w < ENC_WORDS; w += ENC_THREADS) {
+    uint64_t b0 = tile_base + (uint64_t)w * 32;
+    uint32_t lo = 0, hi = 0, inv = 0;
+    uint8_t c[32];
+    if (b0 + 32 <= total) {
+      const uint4* p = reinterpret_cast<const uint4*>(bases + b0);  // tile_base and the buffer are 32-byte aligned
+      *reinterpret_cast<uint4*>(c) = p[0];
+      *reinterpret_cast<uint4*>(c + 16) = p[1];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) c[i] = (b0 + i < total) ? bases[b0 + i] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      uint32_t ch = c[i];
+      bool ok = is_acgt(ch);
+      uint32_t code = base_code(ch);
+      lo |= (code & 1u) << i;
+      hi |= (code >> 1) << i;
+      inv |= (ok ? 0u : 1u) << i;
+      if (!ok && ch != 'N' && b0 + i < total) bad = true;
+    }
+    s_lo[w] = lo; s_hi[w] = hi; s_inv[w] = inv; s_brk[w] = 0;
+  }
+  if (bad) atomicOr(bad_flag, 1u);
+  __syncthreads();
+  // mark the last base of every genome that ends inside this tile's span
+  {
+    const uint64_t span_end = min(total, tile_base + (uint64_t)ENC_WORDS * 32);
+    if (tile_base < total) {
+      uint32_t g0 = genome_of(genome_off, G, tile_base);
+      for (uint32_t g = g0 + tid; g < G; g += ENC_THREADS) {
+        uint64_t beg = genome_off[g], end = genome_off[g + 1];
+        if (beg >= span_end) break;
+        if (end == beg || end > span_end || end - 1 < tile_base) continue;
+        uint64_t r = end - 1 - tile_base;
+        atomicOr(&s_brk[r >> 5], 1u << (r & 31));
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1);
+  uint32_t cnt = 0;
+#pragma unroll 4
+  for (int j = 0; j < ENC_TILE / ENC_THREADS; ++j) {
+    uint32_t s = j * ENC_THREADS + tid;
+    uint64_t gpos = tile_base + s;
+    if (gpos >= total) break;
+    uint32_t w = s >> 5, b = s & 31;
+    uint32_t lo = __funnelshift_r(s_lo[w], s_lo[w + 1], b) & kmask;
+    uint32_t hi = __funnelshift_r(s_hi[w], s_hi[w + 1], b) & kmask;
+    uint32_t inv = __funnelshift_r(s_inv[w], s_inv[w + 1], b) & kmask;
+    uint32_t brk = __funnelshift_r(s_brk[w], s_brk[w + 1], b) & (kmask >> 1);
+    bool valid = (inv | brk) == 0 && gpos + (uint64_t)k <= total;
+    keys[gpos] = valid ? (((uint64_t)hi << k) | lo) : SENTINEL_KEY;
+    vals[gpos] = (uint32_t)gpos;
+    cnt += valid;
+  }
+  cnt = warp_sum(cnt);
+  if ((tid & 31) == 0) s_cnt[tid >> 5] = cnt;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < ENC_THREADS / 32; ++w) t += s_cnt[w];
+    if (t) atomicAdd(n_valid, (unsigned long long)t);
+  }
+}
+
+// ===========================================================================
+// K3: run-length pass over the sorted (key, global position) records.
+//   key head  : first record of a distinct k-mer
+//   run head  : first record of a (k-mer, genome) pair
+// rle_count -> per-tile head counts; scan; rle_scatter writes the CSR.
+// ===========================================================================
+constexpr int RLE_THREADS = 256;
+constexpr int RLE_ITEMS = 8;
+constexpr int RLE_TILE = RLE_THREADS * RLE_ITEMS;
+
+__device__ __forceinline__ void rle_flags(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                          const uint64_t* __restrict__ genome_off, uint32_t G, uint64_t base, uint64_t n,
+                                          uint32_t (&gen)[RLE_ITEMS], uint32_t& kh_mask, uint32_t& rh_mask) {
+  kh_mask = rh_mask = 0;
+  uint64_t prev_key = 0; uint32_t prev_gen = 0;
+  bool have_prev = false;
+  if (base > 0 && base < n) {
+    prev_key = keys[base - 1];
+    prev_gen = genome_of(genome_off, G, vals[base - 1]);
+    have_prev = true;
+  }
+#pragma unroll
+  for (int j = 0; j < RLE_ITEMS; ++j) {
+    uint64_t i = base + j;
+    if (i < n) {
+      uint64_t key = keys[i];
+      uint32_t g = genome_of(genome_off, G, vals[i]);
+      gen[j] = g;
+      bool kh = !have_prev || key != prev_key;
+      bool rh = kh || g != prev_gen;
+      kh_mask |= (uint32_t)kh << j;
+      rh_mask |= (uint32_t)rh << j;
+      prev_key = key; prev_gen = g; have_prev = true;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RLE_THREADS)
+rle_count(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint64_t* __restrict__ genome_off,
+          uint32_t G, uint64_t n, uint64_t* __restrict__ tile_keys, uint64_t* __restrict__ tile_runs) {
+  __shared__ uint32_t ws[2][RLE_THREADS / 32];
+  const uint64_t base = (uint64_t)blockIdx.x * RLE_TILE + (uint64_t)threadIdx.x * RLE_ITEMS;
+  uint32_t gen[RLE_ITEMS], kh, rh;
+  rle_flags(keys, vals, genome_off, G, base, n, gen, kh, rh);
+  uint32_t a = warp_sum((uint32_t)__popc(kh)), b = warp_sum((uint32_t)__popc(rh));
+  if ((threadIdx.x & 31) == 0) { ws[0][threadIdx.x >> 5] = a; ws[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t ta = 0, tb = 0;
+    for (int w = 0; w < RLE_THREADS / 32; ++w) { ta += ws[0][w]; tb += ws[1][w]; }
+    tile_keys[blockIdx.x] = ta; tile_runs[blockIdx.x] = tb;
+  }
+}
+
+__global__ void __launch_bounds__(RLE_THREADS)
+rle_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint64_t* __restrict__ genome_off,
+            uint32_t G, uint64_t n, const uint64_t* __restrict__ tile_keys, const uint64_t* __restrict__ tile_runs,
+            uint64_t* __restrict__ ukeys, uint64_t* __restrict__ run_off, uint32_t* __restrict__ run_genome,
+            uint64_t* __restrict__ pos_off, uint32_t* __restrict__ pos) {
+  __shared__ uint32_t ws[RLE_THREADS / 32];
+  const uint64_t base = (uint64_t)blockIdx.x * RLE_TILE + (uint64_t)threadIdx.x * RLE_ITEMS;
+  uint32_t gen[RLE_ITEMS], kh, rh;
+  rle_flags(keys, vals, genome_off, G, base, n, gen, kh, rh);
+  uint32_t tot;
+  uint64_t kr = tile_keys[blockIdx.x] + block_exclusive_scan<RLE_THREADS, uint32_t>(__popc(kh), tot, ws);
+  uint64_t rr = tile_runs[blockIdx.x] + block_exclusive_scan<RLE_THREADS, uint32_t>(__popc(rh), tot, ws);
+#pragma unroll
+  for (int j = 0; j < RLE_ITEMS; ++j) {
+    uint64_t i = base + j;
+    if (i < n) {
+      if ((rh >> j) & 1) {
+        if ((kh >> j) & 1) { ukeys[kr] = keys[i]; run_off[kr] = rr; ++kr; }
+        run_genome[rr] = gen[j];
+        pos_off[rr] = i;
+        ++rr;
+      }
+      pos[i] = (uint32_t)((uint64_t)vals[i] - genome_off[gen[j]]);
+    }
+  }
+}
+
+__global__ void iota_u32(uint32_t* v, uint64_t n) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (uint32_t)i;
+}
+
+__global__ void set_csr_tails(uint64_t* run_off, uint64_t U, uint64_t R, uint64_t* pos_off, uint64_t N) {
+  run_off[U] = R;
+  pos_off[R] = N;
+}
+
+// ===========================================================================
+// lookup table construction from the CSR
+// ===========================================================================
+__global__ void msector_counts(const uint64_t* __restrict__ run_off, uint64_t U, uint32_t* __restrict__ cnt) {
+  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  uint64_t c = run_off[u + 1] - run_off[u];
+  cnt[u] = c > 1 ? (uint32_t)((c + MLIST_SECTOR - 1) / MLIST_SECTOR) : 0u;
+}
+
+__global__ void mlist_fill(const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome, uint64_t U,
+                           const uint64_t* __restrict__ msec_off, uint32_t* __restrict__ mlist) {
+  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
+  if (c <= 1) return;
+  uint32_t* dst = mlist + msec_off[u] * MLIST_SECTOR;
+  for (uint64_t j = 0; j < c; ++j) dst[j] = run_genome[r0 + j] | (j + 1 == c ? LIST_END : 0u);
+}
+
+struct TableBuildParams {
+  uint32_t tag_bits, val_bits;
+  MixParams mix;
+};
+
+__device__ __forceinline__ uint64_t entry_value(const TableBuildParams& p, bool specific, uint64_t payload) {
+  return ((uint64_t)specific << (p.val_bits - 1)) | payload;
+}
+
+__global__ void table_insert(const uint64_t* __restrict__ ukeys, const uint64_t* __restrict__ run_off,
+                             const uint32_t* __restrict__ run_genome, const uint64_t* __restrict__ msec_off, uint64_t U,
+                             TableBuildParams p, unsigned long long* __restrict__ buckets,
+                             unsigned int* __restrict__ ovf_count, uint32_t* __restrict__ ovf_list, uint32_t ovf_cap) {
+  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
+  uint64_t h = mix_key(ukeys[u], p.mix);
+  uint64_t tag = h & ((1ULL << p.tag_bits) - 1);
+  uint64_t entry = (tag << p.val_bits) | entry_value(p, c == 1, c == 1 ? (uint64_t)run_genome[r0] : msec_off[u]);
+  unsigned long long* b = buckets + (h >> p.tag_bits) * 4;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    if (b[s] != EMPTY64) continue;  // slots fill in order, a taken slot never frees
+    if (atomicCAS(&b[s], (unsigned long long)EMPTY64, (unsigned long long)entry) == EMPTY64) return;
+  }
+  uint32_t at = atomicAdd(ovf_count, 1u);
+  if (at < ovf_cap) ovf_list[at] = (uint32_t)u;
+}
+
+__global__ void stash_insert(const uint64_t* __restrict__ ukeys, const uint64_t* __restrict__ run_off,
+                             const uint32_t* __restrict__ run_genome, const uint64_t* __restrict__ msec_off,
+                             const uint32_t* __restrict__ ovf_list, uint32_t n_ovf, TableBuildParams p,
+                             unsigned long long* __restrict__ stash_key, uint64_t* __restrict__ stash_val,
+                             uint64_t stash_mask) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_ovf) return;
+  uint64_t u = ovf_list[t];
+  uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
+  uint64_t h = mix_key(ukeys[u], p.mix);
+  uint64_t value = entry_value(p, c == 1, c == 1 ? (uint64_t)run_genome[r0] : msec_off[u]);
+  uint64_t i = (h * 0xA24BAED4963EE407ULL) >> 20;
+  for (;;) {
+    i &= stash_mask;
+    if (atomicCAS(&stash_key[i], (unsigned long long)EMPTY64, (unsigned long long)h) == EMPTY64) {
+      stash_val[i] = value;
+      return;
+    }
+    ++i;
+  }
+}
+
+// ===========================================================================
+// CSR consumers
+// ===========================================================================
+__global__ void lookup_ranks(const uint64_t* __restrict__ ukeys, uint64_t U, const uint64_t* __restrict__ q, uint64_t n,
+                             uint64_t* __restrict__ rank) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t key = q[i];
+  uint64_t lo = 0, hi = U;
+  while (lo < hi) {
+    uint64_t mid = (lo + hi) >> 1;
+    if (ukeys[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  rank[i] = (key != SENTINEL_KEY && lo < U && ukeys[lo] == key) ? lo : LOOKUP_MISS;
+}
+
+// first occurrence of each distinct k-mer as a global base position: the dict
+// insertion order of kmer.py:146-147 is the ascending order of this value.
+__global__ void first_occurrence(const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome,
+                                 const uint64_t* __restrict__ pos_off, const uint32_t* __restrict__ pos,
+                                 const uint64_t* __restrict__ genome_off, uint64_t U, uint64_t* __restrict__ keys) {
+  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  uint64_t r = run_off[u];
+  keys[u] = genome_off[run_genome[r]] + pos[pos_off[r]];
+}
+
+// K5: per identifier class, number of distinct k-mers holding it / holding it alone.
+__global__ void extsim_stats_kernel(const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome, uint64_t U,
+                                    const uint32_t* __restrict__ group, int dedupe,
+                                    unsigned long long* __restrict__ total, unsigned long long* __restrict__ unique) {
+  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
+  for (uint64_t j = 0; j < c; ++j) {
+    uint32_t gr = group[run_genome[r0 + j]];
+    bool first = true;
+    if (dedupe)
+      for (uint64_t i = 0; i < j && first; ++i) first = group[run_genome[r0 + i]] != gr;
+    if (!first) continue;
+    atomicAdd(&total[gr], 1ULL);
+    if (c == 1) atomicAdd(&unique[gr], 1ULL);
+  }
+}
+
+// K6: inter[a][b] += 1 for every pair of classes sharing a distinct k-mer (diagonal = total).
+// One warp per k-mer; lanes split the c*c pairs.
+__global__ void extsim_pairwise_kernel(const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome, uint64_t U,
+                                       const uint32_t* __restrict__ group, uint32_t n_groups, int dedupe,
+                                       unsigned long long* __restrict__ inter) {
+  uint64_t u = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  if (u >= U) return;
+  const uint32_t lane = threadIdx.x & 31;
+  uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
+  for (uint64_t t = lane; t < c * c; t += 32) {
+    uint64_t a = t / c, b = t % c;
+    uint32_t ga = group[run_genome[r0 + a]], gb = group[run_genome[r0 + b]];
+    if (dedupe) {
+      bool fa = true, fb = true;
+      for (uint64_t i = 0; i < a && fa; ++i) fa = group[run_genome[r0 + i]] != ga;
+      for (uint64_t i = 0; i < b && fb; ++i) fb = group[run_genome[r0 + i]] != gb;
+      if (!fa || !fb) continue;
+    }
+    atomicAdd(&inter[(size_t)ga * n_groups + gb], 1ULL);
+  }
+}
+
+// K7 (a): per distinct k-mer, how many runs / positions survive the keep mask.
+__global__ void drop_count(const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome,
+                           const uint64_t* __restrict__ pos_off, uint64_t U, const uint8_t* __restrict__ keep,
+                           uint32_t* __restrict__ key_kept, uint32_t* __restrict__ runs_kept, uint32_t* __restrict__ pos_kept) {
+  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  uint32_t nr = 0; uint64_t np = 0;
+  for (uint64_t r = run_off[u]; r < run_off[u + 1]; ++r)
+    if (keep[run_genome[r]]) { ++nr; np += pos_off[r + 1] - pos_off[r]; }
+  key_kept[u] = nr > 0; runs_kept[u] = nr; pos_kept[u] = (uint32_t)np;
+}
+
+// K7 (b): write the surviving CSR with renumbered genomes.
+__global__ void drop_scatter(const uint64_t* __restrict__ ukeys, const uint64_t* __restrict__ run_off,
+                             const uint32_t* __restrict__ run_genome, const uint64_t* __restrict__ pos_off,
+                             const uint32_t* __restrict__ pos, uint64_t U, const uint8_t* __restrict__ keep,
+                             const uint32_t* __restrict__ remap, const uint32_t* __restrict__ key_kept,
+                             const uint64_t* __restrict__ key_rank, const uint64_t* __restrict__ run_rank,
+                             const uint64_t* __restrict__ pos_rank, const uint64_t* __restrict__ first_occ,
+                             uint64_t* __restrict__ n_first_occ, uint64_t* __restrict__ n_ukeys,
+                             uint64_t* __restrict__ n_run_off, uint32_t* __restrict__ n_run_genome,
+                             uint64_t* __restrict__ n_pos_off, uint32_t* __restrict__ n_pos) {
+  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (u >= U || !key_kept[u]) return;
+  uint64_t ku = key_rank[u], rr = run_rank[u], pp = pos_rank[u];
+  n_ukeys[ku] = ukeys[u];
+  n_first_occ[ku] = first_occ[u];
+  n_run_off[ku] = rr;
+  for (uint64_t r = run_off[u]; r < run_off[u + 1]; ++r) {
+    uint32_t g = run_genome[r];
+    if (!keep[g]) continue;
+    n_run_genome[rr] = remap[g];
+    n_pos_off[rr] = pp;
+    for (uint64_t q = pos_off[r]; q < pos_off[r + 1]; ++q) n_pos[pp++] = pos[q];
+    ++rr;
+  }
+}
+
+inline unsigned grid_for(uint64_t n, int threads) { return (unsigned)std::max<uint64_t>(1, (n + threads - 1) / threads); }
+
+float elapsed_ms(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms;
+}
+
+}  // namespace
+
+// ===========================================================================
+// host orchestration
+// ===========================================================================
+int32_t index_build_tables(Index& ix) {
+  cudaStream_t s = ix.stream;
+  const uint64_t U = ix.n_keys;
+  const int k = ix.k;
+  ix.mix.mask = (2 * k >= 64) ? ~0ULL : ((1ULL << (2 * k)) - 1);
+  ix.mix.shift = (uint32_t)std::max(1, k);
+  ix.buckets.release(); ix.stash_key.release(); ix.stash_val.release(); ix.mlist.release();
+  ix.stash_cap = 0; ix.stash_count = 0; ix.n_msectors = 0;
+  if (U == 0 || k <= 0) {
+    // one empty bucket; every hash maps to it (tag_bits = 2k shifts the whole hash away)
+    ix.bucket_bits = 0; ix.tag_bits = k >= 1 ? (uint32_t)(2 * k) : 1u; ix.val_bits = 64 - ix.tag_bits;
+    PA_TRY(ix.buckets.alloc(32));
+    PA_CUDA(cudaMemsetAsync(ix.buckets.p, 0xFF, 32, s));
+    PA_TRY(ix.mlist.alloc(32));
+    PA_CUDA(cudaStreamSynchronize(s));
+    return ST_OK;
+  }
+  // multi-genome lists: 32-byte aligned, 8 ids per sector, last id flagged
+  DevBuf msec_cnt, msec_off, tile_sums, d_total;
+  PA_TRY(msec_cnt.alloc(U * 4));
+  PA_TRY(msec_off.alloc(U * 8));
+  PA_TRY(tile_sums.alloc((scan_tiles(U) + 1) * 8));
+  PA_TRY(d_total.alloc(8));
+  msector_counts<<<grid_for(U, 256), 256, 0, s>>>(ix.run_off.as<uint64_t>(), U, msec_cnt.as<uint32_t>());
+  PA_TRY(exclusive_scan_u32(msec_cnt.as<uint32_t>(), msec_off.as<uint64_t>(), U, tile_sums.as<uint64_t>(),
+                            d_total.as<uint64_t>(), s));
+  uint64_t n_msec = 0;
+  PA_CUDA(cudaMemcpyAsync(&n_msec, d_total.p, 8, cudaMemcpyDeviceToHost, s));
+  PA_CUDA(cudaStreamSynchronize(s));
+  ix.n_msectors = n_msec;
+  PA_TRY(ix.mlist.alloc(std::max<uint64_t>(n_msec, 1) * 32));
+  PA_CUDA(cudaMemsetAsync(ix.mlist.p, 0xFF, ix.mlist.bytes, s));
+  if (n_msec)
+    mlist_fill<<<grid_for(U, 256), 256, 0, s>>>(ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(), U,
+                                                 msec_off.as<uint64_t>(), ix.mlist.as<uint32_t>());
+  // bucket count: load factor <= 0.5 over 4-slot buckets, and enough value bits for the payloads
+  uint32_t b_load = ceil_log2_u64((U + 1) / 2);
+  uint32_t payload_need = std::max(ceil_log2_u64((uint64_t)ix.n_genomes + 1), ceil_log2_u64(n_msec + 1));
+  payload_need = std::max(payload_need, 1u);
+  int64_t b_payload = (int64_t)payload_need + 2 * k - 63;
+  int64_t b = std::max<int64_t>(std::max<int64_t>(b_load, b_payload), 0);
+  b = std::min<int64_t>(b, 2 * k - 1);
+  DevBuf ovf_count, ovf_list;
+  PA_TRY(ovf_count.alloc(4));
+  uint32_t ovf_cap = (uint32_t)std::min<uint64_t>(U / 4 + 4096, 0xFFFFFFF0ull);
+  PA_TRY(ovf_list.alloc((size_t)ovf_cap * 4));
+  for (;;) {
+    ix.bucket_bits = (uint32_t)b;
+    ix.tag_bits = (uint32_t)(2 * k - b);
+    ix.val_bits = 64 - ix.tag_bits;
+    if (ix.val_bits - 1 < payload_need) { set_error("lookup table: payload does not fit (k=%d, b=%lld)", k, (long long)b); return ST_UNSUPPORTED; }
+    const uint64_t n_buckets = 1ULL << b;
+    PA_TRY(ix.buckets.alloc(n_buckets * 32));
+    PA_CUDA(cudaMemsetAsync(ix.buckets.p, 0xFF, n_buckets * 32, s));
+    PA_CUDA(cudaMemsetAsync(ovf_count.p, 0, 4, s));
+    TableBuildParams p{ix.tag_bits, ix.val_bits, ix.mix};
+    table_insert<<<grid_for(U, 256), 256, 0, s>>>(ix.ukeys.as<uint64_t>(), ix.run_off.as<uint64_t>(),
+                                                   ix.run_genome.as<uint32_t>(), msec_off.as<uint64_t>(), U, p,
+                                                   ix.buckets.as<unsigned long long>(), ovf_count.as<unsigned int>(),
+                                                   ovf_list.as<uint32_t>(), ovf_cap);
+    uint32_t n_ovf = 0;
+    PA_CUDA(cudaMemcpyAsync(&n_ovf, ovf_count.p, 4, cudaMemcpyDeviceToHost, s));
+    PA_CUDA(cudaStreamSynchronize(s));
+    if (n_ovf > ovf_cap) {  // pathological: grow the table instead of the stash
+      if (b >= 2 * k - 1) { set_error("lookup table: overflow list exhausted"); return ST_UNSUPPORTED; }
+      ++b;
+      continue;
+    }
+    ix.stash_count = n_ovf;
+    if (n_ovf) {
+      uint64_t cap = 16;
+      while (cap < (uint64_t)n_ovf * 2) cap <<= 1;
+      ix.stash_cap = cap;
+      PA_TRY(ix.stash_key.alloc(cap * 8));
+      PA_TRY(ix.stash_val.alloc(cap * 8));
+      PA_CUDA(cudaMemsetAsync(ix.stash_key.p, 0xFF, cap * 8, s));
+      PA_CUDA(cudaMemsetAsync(ix.stash_val.p, 0xFF, cap * 8, s));
+      stash_insert<<<grid_for(n_ovf, 256), 256, 0, s>>>(ix.ukeys.as<uint64_t>(), ix.run_off.as<uint64_t>(),
+                                                         ix.run_genome.as<uint32_t>(), msec_off.as<uint64_t>(),
+                                                         ovf_list.as<uint32_t>(), n_ovf, p,
+                                                         ix.stash_key.as<unsigned long long>(), ix.stash_val.as<uint64_t>(),
+                                                         cap - 1);
+    }
+    break;
+  }
+  PA_CUDA(cudaGetLastError());
+  PA_CUDA(cudaStreamSynchronize(s));
+  return ST_OK;
+}
+
+int32_t index_build_from_device_bases(Index& ix, const uint8_t* d_bases) {
+  cudaStream_t s = ix.stream;
+  const uint64_t total = ix.total_bases;
+  const uint32_t G = ix.n_genomes;
+  const int k = ix.k;
+  ix.n_keys = ix.n_runs = ix.n_occ = 0;
+  cudaEvent_t ev[5];
+  for (auto& e : ev) PA_CUDA(cudaEventCreate(&e));
+  struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); } } guard{ev};
+
+  if (k <= 0 || total == 0 || G == 0) {  // kmer.py:91-92: no windows at all
+    PA_TRY(ix.ukeys.alloc(8)); PA_TRY(ix.run_off.alloc(8)); PA_TRY(ix.run_genome.alloc(4));
+    PA_TRY(ix.pos_off.alloc(8)); PA_TRY(ix.pos.alloc(4));
+    PA_CUDA(cudaMemsetAsync(ix.run_off.p, 0, 8, s)); PA_CUDA(cudaMemsetAsync(ix.pos_off.p, 0, 8, s));
+    return index_build_tables(ix);
+  }
+  if (total >= 0xFFFFFFFFull) { set_error("index build: %llu bases exceed the 32-bit position space of this build", (unsigned long long)total); return ST_UNSUPPORTED; }
+
+  // ---- K1 ----
+  DevBuf keys_a, keys_b, vals_a, vals_b, counters, sort_tmp;
+  PA_TRY(keys_a.alloc(total * 8)); PA_TRY(vals_a.alloc(total * 4));
+  PA_TRY(counters.alloc(16));
+  PA_CUDA(cudaMemsetAsync(counters.p, 0, 16, s));
+  PA_CUDA(cudaEventRecord(ev[0], s));
+  encode_windows<<<grid_for(total, ENC_TILE), ENC_THREADS, 0, s>>>(
+      d_bases, total, ix.genome_off.as<uint64_t>(), G, k, keys_a.as<uint64_t>(), vals_a.as<uint32_t>(),
+      counters.as<unsigned long long>(), reinterpret_cast<unsigned int*>(counters.as<char>() + 8));
+  PA_CUDA(cudaGetLastError());
+  PA_CUDA(cudaEventRecord(ev[1], s));
+  unsigned long long h_cnt[2] = {0, 0};
+  PA_CUDA(cudaMemcpyAsync(h_cnt, counters.p, 16, cudaMemcpyDeviceToHost, s));
+  PA_CUDA(cudaStreamSynchronize(s));
+  if (h_cnt[1] & 0xFFFFFFFFull) { set_error("genome sequence contains a character outside ACGTN"); return ST_BAD_BASE; }
+  const uint64_t n_valid = h_cnt[0];
+
+  // ---- K2 ----
+  PA_TRY(keys_b.alloc(total * 8)); PA_TRY(vals_b.alloc(total * 4));
+  PA_TRY(sort_tmp.alloc(radix_sort_temp_bytes(total)));
+  int in_b = 0;
+  PA_TRY(radix_sort_pairs(keys_a.as<uint64_t>(), vals_a.as<uint32_t>(), keys_b.as<uint64_t>(), vals_b.as<uint32_t>(), total,
+                          std::min(64, 2 * k + 1), sort_tmp.p, sort_tmp.bytes, s, &in_b));
+  PA_CUDA(cudaEventRecord(ev[2], s));
+  if (in_b) { keys_a.swap(keys_b); vals_a.swap(vals_b); }
+  keys_b.release(); vals_b.release(); sort_tmp.release();
+
+  // ---- K3 ----
+  const uint64_t tiles = std::max<uint64_t>(1, (n_valid + RLE_TILE - 1) / RLE_TILE);
+  DevBuf tile_keys, tile_runs, totals;
+  PA_TRY(tile_keys.alloc((tiles + 1) * 8)); PA_TRY(tile_runs.alloc((tiles + 1) * 8)); PA_TRY(totals.alloc(16));
+  rle_count<<<(unsigned)tiles, RLE_THREADS, 0, s>>>(keys_a.as<uint64_t>(), vals_a.as<uint32_t>(), ix.genome_off.as<uint64_t>(),
+                                                    G, n_valid, tile_keys.as<uint64_t>(), tile_runs.as<uint64_t>());
+  scan_u64_single_block<<<1, 1024, 0, s>>>(tile_keys.as<uint64_t>(), tiles, totals.as<uint64_t>());
+  scan_u64_single_block<<<1, 1024, 0, s>>>(tile_runs.as<uint64_t>(), tiles, totals.as<uint64_t>() + 1);
+  uint64_t h_tot[2];
+  PA_CUDA(cudaMemcpyAsync(h_tot, totals.p, 16, cudaMemcpyDeviceToHost, s));
+  PA_CUDA(cudaStreamSynchronize(s));
+  const uint64_t U = h_tot[0], R = h_tot[1];
+  PA_TRY(ix.ukeys.alloc((U + 1) * 8)); PA_TRY(ix.run_off.alloc((U + 1) * 8));
+  PA_TRY(ix.run_genome.alloc((R + 1) * 4)); PA_TRY(ix.pos_off.alloc((R + 1) * 8)); PA_TRY(ix.pos.alloc((n_valid + 1) * 4));
+  if (n_valid)
+    rle_scatter<<<(unsigned)tiles, RLE_THREADS, 0, s>>>(keys_a.as<uint64_t>(), vals_a.as<uint32_t>(),
+                                                        ix.genome_off.as<uint64_t>(), G, n_valid, tile_keys.as<uint64_t>(),
+                                                        tile_runs.as<uint64_t>(), ix.ukeys.as<uint64_t>(),
+                                                        ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(),
+                                                        ix.pos_off.as<uint64_t>(), ix.pos.as<uint32_t>());
+  set_csr_tails<<<1, 1, 0, s>>>(ix.run_off.as<uint64_t>(), U, R, ix.pos_off.as<uint64_t>(), n_valid);
+  PA_CUDA(cudaGetLastError());
+  PA_CUDA(cudaEventRecord(ev[3], s));
+  ix.n_keys = U; ix.n_runs = R; ix.n_occ = n_valid;
+  keys_a.release(); vals_a.release();
+
+  PA_TRY(index_build_tables(ix));
+  PA_CUDA(cudaEventRecord(ev[4], s));
+  PA_CUDA(cudaStreamSynchronize(s));
+  ix.t_encode_ms = elapsed_ms(ev[0], ev[1]);
+  ix.t_sort_ms = elapsed_ms(ev[1], ev[2]);
+  ix.t_rle_ms = elapsed_ms(ev[2], ev[3]);
+  ix.t_table_ms = elapsed_ms(ev[3], ev[4]);
+  return ST_OK;
+}
+
+int32_t index_ensure_first_occ(Index& ix) {
+  if (ix.has_first_occ) return ST_OK;
+  const uint64_t U = ix.n_keys;
+  PA_TRY(ix.first_occ.alloc((U + 1) * 8));
+  if (U)
+    first_occurrence<<<grid_for(U, 256), 256, 0, ix.stream>>>(ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(),
+                                                              ix.pos_off.as<uint64_t>(), ix.pos.as<uint32_t>(),
+                                                              ix.genome_off.as<uint64_t>(), U, ix.first_occ.as<uint64_t>());
+  PA_CUDA(cudaGetLastError());
+  ix.has_first_occ = true;
+  return ST_OK;
+}
+
+int32_t index_export_order(Index& ix, uint32_t* h_order) {
+  const uint64_t U = ix.n_keys;
+  if (U == 0) return ST_OK;
+  cudaStream_t s = ix.stream;
+  PA_TRY(index_ensure_first_occ(ix));
+  DevBuf ka, kb, va, vb, tmp;
+  PA_TRY(ka.alloc(U * 8)); PA_TRY(kb.alloc(U * 8)); PA_TRY(va.alloc(U * 4)); PA_TRY(vb.alloc(U * 4));
+  PA_TRY(tmp.alloc(radix_sort_temp_bytes(U)));
+  PA_CUDA(cudaMemcpyAsync(ka.p, ix.first_occ.p, U * 8, cudaMemcpyDeviceToDevice, s));
+  iota_u32<<<grid_for(U, 256), 256, 0, s>>>(va.as<uint32_t>(), U);
+  int in_b = 0;
+  PA_TRY(radix_sort_pairs(ka.as<uint64_t>(), va.as<uint32_t>(), kb.as<uint64_t>(), vb.as<uint32_t>(), U, 64, tmp.p,
+                          tmp.bytes, s, &in_b));
+  PA_CUDA(cudaMemcpyAsync(h_order, in_b ? vb.p : va.p, U * 4, cudaMemcpyDeviceToHost, s));
+  PA_CUDA(cudaStreamSynchronize(s));
+  return ST_OK;
+}
+
+int32_t index_lookup_ranks(Index& ix, const uint8_t* h_kmers, uint64_t n, uint64_t* h_rank) {
+  if (n == 0) return ST_OK;
+  if (ix.k <= 0 || ix.n_keys == 0) { for (uint64_t i = 0; i < n; ++i) h_rank[i] = LOOKUP_MISS; return ST_OK; }
+  std::vector<uint64_t> q(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    bool ok;
+    uint64_t key = encode_kmer_host(h_kmers + i * (uint64_t)ix.k, ix.k, &ok);
+    q[i] = ok ? key : SENTINEL_KEY;
+  }
+  cudaStream_t s = ix.stream;
+  DevBuf dq, dr;
+  PA_TRY(dq.alloc(n * 8)); PA_TRY(dr.alloc(n * 8));
+  PA_CUDA(cudaMemcpyAsync(dq.p, q.data(), n * 8, cudaMemcpyHostToDevice, s));
+  lookup_ranks<<<grid_for(n, 256), 256, 0, s>>>(ix.ukeys.as<uint64_t>(), ix.n_keys, dq.as<uint64_t>(), n, dr.as<uint64_t>());
+  PA_CUDA(cudaGetLastError());
+  PA_CUDA(cudaMemcpyAsync(h_rank, dr.p, n * 8, cudaMemcpyDeviceToHost, s));
+  PA_CUDA(cudaStreamSynchronize(s));
+  return ST_OK;
+}
+
+static int32_t upload_groups(Index& ix, const uint32_t* h_group, uint32_t n_groups, DevBuf& d_group, int* dedupe) {
+  const uint32_t G = ix.n_genomes;
+  std::vector<uint8_t> seen(n_groups ? n_groups : 1, 0);
+  *dedupe = 0;
+  for (uint32_t g = 0; g < G; ++g) {
+    if (h_group[g] >= n_groups) { set_error("extsim: group id out of range"); return ST_INVALID_ARG; }
+    if (seen[h_group[g]]) *dedupe = 1;
+    seen[h_group[g]] = 1;
+  }
+  PA_TRY(d_group.alloc((size_t)std::max<uint32_t>(G, 1) * 4));
+  if (G) PA_CUDA(cudaMemcpyAsync(d_group.p, h_group, (size_t)G * 4, cudaMemcpyHostToDevice, ix.stream));
+  return ST_OK;
+}
+
+int32_t index_extsim_stats(Index& ix, const uint32_t* h_group, uint32_t n_groups, uint64_t* h_total, uint64_t* h_unique) {
+  cudaStream_t s = ix.stream;
+  DevBuf d_group, d_out;
+  int dedupe = 0;
+  PA_TRY(upload_groups(ix, h_group, n_groups, d_group, &dedupe));
+  size_t nb = (size_t)std::max<uint32_t>(n_groups, 1) * 8;
+  PA_TRY(d_out.alloc(nb * 2));
+  PA_CUDA(cudaMemsetAsync(d_out.p, 0, nb * 2, s));
+  if (ix.n_keys)
+    extsim_stats_kernel<<<grid_for(ix.n_keys, 256), 256, 0, s>>>(
+        ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(), ix.n_keys, d_group.as<uint32_t>(), dedupe,
+        d_out.as<unsigned long long>(), d_out.as<unsigned long long>() + std::max<uint32_t>(n_groups, 1));
+  PA_CUDA(cudaGetLastError());
+  if (n_groups) {
+    PA_CUDA(cudaMemcpyAsync(h_total, d_out.p, (size_t)n_groups * 8, cudaMemcpyDeviceToHost, s));
+    PA_CUDA(cudaMemcpyAsync(h_unique, d_out.as<char>() + nb, (size_t)n_groups * 8, cudaMemcpyDeviceToHost, s));
+  }
+  PA_CUDA(cudaStreamSynchronize(s));
+  return ST_OK;
+}
+
+int32_t index_extsim_pairwise(Index& ix, const uint32_t* h_group, uint32_t n_groups, uint64_t* h_inter) {
+  cudaStream_t s = ix.stream;
+  DevBuf d_group, d_out;
+  int dedupe = 0;
+  PA_TRY(upload_groups(ix, h_group, n_groups, d_group, &dedupe));
+  size_t nb = std::max<size_t>((size_t)n_groups * n_groups, 1) * 8;
+  PA_TRY(d_out.alloc(nb));
+  PA_CUDA(cudaMemsetAsync(d_out.p, 0, nb, s));
+  if (ix.n_keys)
+    extsim_pairwise_kernel<<<grid_for(ix.n_keys * 32, 256), 256, 0, s>>>(
+        ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(), ix.n_keys, d_group.as<uint32_t>(), n_groups, dedupe,
+        d_out.as<unsigned long long>());
+  PA_CUDA(cudaGetLastError());
+  if (n_groups) PA_CUDA(cudaMemcpyAsync(h_inter, d_out.p, (size_t)n_groups * n_groups * 8, cudaMemcpyDeviceToHost, s));
+  PA_CUDA(cudaStreamSynchronize(s));
+  return ST_OK;
+}
+
+int32_t index_drop_genomes(Index& ix, const uint8_t* h_keep) {
+  cudaStream_t s = ix.stream;
+  const uint32_t G = ix.n_genomes;
+  const uint64_t U = ix.n_keys;
+  std::vector<uint32_t> remap(std::max<uint32_t>(G, 1), 0xFFFFFFFFu);
+  std::vector<uint64_t> new_off(1, 0);
+  uint32_t ng = 0;
+  for (uint32_t g = 0; g < G; ++g)
+    if (h_keep[g]) {
+      remap[g] = ng++;
+      new_off.push_back(new_off.back() + (ix.h_genome_off[g + 1] - ix.h_genome_off[g]));
+    }
+  DevBuf d_keep, d_remap;
+  PA_TRY(d_keep.alloc(std::max<uint32_t>(G, 1)));
+  PA_TRY(d_remap.alloc((size_t)std::max<uint32_t>(G, 1) * 4));
+  if (G) {
+    PA_CUDA(cudaMemcpyAsync(d_keep.p, h_keep, G, cudaMemcpyHostToDevice, s));
+    PA_CUDA(cudaMemcpyAsync(d_remap.p, remap.data(), (size_t)G * 4, cudaMemcpyHostToDevice, s));
+  }
+  uint64_t nU = 0, nR = 0, nN = 0;
+  DevBuf n_ukeys, n_run_off, n_run_genome, n_pos_off, n_pos, n_first;
+  PA_TRY(index_ensure_first_occ(ix));  // order keys refer to the genome list before the removal
+  if (U) {
+    DevBuf key_kept, runs_kept, pos_kept, key_rank, run_rank, pos_rank, tile_sums, totals;
+    PA_TRY(key_kept.alloc(U * 4)); PA_TRY(runs_kept.alloc(U * 4)); PA_TRY(pos_kept.alloc(U * 4));
+    PA_TRY(key_rank.alloc(U * 8)); PA_TRY(run_rank.alloc(U * 8)); PA_TRY(pos_rank.alloc(U * 8));
+    PA_TRY(tile_sums.alloc((scan_tiles(U) + 1) * 8)); PA_TRY(totals.alloc(24));
+    drop_count<<<grid_for(U, 256), 256, 0, s>>>(ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(),
+                                                 ix.pos_off.as<uint64_t>(), U, d_keep.as<uint8_t>(), key_kept.as<uint32_t>(),
+                                                 runs_kept.as<uint32_t>(), pos_kept.as<uint32_t>());
+    PA_TRY(exclusive_scan_u32(key_kept.as<uint32_t>(), key_rank.as<uint64_t>(), U, tile_sums.as<uint64_t>(), totals.as<uint64_t>(), s));
+    PA_TRY(exclusive_scan_u32(runs_kept.as<uint32_t>(), run_rank.as<uint64_t>(), U, tile_sums.as<uint64_t>(), totals.as<uint64_t>() + 1, s));
+    PA_TRY(exclusive_scan_u32(pos_kept.as<uint32_t>(), pos_rank.as<uint64_t>(), U, tile_sums.as<uint64_t>(), totals.as<uint64_t>() + 2, s));
+    uint64_t h_tot[3];
+    PA_CUDA(cudaMemcpyAsync(h_tot, totals.p, 24, cudaMemcpyDeviceToHost, s));
+    PA_CUDA(cudaStreamSynchronize(s));
+    nU = h_tot[0]; nR = h_tot[1]; nN = h_tot[2];
+    PA_TRY(n_ukeys.alloc((nU + 1) * 8)); PA_TRY(n_run_off.alloc((nU + 1) * 8)); PA_TRY(n_run_genome.alloc((nR + 1) * 4));
+    PA_TRY(n_pos_off.alloc((nR + 1) * 8)); PA_TRY(n_pos.alloc((nN + 1) * 4)); PA_TRY(n_first.alloc((nU + 1) * 8));
+    drop_scatter<<<grid_for(U, 256), 256, 0, s>>>(
+        ix.ukeys.as<uint64_t>(), ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(), ix.pos_off.as<uint64_t>(),
+        ix.pos.as<uint32_t>(), U, d_keep.as<uint8_t>(), d_remap.as<uint32_t>(), key_kept.as<uint32_t>(),
+        key_rank.as<uint64_t>(), run_rank.as<uint64_t>(), pos_rank.as<uint64_t>(), ix.first_occ.as<uint64_t>(),
+        n_first.as<uint64_t>(), n_ukeys.as<uint64_t>(),
+        n_run_off.as<uint64_t>(), n_run_genome.as<uint32_t>(), n_pos_off.as<uint64_t>(), n_pos.as<uint32_t>());
+    set_csr_tails<<<1, 1, 0, s>>>(n_run_off.as<uint64_t>(), nU, nR, n_pos_off.as<uint64_t>(), nN);
+    PA_CUDA(cudaGetLastError());
+    PA_CUDA(cudaStreamSynchronize(s));
+  } else {
+    PA_TRY(n_ukeys.alloc(8)); PA_TRY(n_run_off.alloc(8)); PA_TRY(n_run_genome.alloc(4)); PA_TRY(n_pos_off.alloc(8)); PA_TRY(n_pos.alloc(4));
+    PA_TRY(n_first.alloc(8));
+    PA_CUDA(cudaMemsetAsync(n_run_off.p, 0, 8, s)); PA_CUDA(cudaMemsetAsync(n_pos_off.p, 0, 8, s));
+  }
+  ix.ukeys.swap(n_ukeys); ix.run_off.swap(n_run_off); ix.run_genome.swap(n_run_genome);
+  ix.pos_off.swap(n_pos_off); ix.pos.swap(n_pos); ix.first_occ.swap(n_first);
+  ix.n_keys = nU; ix.n_runs = nR; ix.n_occ = nN;
+  ix.n_genomes = ng;
+  ix.h_genome_off = new_off;
+  ix.total_bases = new_off.back();
+  PA_TRY(ix.genome_off.alloc(new_off.size() * 8));
+  PA_CUDA(cudaMemcpyAsync(ix.genome_off.p, new_off.data(), new_off.size() * 8, cudaMemcpyHostToDevice, s));
+  PA_CUDA(cudaStreamSynchronize(s));
+  ix.align_scratch.release(); ix.align_scratch_warps = 0;
+  return index_build_tables(ix);
+}
+
+}  // namespace pa

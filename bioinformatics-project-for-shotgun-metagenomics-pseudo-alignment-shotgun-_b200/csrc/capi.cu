@@ -1,0 +1,441 @@
+// capi.cu -- the extern "C" boundary declared in include/pa_b200.h.
+// Plain pointers and sizes only; no torch types, no C++ exceptions across the ABI.
+#include "../../include/pa_b200.h"
+#include "align.cuh"
+#include "index.cuh"
+#include "sort.cuh"
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+namespace pa {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+namespace {
+
+__global__ void debug_lookup_kernel(TableView t, const uint64_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ n_genomes,
+                                    uint32_t* __restrict__ first_genome) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t key = keys[i];
+  uint32_t c = 0, g0 = 0xFFFFFFFFu;
+  if (key != SENTINEL_KEY) {
+    uint64_t v = table_lookup(t, key);
+    if (v != LOOKUP_MISS) {
+      if (value_is_specific(t, v)) { c = 1; g0 = (uint32_t)value_payload(t, v); }
+      else {
+        uint64_t sector = value_payload(t, v);
+        g0 = t.mlist[sector * MLIST_SECTOR] & ~LIST_END;
+        for (bool more = true; more; ++sector)
+          for (int j = 0; j < 8 && more; ++j) { ++c; if (t.mlist[sector * MLIST_SECTOR + j] & LIST_END) more = false; }
+      }
+    }
+  }
+  n_genomes[i] = c; first_genome[i] = g0;
+}
+
+int32_t new_index(int32_t k, uint32_t G, const uint64_t* genome_off, int32_t device, Index** out) {
+  if (!out) { set_error("null output handle"); return ST_INVALID_ARG; }
+  *out = nullptr;
+  if (k > 31) { set_error("k = %d is outside the built scope (k <= 31: one k-mer per 64-bit word)", k); return ST_UNSUPPORTED; }
+  if (G && !genome_off) { set_error("genome_off is null"); return ST_INVALID_ARG; }
+  for (uint32_t g = 0; g < G; ++g)
+    if (genome_off[g + 1] < genome_off[g]) { set_error("genome_off is not monotonic"); return ST_INVALID_ARG; }
+  PA_CUDA(cudaSetDevice(device));
+  Index* ix = new (std::nothrow) Index();
+  if (!ix) { set_error("out of host memory"); return ST_NOMEM; }
+  ix->k = k; ix->device = device; ix->n_genomes = G;
+  ix->h_genome_off.assign(G + 1, 0);
+  for (uint32_t g = 0; g <= G && G; ++g) ix->h_genome_off[g] = genome_off[g] - genome_off[0];
+  ix->total_bases = G ? ix->h_genome_off[G] : 0;
+  cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e)); delete ix; return ST_CUDA; }
+  int32_t st = ix->genome_off.alloc((size_t)(G + 1) * 8);
+  if (st == ST_OK) {
+    e = cudaMemcpyAsync(ix->genome_off.p, ix->h_genome_off.data(), (size_t)(G + 1) * 8, cudaMemcpyHostToDevice, ix->stream);
+    if (e != cudaSuccess) { set_error("genome_off upload failed: %s", cudaGetErrorString(e)); st = ST_CUDA; }
+  }
+  if (st != ST_OK) { delete ix; return st; }
+  *out = ix;
+  return ST_OK;
+}
+
+AlignParams clamp_params(const pa_align_params* p) {
+  // Clamping keeps every comparison's outcome and makes the int64 products overflow-free:
+  //   quality bytes are 0..255, so a threshold <= 0 never filters and one >= 256 always does;
+  //   genome counts are 1..2^32, so max_genomes < 0 behaves like -1 and > 2^32 like 2^32;
+  //   specific/total counts are < 2^32, so m or p beyond 2^33 behave like 2^33.
+  AlignParams a{};
+  auto cl = [](int64_t v, int64_t lo, int64_t hi) { return v < lo ? lo : (v > hi ? hi : v); };
+  a.m = cl(p->m, 0, 1LL << 33);
+  a.p = cl(p->p, -1, 1LL << 33);
+  a.has_mrq = p->has_min_read_quality != 0; a.has_mkq = p->has_min_kmer_quality != 0; a.has_mg = p->has_max_genomes != 0;
+  a.mrq = cl(p->min_read_quality, 0, 256);
+  a.mkq = cl(p->min_kmer_quality, 0, 256);
+  a.mg = cl(p->max_genomes, -1, 1LL << 32);
+  return a;
+}
+
+}  // namespace
+}  // namespace pa
+
+using namespace pa;
+
+#define IDX(h) (reinterpret_cast<pa::Index*>(h))
+#define NEED(cond, msg) do { if (!(cond)) { pa::set_error(msg); return PA_ERR_INVALID_ARG; } } while (0)
+
+extern "C" {
+
+int32_t pa_abi_version(void) { return PA_ABI_VERSION; }
+
+int32_t pa_last_error(char* buf, size_t n) {
+  const char* e = get_error();
+  size_t len = strlen(e);
+  if (buf && n) { size_t c = std::min(len, n - 1); memcpy(buf, e, c); buf[c] = 0; }
+  return (int32_t)len;
+}
+
+int32_t pa_device_count(int32_t* n) {
+  NEED(n, "null argument");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaGetDeviceCount failed: %s", cudaGetErrorString(e)); *n = 0; return PA_ERR_CUDA; }
+  *n = c;
+  return PA_OK;
+}
+
+int32_t pa_index_build_device(const uint8_t* d_bases, const uint64_t* genome_off, uint32_t n_genomes, int32_t k,
+                              int32_t device, pa_index** out) {
+  Index* ix = nullptr;
+  PA_TRY(new_index(k, n_genomes, genome_off, device, &ix));
+  if (ix->total_bases && !d_bases) { delete ix; set_error("bases is null"); return PA_ERR_INVALID_ARG; }
+  if ((reinterpret_cast<uintptr_t>(d_bases) & 15) != 0) { delete ix; set_error("device bases must be 16-byte aligned"); return PA_ERR_INVALID_ARG; }
+  int32_t st = index_build_from_device_bases(*ix, d_bases + (n_genomes ? genome_off[0] : 0));
+  if (st != ST_OK) { delete ix; return st; }
+  *out = reinterpret_cast<pa_index*>(ix);
+  return PA_OK;
+}
+
+int32_t pa_index_build(const uint8_t* bases, const uint64_t* genome_off, uint32_t n_genomes, int32_t k, int32_t device,
+                       pa_index** out) {
+  Index* ix = nullptr;
+  PA_TRY(new_index(k, n_genomes, genome_off, device, &ix));
+  if (ix->total_bases && !bases) { delete ix; set_error("bases is null"); return PA_ERR_INVALID_ARG; }
+  int32_t st = ST_OK;
+  {
+    DevBuf d_bases;
+    st = d_bases.alloc(ix->total_bases + 64);
+    if (st == ST_OK && ix->total_bases) {
+      cudaError_t e = cudaMemcpyAsync(d_bases.p, bases + genome_off[0], ix->total_bases, cudaMemcpyHostToDevice, ix->stream);
+      if (e != cudaSuccess) { set_error("bases upload failed: %s", cudaGetErrorString(e)); st = ST_CUDA; }
+    }
+    if (st == ST_OK) st = index_build_from_device_bases(*ix, d_bases.as<uint8_t>());
+    cudaStreamSynchronize(ix->stream);
+  }
+  if (st != ST_OK) { delete ix; return st; }
+  *out = reinterpret_cast<pa_index*>(ix);
+  return PA_OK;
+}
+
+int32_t pa_index_import(int32_t k, uint32_t n_genomes, const uint64_t* genome_off, uint64_t n_keys, uint64_t n_runs,
+                        uint64_t n_occ, const uint64_t* keys, const uint64_t* run_off, const uint32_t* run_genome,
+                        const uint64_t* pos_off, const uint32_t* pos, const uint64_t* first_occ, int32_t device,
+                        pa_index** out) {
+  Index* ix = nullptr;
+  PA_TRY(new_index(k, n_genomes, genome_off, device, &ix));
+  auto fail = [&](int32_t st) { delete ix; return st; };
+  if (n_keys && (!keys || !run_off || !run_genome || !pos_off || !pos)) { set_error("null CSR array"); return fail(PA_ERR_INVALID_ARG); }
+  if (n_keys >= 0xFFFFFFFFull) { set_error("too many distinct k-mers"); return fail(PA_ERR_UNSUPPORTED); }
+  int32_t st;
+  cudaStream_t s = ix->stream;
+  if ((st = ix->ukeys.alloc((n_keys + 1) * 8)) || (st = ix->run_off.alloc((n_keys + 1) * 8)) ||
+      (st = ix->run_genome.alloc((n_runs + 1) * 4)) || (st = ix->pos_off.alloc((n_runs + 1) * 8)) ||
+      (st = ix->pos.alloc((n_occ + 1) * 4)))
+    return fail(st);
+  cudaError_t e = cudaSuccess;
+  uint64_t zero = 0;
+  if (n_keys) {
+    e = cudaMemcpyAsync(ix->ukeys.p, keys, n_keys * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ix->run_off.p, run_off, (n_keys + 1) * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ix->run_genome.p, run_genome, n_runs * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ix->pos_off.p, pos_off, (n_runs + 1) * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && n_occ) e = cudaMemcpyAsync(ix->pos.p, pos, n_occ * 4, cudaMemcpyHostToDevice, s);
+  } else {
+    e = cudaMemcpyAsync(ix->run_off.p, &zero, 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ix->pos_off.p, &zero, 8, cudaMemcpyHostToDevice, s);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { set_error("CSR upload failed: %s", cudaGetErrorString(e)); return fail(PA_ERR_CUDA); }
+  ix->n_keys = n_keys; ix->n_runs = n_runs; ix->n_occ = n_occ;
+  if (first_occ && n_keys) {
+    if ((st = ix->first_occ.alloc((n_keys + 1) * 8))) return fail(st);
+    e = cudaMemcpyAsync(ix->first_occ.p, first_occ, n_keys * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { set_error("first_occ upload failed: %s", cudaGetErrorString(e)); return fail(PA_ERR_CUDA); }
+    ix->has_first_occ = true;
+  }
+  if ((st = index_build_tables(*ix)) != ST_OK) return fail(st);
+  *out = reinterpret_cast<pa_index*>(ix);
+  return PA_OK;
+}
+
+int32_t pa_index_free(pa_index* idx) {
+  if (idx) {
+    cudaSetDevice(IDX(idx)->device);
+    cudaStreamSynchronize(IDX(idx)->stream);
+    delete IDX(idx);
+  }
+  return PA_OK;
+}
+
+int32_t pa_index_info_get(pa_index* idx, pa_index_info* info) {
+  NEED(idx && info, "null argument");
+  Index& ix = *IDX(idx);
+  memset(info, 0, sizeof(*info));
+  info->k = ix.k; info->device = ix.device; info->n_genomes = ix.n_genomes;
+  info->bucket_bits = ix.bucket_bits; info->tag_bits = ix.tag_bits; info->stash_count = ix.stash_count;
+  info->n_keys = ix.n_keys; info->n_runs = ix.n_runs; info->n_occ = ix.n_occ; info->total_bases = ix.total_bases;
+  info->n_list_sectors = ix.n_msectors; info->device_bytes = ix.device_bytes();
+  info->build_encode_ms = ix.t_encode_ms; info->build_sort_ms = ix.t_sort_ms;
+  info->build_rle_ms = ix.t_rle_ms; info->build_table_ms = ix.t_table_ms;
+  return PA_OK;
+}
+
+int32_t pa_index_export(pa_index* idx, uint64_t* keys, uint64_t* run_off, uint32_t* run_genome, uint64_t* pos_off,
+                        uint32_t* pos, uint32_t* order, uint64_t* first_occ) {
+  NEED(idx, "null index");
+  Index& ix = *IDX(idx);
+  PA_CUDA(cudaSetDevice(ix.device));
+  cudaStream_t s = ix.stream;
+  if (keys && ix.n_keys) PA_CUDA(cudaMemcpyAsync(keys, ix.ukeys.p, ix.n_keys * 8, cudaMemcpyDeviceToHost, s));
+  if (run_off) PA_CUDA(cudaMemcpyAsync(run_off, ix.run_off.p, (ix.n_keys + 1) * 8, cudaMemcpyDeviceToHost, s));
+  if (run_genome && ix.n_runs) PA_CUDA(cudaMemcpyAsync(run_genome, ix.run_genome.p, ix.n_runs * 4, cudaMemcpyDeviceToHost, s));
+  if (pos_off) PA_CUDA(cudaMemcpyAsync(pos_off, ix.pos_off.p, (ix.n_runs + 1) * 8, cudaMemcpyDeviceToHost, s));
+  if (pos && ix.n_occ) PA_CUDA(cudaMemcpyAsync(pos, ix.pos.p, ix.n_occ * 4, cudaMemcpyDeviceToHost, s));
+  PA_CUDA(cudaStreamSynchronize(s));
+  if (order) PA_TRY(index_export_order(ix, order));
+  if (first_occ && ix.n_keys) {
+    PA_TRY(index_ensure_first_occ(ix));
+    PA_CUDA(cudaMemcpyAsync(first_occ, ix.first_occ.p, ix.n_keys * 8, cudaMemcpyDeviceToHost, s));
+    PA_CUDA(cudaStreamSynchronize(s));
+  }
+  return PA_OK;
+}
+
+int32_t pa_decode_kmers(int32_t k, const uint64_t* keys, uint64_t n, uint8_t* ascii) {
+  NEED(k >= 0 && k <= 31, "k out of range");
+  NEED(n == 0 || (keys && ascii), "null argument");
+  static const char dec[4] = {'A', 'C', 'T', 'G'};
+  for (uint64_t i = 0; i < n; ++i)
+    for (int j = 0; j < k; ++j) {
+      uint32_t lo = (keys[i] >> j) & 1, hi = (keys[i] >> (k + j)) & 1;
+      ascii[i * (uint64_t)k + j] = dec[(hi << 1) | lo];
+    }
+  return PA_OK;
+}
+
+int32_t pa_encode_kmers(int32_t k, const uint8_t* ascii, uint64_t n, uint64_t* keys) {
+  NEED(k >= 1 && k <= 31, "k out of range");
+  NEED(n == 0 || (keys && ascii), "null argument");
+  for (uint64_t i = 0; i < n; ++i) {
+    bool ok;
+    uint64_t key = encode_kmer_host(ascii + i * (uint64_t)k, k, &ok);
+    keys[i] = ok ? key : SENTINEL_KEY;
+  }
+  return PA_OK;
+}
+
+int32_t pa_index_lookup(pa_index* idx, const uint8_t* kmers_ascii, uint64_t n, uint64_t* rank) {
+  NEED(idx, "null index");
+  NEED(n == 0 || (kmers_ascii && rank), "null argument");
+  PA_CUDA(cudaSetDevice(IDX(idx)->device));
+  return index_lookup_ranks(*IDX(idx), kmers_ascii, n, rank);
+}
+
+int32_t pa_extsim_stats(pa_index* idx, const uint32_t* group, uint32_t n_groups, uint64_t* total, uint64_t* unique) {
+  NEED(idx, "null index");
+  NEED(IDX(idx)->n_genomes == 0 || group, "null group map");
+  NEED(n_groups == 0 || (total && unique), "null output");
+  PA_CUDA(cudaSetDevice(IDX(idx)->device));
+  return index_extsim_stats(*IDX(idx), group, n_groups, total, unique);
+}
+
+int32_t pa_extsim_pairwise(pa_index* idx, const uint32_t* group, uint32_t n_groups, uint64_t* inter) {
+  NEED(idx, "null index");
+  NEED(IDX(idx)->n_genomes == 0 || group, "null group map");
+  NEED(n_groups == 0 || inter, "null output");
+  PA_CUDA(cudaSetDevice(IDX(idx)->device));
+  return index_extsim_pairwise(*IDX(idx), group, n_groups, inter);
+}
+
+int32_t pa_index_drop_genomes(pa_index* idx, const uint8_t* keep) {
+  NEED(idx, "null index");
+  NEED(IDX(idx)->n_genomes == 0 || keep, "null keep mask");
+  PA_CUDA(cudaSetDevice(IDX(idx)->device));
+  return index_drop_genomes(*IDX(idx), keep);
+}
+
+int32_t pa_align_batch_device(pa_index* idx, const uint8_t* d_bases, const uint8_t* d_quals, const uint64_t* d_read_off,
+                              uint64_t n_reads, uint64_t max_read_len, const pa_align_params* params,
+                              uint64_t* d_words, uint32_t* d_list, uint64_t list_cap, uint64_t* d_state, void* stream,
+                              int32_t* n_launches) {
+  NEED(idx && params, "null argument");
+  NEED(n_reads == 0 || (d_bases && d_read_off && d_words && d_state), "null device buffer");
+  NEED(params->m >= 0, "m must be bigger than or equal to 0");
+  Index& ix = *IDX(idx);
+  PA_CUDA(cudaSetDevice(ix.device));
+  AlignParams prm = clamp_params(params);
+  cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : ix.stream;
+  return align_batch_device(ix, d_bases, d_quals, d_read_off, n_reads, max_read_len, prm, d_words, d_list, list_cap,
+                            reinterpret_cast<unsigned long long*>(d_state), reinterpret_cast<unsigned long long*>(d_state) + 2,
+                            s, n_launches);
+}
+
+int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals, const uint64_t* read_off,
+                       uint64_t n_reads, const pa_align_params* params, uint64_t* out_words, uint32_t* out_list,
+                       uint64_t list_cap, uint64_t* list_len, uint64_t counters[3]) {
+  NEED(idx && params, "null argument");
+  NEED(params->m >= 0, "m must be bigger than or equal to 0");
+  if (list_len) *list_len = 0;
+  if (n_reads == 0) return PA_OK;
+  NEED(bases && read_off && out_words && counters, "null host buffer");
+  Index& ix = *IDX(idx);
+  PA_CUDA(cudaSetDevice(ix.device));
+  cudaStream_t s = ix.stream;
+  const bool need_q = params->has_min_read_quality || params->has_min_kmer_quality;
+  NEED(!need_q || quals, "quality filters requested without quality data");
+  const uint64_t base0 = read_off[0], n_bytes = read_off[n_reads] - base0;
+  uint64_t max_len = 0;
+  for (uint64_t i = 0; i < n_reads; ++i) {
+    NEED(read_off[i + 1] >= read_off[i], "read_off is not monotonic");
+    max_len = std::max(max_len, read_off[i + 1] - read_off[i]);
+  }
+  DevBuf d_bases, d_quals, d_off, d_words, d_list, d_state;
+  PA_TRY(d_bases.alloc(n_bytes + 64));
+  if (need_q) PA_TRY(d_quals.alloc(n_bytes + 64));
+  PA_TRY(d_off.alloc((n_reads + 1) * 8));
+  PA_TRY(d_words.alloc(n_reads * 8));
+  PA_TRY(d_list.alloc(std::max<uint64_t>(list_cap, 1) * 4));
+  PA_TRY(d_state.alloc(5 * 8));
+  PA_CUDA(cudaMemsetAsync(d_state.p, 0, 40, s));
+  if (n_bytes) PA_CUDA(cudaMemcpyAsync(d_bases.p, bases + base0, n_bytes, cudaMemcpyHostToDevice, s));
+  if (need_q && n_bytes) PA_CUDA(cudaMemcpyAsync(d_quals.p, quals + base0, n_bytes, cudaMemcpyHostToDevice, s));
+  PA_CUDA(cudaMemcpyAsync(d_off.p, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
+  AlignParams prm = clamp_params(params);
+  // the kernel indexes bases with read_off directly: rebase the pointers instead of the offsets
+  PA_TRY(align_batch_device(ix, d_bases.as<uint8_t>() - base0, need_q ? d_quals.as<uint8_t>() - base0 : nullptr,
+                            d_off.as<uint64_t>(), n_reads, max_len, prm, d_words.as<uint64_t>(), d_list.as<uint32_t>(),
+                            list_cap, d_state.as<unsigned long long>(), d_state.as<unsigned long long>() + 2, s, nullptr));
+  uint64_t h_state[5];
+  PA_CUDA(cudaMemcpyAsync(h_state, d_state.p, 40, cudaMemcpyDeviceToHost, s));
+  PA_CUDA(cudaMemcpyAsync(out_words, d_words.p, n_reads * 8, cudaMemcpyDeviceToHost, s));
+  PA_CUDA(cudaStreamSynchronize(s));
+  if (list_len) *list_len = h_state[0];
+  if (h_state[0] > list_cap) {
+    set_error("out_list too small: %llu entries needed", (unsigned long long)h_state[0]);
+    return PA_ERR_CAPACITY;
+  }
+  if (h_state[0]) {
+    NEED(out_list, "null out_list");
+    PA_CUDA(cudaMemcpyAsync(out_list, d_list.p, h_state[0] * 4, cudaMemcpyDeviceToHost, s));
+    PA_CUDA(cudaStreamSynchronize(s));
+  }
+  counters[0] += h_state[2]; counters[1] += h_state[3]; counters[2] += h_state[4];
+  return PA_OK;
+}
+
+int32_t pa_summary_reduce_device(const uint64_t* d_words, const uint32_t* d_list, uint64_t n_reads,
+                                 uint64_t read_index_base, uint32_t n_genomes, uint64_t* d_stats, uint64_t* d_unique_reads,
+                                 uint64_t* d_ambiguous_reads, uint64_t* d_first_seen, void* stream) {
+  NEED(n_reads == 0 || (d_words && d_stats && d_unique_reads && d_ambiguous_reads && d_first_seen), "null device buffer");
+  return summary_reduce_device(d_words, d_list, n_reads, read_index_base, n_genomes,
+                               reinterpret_cast<unsigned long long*>(d_stats), reinterpret_cast<unsigned long long*>(d_unique_reads),
+                               reinterpret_cast<unsigned long long*>(d_ambiguous_reads),
+                               reinterpret_cast<unsigned long long*>(d_first_seen), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t pa_summary_reduce(pa_index* idx, const uint64_t* words, const uint32_t* list, uint64_t n_reads, uint64_t list_len,
+                          uint64_t read_index_base, uint64_t stats[4], uint64_t* unique_reads, uint64_t* ambiguous_reads,
+                          uint64_t* first_seen) {
+  NEED(idx && stats, "null argument");
+  Index& ix = *IDX(idx);
+  const uint32_t G = ix.n_genomes;
+  NEED(G == 0 || (unique_reads && ambiguous_reads && first_seen), "null output");
+  PA_CUDA(cudaSetDevice(ix.device));
+  cudaStream_t s = ix.stream;
+  const size_t gb = (size_t)std::max<uint32_t>(G, 1) * 8;
+  DevBuf d_words, d_list, d_acc;
+  PA_TRY(d_words.alloc(std::max<uint64_t>(n_reads, 1) * 8));
+  PA_TRY(d_list.alloc(std::max<uint64_t>(list_len, 1) * 4));
+  PA_TRY(d_acc.alloc(32 + 3 * gb));
+  unsigned long long* acc = d_acc.as<unsigned long long>();
+  PA_CUDA(cudaMemsetAsync(acc, 0, 32 + 2 * gb, s));
+  PA_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(acc) + 32 + 2 * gb, 0xFF, gb, s));
+  if (n_reads) PA_CUDA(cudaMemcpyAsync(d_words.p, words, n_reads * 8, cudaMemcpyHostToDevice, s));
+  if (list_len) PA_CUDA(cudaMemcpyAsync(d_list.p, list, list_len * 4, cudaMemcpyHostToDevice, s));
+  unsigned long long* d_unique = acc + 4;
+  unsigned long long* d_amb = d_unique + std::max<uint32_t>(G, 1);
+  unsigned long long* d_first = d_amb + std::max<uint32_t>(G, 1);
+  PA_TRY(summary_reduce_device(d_words.as<uint64_t>(), d_list.as<uint32_t>(), n_reads, read_index_base, G, acc, d_unique,
+                               d_amb, d_first, s));
+  PA_CUDA(cudaMemcpyAsync(stats, acc, 32, cudaMemcpyDeviceToHost, s));
+  if (G) {
+    PA_CUDA(cudaMemcpyAsync(unique_reads, d_unique, (size_t)G * 8, cudaMemcpyDeviceToHost, s));
+    PA_CUDA(cudaMemcpyAsync(ambiguous_reads, d_amb, (size_t)G * 8, cudaMemcpyDeviceToHost, s));
+    PA_CUDA(cudaMemcpyAsync(first_seen, d_first, (size_t)G * 8, cudaMemcpyDeviceToHost, s));
+  }
+  PA_CUDA(cudaStreamSynchronize(s));
+  return PA_OK;
+}
+
+int32_t pa_debug_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t n, int32_t end_bit, int32_t device) {
+  NEED(n == 0 || (keys && vals), "null argument");
+  if (n == 0) return PA_OK;
+  PA_CUDA(cudaSetDevice(device));
+  DevBuf ka, kb, va, vb, tmp;
+  PA_TRY(ka.alloc(n * 8)); PA_TRY(kb.alloc(n * 8)); PA_TRY(va.alloc(n * 4)); PA_TRY(vb.alloc(n * 4));
+  PA_TRY(tmp.alloc(radix_sort_temp_bytes(n)));
+  PA_CUDA(cudaMemcpy(ka.p, keys, n * 8, cudaMemcpyHostToDevice));
+  PA_CUDA(cudaMemcpy(va.p, vals, n * 4, cudaMemcpyHostToDevice));
+  int in_b = 0;
+  PA_TRY(radix_sort_pairs(ka.as<uint64_t>(), va.as<uint32_t>(), kb.as<uint64_t>(), vb.as<uint32_t>(), n, end_bit, tmp.p,
+                          tmp.bytes, 0, &in_b));
+  PA_CUDA(cudaDeviceSynchronize());
+  PA_CUDA(cudaMemcpy(keys, in_b ? kb.p : ka.p, n * 8, cudaMemcpyDeviceToHost));
+  PA_CUDA(cudaMemcpy(vals, in_b ? vb.p : va.p, n * 4, cudaMemcpyDeviceToHost));
+  return PA_OK;
+}
+
+int32_t pa_debug_table_lookup(pa_index* idx, const uint8_t* kmers_ascii, uint64_t n, uint32_t* n_genomes,
+                              uint32_t* first_genome) {
+  NEED(idx, "null index");
+  NEED(n == 0 || (kmers_ascii && n_genomes && first_genome), "null argument");
+  if (n == 0) return PA_OK;
+  Index& ix = *IDX(idx);
+  PA_CUDA(cudaSetDevice(ix.device));
+  if (ix.k < 1 || ix.n_keys == 0) { for (uint64_t i = 0; i < n; ++i) { n_genomes[i] = 0; first_genome[i] = 0xFFFFFFFFu; } return PA_OK; }
+  std::vector<uint64_t> q(n);
+  PA_TRY(pa_encode_kmers(ix.k, kmers_ascii, n, q.data()));
+  cudaStream_t s = ix.stream;
+  DevBuf dq, dn, dg;
+  PA_TRY(dq.alloc(n * 8)); PA_TRY(dn.alloc(n * 4)); PA_TRY(dg.alloc(n * 4));
+  PA_CUDA(cudaMemcpyAsync(dq.p, q.data(), n * 8, cudaMemcpyHostToDevice, s));
+  debug_lookup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ix.view(), dq.as<uint64_t>(), n, dn.as<uint32_t>(), dg.as<uint32_t>());
+  PA_CUDA(cudaGetLastError());
+  PA_CUDA(cudaMemcpyAsync(n_genomes, dn.p, n * 4, cudaMemcpyDeviceToHost, s));
+  PA_CUDA(cudaMemcpyAsync(first_genome, dg.p, n * 4, cudaMemcpyDeviceToHost, s));
+  PA_CUDA(cudaStreamSynchronize(s));
+  return PA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+// index.cuh -- the device-resident k-mer index (CSR + lookup table).
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace pa {
+
+// Owns a device allocation; frees on destruction.
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  int32_t alloc(size_t n) {
+    release();
+    if (n == 0) n = 16;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) { p = nullptr; (void)cudaGetLastError(); set_error("cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e)); return ST_NOMEM; }
+    bytes = n;
+    return ST_OK;
+  }
+  void swap(DevBuf& o) { std::swap(p, o.p); std::swap(bytes, o.bytes); }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Index = CSR over distinct k-mers (ascending key) + the align lookup structures.
+//   ukeys[U]                      distinct keys, ascending
+//   run_off[U+1]                  key -> its genome runs
+//   run_genome[R]                 genome index of each run (ascending inside a key)
+//   pos_off[R+1]                  run -> its positions
+//   pos[N]                        positions inside the genome (ascending inside a run)
+//   genome_off[G+1]               base offsets of the genomes in the concatenated input
+//   buckets / stash / mlist       see TableView in common.cuh
+struct Index {
+  int32_t k = 0;
+  int32_t device = 0;
+  uint32_t n_genomes = 0;
+  uint64_t n_keys = 0, n_runs = 0, n_occ = 0;
+  uint64_t total_bases = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf ukeys, run_off, run_genome, pos_off, pos, genome_off;
+  // first_occ[U]: global base position of each k-mer's first occurrence in the ORIGINAL genome list (the dict
+  // insertion order of kmer.py:146-147 survives genome removal, kmer.py:237-243).  Materialised lazily.
+  DevBuf first_occ;
+  bool has_first_occ = false;
+  std::vector<uint64_t> h_genome_off;
+  // lookup structures
+  DevBuf buckets, stash_key, stash_val, mlist;
+  uint32_t bucket_bits = 0, tag_bits = 1, val_bits = 63;
+  uint64_t stash_cap = 0;
+  uint32_t stash_count = 0;
+  uint64_t n_msectors = 0;
+  MixParams mix{1, 1};
+  // per-warp scratch of the align kernel (allocated on first use)
+  DevBuf align_scratch;
+  uint64_t align_scratch_warps = 0, align_scratch_stride = 0;
+  // timing of the last build (ms, CUDA events on `stream`)
+  float t_encode_ms = 0, t_sort_ms = 0, t_rle_ms = 0, t_table_ms = 0;
+
+  TableView view() const {
+    TableView t;
+    t.buckets = buckets.as<uint64_t>();
+    t.stash_key = stash_key.as<uint64_t>();
+    t.stash_val = stash_val.as<uint64_t>();
+    t.mlist = mlist.as<uint32_t>();
+    t.stash_mask = stash_cap ? stash_cap - 1 : 0;
+    t.stash_count = stash_count;
+    t.tag_bits = tag_bits;
+    t.val_bits = val_bits;
+    t.k = (uint32_t)k;
+    t.mix = mix;
+    return t;
+  }
+  size_t device_bytes() const {
+    return ukeys.bytes + run_off.bytes + run_genome.bytes + pos_off.bytes + pos.bytes + genome_off.bytes + first_occ.bytes +
+           buckets.bytes + stash_key.bytes + stash_val.bytes + mlist.bytes + align_scratch.bytes;
+  }
+  ~Index() { if (stream) cudaStreamDestroy(stream); }
+};
+
+// build.cu
+int32_t index_build_from_device_bases(Index& ix, const uint8_t* d_bases);
+int32_t index_build_tables(Index& ix);   // buckets / stash / mlist from the CSR
+int32_t index_export_order(Index& ix, uint32_t* h_order);
+int32_t index_ensure_first_occ(Index& ix);
+int32_t index_lookup_ranks(Index& ix, const uint8_t* h_kmers, uint64_t n, uint64_t* h_rank);
+int32_t index_extsim_stats(Index& ix, const uint32_t* h_group, uint32_t n_groups, uint64_t* h_total, uint64_t* h_unique);
+int32_t index_extsim_pairwise(Index& ix, const uint32_t* h_group, uint32_t n_groups, uint64_t* h_inter);
+int32_t index_drop_genomes(Index& ix, const uint8_t* h_keep);
+
+}  // namespace pa

@@ -1,0 +1,163 @@
+/*
+ * pa_b200.h -- C ABI of the B200-native k-mer reference build + read
+ * pseudo-alignment path (libpa_b200.so, hand-written sm_100a CUDA).
+ *
+ * The reference (nyenyu12/BioInformatics-project-for-Shotgun-Metagenomics-
+ * Pseudo-alignment-shotgun-) has no FFI layer: its boundary for this path is
+ * the Python class surface of src/kmer.py.  Each entry point below names the
+ * reference interface (file:line under /root/reference/src) whose work it
+ * takes over; the Python shim that binds them with ctypes is the package's
+ * _native.py / kmer.py, and INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - every function returns int32: PA_OK or a negative PA_ERR_* code;
+ *     pa_last_error() returns the message of the calling thread's last error.
+ *     No C++ exception crosses the boundary.
+ *   - plain pointers and sizes only; the caller owns every buffer it passes.
+ *     "host" pointers are ordinary (preferably pinned) host memory, "device"
+ *     pointers are CUDA device memory on the index's device (e.g.
+ *     torch.Tensor.data_ptr()).
+ *   - a pa_index owns one CUDA stream and is not thread-safe; calls on
+ *     different handles may run concurrently.  `stream` arguments take a
+ *     cudaStream_t cast to void*; NULL means the handle's own stream.
+ *   - genome indices are positions in the genome list passed to the build
+ *     (FASTA order); after pa_index_drop_genomes they are ranks among the
+ *     surviving genomes.
+ */
+#ifndef PA_B200_H
+#define PA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PA_OK 0
+#define PA_ERR_INVALID_ARG (-1) /* -> ValueError / TypeError in the Python shim */
+#define PA_ERR_BAD_BASE (-2)    /* genome byte outside ACGTN (records.py:229 admits nothing else) -> ValueError */
+#define PA_ERR_CUDA (-3)        /* -> RuntimeError */
+#define PA_ERR_NOMEM (-4)       /* -> MemoryError */
+#define PA_ERR_CAPACITY (-5)    /* an output buffer is too small; the needed size is reported */
+#define PA_ERR_UNSUPPORTED (-6) /* outside the built scope (k > 31, > 2^32-2 bases, ...) -> ValueError */
+
+#define PA_ABI_VERSION 1
+#define PA_RANK_MISS UINT64_MAX
+
+typedef struct pa_index pa_index;
+
+typedef struct pa_index_info {
+  int32_t k;
+  int32_t device;
+  uint32_t n_genomes;
+  uint32_t bucket_bits;     /* log2(number of 32-byte buckets of the lookup table) */
+  uint32_t tag_bits;        /* bits of the hashed k-mer stored in a slot */
+  uint32_t stash_count;     /* k-mers that overflowed their bucket */
+  uint64_t n_keys;          /* distinct k-mers            (len(KmerReference.kmers)) */
+  uint64_t n_runs;          /* (k-mer, genome) pairs      (sum of inner dict sizes) */
+  uint64_t n_occ;           /* k-mer occurrences          (sum of position-set sizes) */
+  uint64_t total_bases;
+  uint64_t n_list_sectors;  /* 32-byte sectors holding multi-genome lists */
+  uint64_t device_bytes;
+  float build_encode_ms, build_sort_ms, build_rle_ms, build_table_ms; /* CUDA-event times of the last build */
+} pa_index_info;
+
+/* thresholds of Read.pseudo_align (kmer.py:482-489); has_* = "is not None" */
+typedef struct pa_align_params {
+  int64_t m, p;
+  int64_t min_read_quality, min_kmer_quality, max_genomes;
+  int32_t has_min_read_quality, has_min_kmer_quality, has_max_genomes;
+  int32_t reserved;
+} pa_align_params;
+
+int32_t pa_abi_version(void);
+/* copies the calling thread's last error message (NUL-terminated) into buf; returns its full length */
+int32_t pa_last_error(char* buf, size_t n);
+int32_t pa_device_count(int32_t* n);
+
+/* ---- index build: KmerReference.__init__ / _build_kmer_mapping (kmer.py:113-150) ------------------
+ * bases      concatenated genome strings, bytes in ACGTN (host); genome_off[G+1] offsets into it.
+ * k <= 0 or k > len(genome) yields no k-mers for that genome (kmer.py:91-92); k > 31 -> PA_ERR_UNSUPPORTED. */
+int32_t pa_index_build(const uint8_t* bases, const uint64_t* genome_off, uint32_t n_genomes, int32_t k, int32_t device,
+                       pa_index** out);
+/* same, with the concatenated bases already resident in device memory (16-byte aligned) */
+int32_t pa_index_build_device(const uint8_t* d_bases, const uint64_t* genome_off, uint32_t n_genomes, int32_t k,
+                              int32_t device, pa_index** out);
+/* rebuild from an exported CSR (KmerReference.load, kmer.py:273-282) */
+int32_t pa_index_import(int32_t k, uint32_t n_genomes, const uint64_t* genome_off, uint64_t n_keys, uint64_t n_runs,
+                        uint64_t n_occ, const uint64_t* keys, const uint64_t* run_off, const uint32_t* run_genome,
+                        const uint64_t* pos_off, const uint32_t* pos, const uint64_t* first_occ /* may be NULL */,
+                        int32_t device, pa_index** out);
+int32_t pa_index_free(pa_index* idx);
+int32_t pa_index_info_get(pa_index* idx, pa_index_info* info);
+
+/* CSR export (KmerReference.kmers / get_summary / save, kmer.py:130, 265-271, 300-329).  Host buffers sized from
+ * pa_index_info: keys[n_keys], run_off[n_keys+1], run_genome[n_runs], pos_off[n_runs+1], pos[n_occ],
+ * order[n_keys] = distinct k-mers in dict insertion order (first occurrence in genome/position order),
+ * first_occ[n_keys] = the order key itself (global base position of the first occurrence in the genome list the
+ * index was BUILT from; it survives pa_index_drop_genomes like the reference's dict order survives deletion,
+ * kmer.py:237-243) -- pass it back to pa_index_import.
+ * keys are private encodings: decode with pa_decode_kmers.  Any pointer may be NULL to skip that array. */
+int32_t pa_index_export(pa_index* idx, uint64_t* keys, uint64_t* run_off, uint32_t* run_genome, uint64_t* pos_off,
+                        uint32_t* pos, uint32_t* order, uint64_t* first_occ);
+int32_t pa_decode_kmers(int32_t k, const uint64_t* keys, uint64_t n, uint8_t* ascii /* n*k bytes */);
+int32_t pa_encode_kmers(int32_t k, const uint8_t* ascii, uint64_t n, uint64_t* keys /* UINT64_MAX when not ACGT */);
+
+/* KmerReference.get_kmer_references / __getitem__ (kmer.py:284-298): rank of each k-mer (n strings of k bytes)
+ * among the exported keys, PA_RANK_MISS when absent. */
+int32_t pa_index_lookup(pa_index* idx, const uint8_t* kmers_ascii, uint64_t n, uint64_t* rank);
+
+/* ---- EXTSIM (kmer.py:152-263) ---------------------------------------------------------------------
+ * group[g] = identifier class of genome g (kmer.py:162 keys everything by record.identifier).
+ * total/unique: _compute_genome_stats (kmer.py:152-177); inter[a*n+b] = number of distinct k-mers shared by
+ * classes a and b, the |A & B| of _apply_greedy_filter (kmer.py:206-207).  Host outputs. */
+int32_t pa_extsim_stats(pa_index* idx, const uint32_t* group, uint32_t n_groups, uint64_t* total, uint64_t* unique);
+int32_t pa_extsim_pairwise(pa_index* idx, const uint32_t* group, uint32_t n_groups, uint64_t* inter);
+/* _remove_filtered_genomes_from_kmers + _update_genomes_list (kmer.py:232-250); keep[g] != 0 survives */
+int32_t pa_index_drop_genomes(pa_index* idx, const uint8_t* keep);
+
+/* ---- alignment: PseudoAlignment.align_reads_from_container (kmer.py:563-620) over a packed batch ---
+ * bases/quals: concatenated read strings (quals may be NULL when no quality filter is on);
+ * read_off[n_reads+1].  Outputs, one 64-bit word per read:
+ *   bits 63:62  0 = dropped by min_read_quality (kmer.py:587-589), 1/2/3 = ReadMappingType value
+ *   bits 61:40  length of genomes_mapped_to
+ *   bits 39:0   the genome index when the length is 1, else the offset of the list in out_list
+ * counters[3] += {filtered_quality_reads, filtered_quality_kmers, filtered_hr_kmers} (kmer.py:587-597).
+ * *list_len receives the number of out_list entries needed; PA_ERR_CAPACITY when it exceeds list_cap
+ * (words are then valid, lists are not: call again with a larger out_list). */
+int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals, const uint64_t* read_off,
+                       uint64_t n_reads, const pa_align_params* params, uint64_t* out_words, uint32_t* out_list,
+                       uint64_t list_cap, uint64_t* list_len, uint64_t counters[3]);
+/* device-resident variant: every pointer except params is device memory; d_state is 5 x uint64 of device
+ * memory = {list cursor, overflow flag, counters[3]}, zeroed by the caller; asynchronous on `stream`. */
+int32_t pa_align_batch_device(pa_index* idx, const uint8_t* d_bases, const uint8_t* d_quals, const uint64_t* d_read_off,
+                              uint64_t n_reads, uint64_t max_read_len, const pa_align_params* params,
+                              uint64_t* d_words, uint32_t* d_list, uint64_t list_cap, uint64_t* d_state, void* stream,
+                              int32_t* n_launches);
+
+/* ---- summary: PseudoAlignment.get_summary (kmer.py:622-657) -----------------------------------------
+ * Device accumulators owned by the caller (so ranks can all-reduce them): stats[4] = {unique, ambiguous,
+ * unmapped, dropped} (SUM), unique_reads[G], ambiguous_reads[G] (SUM, one per list element),
+ * first_seen[G] (MIN of (read_index_base + i) << 22 | list position; initialise to UINT64_MAX). */
+int32_t pa_summary_reduce_device(const uint64_t* d_words, const uint32_t* d_list, uint64_t n_reads,
+                                 uint64_t read_index_base, uint32_t n_genomes, uint64_t* d_stats, uint64_t* d_unique_reads,
+                                 uint64_t* d_ambiguous_reads, uint64_t* d_first_seen, void* stream);
+/* host convenience over the outputs of pa_align_batch */
+int32_t pa_summary_reduce(pa_index* idx, const uint64_t* words, const uint32_t* list, uint64_t n_reads, uint64_t list_len,
+                          uint64_t read_index_base, uint64_t stats[4], uint64_t* unique_reads, uint64_t* ambiguous_reads,
+                          uint64_t* first_seen);
+
+/* ---- diagnostics used by the tests ----------------------------------------------------------------- */
+/* stable LSD radix sort of (key, value) pairs on key bits [0, end_bit), host in / host out (K2) */
+int32_t pa_debug_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t n, int32_t end_bit, int32_t device);
+/* direct table lookups (K4's lookup step): n_genomes[i] = number of genomes of k-mer i (0 = miss),
+ * first_genome[i] = its smallest genome index */
+int32_t pa_debug_table_lookup(pa_index* idx, const uint8_t* kmers_ascii, uint64_t n, uint32_t* n_genomes,
+                              uint32_t* first_genome);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PA_B200_H */

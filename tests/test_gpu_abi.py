@@ -1,0 +1,218 @@
+"""
+GPU parity tests through the raw C ABI (libpa_b200.so via _native.py) against the CPU oracle.
+Bit-exact: everything on this path is integer / index work.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import synth
+import _native as nat
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+NAMES = {1: "UNMAPPED", 2: "UNIQUELY_MAPPED", 3: "AMBIGUOUSLY_MAPPED"}
+
+
+def build_native(case):
+    data, off = nat.pack_strings([g[1] for g in case["genomes"]])
+    return nat.NativeIndex.build(data, off, case["k"])
+
+
+def native_kmers_dict(ix):
+    inf = ix.info()
+    ex = ix.export()
+    kmers = nat.decode_kmers(inf.k, ex["keys"])
+    out = {}
+    for u in ex["order"]:
+        u = int(u)
+        inner = {}
+        for r in range(int(ex["run_off"][u]), int(ex["run_off"][u + 1])):
+            inner[int(ex["run_genome"][r])] = [int(x) for x in ex["pos"][int(ex["pos_off"][r]):int(ex["pos_off"][r + 1])]]
+        out[kmers[u]] = inner
+    return out
+
+
+def native_reads(ix, case, genome_ids):
+    pr = case["params"]
+    reads = case["reads"]
+    seqs, off = nat.pack_strings([r[1] for r in reads])
+    quals, _ = nat.pack_strings([r[2] for r in reads])
+    words, lst, counters = ix.align(seqs, quals, off, nat.make_params(pr["m"], pr["p"], pr["mrq"], pr["mkq"], pr["mg"]))
+    types, lens, payload = nat.decode_words(words)
+    out = {}
+    for i, r in enumerate(reads):
+        t = int(types[i])
+        if t == 0:
+            continue
+        n = int(lens[i])
+        gl = [int(payload[i])] if n == 1 else [int(x) for x in lst[int(payload[i]):int(payload[i]) + n]]
+        out[r[0]] = {"mapping_type": NAMES[t], "genomes_mapped_to": [genome_ids[g] for g in gl]}
+    return out, words, lst, counters
+
+
+def check_case(case):
+    pr = dict(case["params"])
+    pr["filter_similar"] = False  # EXTSIM's host logic is covered through the Python shim tests
+    o = orc.OracleReference(case["k"], case["genomes"])
+    ix = build_native(case)
+    try:
+        want_kmers = o.kmers_dict()
+        got_kmers = native_kmers_dict(ix)
+        assert list(got_kmers.keys()) == list(want_kmers.keys())
+        assert got_kmers == want_kmers
+        inf = ix.info()
+        assert (inf.n_keys, inf.n_runs, inf.n_occ) == o.sizes()
+        # table lookups agree with the CSR for every present k-mer and for some absent ones
+        if inf.k >= 1 and want_kmers:
+            probe = list(want_kmers.keys())
+            rng = np.random.default_rng(case.get("seed", 0))
+            probe += ["".join(rng.choice(list("ACGT"), size=inf.k)) for _ in range(20)]
+            ng, g0 = ix.table_lookup(probe)
+            ranks = ix.lookup(probe)
+            for i, km in enumerate(probe):
+                inner = want_kmers.get(km)
+                assert int(ng[i]) == (len(inner) if inner else 0), km
+                assert (ranks[i] != nat.RANK_MISS) == (inner is not None)
+                if inner:
+                    assert int(g0[i]) == min(inner.keys())
+        # alignment
+        al = o.align(case["reads"], pr["m"], pr["p"], pr["mrq"], pr["mkq"], pr["mg"])
+        got_reads, words, lst, counters = native_reads(ix, case, [g[0] for g in case["genomes"]])
+        want_reads = al.reads()
+        assert list(got_reads.keys()) == list(want_reads.keys())
+        assert got_reads == want_reads, (case.get("seed"), pr)
+        assert int(counters[0]) == al.filtered_quality_reads
+        assert int(counters[1]) == (al.filtered_quality_kmers if pr["mkq"] is not None else 0)
+        assert int(counters[2]) == (al.filtered_hr_kmers if pr["mg"] is not None else 0)
+        # summary (K8) against orc_summary on the oracle's own per-read output
+        G = len(case["genomes"])
+        stats, uniq, amb, first = ix.summary(words, lst)
+        L = orc.lib()
+        ostats = np.zeros(3, np.uint64); ou = np.zeros(max(G, 1), np.uint64); oa = np.zeros(max(G, 1), np.uint64)
+        oorder = np.zeros(max(G, 1), np.uint32)
+        n_seen = L.orc_summary(orc._ptr(al.types), orc._ptr(al.list_off), orc._ptr(al.genomes), len(case["reads"]), G,
+                               orc._ptr(ostats), orc._ptr(ou), orc._ptr(oa), orc._ptr(oorder))
+        assert [int(x) for x in stats[:3]] == [int(x) for x in ostats]
+        assert int(stats[3]) == al.filtered_quality_reads
+        assert np.array_equal(uniq, ou[:G]) and np.array_equal(amb, oa[:G])
+        seen = [g for g in np.argsort(first, kind="stable") if first[g] != np.uint64(0xFFFFFFFFFFFFFFFF)]
+        assert [int(g) for g in seen] == [int(g) for g in oorder[:n_seen]]
+    finally:
+        ix.close()
+
+
+@pytest.mark.parametrize("n,end_bit", [(0, 64), (1, 64), (31, 8), (4095, 64), (4096, 17), (4097, 64), (100_003, 63),
+                                        (1_000_000, 40), (3_000_001, 64)])
+def test_radix_sort_pairs(n, end_bit):
+    rng = np.random.default_rng(n + end_bit)
+    keys = rng.integers(0, 1 << 63, size=n, dtype=np.uint64)
+    if n > 10:
+        keys[rng.integers(0, n, size=n // 3)] = keys[0]          # heavy duplicates
+        keys[rng.integers(0, n, size=n // 50 + 1)] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    if end_bit < 64:
+        keys &= np.uint64((1 << end_bit) - 1)
+    vals = np.arange(n, dtype=np.uint32)
+    k2, v2 = nat.debug_sort_pairs(keys, vals, end_bit)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k2, keys[order])
+    assert np.array_equal(v2, vals[order])      # stability
+
+
+@pytest.mark.parametrize("block", range(6))
+def test_fuzz_small_k_against_oracle(block):
+    for seed in range(block * 100, block * 100 + 100):
+        check_case(synth.fuzz_case(seed))
+
+
+def test_fuzz_wider_k():
+    for seed in range(5000, 5080):
+        check_case(synth.fuzz_case(seed, k_range=(9, 31), max_genomes=8))
+
+
+def test_k31_moderate():
+    genomes = synth.make_genomes(6, 40_000, seed=5, cluster_size=3, shared_frac=0.35, n_every=9000, n_run=11)
+    b, q, off = synth.make_reads(genomes, 4000, 150, seed=6, sub_rate=0.02, random_frac=0.05)
+    for pr in [dict(m=1, p=1, mrq=None, mkq=None, mg=None), dict(m=1, p=1, mrq=62, mkq=60, mg=1),
+               dict(m=0, p=0, mrq=None, mkq=63, mg=3), dict(m=3, p=-1, mrq=None, mkq=None, mg=2)]:
+        check_case({"k": 31, "genomes": synth.genomes_as_pairs(genomes), "reads": synth.reads_as_triples(b, q, off),
+                    "params": pr, "seed": 1})
+
+
+def test_long_reads_take_the_multi_round_path():
+    genomes = synth.make_genomes(5, 6000, seed=9, cluster_size=5, shared_frac=0.5, n_every=2500, n_run=5)
+    b, q, off = synth.make_reads(genomes, 300, 700, seed=10, sub_rate=0.03, random_frac=0.1)
+    for k in (5, 12, 31):
+        for pr in [dict(m=1, p=1, mrq=None, mkq=None, mg=None), dict(m=2, p=0, mrq=60, mkq=61, mg=2)]:
+            check_case({"k": k, "genomes": synth.genomes_as_pairs(genomes), "reads": synth.reads_as_triples(b, q, off),
+                        "params": pr, "seed": k})
+
+
+def test_many_genomes_use_the_global_scratch():
+    rng = np.random.default_rng(3)
+    base = synth.ACGT[rng.integers(0, 4, size=300)]
+    genomes = []
+    for g in range(300):   # > 256 genomes: per-genome table in global memory; most k-mers shared by many genomes
+        seq = base.copy()
+        idx = rng.integers(0, seq.size, size=6)
+        seq[idx] = synth.ACGT[rng.integers(0, 4, size=6)]
+        genomes.append((f"g{g}", seq.tobytes().decode()))
+    reads = []
+    for r in range(60):
+        src = genomes[int(rng.integers(0, 300))][1]
+        s = int(rng.integers(0, 200))
+        reads.append((f"r{r}", src[s:s + 90], "I" * 90))
+    for pr in [dict(m=1, p=1, mrq=None, mkq=None, mg=None), dict(m=1, p=1, mrq=None, mkq=None, mg=50)]:
+        check_case({"k": 11, "genomes": genomes, "reads": reads, "params": pr, "seed": 3})
+
+
+def test_extsim_kernels_against_oracle():
+    for seed in list(range(7000, 7060)) + list(range(10_000, 10_040)):
+        case = synth.fuzz_case(seed, dup_ids=seed >= 10_000)
+        o = orc.OracleReference(case["k"], case["genomes"])
+        ix = build_native(case)
+        try:
+            ids = [g[0] for g in case["genomes"]]
+            classes = {}
+            group = np.array([classes.setdefault(s, len(classes)) for s in ids], dtype=np.uint32)
+            n = len(classes)
+            total, uniq = ix.extsim_stats(group, n)
+            inter = ix.extsim_pairwise(group, n)
+            L = orc.lib()
+            ot = np.zeros(n, np.uint64); ou = np.zeros(n, np.uint64); oi = np.zeros(n * n, np.uint64)
+            L.orc_extsim_stats(o._h, orc._ptr(group), n, orc._ptr(ot), orc._ptr(ou))
+            L.orc_extsim_pairwise(o._h, orc._ptr(group), n, orc._ptr(oi))
+            assert np.array_equal(total, ot) and np.array_equal(uniq, ou)
+            assert np.array_equal(inter.reshape(-1), oi)
+            # drop a pseudo-random subset of genomes and compare the surviving index
+            rng = np.random.default_rng(seed)
+            keep = (rng.random(len(ids)) < 0.6).astype(np.uint8)
+            ix.drop_genomes(keep)
+            h2 = L.orc_index_drop_genomes(o._h, orc._ptr(np.concatenate([keep, [0]]).astype(np.uint8)))
+            L.orc_index_free(o._h)
+            o._h = h2
+            o.genomes = [g for g, kp in zip(o.genomes, keep) if kp]
+            assert native_kmers_dict(ix) == o.kmers_dict()
+            assert list(native_kmers_dict(ix).keys()) == list(o.kmers_dict().keys())
+            case2 = dict(case, genomes=o.genomes)
+            if o.genomes:
+                pr = case["params"]
+                al = o.align(case["reads"], pr["m"], pr["p"], pr["mrq"], pr["mkq"], pr["mg"])
+                got, _, _, _ = native_reads(ix, case2, [g[0] for g in o.genomes])
+                assert got == al.reads()
+        finally:
+            ix.close()
+
+
+def test_bad_genome_character_is_rejected():
+    data, off = nat.pack_strings(["ACGTNNACGT", "ACGXACGT"])
+    with pytest.raises(ValueError):
+        nat.NativeIndex.build(data, off, 3)
+
+
+def test_k_above_31_is_out_of_scope():
+    data, off = nat.pack_strings(["ACGT" * 20])
+    with pytest.raises(ValueError):
+        nat.NativeIndex.build(data, off, 32)
