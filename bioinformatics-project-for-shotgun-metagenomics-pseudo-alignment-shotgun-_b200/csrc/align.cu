@@ -12,6 +12,7 @@
 // arithmetic is integer; the reference's float means are compared as
 // sum < threshold * length, which is exact.
 #include "align.cuh"
+#include <cstdlib>
 
 namespace pa {
 
@@ -51,13 +52,55 @@ __device__ __forceinline__ uint32_t mlist_count(const uint32_t* __restrict__ mli
   }
 }
 
-// generate_genome_counts (kmer.py:431-442) for one kept, de-duplicated k-mer at window `pos`
-__device__ __forceinline__ void count_genome(const WarpScratch& ws, uint32_t* n_touched, uint32_t g, uint32_t pos, bool specific) {
-  uint32_t* e = ws.gtab + (size_t)g * 4;
-  uint32_t old = atomicAdd(e + 1, 1u);
-  if (old == 0) vst(ws.touched + atomicAdd(n_touched, 1u), g);
-  atomicMin(e + 3, pos);
-  if (specific) { atomicAdd(e + 0, 1u); atomicMin(e + 2, pos); }
+// generate_genome_counts (kmer.py:431-442), warp-aggregated.  Every lane may hold one kept, de-duplicated k-mer of
+// round `r` (window position pos = round_base + lane).  The lanes walk their genome lists in lock step; lanes naming
+// the same genome are grouped with match.any and only the lowest lane of a group (which also holds the smallest
+// position) updates that genome's table entry, so the 32 lanes of a read that all hit the same few genomes cost a
+// handful of plain updates instead of 32-way serialised atomics.
+__device__ __forceinline__ void count_round(const TableView& t, const WarpScratch& ws, uint32_t& nT, bool active,
+                                            uint64_t val, uint32_t round_base, uint32_t lane) {
+  const uint32_t kind = value_kind(t, val);
+  const uint64_t payload = value_payload(t, val);
+  const uint32_t gm = (1u << t.gbits) - 1;
+  bool more = active;
+  uint32_t i = 0;
+  while (__any_sync(0xffffffffu, more)) {
+    uint32_t g = 0x80000000u | lane;  // matches nobody
+    bool have = more;
+    if (more) {
+      if (kind == KIND_SPECIFIC) {
+        g = (uint32_t)payload; more = false;
+      } else if (kind == KIND_INLINE) {
+        g = (uint32_t)(payload >> (i * t.gbits)) & gm;
+        more = (i + 1 < t.n_inline) && (((uint32_t)(payload >> ((i + 1) * t.gbits)) & gm) != g);
+      } else {
+        uint32_t id = __ldg(t.mlist + payload * MLIST_SECTOR + i);
+        g = id & ~LIST_END; more = !(id & LIST_END);
+      }
+      ++i;
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, g);
+    const uint32_t spec_lanes = __ballot_sync(0xffffffffu, have && kind == KIND_SPECIFIC);
+    const bool leader = have && (lane == (uint32_t)__ffs(peers) - 1);
+    uint32_t oldT = 1;
+    if (leader) {
+      uint32_t* e = ws.gtab + (size_t)g * 4;
+      oldT = vld(e + 1);
+      vst(e + 1, oldT + __popc(peers));
+      const uint32_t pos = round_base + lane;
+      if (pos < vld(e + 3)) vst(e + 3, pos);
+      const uint32_t sp = peers & spec_lanes;
+      if (sp) {
+        vst(e, vld(e) + __popc(sp));
+        const uint32_t spos = round_base + (uint32_t)__ffs(sp) - 1;
+        if (spos < vld(e + 2)) vst(e + 2, spos);
+      }
+    }
+    const uint32_t first = __ballot_sync(0xffffffffu, leader && oldT == 0);
+    if (leader && oldT == 0) vst(ws.touched + nT + __popc(first & ((1u << lane) - 1)), g);
+    nT += __popc(first);
+    __syncwarp();
+  }
 }
 
 __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
@@ -165,14 +208,13 @@ __device__ void decide_and_emit(const WarpScratch& ws, uint32_t nT, const AlignP
   }
 }
 
-template <bool QUAL>
-__global__ void __launch_bounds__(AL_THREADS)
+template <bool QUAL, int MIN_BLOCKS>
+__global__ void __launch_bounds__(AL_THREADS, MIN_BLOCKS)
 align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals,
              const uint64_t* __restrict__ read_off, uint64_t n_reads, AlignParams prm, Emit em,
              unsigned long long* __restrict__ counters, unsigned char* __restrict__ scratch, uint64_t scratch_stride,
              uint32_t G, uint32_t kset_cap, int gtab_in_smem, int kset_in_smem) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  __shared__ uint32_t s_ntouched[AL_WARPS];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t warp_global = (uint64_t)blockIdx.x * AL_WARPS + warp;
   const uint64_t n_warps = (uint64_t)gridDim.x * AL_WARPS;
@@ -194,33 +236,62 @@ align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __re
     ws.kset_mask = kset_cap - 1;
     if (kset_in_smem) for (uint32_t i = lane; i < kset_cap; i += 32) { ws.kset_key[i] = EMPTY64; ws.kset_pos[i] = NOPOS; }
     if (gtab_in_smem) for (uint32_t i = lane; i < G; i += 32) { ws.gtab[i * 4] = 0; ws.gtab[i * 4 + 1] = 0; ws.gtab[i * 4 + 2] = NOPOS; ws.gtab[i * 4 + 3] = NOPOS; }
-    if (lane == 0) s_ntouched[warp] = 0;
     __syncwarp();
   }
-  uint32_t* n_touched = &s_ntouched[warp];
 
   unsigned long long c_drop = 0, c_nq = 0, c_nr = 0;  // per-lane partial counters
 
+  // Software pipeline over this warp's reads: the offsets of read i+2 and the first 160 bases of read i+1 are
+  // requested while read i is processed, so a read never starts by waiting on its own (sequential) input.
+  uint64_t nx_beg = 0, nx_end = 0;      // offsets of the next read
+  uint32_t nx_ch[AL_ROUNDS + 1];        // its first AL_ROUNDS+1 chunks of bases (one byte per lane)
+  uint64_t cur_beg = 0, cur_end = 0;
+  uint32_t cur_ch[AL_ROUNDS + 1];
+  {
+    uint64_t r0 = warp_global, r1 = warp_global + n_warps;
+    if (r0 < n_reads) { cur_beg = read_off[r0]; cur_end = read_off[r0 + 1]; }
+    if (r1 < n_reads) { nx_beg = read_off[r1]; nx_end = read_off[r1 + 1]; }
+#pragma unroll
+    for (int c = 0; c <= AL_ROUNDS; ++c) {
+      uint64_t bi = (uint64_t)(32 * c) + lane;
+      cur_ch[c] = (r0 < n_reads && bi < cur_end - cur_beg) ? bases[cur_beg + bi] : 0;
+    }
+  }
+
   for (uint64_t read = warp_global; read < n_reads; read += n_warps) {
-    const uint64_t beg = read_off[read];
-    const uint64_t L = read_off[read + 1] - beg;
+    const uint64_t beg = cur_beg;
+    const uint64_t L = cur_end - cur_beg;
     const uint8_t* rb = bases + beg;
     const uint8_t* rq = QUAL ? quals + beg : nullptr;
+    // issue the loads of the following reads (consumed at the bottom of the loop)
+    uint64_t n2_beg = 0, n2_end = 0;
+    {
+      const uint64_t r1 = read + n_warps, r2 = read + 2 * n_warps;
+      const uint64_t nL = nx_end - nx_beg;
+#pragma unroll
+      for (int c = 0; c <= AL_ROUNDS; ++c) {
+        uint64_t bi = (uint64_t)(32 * c) + lane;
+        nx_ch[c] = (r1 < n_reads && bi < nL) ? bases[nx_beg + bi] : 0;
+      }
+      if (r2 < n_reads) { n2_beg = read_off[r2]; n2_end = read_off[r2 + 1]; }
+    }
 
+    bool dropped = false;
     if (QUAL && prm.has_mrq) {  // Read.mean_quality() < min_read_quality  (kmer.py:587)
       uint64_t s = 0;
       for (uint64_t i = lane; i < L; i += 32) s += rq[i];
       s = warp_sum(s);
       if ((int64_t)s < prm.mrq * (int64_t)L) {
         if (lane == 0) { em.out_word[read] = 0; ++c_drop; }
-        continue;
+        dropped = true;
       }
     }
-    const uint64_t W = (k >= 1 && L >= (uint64_t)k) ? L - k + 1 : 0;  // kmer.py:91-92
+    const uint64_t W = (!dropped && k >= 1 && L >= (uint64_t)k) ? L - k + 1 : 0;  // kmer.py:91-92
     const bool single = W <= AL_SUPER;
     bool slow_used = false;
+    uint32_t nT = 0;  // genomes touched by this read (warp-uniform)
     uint32_t read_nq = 0, read_nr = 0;
-    bool done = false;
+    bool done = dropped;
 
     for (uint64_t wbase = 0; wbase < W; wbase += AL_SUPER) {
       // ---- encode AL_ROUNDS+1 chunks of 32 bases into bit planes with ballots ----
@@ -230,7 +301,7 @@ align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __re
 #pragma unroll
       for (int c = 0; c <= AL_ROUNDS; ++c) {
         uint64_t bi = wbase + 32 * c + lane;
-        uint32_t ch = bi < L ? rb[bi] : 0;
+        uint32_t ch = wbase == 0 ? cur_ch[c] : (bi < L ? rb[bi] : 0);
         bool ok = is_acgt(ch);
         uint32_t code = base_code(ch);
         lo[c] = __ballot_sync(0xffffffffu, code & 1u);
@@ -268,44 +339,59 @@ align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __re
         h[r] = mix_key(((uint64_t)wh << k) | wl, t.mix);
         if (look[r]) ld_sector_nc(t.buckets + (h[r] >> t.tag_bits) * 4, bucket[r]);
       }
-      // ---- resolve ----
+      // ---- resolve; classify what can be decided without touching mlist ----
       uint64_t val[AL_ROUNDS];
-      bool any_multi = false, any_found = false;
+      uint32_t cnt[AL_ROUNDS];   // genomes of the k-mer; 0 = unknown yet (mlist kind)
+      bool l_unknown = false, l_kept_spec = false, l_kept_multi = false;
+      uint32_t l_filtered = 0;
 #pragma unroll
       for (int r = 0; r < AL_ROUNDS; ++r) {
         val[r] = look[r] ? bucket_resolve(t, bucket[r], h[r]) : LOOKUP_MISS;
-        if (val[r] != LOOKUP_MISS) { any_found = true; any_multi |= !value_is_specific(t, val[r]); }
+        cnt[r] = 0;
+        if (val[r] == LOOKUP_MISS) continue;
+        const uint32_t kind = value_kind(t, val[r]);
+        if (kind == KIND_SPECIFIC) cnt[r] = 1;
+        else if (kind == KIND_INLINE) cnt[r] = inline_count(t, value_payload(t, val[r]));
+        if (cnt[r] == 0) {
+          if (prm.has_mg) l_unknown = true; else l_kept_multi = true;
+        } else if (prm.has_mg && (int64_t)cnt[r] > prm.mg) {  // kmer.py:425-427
+          ++l_filtered;
+        } else if (cnt[r] == 1) {
+          l_kept_spec = true;
+        } else {
+          l_kept_multi = true;
+        }
       }
-      const bool w_multi = __any_sync(0xffffffffu, any_multi);
-      const bool w_found = __any_sync(0xffffffffu, any_found);
-      const bool spec_kept = !(prm.has_mg && prm.mg < 1);  // a specific k-mer has one genome (kmer.py:425)
-
-      // ---- fast path: one super-round, nothing multi-genome, every kept k-mer names the same genome.
-      // Then S == T == {g: n}: unique whatever m and p are, and duplicates cannot change that.
-      if (single && !w_multi) {
-        if (!w_found) { if (lane == 0) em.out_word[read] = make_word(1, 0, 0); done = true; break; }
-        if (!spec_kept) {
-          uint32_t f = 0;
-#pragma unroll
-          for (int r = 0; r < AL_ROUNDS; ++r) f += val[r] != LOOKUP_MISS;
-          read_nr += f;
-          if (lane == 0) em.out_word[read] = make_word(1, 0, 0);
+      // ---- fast paths (reads of one super-round whose outcome needs no per-genome table) ----
+      if (single && !__any_sync(0xffffffffu, l_unknown)) {
+        const bool w_spec = __any_sync(0xffffffffu, l_kept_spec);
+        const bool w_multi = __any_sync(0xffffffffu, l_kept_multi);
+        if (!w_spec) {
+          // no specific k-mer kept: unmapped when nothing was kept (kmer.py:516-517), else the specific-count dict
+          // is empty and the read is ambiguous with an empty list (kmer.py:461)
+          read_nr += l_filtered;
+          if (lane == 0) em.out_word[read] = make_word(w_multi ? 3 : 1, 0, 0);
           done = true; break;
         }
-        uint32_t mine = 0xFFFFFFFFu;
-        bool same = true;
+        if (!w_multi) {
+          // only specific k-mers kept.  If they all name one genome, S == T == {g: n}: unique whatever m and p
+          // are, and duplicated k-mers cannot change that.
+          uint32_t mine = 0xFFFFFFFFu;
+          bool same = true;
 #pragma unroll
-        for (int r = 0; r < AL_ROUNDS; ++r)
-          if (val[r] != LOOKUP_MISS) {
-            uint32_t g = (uint32_t)value_payload(t, val[r]);
-            if (mine == 0xFFFFFFFFu) mine = g; else same &= (g == mine);
+          for (int r = 0; r < AL_ROUNDS; ++r)
+            if (cnt[r] == 1 && !(prm.has_mg && prm.mg < 1)) {
+              uint32_t g = (uint32_t)value_payload(t, val[r]);
+              if (mine == 0xFFFFFFFFu) mine = g; else same &= (g == mine);
+            }
+          uint32_t have = __ballot_sync(0xffffffffu, mine != 0xFFFFFFFFu);
+          uint32_t g0 = __shfl_sync(0xffffffffu, mine, __ffs(have) - 1);
+          same &= (mine == 0xFFFFFFFFu) || (mine == g0);
+          if (__all_sync(0xffffffffu, same)) {
+            read_nr += l_filtered;
+            if (lane == 0) em.out_word[read] = make_word(2, 1, g0);
+            done = true; break;
           }
-        uint32_t have = __ballot_sync(0xffffffffu, mine != 0xFFFFFFFFu);
-        uint32_t g0 = __shfl_sync(0xffffffffu, mine, __ffs(have) - 1);
-        same &= (mine == 0xFFFFFFFFu) || (mine == g0);
-        if (__all_sync(0xffffffffu, same)) {
-          if (lane == 0) em.out_word[read] = make_word(2, 1, g0);
-          done = true; break;
         }
       }
 
@@ -317,9 +403,8 @@ align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __re
       for (int r = 0; r < AL_ROUNDS; ++r) {
         kept[r] = false;
         if (val[r] == LOOKUP_MISS) continue;
-        bool specific = value_is_specific(t, val[r]);
         if (prm.has_mg) {
-          uint32_t c = specific ? 1u : mlist_count(t.mlist, value_payload(t, val[r]));
+          uint32_t c = cnt[r] ? cnt[r] : mlist_count(t.mlist, value_payload(t, val[r]));
           if ((int64_t)c > prm.mg) { ++read_nr; continue; }
         }
         kept[r] = true;
@@ -337,29 +422,13 @@ align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __re
       __syncwarp();
 #pragma unroll
       for (int r = 0; r < AL_ROUNDS; ++r) {
-        if (!kept[r]) continue;
         const uint32_t pos = (uint32_t)(wbase + 32 * r + lane);
-        if (vld(ws.kset_pos + slot[r]) != pos) continue;  // an earlier occurrence represents this k-mer
-        if (value_is_specific(t, val[r])) {
-          count_genome(ws, n_touched, (uint32_t)value_payload(t, val[r]), pos, true);
-        } else {
-          uint64_t sector = value_payload(t, val[r]);
-          for (bool more = true; more; ++sector) {
-            uint32_t ids[8];
-            ld_sector_u32_nc(t.mlist + sector * MLIST_SECTOR, ids);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (!more) break;
-              count_genome(ws, n_touched, ids[i] & ~LIST_END, pos, false);
-              if (ids[i] & LIST_END) more = false;
-            }
-          }
-        }
+        // a repeated k-mer is represented by its first kept occurrence only
+        const bool rep = kept[r] && vld(ws.kset_pos + slot[r]) == pos;
+        count_round(t, ws, nT, rep, val[r], (uint32_t)(wbase + 32 * r), lane);
       }
-      __syncwarp();
       if (single) {
         // one super-round: decide now, while slot[] is still in scope for a targeted cleanup
-        uint32_t nT = vld(n_touched);
         if (nT == 0) { if (lane == 0) em.out_word[read] = make_word(1, 0, 0); }
         else decide_and_emit(ws, nT, prm, em, read, lane);
         __syncwarp();
@@ -367,7 +436,6 @@ align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __re
 #pragma unroll
         for (int r = 0; r < AL_ROUNDS; ++r)
           if (kept[r]) { vst64(ws.kset_key + slot[r], EMPTY64); vst(ws.kset_pos + slot[r], NOPOS); }
-        if (lane == 0) vst(n_touched, 0u);
         __threadfence_block();
         __syncwarp();
         done = true;
@@ -376,20 +444,23 @@ align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __re
 
     if (!done) {
       // reads longer than one super-round (or without any window)
-      uint32_t nT = vld(n_touched);
       if (nT == 0) { if (lane == 0) em.out_word[read] = make_word(1, 0, 0); }
       else decide_and_emit(ws, nT, prm, em, read, lane);
       __syncwarp();
       if (slow_used) {
         for (uint32_t i = lane; i < nT; i += 32) reset_entry(ws.gtab + (size_t)vld(ws.touched + i) * 4);
         for (uint32_t i = lane; i < kset_cap; i += 32) { vst64(ws.kset_key + i, EMPTY64); vst(ws.kset_pos + i, NOPOS); }
-        if (lane == 0) vst(n_touched, 0u);
         __threadfence_block();
         __syncwarp();
       }
     }
     c_nq += read_nq;
     c_nr += read_nr;
+    // rotate the pipeline registers
+    cur_beg = nx_beg; cur_end = nx_end;
+    nx_beg = n2_beg; nx_end = n2_end;
+#pragma unroll
+    for (int c = 0; c <= AL_ROUNDS; ++c) cur_ch[c] = nx_ch[c];
   }
 
   c_drop = warp_sum(c_drop); c_nq = warp_sum(c_nq); c_nr = warp_sum(c_nr);
@@ -484,7 +555,11 @@ int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_q
   per_warp_smem = (per_warp_smem + 15) & ~(size_t)15;
   const size_t dyn_smem = per_warp_smem * AL_WARPS;
 
-  auto kern = qual ? align_kernel<true> : align_kernel<false>;
+  // resident CTAs per SM the kernel is compiled for (register budget); PA_ALIGN_MINB is a tuning knob
+  static int minb = [] { const char* e = getenv("PA_ALIGN_MINB"); int v = e ? atoi(e) : 2; return (v >= 2 && v <= 4) ? v : 2; }();
+  auto kern = qual ? align_kernel<true, 2> : align_kernel<false, 2>;
+  if (minb == 3) kern = qual ? align_kernel<true, 3> : align_kernel<false, 3>;
+  if (minb == 4) kern = qual ? align_kernel<true, 4> : align_kernel<false, 4>;
   PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(dyn_smem, 1024)));
   int occ = 1;
   PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, AL_THREADS, dyn_smem));

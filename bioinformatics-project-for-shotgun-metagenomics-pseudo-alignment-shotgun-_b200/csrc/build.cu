@@ -279,30 +279,39 @@ __global__ void set_csr_tails(uint64_t* run_off, uint64_t U, uint64_t R, uint64_
 // ===========================================================================
 // lookup table construction from the CSR
 // ===========================================================================
-__global__ void msector_counts(const uint64_t* __restrict__ run_off, uint64_t U, uint32_t* __restrict__ cnt) {
+__global__ void msector_counts(const uint64_t* __restrict__ run_off, uint64_t U, uint32_t n_inline, uint32_t* __restrict__ cnt) {
   uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (u >= U) return;
   uint64_t c = run_off[u + 1] - run_off[u];
-  cnt[u] = c > 1 ? (uint32_t)((c + MLIST_SECTOR - 1) / MLIST_SECTOR) : 0u;
+  cnt[u] = c > n_inline ? (uint32_t)((c + MLIST_SECTOR - 1) / MLIST_SECTOR) : 0u;
 }
 
 __global__ void mlist_fill(const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome, uint64_t U,
-                           const uint64_t* __restrict__ msec_off, uint32_t* __restrict__ mlist) {
+                           uint32_t n_inline, const uint64_t* __restrict__ msec_off, uint32_t* __restrict__ mlist) {
   uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (u >= U) return;
   uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
-  if (c <= 1) return;
+  if (c <= n_inline) return;
   uint32_t* dst = mlist + msec_off[u] * MLIST_SECTOR;
   for (uint64_t j = 0; j < c; ++j) dst[j] = run_genome[r0 + j] | (j + 1 == c ? LIST_END : 0u);
 }
 
 struct TableBuildParams {
-  uint32_t tag_bits, val_bits;
+  uint32_t tag_bits, val_bits, gbits, n_inline;
   MixParams mix;
 };
 
-__device__ __forceinline__ uint64_t entry_value(const TableBuildParams& p, bool specific, uint64_t payload) {
-  return ((uint64_t)specific << (p.val_bits - 1)) | payload;
+// value field of a distinct k-mer with c genomes rg[0..c) (ascending); see TableView in common.cuh
+__device__ __forceinline__ uint64_t entry_value(const TableBuildParams& p, uint64_t c, const uint32_t* __restrict__ rg,
+                                                uint64_t msec) {
+  const uint32_t kshift = p.val_bits - 2;
+  if (c == 1) return ((uint64_t)KIND_SPECIFIC << kshift) | rg[0];
+  if (c <= p.n_inline) {
+    uint64_t v = 0;
+    for (uint32_t i = 0; i < p.n_inline; ++i) v |= (uint64_t)rg[i < c ? i : c - 1] << (i * p.gbits);
+    return ((uint64_t)KIND_INLINE << kshift) | v;
+  }
+  return ((uint64_t)KIND_MLIST << kshift) | msec;
 }
 
 __global__ void table_insert(const uint64_t* __restrict__ ukeys, const uint64_t* __restrict__ run_off,
@@ -314,7 +323,7 @@ __global__ void table_insert(const uint64_t* __restrict__ ukeys, const uint64_t*
   uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
   uint64_t h = mix_key(ukeys[u], p.mix);
   uint64_t tag = h & ((1ULL << p.tag_bits) - 1);
-  uint64_t entry = (tag << p.val_bits) | entry_value(p, c == 1, c == 1 ? (uint64_t)run_genome[r0] : msec_off[u]);
+  uint64_t entry = (tag << p.val_bits) | entry_value(p, c, run_genome + r0, msec_off[u]);
   unsigned long long* b = buckets + (h >> p.tag_bits) * 4;
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
@@ -335,7 +344,7 @@ __global__ void stash_insert(const uint64_t* __restrict__ ukeys, const uint64_t*
   uint64_t u = ovf_list[t];
   uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
   uint64_t h = mix_key(ukeys[u], p.mix);
-  uint64_t value = entry_value(p, c == 1, c == 1 ? (uint64_t)run_genome[r0] : msec_off[u]);
+  uint64_t value = entry_value(p, c, run_genome + r0, msec_off[u]);
   uint64_t i = (h * 0xA24BAED4963EE407ULL) >> 20;
   for (;;) {
     i &= stash_mask;
@@ -482,31 +491,41 @@ int32_t index_build_tables(Index& ix) {
     PA_CUDA(cudaStreamSynchronize(s));
     return ST_OK;
   }
-  // multi-genome lists: 32-byte aligned, 8 ids per sector, last id flagged
+  // Table geometry.  load factor <= 0.5 over 4-slot buckets; the value field (val_bits = 64 - tag_bits) must hold
+  // 2 kind bits + a genome id (with the all-ones id left unused so that no entry equals EMPTY64) + any mlist sector.
+  const uint32_t G = ix.n_genomes;
+  const uint32_t gb = std::max(1u, ceil_log2_u64(G));
+  const uint32_t need_spec = std::max(1u, ceil_log2_u64((uint64_t)G + 1));
+  int64_t b = std::max<int64_t>(std::max<int64_t>(ceil_log2_u64((U + 1) / 2), (int64_t)need_spec + 2 * k - 62), 0);
+  b = std::min<int64_t>(b, 2 * k - 1);
   DevBuf msec_cnt, msec_off, tile_sums, d_total;
   PA_TRY(msec_cnt.alloc(U * 4));
   PA_TRY(msec_off.alloc(U * 8));
   PA_TRY(tile_sums.alloc((scan_tiles(U) + 1) * 8));
   PA_TRY(d_total.alloc(8));
-  msector_counts<<<grid_for(U, 256), 256, 0, s>>>(ix.run_off.as<uint64_t>(), U, msec_cnt.as<uint32_t>());
-  PA_TRY(exclusive_scan_u32(msec_cnt.as<uint32_t>(), msec_off.as<uint64_t>(), U, tile_sums.as<uint64_t>(),
-                            d_total.as<uint64_t>(), s));
   uint64_t n_msec = 0;
-  PA_CUDA(cudaMemcpyAsync(&n_msec, d_total.p, 8, cudaMemcpyDeviceToHost, s));
-  PA_CUDA(cudaStreamSynchronize(s));
+  for (;;) {
+    const uint32_t P = (uint32_t)(64 - (2 * k - b)) - 2;
+    if (P < need_spec) { set_error("lookup table: genome ids do not fit (k=%d, G=%u)", k, G); return ST_UNSUPPORTED; }
+    uint32_t n_in = std::min<uint32_t>(4, P / gb);
+    if (n_in < 2) n_in = 1;
+    ix.gbits = gb; ix.n_inline = n_in;
+    // lists longer than n_inline: 32-byte aligned, 8 ids per sector, last id flagged
+    msector_counts<<<grid_for(U, 256), 256, 0, s>>>(ix.run_off.as<uint64_t>(), U, n_in, msec_cnt.as<uint32_t>());
+    PA_TRY(exclusive_scan_u32(msec_cnt.as<uint32_t>(), msec_off.as<uint64_t>(), U, tile_sums.as<uint64_t>(),
+                              d_total.as<uint64_t>(), s));
+    PA_CUDA(cudaMemcpyAsync(&n_msec, d_total.p, 8, cudaMemcpyDeviceToHost, s));
+    PA_CUDA(cudaStreamSynchronize(s));
+    if (ceil_log2_u64(n_msec + 1) <= P) break;
+    if (b >= 2 * k - 1) { set_error("lookup table: list references do not fit (k=%d)", k); return ST_UNSUPPORTED; }
+    ++b;
+  }
   ix.n_msectors = n_msec;
   PA_TRY(ix.mlist.alloc(std::max<uint64_t>(n_msec, 1) * 32));
   PA_CUDA(cudaMemsetAsync(ix.mlist.p, 0xFF, ix.mlist.bytes, s));
   if (n_msec)
-    mlist_fill<<<grid_for(U, 256), 256, 0, s>>>(ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(), U,
+    mlist_fill<<<grid_for(U, 256), 256, 0, s>>>(ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(), U, ix.n_inline,
                                                  msec_off.as<uint64_t>(), ix.mlist.as<uint32_t>());
-  // bucket count: load factor <= 0.5 over 4-slot buckets, and enough value bits for the payloads
-  uint32_t b_load = ceil_log2_u64((U + 1) / 2);
-  uint32_t payload_need = std::max(ceil_log2_u64((uint64_t)ix.n_genomes + 1), ceil_log2_u64(n_msec + 1));
-  payload_need = std::max(payload_need, 1u);
-  int64_t b_payload = (int64_t)payload_need + 2 * k - 63;
-  int64_t b = std::max<int64_t>(std::max<int64_t>(b_load, b_payload), 0);
-  b = std::min<int64_t>(b, 2 * k - 1);
   DevBuf ovf_count, ovf_list;
   PA_TRY(ovf_count.alloc(4));
   uint32_t ovf_cap = (uint32_t)std::min<uint64_t>(U / 4 + 4096, 0xFFFFFFF0ull);
@@ -515,12 +534,11 @@ int32_t index_build_tables(Index& ix) {
     ix.bucket_bits = (uint32_t)b;
     ix.tag_bits = (uint32_t)(2 * k - b);
     ix.val_bits = 64 - ix.tag_bits;
-    if (ix.val_bits - 1 < payload_need) { set_error("lookup table: payload does not fit (k=%d, b=%lld)", k, (long long)b); return ST_UNSUPPORTED; }
     const uint64_t n_buckets = 1ULL << b;
     PA_TRY(ix.buckets.alloc(n_buckets * 32));
     PA_CUDA(cudaMemsetAsync(ix.buckets.p, 0xFF, n_buckets * 32, s));
     PA_CUDA(cudaMemsetAsync(ovf_count.p, 0, 4, s));
-    TableBuildParams p{ix.tag_bits, ix.val_bits, ix.mix};
+    TableBuildParams p{ix.tag_bits, ix.val_bits, ix.gbits, ix.n_inline, ix.mix};
     table_insert<<<grid_for(U, 256), 256, 0, s>>>(ix.ukeys.as<uint64_t>(), ix.run_off.as<uint64_t>(),
                                                    ix.run_genome.as<uint32_t>(), msec_off.as<uint64_t>(), U, p,
                                                    ix.buckets.as<unsigned long long>(), ovf_count.as<unsigned int>(),

@@ -6,6 +6,8 @@
 #include "sort.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -32,9 +34,12 @@ __global__ void debug_lookup_kernel(TableView t, const uint64_t* __restrict__ ke
   if (key != SENTINEL_KEY) {
     uint64_t v = table_lookup(t, key);
     if (v != LOOKUP_MISS) {
-      if (value_is_specific(t, v)) { c = 1; g0 = (uint32_t)value_payload(t, v); }
+      const uint32_t kind = value_kind(t, v);
+      const uint64_t payload = value_payload(t, v);
+      if (kind == KIND_SPECIFIC) { c = 1; g0 = (uint32_t)payload; }
+      else if (kind == KIND_INLINE) { c = inline_count(t, payload); g0 = (uint32_t)payload & ((1u << t.gbits) - 1); }
       else {
-        uint64_t sector = value_payload(t, v);
+        uint64_t sector = payload;
         g0 = t.mlist[sector * MLIST_SECTOR] & ~LIST_END;
         for (bool more = true; more; ++sector)
           for (int j = 0; j < 8 && more; ++j) { ++c; if (t.mlist[sector * MLIST_SECTOR + j] & LIST_END) more = false; }
@@ -320,6 +325,16 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
     NEED(read_off[i + 1] >= read_off[i], "read_off is not monotonic");
     max_len = std::max(max_len, read_off[i + 1] - read_off[i]);
   }
+  const bool trace = getenv("PA_TRACE") != nullptr;
+  auto t_start = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(s);
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[pa_align_batch] %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_start).count());
+    t_start = now;
+  };
+  lap("scan_off");
   DevBuf d_bases, d_quals, d_off, d_words, d_list, d_state;
   PA_TRY(d_bases.alloc(n_bytes + 64));
   if (need_q) PA_TRY(d_quals.alloc(n_bytes + 64));
@@ -328,18 +343,22 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
   PA_TRY(d_list.alloc(std::max<uint64_t>(list_cap, 1) * 4));
   PA_TRY(d_state.alloc(5 * 8));
   PA_CUDA(cudaMemsetAsync(d_state.p, 0, 40, s));
+  lap("alloc");
   if (n_bytes) PA_CUDA(cudaMemcpyAsync(d_bases.p, bases + base0, n_bytes, cudaMemcpyHostToDevice, s));
   if (need_q && n_bytes) PA_CUDA(cudaMemcpyAsync(d_quals.p, quals + base0, n_bytes, cudaMemcpyHostToDevice, s));
   PA_CUDA(cudaMemcpyAsync(d_off.p, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
+  lap("h2d");
   AlignParams prm = clamp_params(params);
   // the kernel indexes bases with read_off directly: rebase the pointers instead of the offsets
   PA_TRY(align_batch_device(ix, d_bases.as<uint8_t>() - base0, need_q ? d_quals.as<uint8_t>() - base0 : nullptr,
                             d_off.as<uint64_t>(), n_reads, max_len, prm, d_words.as<uint64_t>(), d_list.as<uint32_t>(),
                             list_cap, d_state.as<unsigned long long>(), d_state.as<unsigned long long>() + 2, s, nullptr));
+  lap("kernel");
   uint64_t h_state[5];
   PA_CUDA(cudaMemcpyAsync(h_state, d_state.p, 40, cudaMemcpyDeviceToHost, s));
   PA_CUDA(cudaMemcpyAsync(out_words, d_words.p, n_reads * 8, cudaMemcpyDeviceToHost, s));
   PA_CUDA(cudaStreamSynchronize(s));
+  lap("d2h");
   if (list_len) *list_len = h_state[0];
   if (h_state[0] > list_cap) {
     set_error("out_list too small: %llu entries needed", (unsigned long long)h_state[0]);

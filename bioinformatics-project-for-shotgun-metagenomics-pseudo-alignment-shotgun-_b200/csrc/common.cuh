@@ -89,9 +89,14 @@ __host__ __device__ __forceinline__ uint64_t mix_key(uint64_t x, const MixParams
 
 // ---------------------------------------------------------------------------
 // Lookup table view (device pointers).  One bucket = one 32-byte sector = four
-// 8-byte slots.  slot = (tag << val_bits) | value;  value = flag | payload with
-// flag (bit val_bits-1) = 1: specific k-mer, payload = genome id;
-//                        0: multi-genome k-mer, payload = first mlist sector.
+// 8-byte slots.  slot = (tag << val_bits) | value;  value = kind (2 bits) | payload:
+//   KIND_SPECIFIC  k-mer of exactly one genome, payload = genome id
+//   KIND_INLINE    2..n_inline genomes packed in the payload, gbits each, ascending;
+//                  a field equal to its predecessor means "no more genomes"
+//   KIND_MLIST     longer lists: payload = first 32-byte sector of the list in mlist
+// so that the common cases resolve inside the one sector a lookup has to fetch anyway
+// (a B200 moves a whole 128-byte line from HBM per missing sector; see
+// profiles/r01_gather_ncu_dram_per_request.csv).
 // Keys that do not fit their bucket live in the stash (full hashed key, linear
 // probing); a bucket is only ever followed into the stash when it is full.
 // ---------------------------------------------------------------------------
@@ -105,8 +110,12 @@ struct TableView {
   uint32_t tag_bits;
   uint32_t val_bits;
   uint32_t k;
+  uint32_t gbits;     // bits per genome id inside an inline list
+  uint32_t n_inline;  // longest inline list (1 = inline lists unused)
   MixParams mix;
 };
+
+enum : uint32_t { KIND_MLIST = 0, KIND_INLINE = 2, KIND_SPECIFIC = 3 };
 
 constexpr uint64_t LOOKUP_MISS = 0xFFFFFFFFFFFFFFFFULL;
 
@@ -149,9 +158,20 @@ __device__ __forceinline__ uint64_t table_lookup(const TableView& t, uint64_t ke
   return bucket_resolve(t, s, h);
 }
 
-__device__ __forceinline__ bool value_is_specific(const TableView& t, uint64_t v) { return (v >> (t.val_bits - 1)) & 1; }
-__device__ __forceinline__ uint64_t value_payload(const TableView& t, uint64_t v) {
-  return v & ((1ULL << (t.val_bits - 1)) - 1);
+__host__ __device__ __forceinline__ uint32_t value_kind(const TableView& t, uint64_t v) { return (uint32_t)(v >> (t.val_bits - 2)) & 3u; }
+__host__ __device__ __forceinline__ uint64_t value_payload(const TableView& t, uint64_t v) {
+  return v & ((1ULL << (t.val_bits - 2)) - 1);
+}
+// number of genomes of an inline list
+__device__ __forceinline__ uint32_t inline_count(const TableView& t, uint64_t payload) {
+  const uint32_t gm = (1u << t.gbits) - 1;
+  uint32_t c = 1, prev = (uint32_t)payload & gm;
+  for (uint32_t i = 1; i < t.n_inline; ++i) {
+    uint32_t g = (uint32_t)(payload >> (i * t.gbits)) & gm;
+    if (g == prev) break;
+    prev = g; ++c;
+  }
+  return c;
 }
 
 // ---------------------------------------------------------------------------

@@ -49,7 +49,7 @@ struct Index {
   std::vector<uint64_t> h_genome_off;
   // lookup structures
   DevBuf buckets, stash_key, stash_val, mlist;
-  uint32_t bucket_bits = 0, tag_bits = 1, val_bits = 63;
+  uint32_t bucket_bits = 0, tag_bits = 1, val_bits = 63, gbits = 1, n_inline = 1;
   uint64_t stash_cap = 0;
   uint32_t stash_count = 0;
   uint64_t n_msectors = 0;
@@ -71,6 +71,8 @@ struct Index {
     t.tag_bits = tag_bits;
     t.val_bits = val_bits;
     t.k = (uint32_t)k;
+    t.gbits = gbits;
+    t.n_inline = n_inline;
     t.mix = mix;
     return t;
   }

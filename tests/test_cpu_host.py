@@ -1,0 +1,239 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, host-side record / CLI logic,
+and the world_size-2 summary exchange over gloo.  No compute call needs a GPU here."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import conftest
+import synth
+from oracle import oracle as orc
+
+PKG = conftest.PKG_DIR
+ROOT = conftest.ROOT
+
+
+def test_abi_library_exports_every_declared_symbol():
+    import _native as nat
+    header = open(os.path.join(ROOT, "include", "pa_b200.h")).read()
+    declared = re.findall(r"^int32_t\s+(pa_\w+)\s*\(", header, flags=re.M)
+    assert len(declared) >= 20
+    lib = nat.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/pa_b200.h but not exported"
+    assert sorted(declared) == sorted(nat.EXPORTED_SYMBOLS)
+    assert lib.pa_abi_version() == 1
+
+
+def test_encode_decode_kmers_round_trip_on_host():
+    import _native as nat
+    kmers = ["ACGTACGTACGTACGTACGTACGTACGTACG", "T" * 31, "G" * 31]
+    keys = np.zeros(3, dtype=np.uint64)
+    flat = np.frombuffer("".join(kmers).encode(), dtype=np.uint8).copy()
+    nat.check(nat.lib().pa_encode_kmers(31, nat._p(flat), 3, nat._p(keys)))
+    assert nat.decode_kmers(31, keys) == kmers
+    assert len(set(keys.tolist())) == 3 and int(keys.max()) < (1 << 62)
+    bad = np.frombuffer(("ACGN" + "A" * 27).encode(), dtype=np.uint8).copy()
+    nat.check(nat.lib().pa_encode_kmers(31, nat._p(bad), 1, nat._p(keys)))
+    assert int(keys[0]) == 0xFFFFFFFFFFFFFFFF
+
+
+def test_product_fails_loudly_without_a_device():
+    import _native as nat
+    if nat.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from kmer import KmerReference
+    from records import FASTARecordContainer
+    c = FASTARecordContainer()
+    c.parse_records(">g\nACGTACGT\n")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        KmerReference(3, c)
+
+
+# ---------------------------------------------------------------------------
+# records / data_file (API-compatible host shims)
+# ---------------------------------------------------------------------------
+def test_fasta_and_fastq_parsing_rules():
+    from records import (FASTAQRecordContainer, FASTARecordContainer, DuplicateRecordError, InvalidRecordData,
+                         NoRecordsInData, Record, Section, UnparsedDataError)
+    c = FASTARecordContainer()
+    c.parse_records(">g1 some description\nACGT\nNNAC\r\n>g2\nTTTT")
+    recs = list(c)
+    assert [r.identifier for r in recs] == ["g1 some description", "g2"]
+    assert recs[0]["genome"] == "ACGTNNAC" and recs[1]["genome"] == "TTTT" and recs[0]["description"] == recs[0].identifier
+    with pytest.raises(UnparsedDataError):
+        FASTARecordContainer().parse_records(">g1\nACGT\n>g2\nacgt\n")
+    with pytest.raises(NoRecordsInData, match="No valid records found in the data."):
+        FASTARecordContainer().parse_records("")
+    q = FASTAQRecordContainer()
+    q.parse_records("@r1\nACGT\n+\nIIII\n@r2\nGG\n+..\n!~\n")
+    assert [(r.identifier, r["sequence"], r["quality_sequence"]) for r in q] == [("r1", "ACGT", "IIII"), ("r2", "GG", "!~")]
+    with pytest.raises(NoRecordsInData):
+        FASTAQRecordContainer().parse_records("@r1\nACGN\n+\nIIII\n")          # N is not allowed in reads
+    with pytest.raises(InvalidRecordData):
+        FASTAQRecordContainer().parse_records("@r1\nACGT\n+\nIII\n")
+    with pytest.raises(DuplicateRecordError):
+        FASTAQRecordContainer().parse_records("@r1\nACGT\n+\nIIII\n@r1\nACGT\n+\nIIII\n")
+    with pytest.raises(InvalidRecordData, match="has no sections"):
+        Record([])
+    with pytest.raises(InvalidRecordData, match="has appeared twice"):
+        Record([Section("a", "x"), Section("a", "y")])
+
+
+def test_parsers_agree_with_the_reference_when_it_is_present():
+    import refimpl
+    if not refimpl.reference_available():
+        pytest.skip("/root/reference not present")
+    ref = refimpl.load_reference()
+    import records as mine
+    rng = np.random.default_rng(5)
+    fasta_alpha = list("ACGTN\n\r >@+acgt \t")
+    fastq_alpha = list("ACGT\n\n\r@+I!~N ")
+    for trial in range(400):
+        for alpha, mine_cls, ref_cls in ((fasta_alpha, mine.FASTARecordContainer, ref.records.FASTARecordContainer),
+                                         (fastq_alpha, mine.FASTAQRecordContainer, ref.records.FASTAQRecordContainer)):
+            if trial % 2 == 0:
+                text = "".join(rng.choice(alpha, size=int(rng.integers(0, 60))))
+            elif mine_cls is mine.FASTARecordContainer:
+                text = "".join(f">g{i}\n" + "".join(rng.choice(list("ACGTN\n"), size=int(rng.integers(1, 30)))) + "\n" for i in range(3))
+            else:
+                text = "".join(f"@r{i % 2 if trial % 7 == 0 else i}\n{s}\n+\n{'I' * (len(s) - (trial % 5 == 0))}\n"
+                               for i, s in enumerate("".join(rng.choice(list("ACGT"), size=int(rng.integers(1, 9)))) for _ in range(3)))
+            outcomes = []
+            for cls in (mine_cls, ref_cls):
+                cont = cls()
+                try:
+                    cont.parse_records(text)
+                    outcomes.append([str(r) for r in cont])
+                except Exception as e:  # same exception type and message
+                    outcomes.append((type(e).__name__, str(e)))
+            assert outcomes[0] == outcomes[1], repr(text)
+
+
+def test_data_file_errors(tmp_path):
+    from data_file import FASTAFile, FASTAQFile, InvalidExtensionError, NoRecordsInDataFile
+    p = tmp_path / "x.txt"
+    p.write_text(">g\nACGT\n")
+    with pytest.raises(InvalidExtensionError, match="Invalid file extension"):
+        FASTAFile(str(p))
+    e = tmp_path / "e.fa"
+    e.write_text("")
+    with pytest.raises(NoRecordsInDataFile):
+        FASTAFile(str(e))
+    import gzip
+    g = tmp_path / "r.fq.gz"
+    with gzip.open(g, "wt") as f:
+        f.write("@r\nACGT\n+\nIIII\n")
+    assert [r.identifier for r in FASTAQFile(str(g)).container] == ["r"]
+
+
+def run_cli(*argv):
+    r = subprocess.run([sys.executable, os.path.join(PKG, "main.py"), *argv], capture_output=True, text=True, cwd=PKG)
+    return r.stdout, r.stderr, r.returncode
+
+
+def test_cli_error_paths_that_never_reach_the_device(tmp_path):
+    out, err, rc = run_cli("-t", "reference", "-g", str(tmp_path / "missing.fa"), "-k", "4", "-r", str(tmp_path / "o.kdb"))
+    assert rc != 0 and "does not exist" in err
+    bad = tmp_path / "genome.txt"
+    bad.write_text(">g\nACGT\n")
+    out, err, rc = run_cli("-t", "reference", "-g", str(bad), "-k", "4", "-r", str(tmp_path / "o.kdb"))
+    assert rc != 0 and "Invalid file extension" in err
+    out, err, rc = run_cli("-t", "nonsense")
+    assert rc != 0 and "Unsupported task" in err
+    fa = tmp_path / "g.fa"
+    fa.write_text(">g\nACGT\n")
+    out, err, rc = run_cli("-t", "reference", "-g", str(fa), "-k", "4", "-r", str(tmp_path / "o.kdb"), "-m", "2")
+    assert rc != 0 and "For task 'reference'" in err
+    out, err, rc = run_cli("-t", "align", "-g", str(fa))
+    assert rc != 0 and "For task 'align'" in err
+    out, err, rc = run_cli("-t", "dumpalign")
+    assert rc != 0 and "For task 'dumpalign'" in err
+    notgz = tmp_path / "x.kdb"
+    notgz.write_text("not a gzip file")
+    out, err, rc = run_cli("-t", "dumpref", "-r", str(notgz))
+    assert rc != 0 and "Incorrect format of input file" in err
+
+
+def test_cli_argument_parsing_keeps_the_reference_flags():
+    import main
+    a = main.parse_arguments(["-t", "dumpalign", "-r", "x.kdb", "--reads", "r.fq", "-m", "2", "-p", "3", "--reverse-complement",
+                              "--min-read-quality", "10", "--min-kmer-quality", "11", "--max-genomes", "4",
+                              "--filter-similar", "--similarity-threshold", "0.5"])
+    assert (a.task, a.unique_threshold, a.ambiguous_threhold, a.reverse_complement) == ("dumpalign", 2, 3, True)
+    assert (a.min_read_quality, a.min_kmer_quality, a.max_genomes, a.filter_similar, a.similarity_threshold) == (10, 11, 4, True, 0.5)
+
+
+# ---------------------------------------------------------------------------
+# world_size-2 summary exchange (gloo)
+# ---------------------------------------------------------------------------
+WORKER = r'''
+import json, os, sys
+sys.path[:0] = [{root!r}, {pkg!r}, os.path.join({root!r}, "tests")]
+import numpy as np, torch, torch.distributed as dist
+import synth, multi_gpu
+from oracle import oracle as orc
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+case = synth.fuzz_case(int(sys.argv[1]), max_genomes=5)
+pr = case["params"]
+o = orc.OracleReference(case["k"], case["genomes"])
+reads = case["reads"] * 3
+reads = [(f"{{r[0]}}_{{i}}", r[1], r[2]) for i, r in enumerate(reads)]
+lo, hi = multi_gpu.shard_bounds(len(reads), world, rank)
+al = o.align(reads[lo:hi], pr["m"], pr["p"], pr["mrq"], pr["mkq"], pr["mg"])
+G = len(case["genomes"])
+# per-rank accumulators in the layout K8 produces on the device
+acc = np.zeros(4 + 2 * G, dtype=np.int64)
+first = np.full(G, -1, dtype=np.int64)
+for i in range(hi - lo):
+    t = int(al.types[i])
+    if t == 0: acc[3] += 1; continue
+    if t == 1: acc[2] += 1; continue
+    acc[0 if t == 2 else 1] += 1
+    for j, g in enumerate(al.genomes[int(al.list_off[i]):int(al.list_off[i + 1])]):
+        acc[4 + (0 if t == 2 else G) + int(g)] += 1
+        key = ((lo + i) << 22) | j
+        first[g] = key if first[g] < 0 else min(first[g], key)
+counters = torch.tensor([al.filtered_quality_reads, al.filtered_quality_kmers, al.filtered_hr_kmers], dtype=torch.int64)
+acc_t, first_t = torch.from_numpy(acc), torch.from_numpy(first)
+multi_gpu.allreduce_summary(acc_t, first_t)
+dist.all_reduce(counters)
+if rank == 0:
+    flags = (pr["mrq"] is not None, pr["mkq"] is not None, pr["mg"] is not None)
+    got = multi_gpu.summary_from_accumulators(acc[:4], acc[4:4 + G], acc[4 + G:], first.astype(np.uint64),
+                                              [g[0] for g in case["genomes"]], flags, counters.tolist())
+    want = o.align(reads, pr["m"], pr["p"], pr["mrq"], pr["mkq"], pr["mg"]).get_summary()
+    assert json.dumps(got) == json.dumps(want), (got, want)
+    print("OK")
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("seed", [3, 17, 64, 301])
+def test_world_size_2_summary_exchange_matches_single_process(tmp_path, seed):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, pkg=PKG))
+    port = 29500 + (os.getpid() + seed) % 2000
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), str(seed)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=180) for p in procs]
+    for p, (out, err) in zip(procs, outs):
+        assert p.returncode == 0, err[-2000:]
+    assert "OK" in outs[0][0]
+
+
+def test_shard_bounds_cover_everything_once():
+    import multi_gpu
+    for n in (0, 1, 7, 1000):
+        for world in (1, 2, 3, 8):
+            blocks = [multi_gpu.shard_bounds(n, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))

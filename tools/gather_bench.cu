@@ -136,6 +136,11 @@ int main(int argc, char** argv) {
   double max_gib = argc > 1 ? atof(argv[1]) : 16.0;
   int iters = argc > 2 ? atoi(argv[2]) : 64;
   uint64_t max_bytes = (uint64_t)(max_gib * (1ULL << 30));
+  if (argc > 3) {  // L2 fetch granularity hint (bytes): 32, 64 or 128
+    CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(argv[3])));
+  }
+  size_t gran = 0; CK(cudaDeviceGetLimit(&gran, cudaLimitMaxL2FetchGranularity));
+  printf("{\"l2_fetch_granularity\": %zu}\n", gran);
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   printf("{\"device\": \"%s\", \"sms\": %d, \"l2_bytes\": %d}\n", prop.name, prop.multiProcessorCount, prop.l2CacheSize);
   uint8_t* table; CK(cudaMalloc(&table, max_bytes));
@@ -156,7 +161,13 @@ int main(int argc, char** argv) {
     }
     printf("{\"stream_copy_GBps\": %.1f}\n", 2.0 * half * 16 / (best * 1e-3) / 1e9);
   }
-  for (double gib : {0.25, 1.0, 4.0, 16.0, 64.0}) {
+  if (argc > 4) {  // single-mode run for ncu: one table size, nc32 only
+    uint64_t bytes = max_bytes;
+    run<M_NC32, 8>(table, bytes, iters, 8, sms, sink);
+    CK(cudaFree(table));
+    return 0;
+  }
+  for (double gib : {0.25, 8.0, 64.0}) {
     if (gib > max_gib) break;
     uint64_t bytes = (uint64_t)(gib * (1ULL << 30));
     for (int cps : {4, 8}) {
