@@ -14,7 +14,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpa_b200.so")
+LIB_PATH = os.environ.get("PA_B200_LIB") or os.path.join(_HERE, "libpa_b200.so")  # PA_B200_LIB: tuning builds
 
 PA_OK = 0
 PA_ERR_INVALID_ARG = -1

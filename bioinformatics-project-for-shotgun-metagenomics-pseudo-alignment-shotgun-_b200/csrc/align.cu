@@ -345,8 +345,9 @@ align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __re
       bool l_unknown = false, l_kept_spec = false, l_kept_multi = false;
       uint32_t l_filtered = 0;
 #pragma unroll
+      for (int r = 0; r < AL_ROUNDS; ++r) val[r] = look[r] ? bucket_resolve(t, bucket[r], h[r]) : LOOKUP_MISS;
+#pragma unroll
       for (int r = 0; r < AL_ROUNDS; ++r) {
-        val[r] = look[r] ? bucket_resolve(t, bucket[r], h[r]) : LOOKUP_MISS;
         cnt[r] = 0;
         if (val[r] == LOOKUP_MISS) continue;
         const uint32_t kind = value_kind(t, val[r]);

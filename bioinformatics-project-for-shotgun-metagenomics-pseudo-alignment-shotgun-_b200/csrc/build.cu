@@ -12,6 +12,7 @@
 #include "sort.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace pa {
@@ -337,19 +338,18 @@ __global__ void table_insert(const uint64_t* __restrict__ ukeys, const uint64_t*
 __global__ void stash_insert(const uint64_t* __restrict__ ukeys, const uint64_t* __restrict__ run_off,
                              const uint32_t* __restrict__ run_genome, const uint64_t* __restrict__ msec_off,
                              const uint32_t* __restrict__ ovf_list, uint32_t n_ovf, TableBuildParams p,
-                             unsigned long long* __restrict__ stash_key, uint64_t* __restrict__ stash_val,
-                             uint64_t stash_mask) {
+                             unsigned long long* __restrict__ stash /* {key, value} pairs */, uint64_t stash_mask) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_ovf) return;
   uint64_t u = ovf_list[t];
   uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
   uint64_t h = mix_key(ukeys[u], p.mix);
   uint64_t value = entry_value(p, c, run_genome + r0, msec_off[u]);
-  uint64_t i = (h * 0xA24BAED4963EE407ULL) >> 20;
+  uint64_t i = stash_slot(h);
   for (;;) {
     i &= stash_mask;
-    if (atomicCAS(&stash_key[i], (unsigned long long)EMPTY64, (unsigned long long)h) == EMPTY64) {
-      stash_val[i] = value;
+    if (atomicCAS(&stash[2 * i], (unsigned long long)EMPTY64, (unsigned long long)h) == EMPTY64) {
+      stash[2 * i + 1] = value;
       return;
     }
     ++i;
@@ -480,7 +480,7 @@ int32_t index_build_tables(Index& ix) {
   const int k = ix.k;
   ix.mix.mask = (2 * k >= 64) ? ~0ULL : ((1ULL << (2 * k)) - 1);
   ix.mix.shift = (uint32_t)std::max(1, k);
-  ix.buckets.release(); ix.stash_key.release(); ix.stash_val.release(); ix.mlist.release();
+  ix.buckets.release(); ix.stash.release(); ix.mlist.release();
   ix.stash_cap = 0; ix.stash_count = 0; ix.n_msectors = 0;
   if (U == 0 || k <= 0) {
     // one empty bucket; every hash maps to it (tag_bits = 2k shifts the whole hash away)
@@ -496,7 +496,13 @@ int32_t index_build_tables(Index& ix) {
   const uint32_t G = ix.n_genomes;
   const uint32_t gb = std::max(1u, ceil_log2_u64(G));
   const uint32_t need_spec = std::max(1u, ceil_log2_u64((uint64_t)G + 1));
-  int64_t b = std::max<int64_t>(std::max<int64_t>(ceil_log2_u64((U + 1) / 2), (int64_t)need_spec + 2 * k - 62), 0);
+  // load factor: <= 0.25 (one bucket per k-mer; 0.9 % of the buckets full, almost no stash traffic) when that
+  // table takes less than a quarter of the free device memory, else <= 0.5 (7 % full buckets)
+  size_t free_b = 0, total_b = 0;
+  PA_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  uint32_t b_load = ceil_log2_u64(U);
+  if ((32ull << b_load) > free_b / 4 || (getenv("PA_TABLE_DENSE") && *getenv("PA_TABLE_DENSE"))) b_load = ceil_log2_u64((U + 1) / 2);
+  int64_t b = std::max<int64_t>(std::max<int64_t>(b_load, (int64_t)need_spec + 2 * k - 62), 0);
   b = std::min<int64_t>(b, 2 * k - 1);
   DevBuf msec_cnt, msec_off, tile_sums, d_total;
   PA_TRY(msec_cnt.alloc(U * 4));
@@ -556,15 +562,12 @@ int32_t index_build_tables(Index& ix) {
       uint64_t cap = 16;
       while (cap < (uint64_t)n_ovf * 2) cap <<= 1;
       ix.stash_cap = cap;
-      PA_TRY(ix.stash_key.alloc(cap * 8));
-      PA_TRY(ix.stash_val.alloc(cap * 8));
-      PA_CUDA(cudaMemsetAsync(ix.stash_key.p, 0xFF, cap * 8, s));
-      PA_CUDA(cudaMemsetAsync(ix.stash_val.p, 0xFF, cap * 8, s));
+      PA_TRY(ix.stash.alloc(cap * 16));
+      PA_CUDA(cudaMemsetAsync(ix.stash.p, 0xFF, cap * 16, s));
       stash_insert<<<grid_for(n_ovf, 256), 256, 0, s>>>(ix.ukeys.as<uint64_t>(), ix.run_off.as<uint64_t>(),
                                                          ix.run_genome.as<uint32_t>(), msec_off.as<uint64_t>(),
                                                          ovf_list.as<uint32_t>(), n_ovf, p,
-                                                         ix.stash_key.as<unsigned long long>(), ix.stash_val.as<uint64_t>(),
-                                                         cap - 1);
+                                                         ix.stash.as<unsigned long long>(), cap - 1);
     }
     break;
   }

@@ -306,6 +306,11 @@ int32_t pa_align_batch_device(pa_index* idx, const uint8_t* d_bases, const uint8
                             s, n_launches);
 }
 
+static int32_t ensure(DevBuf& b, size_t bytes) {
+  if (b.bytes >= bytes && b.p) return ST_OK;
+  return b.alloc(bytes + bytes / 8 + 256);
+}
+
 int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals, const uint64_t* read_off,
                        uint64_t n_reads, const pa_align_params* params, uint64_t* out_words, uint32_t* out_list,
                        uint64_t list_cap, uint64_t* list_len, uint64_t counters[3]) {
@@ -316,49 +321,59 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
   NEED(bases && read_off && out_words && counters, "null host buffer");
   Index& ix = *IDX(idx);
   PA_CUDA(cudaSetDevice(ix.device));
-  cudaStream_t s = ix.stream;
   const bool need_q = params->has_min_read_quality || params->has_min_kmer_quality;
   NEED(!need_q || quals, "quality filters requested without quality data");
-  const uint64_t base0 = read_off[0], n_bytes = read_off[n_reads] - base0;
-  uint64_t max_len = 0;
-  for (uint64_t i = 0; i < n_reads; ++i) {
-    NEED(read_off[i + 1] >= read_off[i], "read_off is not monotonic");
-    max_len = std::max(max_len, read_off[i + 1] - read_off[i]);
-  }
+  const AlignParams prm = clamp_params(params);
   const bool trace = getenv("PA_TRACE") != nullptr;
-  auto t_start = std::chrono::steady_clock::now();
-  auto lap = [&](const char* what) {
-    if (!trace) return;
-    cudaStreamSynchronize(s);
-    auto now = std::chrono::steady_clock::now();
-    fprintf(stderr, "[pa_align_batch] %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_start).count());
-    t_start = now;
-  };
-  lap("scan_off");
-  DevBuf d_bases, d_quals, d_off, d_words, d_list, d_state;
-  PA_TRY(d_bases.alloc(n_bytes + 64));
-  if (need_q) PA_TRY(d_quals.alloc(n_bytes + 64));
-  PA_TRY(d_off.alloc((n_reads + 1) * 8));
-  PA_TRY(d_words.alloc(n_reads * 8));
-  PA_TRY(d_list.alloc(std::max<uint64_t>(list_cap, 1) * 4));
-  PA_TRY(d_state.alloc(5 * 8));
-  PA_CUDA(cudaMemsetAsync(d_state.p, 0, 40, s));
-  lap("alloc");
-  if (n_bytes) PA_CUDA(cudaMemcpyAsync(d_bases.p, bases + base0, n_bytes, cudaMemcpyHostToDevice, s));
-  if (need_q && n_bytes) PA_CUDA(cudaMemcpyAsync(d_quals.p, quals + base0, n_bytes, cudaMemcpyHostToDevice, s));
-  PA_CUDA(cudaMemcpyAsync(d_off.p, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
-  lap("h2d");
-  AlignParams prm = clamp_params(params);
-  // the kernel indexes bases with read_off directly: rebase the pointers instead of the offsets
-  PA_TRY(align_batch_device(ix, d_bases.as<uint8_t>() - base0, need_q ? d_quals.as<uint8_t>() - base0 : nullptr,
-                            d_off.as<uint64_t>(), n_reads, max_len, prm, d_words.as<uint64_t>(), d_list.as<uint32_t>(),
-                            list_cap, d_state.as<unsigned long long>(), d_state.as<unsigned long long>() + 2, s, nullptr));
-  lap("kernel");
+  auto t0 = std::chrono::steady_clock::now();
+
+  // Chunked pipeline: chunk c uses slot c & 1 (its own stream): H2D(bases, quals, offsets) -> K4 -> D2H(words).
+  // The copy engine moves chunk c+1 in while the SMs align chunk c; kernels are chained with an event because they
+  // share the index's per-warp scratch.  The list cursor and the filter counters live in one device state block
+  // shared by all chunks, so list offsets in the result words are global to the call.
+  for (auto& sl : ix.slot) {
+    if (!sl.stream) PA_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    if (!sl.kernel_done) PA_CUDA(cudaEventCreateWithFlags(&sl.kernel_done, cudaEventDisableTiming));
+  }
+  PA_TRY(ensure(ix.host_list, std::max<uint64_t>(list_cap, 1) * 4));
+  PA_TRY(ensure(ix.host_state, 64));
+  PA_CUDA(cudaMemsetAsync(ix.host_state.p, 0, 40, ix.slot[0].stream));
+  PA_CUDA(cudaEventRecord(ix.slot[1].kernel_done, ix.slot[0].stream));  // "previous kernel" of chunk 0 = the memset
+  uint64_t chunk = std::min<uint64_t>(std::max<uint64_t>(n_reads / 8, 1u << 16), 1u << 21);
+  if (const char* e = getenv("PA_CHUNK_READS")) { uint64_t v = strtoull(e, nullptr, 10); if (v) chunk = v; }
+  uint64_t c = 0;
+  for (uint64_t lo = 0; lo < n_reads; lo += chunk, ++c) {
+    const uint64_t hi = std::min(n_reads, lo + chunk), n = hi - lo;
+    Index::HostSlot& sl = ix.slot[c & 1];
+    Index::HostSlot& prev = ix.slot[(c & 1) ^ 1];
+    const uint64_t b0 = read_off[lo], nb = read_off[hi] - b0;
+    uint64_t max_len = 0;
+    for (uint64_t i = lo; i < hi; ++i) {
+      NEED(read_off[i + 1] >= read_off[i], "read_off is not monotonic");
+      max_len = std::max(max_len, read_off[i + 1] - read_off[i]);
+    }
+    // slot buffers are free once the slot's previous chunk (c - 2) has finished: its stream is in order
+    PA_CUDA(cudaStreamSynchronize(sl.stream));
+    PA_TRY(ensure(sl.bases, nb + 64));
+    if (need_q) PA_TRY(ensure(sl.quals, nb + 64));
+    PA_TRY(ensure(sl.off, (n + 1) * 8));
+    PA_TRY(ensure(sl.words, n * 8));
+    if (nb) PA_CUDA(cudaMemcpyAsync(sl.bases.p, bases + b0, nb, cudaMemcpyHostToDevice, sl.stream));
+    if (need_q && nb) PA_CUDA(cudaMemcpyAsync(sl.quals.p, quals + b0, nb, cudaMemcpyHostToDevice, sl.stream));
+    PA_CUDA(cudaMemcpyAsync(sl.off.p, read_off + lo, (n + 1) * 8, cudaMemcpyHostToDevice, sl.stream));
+    PA_CUDA(cudaStreamWaitEvent(sl.stream, prev.kernel_done, 0));
+    // the kernel indexes bases with the absolute offsets: rebase the pointers instead of rewriting the offsets
+    PA_TRY(align_batch_device(ix, sl.bases.as<uint8_t>() - b0, need_q ? sl.quals.as<uint8_t>() - b0 : nullptr,
+                              sl.off.as<uint64_t>(), n, max_len, prm, sl.words.as<uint64_t>(), ix.host_list.as<uint32_t>(),
+                              list_cap, ix.host_state.as<unsigned long long>(), ix.host_state.as<unsigned long long>() + 2,
+                              sl.stream, nullptr));
+    PA_CUDA(cudaEventRecord(sl.kernel_done, sl.stream));
+    PA_CUDA(cudaMemcpyAsync(out_words + lo, sl.words.p, n * 8, cudaMemcpyDeviceToHost, sl.stream));
+  }
+  PA_CUDA(cudaStreamSynchronize(ix.slot[0].stream));
+  PA_CUDA(cudaStreamSynchronize(ix.slot[1].stream));
   uint64_t h_state[5];
-  PA_CUDA(cudaMemcpyAsync(h_state, d_state.p, 40, cudaMemcpyDeviceToHost, s));
-  PA_CUDA(cudaMemcpyAsync(out_words, d_words.p, n_reads * 8, cudaMemcpyDeviceToHost, s));
-  PA_CUDA(cudaStreamSynchronize(s));
-  lap("d2h");
+  PA_CUDA(cudaMemcpy(h_state, ix.host_state.p, 40, cudaMemcpyDeviceToHost));
   if (list_len) *list_len = h_state[0];
   if (h_state[0] > list_cap) {
     set_error("out_list too small: %llu entries needed", (unsigned long long)h_state[0]);
@@ -366,10 +381,12 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
   }
   if (h_state[0]) {
     NEED(out_list, "null out_list");
-    PA_CUDA(cudaMemcpyAsync(out_list, d_list.p, h_state[0] * 4, cudaMemcpyDeviceToHost, s));
-    PA_CUDA(cudaStreamSynchronize(s));
+    PA_CUDA(cudaMemcpy(out_list, ix.host_list.p, h_state[0] * 4, cudaMemcpyDeviceToHost));
   }
   counters[0] += h_state[2]; counters[1] += h_state[3]; counters[2] += h_state[4];
+  if (trace)
+    fprintf(stderr, "[pa_align_batch] %llu reads in %llu chunks: %.3f ms\n", (unsigned long long)n_reads,
+            (unsigned long long)c, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   return PA_OK;
 }
 

@@ -102,8 +102,7 @@ __host__ __device__ __forceinline__ uint64_t mix_key(uint64_t x, const MixParams
 // ---------------------------------------------------------------------------
 struct TableView {
   const uint64_t* buckets;
-  const uint64_t* stash_key;  // hashed keys, EMPTY64 = free
-  const uint64_t* stash_val;
+  const ulonglong2* stash;    // {hashed key (EMPTY64 = free), value} pairs, linear probing
   const uint32_t* mlist;
   uint64_t stash_mask;        // capacity - 1 (capacity is a power of two), 0 when there is no stash
   uint32_t stash_count;
@@ -129,26 +128,43 @@ __device__ __forceinline__ void ld_sector_u32_nc(const void* p, uint32_t (&s)[8]
                : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]) : "l"(p));
 }
 
-__device__ __forceinline__ uint64_t stash_lookup(const TableView& t, uint64_t h) {
-  uint64_t i = (h * 0xA24BAED4963EE407ULL) >> 20;
+__host__ __device__ __forceinline__ uint64_t stash_slot(uint64_t h) { return (h * 0xA24BAED4963EE407ULL) >> 20; }
+
+__device__ __forceinline__ ulonglong2 ld_stash_nc(const ulonglong2* p) {
+  ulonglong2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+  return r;
+}
+
+// probe the stash starting at slot i (masked by the caller or not)
+__device__ __forceinline__ uint64_t stash_lookup_from(const TableView& t, uint64_t h, uint64_t i) {
   for (;;) {
     i &= t.stash_mask;
-    uint64_t kk = t.stash_key[i];
-    if (kk == h) return t.stash_val[i];
-    if (kk == EMPTY64) return LOOKUP_MISS;
+    ulonglong2 e = ld_stash_nc(t.stash + i);
+    if (e.x == h) return e.y;
+    if (e.x == EMPTY64) return LOOKUP_MISS;
     ++i;
   }
 }
+__device__ __forceinline__ uint64_t stash_lookup(const TableView& t, uint64_t h) { return stash_lookup_from(t, h, stash_slot(h)); }
 
-// Resolve a bucket that has already been loaded.  Returns the value field or LOOKUP_MISS.
-__device__ __forceinline__ uint64_t bucket_resolve(const TableView& t, const uint64_t (&s)[4], uint64_t h) {
+// Resolve a bucket that has already been loaded, without following it into the stash.  Returns the value field or
+// LOOKUP_MISS; *overflow tells whether the stash has to be consulted (the bucket is full and held no match).
+__device__ __forceinline__ uint64_t bucket_resolve_local(const TableView& t, const uint64_t (&s)[4], uint64_t h, bool* overflow) {
   const uint64_t tag = h & ((1ULL << t.tag_bits) - 1);
   const uint64_t vmask = (1ULL << t.val_bits) - 1;
+  *overflow = false;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     if ((s[i] >> t.val_bits) == tag && s[i] != EMPTY64) return s[i] & vmask;
-  if (s[3] != EMPTY64 && t.stash_count) return stash_lookup(t, h);
+  *overflow = s[3] != EMPTY64 && t.stash_count != 0;
   return LOOKUP_MISS;
+}
+
+__device__ __forceinline__ uint64_t bucket_resolve(const TableView& t, const uint64_t (&s)[4], uint64_t h) {
+  bool overflow;
+  uint64_t v = bucket_resolve_local(t, s, h, &overflow);
+  return overflow ? stash_lookup(t, h) : v;
 }
 
 __device__ __forceinline__ uint64_t table_lookup(const TableView& t, uint64_t key) {

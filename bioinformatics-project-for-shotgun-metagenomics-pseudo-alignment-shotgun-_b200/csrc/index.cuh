@@ -48,7 +48,7 @@ struct Index {
   bool has_first_occ = false;
   std::vector<uint64_t> h_genome_off;
   // lookup structures
-  DevBuf buckets, stash_key, stash_val, mlist;
+  DevBuf buckets, stash, mlist;
   uint32_t bucket_bits = 0, tag_bits = 1, val_bits = 63, gbits = 1, n_inline = 1;
   uint64_t stash_cap = 0;
   uint32_t stash_count = 0;
@@ -57,14 +57,21 @@ struct Index {
   // per-warp scratch of the align kernel (allocated on first use)
   DevBuf align_scratch;
   uint64_t align_scratch_warps = 0, align_scratch_stride = 0;
+  // host-buffer alignment path (pa_align_batch): two chunk slots so that the H2D copy of chunk i+1 overlaps the
+  // kernel of chunk i; buffers grow on demand and are kept for the next call
+  struct HostSlot {
+    DevBuf bases, quals, off, words;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t kernel_done = nullptr;
+  } slot[2];
+  DevBuf host_list, host_state;
   // timing of the last build (ms, CUDA events on `stream`)
   float t_encode_ms = 0, t_sort_ms = 0, t_rle_ms = 0, t_table_ms = 0;
 
   TableView view() const {
     TableView t;
     t.buckets = buckets.as<uint64_t>();
-    t.stash_key = stash_key.as<uint64_t>();
-    t.stash_val = stash_val.as<uint64_t>();
+    t.stash = stash.as<ulonglong2>();
     t.mlist = mlist.as<uint32_t>();
     t.stash_mask = stash_cap ? stash_cap - 1 : 0;
     t.stash_count = stash_count;
@@ -78,9 +85,12 @@ struct Index {
   }
   size_t device_bytes() const {
     return ukeys.bytes + run_off.bytes + run_genome.bytes + pos_off.bytes + pos.bytes + genome_off.bytes + first_occ.bytes +
-           buckets.bytes + stash_key.bytes + stash_val.bytes + mlist.bytes + align_scratch.bytes;
+           buckets.bytes + stash.bytes + mlist.bytes + align_scratch.bytes;
   }
-  ~Index() { if (stream) cudaStreamDestroy(stream); }
+  ~Index() {
+    for (auto& sl : slot) { if (sl.stream) cudaStreamDestroy(sl.stream); if (sl.kernel_done) cudaEventDestroy(sl.kernel_done); }
+    if (stream) cudaStreamDestroy(stream);
+  }
 };
 
 // build.cu
