@@ -410,6 +410,14 @@ def gpu_arm(args):
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:  # DRAM bytes per launch from the committed ncu capture of this exact workload
+            tr = json.load(open(os.path.join(ROOT, "profiles", "align_traffic.json")))
+            w = tr["workload"]
+            if (w["genomes"], w["genome_len"], w["reads"], w["read_len"], w["k"], w["extquality"]) == (G, GL, NR, RL, k, need_q):
+                traffic = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
         line = {
             "metric": "reads/s pseudo-aligned (k=31,150bp)", "value": value, "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -418,7 +426,7 @@ def gpu_arm(args):
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "align_kernel (K4)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                         "traffic": None, "kernel_ms": k4_ms, "algorithmic_bytes_per_read": alg,
+                         "traffic": traffic, "kernel_ms": k4_ms, "algorithmic_bytes_per_read": alg,
                          "random_access": {"peak": RANDOM_SECTOR_PEAK_GBS, "unit": "GB/s of 32-B sectors",
                                            "achieved": NR * 32 * max(RL - k + 1, 0) / (k4_ms * 1e-3) / 1e9,
                                            "frac": NR * 32 * max(RL - k + 1, 0) / (k4_ms * 1e-3) / 1e9 / RANDOM_SECTOR_PEAK_GBS,

@@ -1,0 +1,104 @@
+#!/usr/bin/env python3
+"""
+EXTSIM reference build (BASELINE.json configs[3]): G genomes in near-duplicate clusters (~99 % identity), k=31, greedy
+similarity filter.  Times the device passes (K1-K3 build, K5 stats, K6 pairwise, K7 removal) and checks a down-scaled
+instance bit-exactly against the oracle.  Prints one JSON line.
+
+    python tools/bench_extsim.py [--genomes 1000] [--genome-len 1000000] [--cluster 10] [--threshold 0.5]
+"""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "bioinformatics-project-for-shotgun-metagenomics-pseudo-alignment-shotgun-_b200")
+sys.path[:0] = [ROOT, PKG]
+import numpy as np
+
+
+def cluster_genomes(torch, dev, G, L, cluster, sub, seed):
+    gen = torch.Generator(device=dev); gen.manual_seed(seed)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=dev)
+    out = torch.empty(G * L, dtype=torch.uint8, device=dev)
+    anc = None
+    for g in range(G):
+        if g % cluster == 0:
+            anc = lut[torch.randint(0, 4, (L,), generator=gen, device=dev)]
+        seq = anc.clone()
+        hit = torch.rand(L, generator=gen, device=dev) < sub
+        seq[hit] = lut[torch.randint(0, 4, (int(hit.sum().item()),), generator=gen, device=dev)]
+        out[g * L:(g + 1) * L] = seq
+    return out
+
+
+def greedy(stats_total, stats_unique, inter, lengths, threshold):
+    """_sort_genomes_for_filtering + _apply_greedy_filter (kmer.py:179-230) on integers (identifiers are distinct here)."""
+    G = len(lengths)
+    order = sorted(range(G), key=lambda g: (int(stats_unique[g]), int(stats_total[g]), lengths[g], g))
+    kept, dropped = [], 0
+    for g in order:
+        hit = False
+        for h in kept:
+            mn = min(int(stats_total[g]), int(stats_total[h]))
+            if mn > 0 and int(inter[g, h]) / mn > threshold:
+                hit = True
+                break
+        if hit:
+            dropped += 1
+        else:
+            kept.append(g)
+    keep = np.zeros(G, dtype=np.uint8)
+    keep[kept] = 1
+    return keep, dropped
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--genomes", type=int, default=1000)
+    ap.add_argument("--genome-len", type=int, default=1_000_000)
+    ap.add_argument("--cluster", type=int, default=10)
+    ap.add_argument("--sub", type=float, default=0.01)
+    ap.add_argument("--threshold", type=float, default=0.5)
+    ap.add_argument("-k", type=int, default=31)
+    a = ap.parse_args()
+    import torch
+    import _native as nat
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    nat.require_device()
+    # ---- parity on a down-scaled instance (oracle = CPU checker) ----
+    from oracle import oracle as orc
+    import synth
+    small = cluster_genomes(torch, dev, 24, 20_000, 6, a.sub, seed=5).cpu().numpy()
+    pairs = [(f"g{i}", small[i * 20_000:(i + 1) * 20_000].tobytes().decode()) for i in range(24)]
+    o = orc.OracleReference(a.k, pairs, filter_similar=True, similarity_threshold=a.threshold)
+    import kmer as km
+    from records import Record, Section
+    ref = km.KmerReference(a.k, [Record([Section("description", i), Section("genome", s)]) for i, s in pairs],
+                           filter_similar=True, similarity_threshold=a.threshold)
+    parity = (json.dumps(ref.similarity_info) == json.dumps(o.similarity_info)
+              and [g.identifier for g in ref.genomes] == [g[0] for g in o.genomes] and len(ref.kmers) == o.sizes()[0])
+    # ---- timed instance ----
+    G, L = a.genomes, a.genome_len
+    bases = cluster_genomes(torch, dev, G, L, a.cluster, a.sub, seed=7)
+    goff = (np.arange(G + 1, dtype=np.uint64) * np.uint64(L)).astype(np.uint64)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ix = nat.NativeIndex.build_device(bases.data_ptr(), goff, a.k)
+    t_build = time.perf_counter() - t0
+    inf = ix.info()
+    group = np.arange(G, dtype=np.uint32)
+    t0 = time.perf_counter(); total, uniq = ix.extsim_stats(group, G); t_stats = time.perf_counter() - t0
+    t0 = time.perf_counter(); inter = ix.extsim_pairwise(group, G); t_pair = time.perf_counter() - t0
+    t0 = time.perf_counter(); keep, dropped = greedy(total, uniq, inter, [L] * G, a.threshold); t_greedy = time.perf_counter() - t0
+    t0 = time.perf_counter(); ix.drop_genomes(keep); t_drop = time.perf_counter() - t0
+    inf2 = ix.info()
+    print(json.dumps({
+        "workload": f"configs[3]: {G} genomes x {L} bp in clusters of {a.cluster} ({100 * (1 - a.sub):.0f} % identity), k={a.k}, threshold {a.threshold}",
+        "kmer_occurrences": int(inf.n_occ), "distinct_kmers": int(inf.n_keys), "key_genome_pairs": int(inf.n_runs),
+        "build_s": t_build, "build_kmers_per_s": inf.n_occ / t_build,
+        "build_kernels_ms": {"encode": inf.build_encode_ms, "sort": inf.build_sort_ms, "csr": inf.build_rle_ms, "table": inf.build_table_ms},
+        "extsim_stats_s": t_stats, "extsim_pairwise_s": t_pair, "greedy_host_s": t_greedy, "drop_genomes_s": t_drop,
+        "genomes_filtered": int(dropped), "genomes_kept": int(inf2.n_genomes), "distinct_kmers_after": int(inf2.n_keys),
+        "parity_small_instance": "bit-exact vs oracle" if parity else "MISMATCH"}))
+
+
+if __name__ == "__main__":
+    main()
