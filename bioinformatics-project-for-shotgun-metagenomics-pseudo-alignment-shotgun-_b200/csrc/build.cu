@@ -111,7 +111,7 @@ constexpr int ENC_WORDS = ENC_TILE / 32 + 2;
 
 __global__ void __launch_bounds__(ENC_THREADS)
 encode_windows(const uint8_t* __restrict__ bases, uint64_t total, const uint64_t* __restrict__ genome_off, uint32_t G,
-               int k, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned long long* __restrict__ n_valid,
+               int k, MixParams mix, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned long long* __restrict__ n_valid,
                unsigned int* __restrict__ bad_flag) {
   __shared__ uint32_t s_lo[ENC_WORDS], s_hi[ENC_WORDS], s_inv[ENC_WORDS], s_brk[ENC_WORDS];
   __shared__ uint32_t s_cnt[ENC_THREADS / 32];
@@ -172,7 +172,9 @@ encode_windows(const uint8_t* __restrict__ bases, uint64_t total, const uint64_t
     uint32_t inv = __funnelshift_r(s_inv[w], s_inv[w + 1], b) & kmask;
     uint32_t brk = __funnelshift_r(s_brk[w], s_brk[w + 1], b) & (kmask >> 1);
     bool valid = (inv | brk) == 0 && gpos + (uint64_t)k <= total;
-    keys[gpos] = valid ? (((uint64_t)hi << k) | lo) : SENTINEL_KEY;
+    // the bijectively hashed k-mer is the sort key: equal k-mers still group, and the sorted order is the bucket
+    // order of the lookup table (and the rank partition of a multi-GPU build)
+    keys[gpos] = valid ? mix_key(((uint64_t)hi << k) | lo, mix) : SENTINEL_KEY;
     vals[gpos] = (uint32_t)gpos;
     cnt += valid;
   }
@@ -315,24 +317,27 @@ __device__ __forceinline__ uint64_t entry_value(const TableBuildParams& p, uint6
   return ((uint64_t)KIND_MLIST << kshift) | msec;
 }
 
-__global__ void table_insert(const uint64_t* __restrict__ ukeys, const uint64_t* __restrict__ run_off,
-                             const uint32_t* __restrict__ run_genome, const uint64_t* __restrict__ msec_off, uint64_t U,
-                             TableBuildParams p, unsigned long long* __restrict__ buckets,
-                             unsigned int* __restrict__ ovf_count, uint32_t* __restrict__ ovf_list, uint32_t ovf_cap) {
+// The CSR is sorted by hashed k-mer, i.e. by bucket: the k-mers of one bucket are adjacent, so the table is written
+// by one streaming pass without atomics.  The j-th k-mer of a bucket takes slot j; from the fifth on they go to the
+// stash (collected in ovf_list).
+__global__ void table_fill(const uint64_t* __restrict__ ukeys, const uint64_t* __restrict__ run_off,
+                           const uint32_t* __restrict__ run_genome, const uint64_t* __restrict__ msec_off, uint64_t U,
+                           TableBuildParams p, uint64_t* __restrict__ buckets, unsigned int* __restrict__ ovf_count,
+                           uint32_t* __restrict__ ovf_list, uint32_t ovf_cap) {
   uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (u >= U) return;
-  uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
-  uint64_t h = mix_key(ukeys[u], p.mix);
-  uint64_t tag = h & ((1ULL << p.tag_bits) - 1);
-  uint64_t entry = (tag << p.val_bits) | entry_value(p, c, run_genome + r0, msec_off[u]);
-  unsigned long long* b = buckets + (h >> p.tag_bits) * 4;
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    if (b[s] != EMPTY64) continue;  // slots fill in order, a taken slot never frees
-    if (atomicCAS(&b[s], (unsigned long long)EMPTY64, (unsigned long long)entry) == EMPTY64) return;
+  const uint64_t h = ukeys[u];
+  const uint64_t bucket = h >> p.tag_bits;
+  uint32_t j = 0;
+  while (j < 4 && u > j && (ukeys[u - 1 - j] >> p.tag_bits) == bucket) ++j;
+  if (j == 4) {
+    uint32_t at = atomicAdd(ovf_count, 1u);
+    if (at < ovf_cap) ovf_list[at] = (uint32_t)u;
+    return;
   }
-  uint32_t at = atomicAdd(ovf_count, 1u);
-  if (at < ovf_cap) ovf_list[at] = (uint32_t)u;
+  uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
+  uint64_t tag = h & ((1ULL << p.tag_bits) - 1);
+  buckets[bucket * 4 + j] = (tag << p.val_bits) | entry_value(p, c, run_genome + r0, msec_off[u]);
 }
 
 __global__ void stash_insert(const uint64_t* __restrict__ ukeys, const uint64_t* __restrict__ run_off,
@@ -343,7 +348,7 @@ __global__ void stash_insert(const uint64_t* __restrict__ ukeys, const uint64_t*
   if (t >= n_ovf) return;
   uint64_t u = ovf_list[t];
   uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
-  uint64_t h = mix_key(ukeys[u], p.mix);
+  uint64_t h = ukeys[u];
   uint64_t value = entry_value(p, c, run_genome + r0, msec_off[u]);
   uint64_t i = stash_slot(h);
   for (;;) {
@@ -478,8 +483,7 @@ int32_t index_build_tables(Index& ix) {
   cudaStream_t s = ix.stream;
   const uint64_t U = ix.n_keys;
   const int k = ix.k;
-  ix.mix.mask = (2 * k >= 64) ? ~0ULL : ((1ULL << (2 * k)) - 1);
-  ix.mix.shift = (uint32_t)std::max(1, k);
+  ix.mix = mix_params_for_k(k);
   ix.buckets.release(); ix.stash.release(); ix.mlist.release();
   ix.stash_cap = 0; ix.stash_count = 0; ix.n_msectors = 0;
   if (U == 0 || k <= 0) {
@@ -545,10 +549,10 @@ int32_t index_build_tables(Index& ix) {
     PA_CUDA(cudaMemsetAsync(ix.buckets.p, 0xFF, n_buckets * 32, s));
     PA_CUDA(cudaMemsetAsync(ovf_count.p, 0, 4, s));
     TableBuildParams p{ix.tag_bits, ix.val_bits, ix.gbits, ix.n_inline, ix.mix};
-    table_insert<<<grid_for(U, 256), 256, 0, s>>>(ix.ukeys.as<uint64_t>(), ix.run_off.as<uint64_t>(),
-                                                   ix.run_genome.as<uint32_t>(), msec_off.as<uint64_t>(), U, p,
-                                                   ix.buckets.as<unsigned long long>(), ovf_count.as<unsigned int>(),
-                                                   ovf_list.as<uint32_t>(), ovf_cap);
+    table_fill<<<grid_for(U, 256), 256, 0, s>>>(ix.ukeys.as<uint64_t>(), ix.run_off.as<uint64_t>(),
+                                                 ix.run_genome.as<uint32_t>(), msec_off.as<uint64_t>(), U, p,
+                                                 ix.buckets.as<uint64_t>(), ovf_count.as<unsigned int>(),
+                                                 ovf_list.as<uint32_t>(), ovf_cap);
     uint32_t n_ovf = 0;
     PA_CUDA(cudaMemcpyAsync(&n_ovf, ovf_count.p, 4, cudaMemcpyDeviceToHost, s));
     PA_CUDA(cudaStreamSynchronize(s));
@@ -601,7 +605,7 @@ int32_t index_build_from_device_bases(Index& ix, const uint8_t* d_bases) {
   PA_CUDA(cudaMemsetAsync(counters.p, 0, 16, s));
   PA_CUDA(cudaEventRecord(ev[0], s));
   encode_windows<<<grid_for(total, ENC_TILE), ENC_THREADS, 0, s>>>(
-      d_bases, total, ix.genome_off.as<uint64_t>(), G, k, keys_a.as<uint64_t>(), vals_a.as<uint32_t>(),
+      d_bases, total, ix.genome_off.as<uint64_t>(), G, k, ix.mix, keys_a.as<uint64_t>(), vals_a.as<uint32_t>(),
       counters.as<unsigned long long>(), reinterpret_cast<unsigned int*>(counters.as<char>() + 8));
   PA_CUDA(cudaGetLastError());
   PA_CUDA(cudaEventRecord(ev[1], s));
@@ -695,7 +699,7 @@ int32_t index_lookup_ranks(Index& ix, const uint8_t* h_kmers, uint64_t n, uint64
   for (uint64_t i = 0; i < n; ++i) {
     bool ok;
     uint64_t key = encode_kmer_host(h_kmers + i * (uint64_t)ix.k, ix.k, &ok);
-    q[i] = ok ? key : SENTINEL_KEY;
+    q[i] = ok ? mix_key(key, ix.mix) : SENTINEL_KEY;
   }
   cudaStream_t s = ix.stream;
   DevBuf dq, dr;

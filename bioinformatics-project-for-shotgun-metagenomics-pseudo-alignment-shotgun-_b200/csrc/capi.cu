@@ -32,7 +32,9 @@ __global__ void debug_lookup_kernel(TableView t, const uint64_t* __restrict__ ke
   uint64_t key = keys[i];
   uint32_t c = 0, g0 = 0xFFFFFFFFu;
   if (key != SENTINEL_KEY) {
-    uint64_t v = table_lookup(t, key);
+    uint64_t bucket[4];
+    ld_sector_nc(t.buckets + (key >> t.tag_bits) * 4, bucket);
+    uint64_t v = bucket_resolve(t, bucket, key);  // `key` is the hashed k-mer (pa_encode_kmers)
     if (v != LOOKUP_MISS) {
       const uint32_t kind = value_kind(t, v);
       const uint64_t payload = value_payload(t, v);
@@ -60,6 +62,7 @@ int32_t new_index(int32_t k, uint32_t G, const uint64_t* genome_off, int32_t dev
   Index* ix = new (std::nothrow) Index();
   if (!ix) { set_error("out of host memory"); return ST_NOMEM; }
   ix->k = k; ix->device = device; ix->n_genomes = G;
+  ix->mix = mix_params_for_k(k);
   ix->h_genome_off.assign(G + 1, 0);
   for (uint32_t g = 0; g <= G && G; ++g) ix->h_genome_off[g] = genome_off[g] - genome_off[0];
   ix->total_bases = G ? ix->h_genome_off[G] : 0;
@@ -241,11 +244,14 @@ int32_t pa_decode_kmers(int32_t k, const uint64_t* keys, uint64_t n, uint8_t* as
   NEED(k >= 0 && k <= 31, "k out of range");
   NEED(n == 0 || (keys && ascii), "null argument");
   static const char dec[4] = {'A', 'C', 'T', 'G'};
-  for (uint64_t i = 0; i < n; ++i)
+  const MixParams mix = mix_params_for_k(k);
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint64_t key = unmix_key(keys[i], mix);  // exported keys are the hashed k-mers the index is sorted by
     for (int j = 0; j < k; ++j) {
-      uint32_t lo = (keys[i] >> j) & 1, hi = (keys[i] >> (k + j)) & 1;
+      uint32_t lo = (key >> j) & 1, hi = (key >> (k + j)) & 1;
       ascii[i * (uint64_t)k + j] = dec[(hi << 1) | lo];
     }
+  }
   return PA_OK;
 }
 
@@ -255,7 +261,7 @@ int32_t pa_encode_kmers(int32_t k, const uint8_t* ascii, uint64_t n, uint64_t* k
   for (uint64_t i = 0; i < n; ++i) {
     bool ok;
     uint64_t key = encode_kmer_host(ascii + i * (uint64_t)k, k, &ok);
-    keys[i] = ok ? key : SENTINEL_KEY;
+    keys[i] = ok ? mix_key(key, mix_params_for_k(k)) : SENTINEL_KEY;
   }
   return PA_OK;
 }

@@ -116,6 +116,24 @@ struct TableView {
 
 enum : uint32_t { KIND_MLIST = 0, KIND_INLINE = 2, KIND_SPECIFIC = 3 };
 
+// inverse of mix_key (host side: decoding exported keys back into k-mer strings)
+inline uint64_t unmix_key(uint64_t x, const MixParams& p) {
+  auto unxorshift = [&](uint64_t v) { uint64_t r = v; for (uint32_t s = p.shift; s < 64; s += p.shift) r = v ^ (r >> p.shift); return r & p.mask; };
+  auto inv_odd = [](uint64_t a) { uint64_t inv = a; for (int i = 0; i < 6; ++i) inv *= 2 - a * inv; return inv; };  // Newton, mod 2^64
+  x = unxorshift(x);
+  x = (x * inv_odd(0xD6E8FEB86659FD93ULL)) & p.mask;
+  x = unxorshift(x);
+  x = (x * inv_odd(0x9E3779B97F4A7C15ULL)) & p.mask;
+  x = unxorshift(x);
+  return x;
+}
+inline MixParams mix_params_for_k(int k) {
+  MixParams m;
+  m.mask = (k < 1) ? 1 : ((2 * k >= 64) ? ~0ULL : ((1ULL << (2 * k)) - 1));
+  m.shift = (uint32_t)(k < 1 ? 1 : k);
+  return m;
+}
+
 constexpr uint64_t LOOKUP_MISS = 0xFFFFFFFFFFFFFFFFULL;
 
 __device__ __forceinline__ void ld_sector_nc(const void* p, uint64_t (&s)[4]) {
