@@ -436,7 +436,7 @@ def gpu_arm(args):
                       "kmers_per_s_call": inf.n_occ / min(build_times), "kmer_occurrences": int(inf.n_occ),
                       "distinct_kmers": int(inf.n_keys), "encode_ms": inf.build_encode_ms, "sort_ms": inf.build_sort_ms,
                       "rle_ms": inf.build_rle_ms, "table_ms": inf.build_table_ms, "index_bytes": int(inf.device_bytes),
-                      "stash_count": int(inf.stash_count), "bucket_bits": int(inf.bucket_bits),
+                      "stash_count": int(inf.stash_count), "block_bits": int(inf.block_bits), "minimizer_len": int(inf.minimizer_len),
                       "roofline_frac_17B": (inf.n_occ * BUILD_BYTES_PER_KMER / (build_kernel_ms * 1e-3) / 1e9 / hbm_peak) if build_kernel_ms > 0 else None},
             "result": {"unique": stats_host[0], "ambiguous": stats_host[1], "unmapped": stats_host[2], "dropped": stats_host[3]},
         }

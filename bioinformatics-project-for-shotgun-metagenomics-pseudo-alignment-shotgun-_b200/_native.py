@@ -40,11 +40,11 @@ class NativeLibraryMissing(ImportError):
 class IndexInfo(ctypes.Structure):
     _fields_ = [
         ("k", ctypes.c_int32), ("device", ctypes.c_int32), ("n_genomes", ctypes.c_uint32),
-        ("bucket_bits", ctypes.c_uint32), ("tag_bits", ctypes.c_uint32), ("stash_count", ctypes.c_uint32),
+        ("block_bits", ctypes.c_uint32), ("tag_bits", ctypes.c_uint32), ("stash_count", ctypes.c_uint32),
         ("n_keys", ctypes.c_uint64), ("n_runs", ctypes.c_uint64), ("n_occ", ctypes.c_uint64),
         ("total_bases", ctypes.c_uint64), ("n_list_sectors", ctypes.c_uint64), ("device_bytes", ctypes.c_uint64),
         ("build_encode_ms", ctypes.c_float), ("build_sort_ms", ctypes.c_float), ("build_rle_ms", ctypes.c_float),
-        ("build_table_ms", ctypes.c_float),
+        ("build_table_ms", ctypes.c_float), ("minimizer_len", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
     ]
 
 

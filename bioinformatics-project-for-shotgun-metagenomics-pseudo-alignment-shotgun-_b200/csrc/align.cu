@@ -114,6 +114,32 @@ __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
   return v;
 }
 
+
+// One doubling step of the sliding minimum over the per-position m-mer hashes: entry (c, lane) stands for position
+// 32c + lane and takes the smaller of itself and the entry d positions to its right (the left one wins ties, so the
+// leftmost minimum survives).  Chunks are updated in ascending order, so every read sees pre-step values.
+__device__ __forceinline__ void window_min_step(uint32_t (&mh)[AL_ROUNDS + 1], uint32_t (&mpos)[AL_ROUNDS + 1], uint32_t d,
+                                                uint32_t lane) {
+  const uint32_t src = (lane + d) & 31;
+  const bool wrap = lane + d >= 32;
+#pragma unroll
+  for (int c = 0; c <= AL_ROUNDS; ++c) {
+    uint32_t h_same = __shfl_sync(0xffffffffu, mh[c], src), p_same = __shfl_sync(0xffffffffu, mpos[c], src);
+    uint32_t h_next = 0xFFFFFFFFu, p_next = 0;
+    if (c < AL_ROUNDS) { h_next = __shfl_sync(0xffffffffu, mh[c + 1], src); p_next = __shfl_sync(0xffffffffu, mpos[c + 1], src); }
+    const uint32_t h2 = wrap ? h_next : h_same, p2 = wrap ? p_next : p_same;
+    if (h2 < mh[c]) { mh[c] = h2; mpos[c] = p2; }
+  }
+}
+
+// rare continuation of a lookup whose home bucket was full, without a match, and has CONT set (kept out of line:
+// the fast path only carries the tag)
+__device__ __noinline__ uint64_t lookup_chain_window(const TableView& t, uint64_t raw, uint32_t mhash, uint32_t p) {
+  const uint32_t kmask = (t.k >= 32) ? 0xFFFFFFFFu : ((1u << t.k) - 1);
+  const SlotAddr a = slot_addr(t, (uint32_t)raw & kmask, (uint32_t)(raw >> t.k) & kmask, mhash, p);
+  return lookup_chain(t, a, raw);
+}
+
 struct Emit {
   uint64_t* out_word;
   uint32_t* out_list;
@@ -213,8 +239,12 @@ __global__ void __launch_bounds__(AL_THREADS, MIN_BLOCKS)
 align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals,
              const uint64_t* __restrict__ read_off, uint64_t n_reads, AlignParams prm, Emit em,
              unsigned long long* __restrict__ counters, unsigned char* __restrict__ scratch, uint64_t scratch_stride,
-             uint32_t G, uint32_t kset_cap, int gtab_in_smem, int kset_in_smem) {
+             uint32_t G, uint32_t kset_cap, int gtab_in_smem, int kset_in_smem,
+             const uint32_t* __restrict__ queue, const unsigned long long* __restrict__ queue_count) {
+  // queue != nullptr: process the reads queue[0 .. *queue_count) the fast kernel could not finish (general path);
+  // queue == nullptr: process every read 0 .. n_reads
   extern __shared__ __align__(16) unsigned char dyn_smem[];
+  const uint64_t n_items = queue ? (uint64_t)*queue_count : n_reads;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t warp_global = (uint64_t)blockIdx.x * AL_WARPS + warp;
   const uint64_t n_warps = (uint64_t)gridDim.x * AL_WARPS;
@@ -247,33 +277,35 @@ align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __re
   uint32_t nx_ch[AL_ROUNDS + 1];        // its first AL_ROUNDS+1 chunks of bases (one byte per lane)
   uint64_t cur_beg = 0, cur_end = 0;
   uint32_t cur_ch[AL_ROUNDS + 1];
+  uint64_t cur_read = 0, nx_read = 0;
   {
     uint64_t r0 = warp_global, r1 = warp_global + n_warps;
-    if (r0 < n_reads) { cur_beg = read_off[r0]; cur_end = read_off[r0 + 1]; }
-    if (r1 < n_reads) { nx_beg = read_off[r1]; nx_end = read_off[r1 + 1]; }
+    if (r0 < n_items) { cur_read = queue ? queue[r0] : r0; cur_beg = read_off[cur_read]; cur_end = read_off[cur_read + 1]; }
+    if (r1 < n_items) { nx_read = queue ? queue[r1] : r1; nx_beg = read_off[nx_read]; nx_end = read_off[nx_read + 1]; }
 #pragma unroll
     for (int c = 0; c <= AL_ROUNDS; ++c) {
       uint64_t bi = (uint64_t)(32 * c) + lane;
-      cur_ch[c] = (r0 < n_reads && bi < cur_end - cur_beg) ? bases[cur_beg + bi] : 0;
+      cur_ch[c] = (r0 < n_items && bi < cur_end - cur_beg) ? bases[cur_beg + bi] : 0;
     }
   }
 
-  for (uint64_t read = warp_global; read < n_reads; read += n_warps) {
+  for (uint64_t item = warp_global; item < n_items; item += n_warps) {
+    const uint64_t read = cur_read;
     const uint64_t beg = cur_beg;
     const uint64_t L = cur_end - cur_beg;
     const uint8_t* rb = bases + beg;
     const uint8_t* rq = QUAL ? quals + beg : nullptr;
     // issue the loads of the following reads (consumed at the bottom of the loop)
-    uint64_t n2_beg = 0, n2_end = 0;
+    uint64_t n2_beg = 0, n2_end = 0, n2_read = 0;
     {
-      const uint64_t r1 = read + n_warps, r2 = read + 2 * n_warps;
+      const uint64_t r1 = item + n_warps, r2 = item + 2 * n_warps;
       const uint64_t nL = nx_end - nx_beg;
 #pragma unroll
       for (int c = 0; c <= AL_ROUNDS; ++c) {
         uint64_t bi = (uint64_t)(32 * c) + lane;
-        nx_ch[c] = (r1 < n_reads && bi < nL) ? bases[nx_beg + bi] : 0;
+        nx_ch[c] = (r1 < n_items && bi < nL) ? bases[nx_beg + bi] : 0;
       }
-      if (r2 < n_reads) { n2_beg = read_off[r2]; n2_end = read_off[r2 + 1]; }
+      if (r2 < n_items) { n2_read = queue ? queue[r2] : r2; n2_beg = read_off[n2_read]; n2_end = read_off[n2_read + 1]; }
     }
 
     bool dropped = false;
@@ -315,9 +347,24 @@ align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __re
           carry += __shfl_sync(0xffffffffu, incl, 31);
         }
       }
-      // ---- per window: quality filter, key, bucket load ----
-      uint64_t h[AL_ROUNDS];
-      uint64_t bucket[AL_ROUNDS][4];
+      // ---- minimizers: hash of the m-mer at every base position, sliding minimum over the w candidates ----
+      uint32_t mh[AL_ROUNDS + 1], mpos[AL_ROUNDS + 1];
+#pragma unroll
+      for (int c = 0; c <= AL_ROUNDS; ++c) {
+        const uint32_t nl = c < AL_ROUNDS ? lo[c + 1] : 0u, nh = c < AL_ROUNDS ? hi[c + 1] : 0u;
+        const uint32_t xl = __funnelshift_r(lo[c], nl, lane) & t.mmask;
+        const uint32_t xh = __funnelshift_r(hi[c], nh, lane) & t.mmask;
+        mh[c] = mmer_hash((xh << t.m) | xl, t.hmask, t.m);
+        mpos[c] = 32 * c + lane;
+      }
+      {
+        uint32_t span = 1;
+        for (; 2 * span <= t.w; span <<= 1) window_min_step(mh, mpos, span, lane);
+        if (t.w > span) window_min_step(mh, mpos, t.w - span, lane);   // two overlapping spans cover the w candidates
+      }
+      // ---- per window: quality filter, block / bucket / tag, one sector load ----
+      uint64_t raw[AL_ROUNDS], tag[AL_ROUNDS];
+      uint64_t sector[AL_ROUNDS][4];
       bool look[AL_ROUNDS];
 #pragma unroll
       for (int r = 0; r < AL_ROUNDS; ++r) {
@@ -336,16 +383,26 @@ align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __re
         uint32_t wh = __funnelshift_r(hi[r], hi[r + 1], lane) & kmask;
         uint32_t wi = __funnelshift_r(inv[r], inv[r + 1], lane) & kmask;
         look[r] = exists && !qf && wi == 0;
-        h[r] = mix_key(((uint64_t)wh << k) | wl, t.mix);
-        if (look[r]) ld_sector_nc(t.buckets + (h[r] >> t.tag_bits) * 4, bucket[r]);
+        raw[r] = ((uint64_t)wh << k) | wl;
+        mpos[r] -= 32 * r + lane;   // minimizer offset inside the window, 0 .. w-1
+        const SlotAddr a = slot_addr(t, wl, wh, mh[r], mpos[r]);
+        tag[r] = a.tag;
+        if (look[r]) ld_sector_nc(bucket_ptr(t, a.block, a.bucket), sector[r]);
       }
       // ---- resolve; classify what can be decided without touching mlist ----
       uint64_t val[AL_ROUNDS];
+#pragma unroll
+      for (int r = 0; r < AL_ROUNDS; ++r) {
+        val[r] = LOOKUP_MISS;
+        if (look[r]) {
+          bool cont;
+          val[r] = bucket_resolve(t, sector[r], tag[r], &cont);
+          if (cont) val[r] = lookup_chain_window(t, raw[r], mh[r], mpos[r]);
+        }
+      }
       uint32_t cnt[AL_ROUNDS];   // genomes of the k-mer; 0 = unknown yet (mlist kind)
       bool l_unknown = false, l_kept_spec = false, l_kept_multi = false;
       uint32_t l_filtered = 0;
-#pragma unroll
-      for (int r = 0; r < AL_ROUNDS; ++r) val[r] = look[r] ? bucket_resolve(t, bucket[r], h[r]) : LOOKUP_MISS;
 #pragma unroll
       for (int r = 0; r < AL_ROUNDS; ++r) {
         cnt[r] = 0;
@@ -411,10 +468,10 @@ align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __re
         kept[r] = true;
         // self.kmers[kmer] = ...: a repeated k-mer keeps the position of its first kept occurrence (kmer.py:429)
         const uint32_t pos = (uint32_t)(wbase + 32 * r + lane);
-        uint32_t sl = (uint32_t)(h[r] ^ (h[r] >> 29)) & ws.kset_mask;
+        uint32_t sl = ((((uint32_t)raw[r] ^ (uint32_t)(raw[r] >> 31)) * 0x9E3779B1u) >> 7) & ws.kset_mask;
         for (;;) {
-          unsigned long long old = atomicCAS(ws.kset_key + sl, (unsigned long long)EMPTY64, (unsigned long long)h[r]);
-          if (old == EMPTY64 || old == h[r]) break;
+          unsigned long long old = atomicCAS(ws.kset_key + sl, (unsigned long long)EMPTY64, (unsigned long long)raw[r]);
+          if (old == EMPTY64 || old == raw[r]) break;
           sl = (sl + 1) & ws.kset_mask;
         }
         atomicMin(ws.kset_pos + sl, pos);
@@ -458,12 +515,244 @@ align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __re
     c_nq += read_nq;
     c_nr += read_nr;
     // rotate the pipeline registers
+    cur_beg = nx_beg; cur_end = nx_end; cur_read = nx_read;
+    nx_beg = n2_beg; nx_end = n2_end; nx_read = n2_read;
+#pragma unroll
+    for (int c = 0; c <= AL_ROUNDS; ++c) cur_ch[c] = nx_ch[c];
+  }
+
+  c_drop = warp_sum(c_drop); c_nq = warp_sum(c_nq); c_nr = warp_sum(c_nr);
+  if (lane == 0) {
+    if (c_drop) atomicAdd(counters + 0, c_drop);
+    if (c_nq) atomicAdd(counters + 1, c_nq);
+    if (c_nr) atomicAdd(counters + 2, c_nr);
+  }
+}
+
+
+// ===========================================================================
+// K4 fast kernel.  Almost every read is decided by rules that need no per-genome table (SURVEY.md 8(a) rows
+// 10-14; the cases are proved next to the code), so they run in a small kernel -- no shared memory, few registers,
+// many resident warps -- and only the remaining reads are queued for the general kernel above:
+//   * no kept k-mer                                    -> UNMAPPED            (kmer.py:516-517)
+//   * kept k-mers, none specific                       -> AMBIGUOUS []        (kmer.py:461: the specific-count dict is empty)
+//   * every kept specific k-mer names one genome g, and (p < 0, or no multi-genome k-mer kept, or every kept
+//     multi-genome k-mer's set contains g)             -> UNIQUE [g]
+//     proof: S = {g: n} has one entry, so try_to_align_specific maps uniquely whatever m is (kmer.py:452-454);
+//     validate_unique_mappings (kmer.py:464-480) compares max(T) with T[g]: every kept distinct k-mer contains g, so
+//     T[g] is the number of kept distinct k-mers and no genome can exceed it -- max(T) - T[g] = 0 <= p.  Repeated
+//     k-mers inside the read change n and T[g] but not the argument.
+// A read sequenced from genome g only carries k-mers of g (its private ones and the ones it shares), so the last
+// rule covers all reads whose erroneous windows miss the index.
+// ===========================================================================
+#ifndef PA_FAST_MINB
+#define PA_FAST_MINB 2
+#endif
+constexpr int FA_THREADS = 256;
+constexpr int FA_WARPS = FA_THREADS / 32;
+constexpr uint32_t NO_GENOME = 0xFFFFFFFFu;
+
+// 8 genome ids of a set sector, cached in L1 (the sets are de-duplicated, so the hot ones stay resident)
+__device__ __forceinline__ void ld_set_sector(const uint32_t* p, uint32_t (&ids)[8]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  ids[0] = a.x; ids[1] = a.y; ids[2] = a.z; ids[3] = a.w; ids[4] = b.x; ids[5] = b.y; ids[6] = b.z; ids[7] = b.w;
+}
+
+// does the genome set of a multi-genome k-mer contain genome g?
+__device__ __forceinline__ bool set_contains(const TableView& t, uint64_t val, uint32_t g) {
+  const uint64_t payload = value_payload(t, val);
+  if (value_kind(t, val) == KIND_INLINE) {
+    const uint32_t gm = (1u << t.gbits) - 1;
+    bool hit = false;
+    for (uint32_t i = 0; i < t.n_inline; ++i) hit |= ((uint32_t)(payload >> (i * t.gbits)) & gm) == g;  // padding fields repeat a member
+    return hit;
+  }
+  for (uint64_t sector = payload;; ++sector) {
+    uint32_t ids[8];
+    ld_set_sector(t.mlist + sector * MLIST_SECTOR, ids);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if ((ids[i] & ~LIST_END) == g) return true;
+      if (ids[i] & LIST_END) return false;
+    }
+  }
+}
+
+template <bool QUAL>
+__global__ void __launch_bounds__(FA_THREADS, PA_FAST_MINB)
+align_fast_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals,
+                  const uint64_t* __restrict__ read_off, uint64_t n_reads, AlignParams prm, uint64_t* __restrict__ out_word,
+                  unsigned long long* __restrict__ counters, uint32_t* __restrict__ queue,
+                  unsigned long long* __restrict__ queue_count) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp_global = (uint64_t)blockIdx.x * FA_WARPS + (threadIdx.x >> 5);
+  const uint64_t n_warps = (uint64_t)gridDim.x * FA_WARPS;
+  const int k = (int)t.k;
+  const uint32_t kmask = (k >= 1 && k < 32) ? ((1u << k) - 1) : 0u;
+  unsigned long long c_drop = 0, c_nq = 0, c_nr = 0;  // per-lane partial counters
+
+  // software pipeline: offsets of read i+2 and the first 160 bases of read i+1 are requested while read i is processed
+  uint64_t nx_beg = 0, nx_end = 0, cur_beg = 0, cur_end = 0;
+  uint32_t nx_ch[AL_ROUNDS + 1], cur_ch[AL_ROUNDS + 1];
+  {
+    uint64_t r0 = warp_global, r1 = warp_global + n_warps;
+    if (r0 < n_reads) { cur_beg = read_off[r0]; cur_end = read_off[r0 + 1]; }
+    if (r1 < n_reads) { nx_beg = read_off[r1]; nx_end = read_off[r1 + 1]; }
+#pragma unroll
+    for (int c = 0; c <= AL_ROUNDS; ++c) {
+      uint64_t bi = (uint64_t)(32 * c) + lane;
+      cur_ch[c] = (r0 < n_reads && bi < cur_end - cur_beg) ? bases[cur_beg + bi] : 0;
+    }
+  }
+
+  for (uint64_t read = warp_global; read < n_reads; read += n_warps) {
+    const uint64_t L = cur_end - cur_beg;
+    const uint8_t* rq = QUAL ? quals + cur_beg : nullptr;
+    uint64_t n2_beg = 0, n2_end = 0;
+    {
+      const uint64_t r1 = read + n_warps, r2 = read + 2 * n_warps;
+      const uint64_t nL = nx_end - nx_beg;
+#pragma unroll
+      for (int c = 0; c <= AL_ROUNDS; ++c) {
+        uint64_t bi = (uint64_t)(32 * c) + lane;
+        nx_ch[c] = (r1 < n_reads && bi < nL) ? bases[nx_beg + bi] : 0;
+      }
+      if (r2 < n_reads) { n2_beg = read_off[r2]; n2_end = read_off[r2 + 1]; }
+    }
+
+    uint64_t res = make_word(1, 0, 0);   // UNMAPPED unless decided otherwise
+    bool defer = false;
+    uint32_t read_nq = 0, read_nr = 0;
+    bool dropped = false;
+    if (QUAL && prm.has_mrq) {  // Read.mean_quality() < min_read_quality  (kmer.py:587)
+      uint64_t s = 0;
+      for (uint64_t i = lane; i < L; i += 32) s += rq[i];
+      s = warp_sum(s);
+      if ((int64_t)s < prm.mrq * (int64_t)L) { dropped = true; res = 0; if (lane == 0) ++c_drop; }
+    }
+    const uint64_t W = (!dropped && k >= 1 && L >= (uint64_t)k) ? L - k + 1 : 0;  // kmer.py:91-92
+    if (W > AL_SUPER) {
+      defer = true;   // longer than one super-round: the general kernel loops over super-rounds
+    } else if (W > 0) {
+      // ---- encode the bases into bit planes with ballots ----
+      uint32_t lo[AL_ROUNDS + 1], hi[AL_ROUNDS + 1], inv[AL_ROUNDS + 1];
+      uint32_t qex[AL_ROUNDS + 1];  // exclusive quality prefix at this lane's base
+      uint32_t carry = 0;
+#pragma unroll
+      for (int c = 0; c <= AL_ROUNDS; ++c) {
+        const uint32_t ch = cur_ch[c];
+        const uint32_t code = base_code(ch);
+        lo[c] = __ballot_sync(0xffffffffu, code & 1u);
+        hi[c] = __ballot_sync(0xffffffffu, code >> 1);
+        inv[c] = __ballot_sync(0xffffffffu, !is_acgt(ch));
+        if (QUAL && prm.has_mkq) {
+          const uint64_t bi = 32 * c + lane;
+          uint32_t q = bi < L ? rq[bi] : 0, incl = q;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+          qex[c] = carry + incl - q;
+          carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+      }
+      // ---- minimizers ----
+      uint32_t mh[AL_ROUNDS + 1], mpos[AL_ROUNDS + 1];
+#pragma unroll
+      for (int c = 0; c <= AL_ROUNDS; ++c) {
+        const uint32_t nl = c < AL_ROUNDS ? lo[c + 1] : 0u, nh = c < AL_ROUNDS ? hi[c + 1] : 0u;
+        const uint32_t xl = __funnelshift_r(lo[c], nl, lane) & t.mmask;
+        const uint32_t xh = __funnelshift_r(hi[c], nh, lane) & t.mmask;
+        mh[c] = mmer_hash((xh << t.m) | xl, t.hmask, t.m);
+        mpos[c] = 32 * c + lane;
+      }
+      {
+        uint32_t span = 1;
+        for (; 2 * span <= t.w; span <<= 1) window_min_step(mh, mpos, span, lane);
+        if (t.w > span) window_min_step(mh, mpos, t.w - span, lane);
+      }
+      // ---- per window: quality filter, block / bucket / tag, one sector load ----
+      uint64_t tag[AL_ROUNDS];
+      uint64_t sector[AL_ROUNDS][4];
+      uint32_t look = 0;   // bit r: window r of this lane is looked up
+#pragma unroll
+      for (int r = 0; r < AL_ROUNDS; ++r) {
+        const uint32_t s = 32 * r + lane;
+        const bool exists = s < W;
+        bool qf = false;
+        if (QUAL && prm.has_mkq) {  // kmer_quality(start, k) < min_kmer_quality, before the lookup (kmer.py:420-422)
+          const uint32_t tl = lane + k;
+          const uint32_t p_a = __shfl_sync(0xffffffffu, qex[r], tl & 31);
+          const uint32_t p_b = __shfl_sync(0xffffffffu, qex[r + 1], tl & 31);
+          const uint32_t end = tl < 32 ? p_a : p_b;
+          qf = exists && ((int64_t)(end - qex[r]) < prm.mkq * (int64_t)k);
+          read_nq += qf;
+        }
+        const uint32_t wl = __funnelshift_r(lo[r], lo[r + 1], lane) & kmask;
+        const uint32_t wh = __funnelshift_r(hi[r], hi[r + 1], lane) & kmask;
+        const uint32_t wi = __funnelshift_r(inv[r], inv[r + 1], lane) & kmask;
+        mpos[r] -= s;   // minimizer offset inside the window, 0 .. w-1
+        const SlotAddr a = slot_addr(t, wl, wh, mh[r], mpos[r]);
+        tag[r] = a.tag;
+        if (exists && !qf && wi == 0) { look |= 1u << r; ld_sector_nc(bucket_ptr(t, a.block, a.bucket), sector[r]); }
+      }
+      // ---- resolve and classify ----
+      uint32_t mine = NO_GENOME, l_filtered = 0;
+      bool same = true;
+      uint64_t multi[AL_ROUNDS];   // kept multi-genome values of this lane (LOOKUP_MISS = none)
+#pragma unroll
+      for (int r = 0; r < AL_ROUNDS; ++r) {
+        multi[r] = LOOKUP_MISS;
+        if (!((look >> r) & 1)) continue;
+        bool cont;
+        uint64_t v = bucket_resolve(t, sector[r], tag[r], &cont);
+        if (cont) {
+          const uint32_t wl = __funnelshift_r(lo[r], lo[r + 1], lane) & kmask;
+          const uint32_t wh = __funnelshift_r(hi[r], hi[r + 1], lane) & kmask;
+          v = lookup_chain_window(t, ((uint64_t)wh << k) | wl, mh[r], mpos[r]);
+        }
+        if (v == LOOKUP_MISS) continue;
+        const uint32_t kind = value_kind(t, v);
+        if (prm.has_mg) {  // max-genomes filter, per occurrence (kmer.py:425-427)
+          uint32_t c = 1;
+          if (kind == KIND_INLINE) c = inline_count(t, value_payload(t, v));
+          else if (kind == KIND_MLIST) c = (prm.mg <= (int64_t)t.n_inline) ? t.n_inline + 1 : mlist_count(t.mlist, value_payload(t, v));
+          if ((int64_t)c > prm.mg) { ++l_filtered; continue; }
+        }
+        if (kind == KIND_SPECIFIC) {
+          const uint32_t g = (uint32_t)value_payload(t, v);
+          if (mine == NO_GENOME) mine = g; else same &= (g == mine);
+        } else {
+          multi[r] = v;
+        }
+      }
+      read_nr += l_filtered;
+      const uint32_t have = __ballot_sync(0xffffffffu, mine != NO_GENOME);
+      const bool l_multi = (multi[0] & multi[1] & multi[2] & multi[3]) != LOOKUP_MISS;
+      const bool w_multi = __any_sync(0xffffffffu, l_multi);
+      if (have == 0) {
+        res = make_word(w_multi ? 3 : 1, 0, 0);
+      } else {
+        const uint32_t g0 = __shfl_sync(0xffffffffu, mine, __ffs(have) - 1);
+        bool ok = same && (mine == NO_GENOME || mine == g0);
+        if (w_multi && prm.p >= 0) {
+#pragma unroll
+          for (int r = 0; r < AL_ROUNDS; ++r)
+            if (multi[r] != LOOKUP_MISS) ok = ok && set_contains(t, multi[r], g0);
+        }
+        if (__all_sync(0xffffffffu, ok)) res = make_word(2, 1, g0); else defer = true;
+      }
+    }
+    if (defer) {
+      if (lane == 0) queue[atomicAdd(queue_count, 1ULL)] = (uint32_t)read;
+    } else {
+      if (lane == 0) out_word[read] = res;
+      c_nq += read_nq;
+      c_nr += read_nr;
+    }
     cur_beg = nx_beg; cur_end = nx_end;
     nx_beg = n2_beg; nx_end = n2_end;
 #pragma unroll
     for (int c = 0; c <= AL_ROUNDS; ++c) cur_ch[c] = nx_ch[c];
   }
-
   c_drop = warp_sum(c_drop); c_nq = warp_sum(c_nq); c_nr = warp_sum(c_nr);
   if (lane == 0) {
     if (c_drop) atomicAdd(counters + 0, c_drop);
@@ -538,6 +827,16 @@ int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_q
                            unsigned long long* d_counters /*[3]*/, cudaStream_t s, int32_t* launches) {
   if (launches) *launches = 0;
   if (n_reads == 0) return ST_OK;
+  constexpr uint64_t MAX_BATCH = 1ULL << 31;   // read indices travel through the queue as uint32
+  if (n_reads > MAX_BATCH) {
+    for (uint64_t lo = 0; lo < n_reads; lo += MAX_BATCH) {
+      int32_t l = 0;
+      PA_TRY(align_batch_device(ix, d_bases, d_quals, d_read_off + lo, std::min(MAX_BATCH, n_reads - lo), max_read_len, prm_in,
+                                d_words + lo, d_list, list_cap, d_cursor, d_counters, s, &l));
+      if (launches) *launches += l;
+    }
+    return ST_OK;
+  }
   AlignParams prm = prm_in;
   const int k = ix.k;
   const bool qual = (prm.has_mrq || prm.has_mkq);
@@ -545,7 +844,26 @@ int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_q
   int dev = 0, sms = 148;
   PA_CUDA(cudaGetDevice(&dev));
   PA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  TableView tv = ix.view();  // k <= 0: the kernels see no windows (kmer.py:91-92) and only apply the read-quality drop
 
+  // ---- fast kernel over all reads; what it cannot decide goes to the queue ----
+  if (ix.align_queue.bytes < 16 + n_reads * 4) PA_TRY(ix.align_queue.alloc(16 + n_reads * 4 + n_reads / 2));
+  unsigned long long* q_count = ix.align_queue.as<unsigned long long>();
+  uint32_t* q_items = reinterpret_cast<uint32_t*>(ix.align_queue.as<unsigned char>() + 16);
+  PA_CUDA(cudaMemsetAsync(q_count, 0, 8, s));
+  {
+    auto fk = qual ? align_fast_kernel<true> : align_fast_kernel<false>;
+    int occ = 1;
+    PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fk, FA_THREADS, 0));
+    if (occ < 1) occ = 1;
+    uint64_t grid = std::min<uint64_t>((uint64_t)sms * occ, (n_reads + FA_WARPS - 1) / FA_WARPS);
+    fk<<<(unsigned)std::max<uint64_t>(grid, 1), FA_THREADS, 0, s>>>(tv, d_bases, d_quals, d_read_off, n_reads, prm, d_words,
+                                                                     d_counters, q_items, q_count);
+    PA_CUDA(cudaGetLastError());
+    if (launches) ++*launches;
+  }
+
+  // ---- general kernel over the queue ----
   const uint32_t G = std::max<uint32_t>(ix.n_genomes, 1);
   const uint64_t Wmax = (k >= 1 && max_read_len >= (uint64_t)k) ? max_read_len - k + 1 : 0;
   uint32_t kset_cap = 256;
@@ -555,12 +873,7 @@ int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_q
   size_t per_warp_smem = (kset_in_smem ? (size_t)kset_cap * 12 : 0) + (gtab_in_smem ? (size_t)G * 20 : 0);
   per_warp_smem = (per_warp_smem + 15) & ~(size_t)15;
   const size_t dyn_smem = per_warp_smem * AL_WARPS;
-
-  // resident CTAs per SM the kernel is compiled for (register budget); PA_ALIGN_MINB is a tuning knob
-  static int minb = [] { const char* e = getenv("PA_ALIGN_MINB"); int v = e ? atoi(e) : 2; return (v >= 2 && v <= 4) ? v : 2; }();
   auto kern = qual ? align_kernel<true, 2> : align_kernel<false, 2>;
-  if (minb == 3) kern = qual ? align_kernel<true, 3> : align_kernel<false, 3>;
-  if (minb == 4) kern = qual ? align_kernel<true, 4> : align_kernel<false, 4>;
   PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(dyn_smem, 1024)));
   int occ = 1;
   PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, AL_THREADS, dyn_smem));
@@ -584,11 +897,10 @@ int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_q
       if (launches) ++*launches;
     }
   }
-  TableView tv = ix.view();  // k <= 0: the kernel sees no windows (kmer.py:91-92) and only applies the read-quality drop
   Emit em{d_words, d_list, list_cap, d_cursor};
   kern<<<(unsigned)grid, AL_THREADS, dyn_smem, s>>>(tv, d_bases, d_quals, d_read_off, n_reads, prm, em, d_counters,
                                                     ix.align_scratch.as<unsigned char>(), stride, G, kset_cap,
-                                                    gtab_in_smem, kset_in_smem);
+                                                    gtab_in_smem, kset_in_smem, q_items, q_count);
   PA_CUDA(cudaGetLastError());
   if (launches) ++*launches;
   return ST_OK;

@@ -282,78 +282,124 @@ __global__ void set_csr_tails(uint64_t* run_off, uint64_t U, uint64_t R, uint64_
 // ===========================================================================
 // lookup table construction from the CSR
 // ===========================================================================
-__global__ void msector_counts(const uint64_t* __restrict__ run_off, uint64_t U, uint32_t n_inline, uint32_t* __restrict__ cnt) {
+// ---- genome sets of the k-mers with more than n_inline genomes, de-duplicated ("colour sets") ----------------
+// Related genomes share long runs of k-mers, so the number of DISTINCT genome sets is tiny next to the number of
+// k-mers carrying them (config B: a few hundred sets for 10^7 k-mers).  Storing each set once keeps mlist inside
+// L1/L2 and keeps the slot payload (a sector index) short.
+//   long_flags    flag[u] = 1 when k-mer u has more than n_inline genomes
+//   set_hash_keys (hash of the genome list, u) for every flagged k-mer, compacted by the scan of the flags
+//   [radix sort by hash]
+//   set_heads     an entry opens a new set unless its list equals its sorted predecessor's (hash AND content)
+//   set_assign    msec_off[u] = first sector of the k-mer's set; heads write their list into mlist
+__global__ void long_flags(const uint64_t* __restrict__ run_off, uint64_t U, uint32_t n_inline, uint32_t* __restrict__ flag) {
   uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (u >= U) return;
-  uint64_t c = run_off[u + 1] - run_off[u];
-  cnt[u] = c > n_inline ? (uint32_t)((c + MLIST_SECTOR - 1) / MLIST_SECTOR) : 0u;
+  flag[u] = (run_off[u + 1] - run_off[u]) > n_inline ? 1u : 0u;
 }
 
-__global__ void mlist_fill(const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome, uint64_t U,
-                           uint32_t n_inline, const uint64_t* __restrict__ msec_off, uint32_t* __restrict__ mlist) {
+__global__ void set_hash_keys(const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome, uint64_t U,
+                              const uint32_t* __restrict__ flag, const uint64_t* __restrict__ rank,
+                              uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (u >= U) return;
-  uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
-  if (c <= n_inline) return;
-  uint32_t* dst = mlist + msec_off[u] * MLIST_SECTOR;
-  for (uint64_t j = 0; j < c; ++j) dst[j] = run_genome[r0 + j] | (j + 1 == c ? LIST_END : 0u);
+  if (u >= U || !flag[u]) return;
+  uint64_t h = 0xCBF29CE484222325ULL;
+  for (uint64_t r = run_off[u]; r < run_off[u + 1]; ++r) { h ^= run_genome[r]; h *= 0x100000001B3ULL; h ^= h >> 29; }
+  keys[rank[u]] = h;
+  vals[rank[u]] = (uint32_t)u;
 }
 
-struct TableBuildParams {
-  uint32_t tag_bits, val_bits, gbits, n_inline;
-  MixParams mix;
-};
+__global__ void set_heads(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t n,
+                          const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome,
+                          uint32_t* __restrict__ head_secs) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t u = vals[i], r0 = run_off[u], c = run_off[u + 1] - r0;
+  bool head = true;
+  if (i > 0 && keys[i] == keys[i - 1]) {
+    const uint64_t v = vals[i - 1], q0 = run_off[v];
+    if (run_off[v + 1] - q0 == c) {
+      head = false;
+      for (uint64_t j = 0; j < c && !head; ++j) head = run_genome[r0 + j] != run_genome[q0 + j];
+    }
+  }
+  head_secs[i] = head ? (uint32_t)((c + MLIST_SECTOR - 1) / MLIST_SECTOR) : 0u;
+}
+
+__global__ void set_assign(const uint32_t* __restrict__ vals, uint64_t n, const uint32_t* __restrict__ head_secs,
+                           const uint64_t* __restrict__ sec_off, const uint64_t* __restrict__ run_off,
+                           const uint32_t* __restrict__ run_genome, uint64_t* __restrict__ msec_off,
+                           uint32_t* __restrict__ mlist) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t u = vals[i], r0 = run_off[u], c = run_off[u + 1] - r0;
+  const uint64_t secs = (c + MLIST_SECTOR - 1) / MLIST_SECTOR;
+  if (head_secs[i]) {
+    msec_off[u] = sec_off[i];
+    uint32_t* dst = mlist + sec_off[i] * MLIST_SECTOR;
+    for (uint64_t j = 0; j < c; ++j) dst[j] = run_genome[r0 + j] | (j + 1 == c ? LIST_END : 0u);
+  } else {
+    msec_off[u] = sec_off[i] - secs;   // sec_off is an exclusive scan: the set of the nearest head before i ends at sec_off[i]
+  }
+}
 
 // value field of a distinct k-mer with c genomes rg[0..c) (ascending); see TableView in common.cuh
-__device__ __forceinline__ uint64_t entry_value(const TableBuildParams& p, uint64_t c, const uint32_t* __restrict__ rg,
-                                                uint64_t msec) {
-  const uint32_t kshift = p.val_bits - 2;
+__device__ __forceinline__ uint64_t entry_value(const TableView& t, uint64_t c, const uint32_t* __restrict__ rg, uint64_t msec) {
+  const uint32_t kshift = t.val_bits - 3;
   if (c == 1) return ((uint64_t)KIND_SPECIFIC << kshift) | rg[0];
-  if (c <= p.n_inline) {
+  if (c <= t.n_inline) {
     uint64_t v = 0;
-    for (uint32_t i = 0; i < p.n_inline; ++i) v |= (uint64_t)rg[i < c ? i : c - 1] << (i * p.gbits);
+    for (uint32_t i = 0; i < t.n_inline; ++i) v |= (uint64_t)rg[i < c ? i : c - 1] << (i * t.gbits);
     return ((uint64_t)KIND_INLINE << kshift) | v;
   }
   return ((uint64_t)KIND_MLIST << kshift) | msec;
 }
 
-// The CSR is sorted by hashed k-mer, i.e. by bucket: the k-mers of one bucket are adjacent, so the table is written
-// by one streaming pass without atomics.  The j-th k-mer of a bucket takes slot j; from the fifth on they go to the
-// stash (collected in ovf_list).
-__global__ void table_fill(const uint64_t* __restrict__ ukeys, const uint64_t* __restrict__ run_off,
-                           const uint32_t* __restrict__ run_genome, const uint64_t* __restrict__ msec_off, uint64_t U,
-                           TableBuildParams p, uint64_t* __restrict__ buckets, unsigned int* __restrict__ ovf_count,
-                           uint32_t* __restrict__ ovf_list, uint32_t ovf_cap) {
+// One thread per distinct k-mer: un-hash the CSR key, find its minimizer, and claim the first free slot of its bucket
+// with atomicCAS -- in the home block or, when that bucket is full, in the same bucket of the next blocks, setting
+// CONT on the last slot of every bucket it passes (readers only go on from a full bucket that has CONT).  Slots of a
+// bucket fill in order, so "last slot taken" means "bucket full".  K-mers that find no free slot within CHAIN_LEN
+// blocks are collected for the stash (the last bucket of their chain then has CONT set, which sends readers there).
+__global__ void table_insert(const uint64_t* __restrict__ ukeys, const uint64_t* __restrict__ run_off,
+                             const uint32_t* __restrict__ run_genome, const uint64_t* __restrict__ msec_off, uint64_t U,
+                             TableView t, MixParams mix, unsigned long long* __restrict__ slots,
+                             unsigned int* __restrict__ ovf_count, uint32_t* __restrict__ ovf_list, uint32_t ovf_cap) {
   uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (u >= U) return;
-  const uint64_t h = ukeys[u];
-  const uint64_t bucket = h >> p.tag_bits;
-  uint32_t j = 0;
-  while (j < 4 && u > j && (ukeys[u - 1 - j] >> p.tag_bits) == bucket) ++j;
-  if (j == 4) {
-    uint32_t at = atomicAdd(ovf_count, 1u);
-    if (at < ovf_cap) ovf_list[at] = (uint32_t)u;
-    return;
+  const uint64_t raw = unmix_key(ukeys[u], mix);
+  const uint32_t kmask = (t.k >= 32) ? 0xFFFFFFFFu : ((1u << t.k) - 1);
+  const uint32_t lo = (uint32_t)raw & kmask, hi = (uint32_t)(raw >> t.k) & kmask;
+  uint32_t mh, p;
+  kmer_minimizer(t, lo, hi, &mh, &p);
+  const SlotAddr a = slot_addr(t, lo, hi, mh, p);
+  const uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
+  const unsigned long long value = entry_value(t, c, run_genome + r0, msec_off[u]);
+  const unsigned long long cont_bit = 1ULL << (t.val_bits - 1);
+  const uint64_t bmask = (1ULL << t.block_bits) - 1;
+  for (uint32_t d = 0; d < CHAIN_LEN; ++d) {
+    unsigned long long* b = slots + (((a.block + d) & bmask) * BLOCK_BUCKETS + a.bucket) * BUCKET_SLOTS;
+    const unsigned long long word = ((a.tag | ((uint64_t)d << t.hi_bits)) << t.val_bits) | value;
+    for (uint32_t i = 0; i < BUCKET_SLOTS; ++i)
+      if (atomicCAS(b + i, (unsigned long long)EMPTY64, word) == EMPTY64) return;
+    atomicOr(b + BUCKET_SLOTS - 1, cont_bit);
   }
-  uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
-  uint64_t tag = h & ((1ULL << p.tag_bits) - 1);
-  buckets[bucket * 4 + j] = (tag << p.val_bits) | entry_value(p, c, run_genome + r0, msec_off[u]);
+  uint32_t at = atomicAdd(ovf_count, 1u);
+  if (at < ovf_cap) ovf_list[at] = (uint32_t)u;
 }
 
 __global__ void stash_insert(const uint64_t* __restrict__ ukeys, const uint64_t* __restrict__ run_off,
                              const uint32_t* __restrict__ run_genome, const uint64_t* __restrict__ msec_off,
-                             const uint32_t* __restrict__ ovf_list, uint32_t n_ovf, TableBuildParams p,
-                             unsigned long long* __restrict__ stash /* {key, value} pairs */, uint64_t stash_mask) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_ovf) return;
-  uint64_t u = ovf_list[t];
+                             const uint32_t* __restrict__ ovf_list, uint32_t n_ovf, TableView t, MixParams mix,
+                             unsigned long long* __restrict__ stash /* {raw key, value} pairs */, uint64_t stash_mask) {
+  uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= n_ovf) return;
+  uint64_t u = ovf_list[i0];
   uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
-  uint64_t h = ukeys[u];
-  uint64_t value = entry_value(p, c, run_genome + r0, msec_off[u]);
-  uint64_t i = stash_slot(h);
+  uint64_t raw = unmix_key(ukeys[u], mix);
+  uint64_t value = entry_value(t, c, run_genome + r0, msec_off[u]);
+  uint64_t i = stash_slot(raw);
   for (;;) {
     i &= stash_mask;
-    if (atomicCAS(&stash[2 * i], (unsigned long long)EMPTY64, (unsigned long long)h) == EMPTY64) {
+    if (atomicCAS(&stash[2 * i], (unsigned long long)EMPTY64, (unsigned long long)raw) == EMPTY64) {
       stash[2 * i + 1] = value;
       return;
     }
@@ -482,83 +528,113 @@ float elapsed_ms(cudaEvent_t a, cudaEvent_t b) {
 int32_t index_build_tables(Index& ix) {
   cudaStream_t s = ix.stream;
   const uint64_t U = ix.n_keys;
-  const int k = ix.k;
-  ix.mix = mix_params_for_k(k);
-  ix.buckets.release(); ix.stash.release(); ix.mlist.release();
+  const int k = ix.k < 1 ? 1 : ix.k;   // k <= 0: no k-mers at all; the geometry below only has to be benign
+  ix.mix = mix_params_for_k(ix.k);
+  ix.slots.release(); ix.stash.release(); ix.mlist.release();
   ix.stash_cap = 0; ix.stash_count = 0; ix.n_msectors = 0;
-  if (U == 0 || k <= 0) {
-    // one empty bucket; every hash maps to it (tag_bits = 2k shifts the whole hash away)
-    ix.bucket_bits = 0; ix.tag_bits = k >= 1 ? (uint32_t)(2 * k) : 1u; ix.val_bits = 64 - ix.tag_bits;
-    PA_TRY(ix.buckets.alloc(32));
-    PA_CUDA(cudaMemsetAsync(ix.buckets.p, 0xFF, 32, s));
-    PA_TRY(ix.mlist.alloc(32));
-    PA_CUDA(cudaStreamSynchronize(s));
-    return ST_OK;
-  }
-  // Table geometry.  load factor <= 0.5 over 4-slot buckets; the value field (val_bits = 64 - tag_bits) must hold
-  // 2 kind bits + a genome id (with the all-ones id left unused so that no entry equals EMPTY64) + any mlist sector.
+  // Table geometry (see TableView in common.cuh).  tag = 2(k-m) + CHAIN_BITS + (2m - line_bits) bits; the value field
+  // (val_bits = 64 - tag_bits) must hold the CONT bit + 2 kind bits + a genome id (with the all-ones id left unused so that no slot
+  // equals EMPTY64) + any mlist sector index.
   const uint32_t G = ix.n_genomes;
+  const uint32_t m = minimizer_len_for_k(k);
+  const int64_t tag_fixed = 2 * ((int64_t)k - m) + CHAIN_BITS + 2 * m;   // tag_bits = tag_fixed - block_bits
   const uint32_t gb = std::max(1u, ceil_log2_u64(G));
   const uint32_t need_spec = std::max(1u, ceil_log2_u64((uint64_t)G + 1));
-  // load factor: <= 0.25 (one bucket per k-mer; 0.9 % of the buckets full, almost no stash traffic) when that
-  // table takes less than a quarter of the free device memory, else <= 0.5 (7 % full buckets)
+  const int64_t lb_max = 2 * m;   // the block index comes out of the 2m hash bits
+  // load factor over the slots: in (1/8, 1/4] (99.6 % of the k-mers in their home bucket; simulated and measured),
+  // halved while the table would take more than a third of the free device memory
   size_t free_b = 0, total_b = 0;
   PA_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  uint32_t b_load = ceil_log2_u64(U);
-  if ((32ull << b_load) > free_b / 4 || (getenv("PA_TABLE_DENSE") && *getenv("PA_TABLE_DENSE"))) b_load = ceil_log2_u64((U + 1) / 2);
-  int64_t b = std::max<int64_t>(std::max<int64_t>(b_load, (int64_t)need_spec + 2 * k - 62), 0);
-  b = std::min<int64_t>(b, 2 * k - 1);
-  DevBuf msec_cnt, msec_off, tile_sums, d_total;
-  PA_TRY(msec_cnt.alloc(U * 4));
-  PA_TRY(msec_off.alloc(U * 8));
+  int64_t lb = 0;
+  {
+    const char* dense = getenv("PA_TABLE_DENSE");
+    int shift = dense && *dense ? atoi(dense) : 0;      // tuning knob: +1 doubles the load factor, -1 halves it
+    lb = (int64_t)ceil_log2_u64((U * 4 + 63) / 64) - shift;
+    while (lb > 0 && (512ull << lb) > free_b / 3) --lb;
+    if (lb < 0) lb = 0;
+  }
+  lb = std::max<int64_t>(lb, tag_fixed - 61 + need_spec);
+  lb = std::max<int64_t>(std::min<int64_t>(lb, lb_max), 0);
+  DevBuf flag, lrank, msec_off, tile_sums, d_total, set_ka, set_kb, set_va, set_vb, set_tmp, head_secs, sec_off;
+  PA_TRY(flag.alloc((U + 1) * 4));
+  PA_TRY(lrank.alloc((U + 1) * 8));
+  PA_TRY(msec_off.alloc((U + 1) * 8));
   PA_TRY(tile_sums.alloc((scan_tiles(U) + 1) * 8));
   PA_TRY(d_total.alloc(8));
-  uint64_t n_msec = 0;
+  uint64_t n_msec = 0, n_long = 0;
+  uint32_t* set_vals = nullptr;   // k-mers with long lists, sorted by set
   for (;;) {
-    const uint32_t P = (uint32_t)(64 - (2 * k - b)) - 2;
-    if (P < need_spec) { set_error("lookup table: genome ids do not fit (k=%d, G=%u)", k, G); return ST_UNSUPPORTED; }
-    uint32_t n_in = std::min<uint32_t>(4, P / gb);
+    const int64_t T = tag_fixed - lb;
+    const int64_t P = 64 - T - 3;
+    if (P < (int64_t)need_spec) {
+      if (lb >= lb_max) { set_error("lookup table: genome ids do not fit (k=%d, G=%u)", k, G); return ST_UNSUPPORTED; }
+      ++lb; continue;
+    }
+    uint32_t n_in = std::min<uint32_t>(4, (uint32_t)P / gb);
     if (n_in < 2) n_in = 1;
     ix.gbits = gb; ix.n_inline = n_in;
-    // lists longer than n_inline: 32-byte aligned, 8 ids per sector, last id flagged
-    msector_counts<<<grid_for(U, 256), 256, 0, s>>>(ix.run_off.as<uint64_t>(), U, n_in, msec_cnt.as<uint32_t>());
-    PA_TRY(exclusive_scan_u32(msec_cnt.as<uint32_t>(), msec_off.as<uint64_t>(), U, tile_sums.as<uint64_t>(),
-                              d_total.as<uint64_t>(), s));
-    PA_CUDA(cudaMemcpyAsync(&n_msec, d_total.p, 8, cudaMemcpyDeviceToHost, s));
-    PA_CUDA(cudaStreamSynchronize(s));
-    if (ceil_log2_u64(n_msec + 1) <= P) break;
-    if (b >= 2 * k - 1) { set_error("lookup table: list references do not fit (k=%d)", k); return ST_UNSUPPORTED; }
-    ++b;
+    n_msec = 0; n_long = 0;
+    if (U) {
+      long_flags<<<grid_for(U, 256), 256, 0, s>>>(ix.run_off.as<uint64_t>(), U, n_in, flag.as<uint32_t>());
+      PA_TRY(exclusive_scan_u32(flag.as<uint32_t>(), lrank.as<uint64_t>(), U, tile_sums.as<uint64_t>(), d_total.as<uint64_t>(), s));
+      PA_CUDA(cudaMemcpyAsync(&n_long, d_total.p, 8, cudaMemcpyDeviceToHost, s));
+      PA_CUDA(cudaStreamSynchronize(s));
+    }
+    if (n_long) {
+      PA_TRY(set_ka.alloc(n_long * 8)); PA_TRY(set_kb.alloc(n_long * 8)); PA_TRY(set_va.alloc(n_long * 4)); PA_TRY(set_vb.alloc(n_long * 4));
+      PA_TRY(set_tmp.alloc(radix_sort_temp_bytes(n_long)));
+      PA_TRY(head_secs.alloc(n_long * 4)); PA_TRY(sec_off.alloc(n_long * 8));
+      set_hash_keys<<<grid_for(U, 256), 256, 0, s>>>(ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(), U, flag.as<uint32_t>(),
+                                                      lrank.as<uint64_t>(), set_ka.as<uint64_t>(), set_va.as<uint32_t>());
+      int in_b = 0;
+      PA_TRY(radix_sort_pairs(set_ka.as<uint64_t>(), set_va.as<uint32_t>(), set_kb.as<uint64_t>(), set_vb.as<uint32_t>(), n_long, 64,
+                              set_tmp.p, set_tmp.bytes, s, &in_b));
+      const uint64_t* skeys = in_b ? set_kb.as<uint64_t>() : set_ka.as<uint64_t>();
+      set_vals = in_b ? set_vb.as<uint32_t>() : set_va.as<uint32_t>();
+      set_heads<<<grid_for(n_long, 256), 256, 0, s>>>(skeys, set_vals, n_long, ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(),
+                                                      head_secs.as<uint32_t>());
+      if (scan_tiles(n_long) > scan_tiles(U)) PA_TRY(tile_sums.alloc((scan_tiles(n_long) + 1) * 8));
+      PA_TRY(exclusive_scan_u32(head_secs.as<uint32_t>(), sec_off.as<uint64_t>(), n_long, tile_sums.as<uint64_t>(), d_total.as<uint64_t>(), s));
+      PA_CUDA(cudaMemcpyAsync(&n_msec, d_total.p, 8, cudaMemcpyDeviceToHost, s));
+      PA_CUDA(cudaStreamSynchronize(s));
+    }
+    if ((int64_t)ceil_log2_u64(n_msec + 1) <= P) break;
+    if (lb >= lb_max) { set_error("lookup table: list references do not fit (k=%d)", k); return ST_UNSUPPORTED; }
+    ++lb;
   }
   ix.n_msectors = n_msec;
   PA_TRY(ix.mlist.alloc(std::max<uint64_t>(n_msec, 1) * 32));
   PA_CUDA(cudaMemsetAsync(ix.mlist.p, 0xFF, ix.mlist.bytes, s));
-  if (n_msec)
-    mlist_fill<<<grid_for(U, 256), 256, 0, s>>>(ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(), U, ix.n_inline,
-                                                 msec_off.as<uint64_t>(), ix.mlist.as<uint32_t>());
+  if (n_long)
+    set_assign<<<grid_for(n_long, 256), 256, 0, s>>>(set_vals, n_long, head_secs.as<uint32_t>(), sec_off.as<uint64_t>(),
+                                                     ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(),
+                                                     msec_off.as<uint64_t>(), ix.mlist.as<uint32_t>());
+  set_ka.release(); set_kb.release(); set_tmp.release(); flag.release(); lrank.release();
   DevBuf ovf_count, ovf_list;
   PA_TRY(ovf_count.alloc(4));
   uint32_t ovf_cap = (uint32_t)std::min<uint64_t>(U / 4 + 4096, 0xFFFFFFF0ull);
   PA_TRY(ovf_list.alloc((size_t)ovf_cap * 4));
   for (;;) {
-    ix.bucket_bits = (uint32_t)b;
-    ix.tag_bits = (uint32_t)(2 * k - b);
+    ix.min_len = m;
+    ix.block_bits = (uint32_t)lb;
+    ix.tag_bits = (uint32_t)(tag_fixed - lb);
     ix.val_bits = 64 - ix.tag_bits;
-    const uint64_t n_buckets = 1ULL << b;
-    PA_TRY(ix.buckets.alloc(n_buckets * 32));
-    PA_CUDA(cudaMemsetAsync(ix.buckets.p, 0xFF, n_buckets * 32, s));
+    const uint64_t n_blocks = 1ULL << lb;
+    PA_TRY(ix.slots.alloc(n_blocks * 512));
+    PA_CUDA(cudaMemsetAsync(ix.slots.p, 0xFF, n_blocks * 512, s));
     PA_CUDA(cudaMemsetAsync(ovf_count.p, 0, 4, s));
-    TableBuildParams p{ix.tag_bits, ix.val_bits, ix.gbits, ix.n_inline, ix.mix};
-    table_fill<<<grid_for(U, 256), 256, 0, s>>>(ix.ukeys.as<uint64_t>(), ix.run_off.as<uint64_t>(),
-                                                 ix.run_genome.as<uint32_t>(), msec_off.as<uint64_t>(), U, p,
-                                                 ix.buckets.as<uint64_t>(), ovf_count.as<unsigned int>(),
-                                                 ovf_list.as<uint32_t>(), ovf_cap);
     uint32_t n_ovf = 0;
-    PA_CUDA(cudaMemcpyAsync(&n_ovf, ovf_count.p, 4, cudaMemcpyDeviceToHost, s));
-    PA_CUDA(cudaStreamSynchronize(s));
+    if (U) {
+      table_insert<<<grid_for(U, 256), 256, 0, s>>>(ix.ukeys.as<uint64_t>(), ix.run_off.as<uint64_t>(),
+                                                     ix.run_genome.as<uint32_t>(), msec_off.as<uint64_t>(), U, ix.view(),
+                                                     ix.mix, ix.slots.as<unsigned long long>(), ovf_count.as<unsigned int>(),
+                                                     ovf_list.as<uint32_t>(), ovf_cap);
+      PA_CUDA(cudaMemcpyAsync(&n_ovf, ovf_count.p, 4, cudaMemcpyDeviceToHost, s));
+      PA_CUDA(cudaStreamSynchronize(s));
+    }
     if (n_ovf > ovf_cap) {  // pathological: grow the table instead of the stash
-      if (b >= 2 * k - 1) { set_error("lookup table: overflow list exhausted"); return ST_UNSUPPORTED; }
-      ++b;
+      if (lb >= lb_max) { set_error("lookup table: overflow list exhausted"); return ST_UNSUPPORTED; }
+      ++lb;
       continue;
     }
     ix.stash_count = n_ovf;
@@ -570,7 +646,7 @@ int32_t index_build_tables(Index& ix) {
       PA_CUDA(cudaMemsetAsync(ix.stash.p, 0xFF, cap * 16, s));
       stash_insert<<<grid_for(n_ovf, 256), 256, 0, s>>>(ix.ukeys.as<uint64_t>(), ix.run_off.as<uint64_t>(),
                                                          ix.run_genome.as<uint32_t>(), msec_off.as<uint64_t>(),
-                                                         ovf_list.as<uint32_t>(), n_ovf, p,
+                                                         ovf_list.as<uint32_t>(), n_ovf, ix.view(), ix.mix,
                                                          ix.stash.as<unsigned long long>(), cap - 1);
     }
     break;

@@ -25,16 +25,14 @@ const char* get_error() { return g_err; }
 
 namespace {
 
-__global__ void debug_lookup_kernel(TableView t, const uint64_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ n_genomes,
+__global__ void debug_lookup_kernel(TableView t, MixParams mix, const uint64_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ n_genomes,
                                     uint32_t* __restrict__ first_genome) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint64_t key = keys[i];
   uint32_t c = 0, g0 = 0xFFFFFFFFu;
   if (key != SENTINEL_KEY) {
-    uint64_t bucket[4];
-    ld_sector_nc(t.buckets + (key >> t.tag_bits) * 4, bucket);
-    uint64_t v = bucket_resolve(t, bucket, key);  // `key` is the hashed k-mer (pa_encode_kmers)
+    uint64_t v = table_lookup(t, unmix_key(key, mix));  // `key` is the hashed k-mer (pa_encode_kmers)
     if (v != LOOKUP_MISS) {
       const uint32_t kind = value_kind(t, v);
       const uint64_t payload = value_payload(t, v);
@@ -211,7 +209,7 @@ int32_t pa_index_info_get(pa_index* idx, pa_index_info* info) {
   Index& ix = *IDX(idx);
   memset(info, 0, sizeof(*info));
   info->k = ix.k; info->device = ix.device; info->n_genomes = ix.n_genomes;
-  info->bucket_bits = ix.bucket_bits; info->tag_bits = ix.tag_bits; info->stash_count = ix.stash_count;
+  info->block_bits = ix.block_bits; info->minimizer_len = ix.min_len; info->tag_bits = ix.tag_bits; info->stash_count = ix.stash_count;
   info->n_keys = ix.n_keys; info->n_runs = ix.n_runs; info->n_occ = ix.n_occ; info->total_bases = ix.total_bases;
   info->n_list_sectors = ix.n_msectors; info->device_bytes = ix.device_bytes();
   info->build_encode_ms = ix.t_encode_ms; info->build_sort_ms = ix.t_sort_ms;
@@ -472,7 +470,7 @@ int32_t pa_debug_table_lookup(pa_index* idx, const uint8_t* kmers_ascii, uint64_
   DevBuf dq, dn, dg;
   PA_TRY(dq.alloc(n * 8)); PA_TRY(dn.alloc(n * 4)); PA_TRY(dg.alloc(n * 4));
   PA_CUDA(cudaMemcpyAsync(dq.p, q.data(), n * 8, cudaMemcpyHostToDevice, s));
-  debug_lookup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ix.view(), dq.as<uint64_t>(), n, dn.as<uint32_t>(), dg.as<uint32_t>());
+  debug_lookup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ix.view(), ix.mix, dq.as<uint64_t>(), n, dn.as<uint32_t>(), dg.as<uint32_t>());
   PA_CUDA(cudaGetLastError());
   PA_CUDA(cudaMemcpyAsync(n_genomes, dn.p, n * 4, cudaMemcpyDeviceToHost, s));
   PA_CUDA(cudaMemcpyAsync(first_genome, dg.p, n * 4, cudaMemcpyDeviceToHost, s));

@@ -88,42 +88,116 @@ __host__ __device__ __forceinline__ uint64_t mix_key(uint64_t x, const MixParams
 }
 
 // ---------------------------------------------------------------------------
-// Lookup table view (device pointers).  One bucket = one 32-byte sector = four
-// 8-byte slots.  slot = (tag << val_bits) | value;  value = kind (2 bits) | payload:
-//   KIND_SPECIFIC  k-mer of exactly one genome, payload = genome id
-//   KIND_INLINE    2..n_inline genomes packed in the payload, gbits each, ascending;
-//                  a field equal to its predecessor means "no more genomes"
-//   KIND_MLIST     longer lists: payload = first 32-byte sector of the list in mlist
-// so that the common cases resolve inside the one sector a lookup has to fetch anyway
-// (a B200 moves a whole 128-byte line from HBM per missing sector; see
-// profiles/r01_gather_ncu_dram_per_request.csv).
-// Keys that do not fit their bucket live in the stash (full hashed key, linear
-// probing); a bucket is only ever followed into the stash when it is full.
+// Lookup table view (device pointers) -- minimizer-bucketed.
+//
+// A B200 serves random table reads at a fixed rate of distinct 128-byte LINES per second; the lanes of one load
+// instruction that fall into the same line are served together (profiles/r01_locality_roofline.jsonl: 8 lanes per
+// line = 7x the lane-lookups/s of one lane per line), while the same line requested by separate in-flight
+// instructions costs full price each time.  The k-mer windows of a read are looked up 32 consecutive windows per
+// instruction, so the table puts the k-mers that are consecutive in a sequence next to each other:
+//
+//   minimizer of a k-mer = its m-mer (m = min(k, 16), w = k-m+1 <= 16 candidates) with the smallest bijective
+//   2m-bit hash, leftmost on ties; consecutive windows share their minimizer (8.5 windows on average at w = 16,
+//   27 % of the groups have all 16), and inside a group the minimizer offset p takes consecutive values.
+//   block  = low block_bits of the minimizer hash    (one block = 16 buckets = 512 bytes = 4 lines)
+//   bucket = (p + hash >> block_bits) & 15           (one bucket = one 32-byte sector = 4 slots of 8 bytes)
+//            -- a group of consecutive windows reads consecutive sectors: 32 windows touch ~12 lines instead of 32
+//   tag    = [k-mer without the minimizer's bases : 2(k-m)] [chain distance d : 2] [hash >> block_bits]
+//            -- block, bucket and tag identify the k-mer exactly (no false positives)
+//   word   = tag | CONT | kind (2 bits) | payload
+//     KIND_SPECIFIC  k-mer of exactly one genome, payload = genome id
+//     KIND_INLINE    2..n_inline genomes packed in the payload, gbits each, ascending;
+//                    a field equal to its predecessor means "no more genomes"
+//     KIND_MLIST     longer lists: payload = first 32-byte sector of the (de-duplicated) genome set in mlist
+// The four slots of a bucket absorb the k-mers of other minimizers that hash to the same block and the strain
+// variants that share minimizer and offset; a k-mer whose bucket is full moves to the same bucket of the next
+// block (d = 1..3, then the stash) and sets CONT on the last slot of every bucket it passed.  A lookup reads ONE
+// sector and goes on only when that bucket is full, has no match AND has CONT set (0.4 % of the lookups at the
+// default load factor), so a miss costs one sector too.  The stash holds {raw k-mer key, value} pairs with linear
+// probing.
 // ---------------------------------------------------------------------------
+constexpr uint32_t BLOCK_BUCKETS = 16;
+constexpr uint32_t BUCKET_SLOTS = 4;
+constexpr uint32_t CHAIN_BITS = 2;
+constexpr uint32_t CHAIN_LEN = 1u << CHAIN_BITS;
+
 struct TableView {
-  const uint64_t* buckets;
-  const ulonglong2* stash;    // {hashed key (EMPTY64 = free), value} pairs, linear probing
+  const uint64_t* slots;      // 2^block_bits blocks of BLOCK_BUCKETS buckets of BUCKET_SLOTS slots
+  const ulonglong2* stash;    // {raw k-mer key (EMPTY64 = free), value} pairs, linear probing
   const uint32_t* mlist;
   uint64_t stash_mask;        // capacity - 1 (capacity is a power of two), 0 when there is no stash
   uint32_t stash_count;
-  uint32_t tag_bits;
-  uint32_t val_bits;
   uint32_t k;
-  uint32_t gbits;     // bits per genome id inside an inline list
-  uint32_t n_inline;  // longest inline list (1 = inline lists unused)
-  MixParams mix;
+  uint32_t m;          // minimizer length
+  uint32_t w;          // minimizer candidates per k-mer = k - m + 1 (1..16)
+  uint32_t block_bits;
+  uint32_t hi_bits;    // 2m - block_bits: bits of the minimizer hash kept in the tag
+  uint32_t tag_bits;   // 2(k-m) + CHAIN_BITS + hi_bits
+  uint32_t val_bits;   // 64 - tag_bits = CONT bit + 2 kind bits + payload
+  uint32_t gbits;      // bits per genome id inside an inline list
+  uint32_t n_inline;   // longest inline list (1 = inline lists unused)
+  uint32_t mmask;      // 2^m - 1
+  uint32_t hmask;      // 2^(2m) - 1
 };
 
 enum : uint32_t { KIND_MLIST = 0, KIND_INLINE = 2, KIND_SPECIFIC = 3 };
 
-// inverse of mix_key (host side: decoding exported keys back into k-mer strings)
-inline uint64_t unmix_key(uint64_t x, const MixParams& p) {
+constexpr uint32_t MINIMIZER_MAX = 16;
+__host__ __device__ __forceinline__ uint32_t minimizer_len_for_k(int k) { return k < 1 ? 1u : (k > (int)MINIMIZER_MAX ? MINIMIZER_MAX : (uint32_t)k); }
+
+// bijective hash of an m-mer (2m <= 32 bits): xorshift and odd multiplication mod 2^(2m) are invertible
+__host__ __device__ __forceinline__ uint32_t mmer_hash(uint32_t x, uint32_t hmask, uint32_t m) {
+  x ^= x >> m;
+  x = (x * 0x7FEB352DU) & hmask;
+  x ^= x >> m;
+  x = (x * 0x846CA68BU) & hmask;
+  x ^= x >> m;
+  return x;
+}
+
+struct SlotAddr {
+  uint64_t block;   // home block
+  uint64_t tag;     // tag at chain distance 0; at distance d add (d << hi_bits)
+  uint32_t bucket;  // bucket inside the block, 0..15 (the same in every block of the chain)
+};
+
+// home block / bucket / tag of a k-mer given as planes (lo, hi: exactly k bits each) and its minimizer (hash, offset p)
+__host__ __device__ __forceinline__ SlotAddr slot_addr(const TableView& t, uint32_t lo, uint32_t hi, uint32_t mhash, uint32_t p) {
+  SlotAddr a;
+  const uint32_t km = t.k - t.m;                     // bases outside the minimizer
+  const uint32_t below = (1u << p) - 1;              // p <= 15
+  const uint32_t rl = (lo & below) | ((lo >> (p + t.m)) << p);   // p + m <= k <= 31
+  const uint32_t rh = (hi & below) | ((hi >> (p + t.m)) << p);
+  const uint32_t rest = (rh << km) | rl;             // 2(k-m) <= 30 bits
+  a.block = mhash & (uint32_t)((1ULL << t.block_bits) - 1);
+  const uint64_t mh = (uint64_t)mhash >> t.block_bits;
+  a.tag = ((uint64_t)rest << (CHAIN_BITS + t.hi_bits)) | mh;
+  a.bucket = (p + (uint32_t)mh) & (BLOCK_BUCKETS - 1);
+  return a;
+}
+
+// minimizer of a whole k-mer (sequential; build side and debug lookups -- the align kernel computes it with a
+// sliding window over the read instead).  Leftmost candidate wins ties.
+__host__ __device__ __forceinline__ void kmer_minimizer(const TableView& t, uint32_t lo, uint32_t hi, uint32_t* mhash, uint32_t* p) {
+  uint32_t best = 0xFFFFFFFFu, bp = 0;
+  for (uint32_t j = 0; j < t.w; ++j) {
+    uint32_t x = (((hi >> j) & t.mmask) << t.m) | ((lo >> j) & t.mmask);
+    uint32_t h = mmer_hash(x, t.hmask, t.m);
+    if (j == 0 || h < best) { best = h; bp = j; }
+  }
+  *mhash = best; *p = bp;
+}
+
+// inverse of mix_key (decoding exported keys back into k-mer strings; the table build un-hashes the CSR keys)
+__host__ __device__ inline uint64_t unmix_key(uint64_t x, const MixParams& p) {
+  // inverses of the two odd multipliers modulo 2^64 (valid modulo every 2^n)
+  const uint64_t inv2 = 0xCFEE444D8B59A89BULL;   // 0xD6E8FEB86659FD93 ^ -1
+  const uint64_t inv1 = 0xF1DE83E19937733DULL;   // 0x9E3779B97F4A7C15 ^ -1
   auto unxorshift = [&](uint64_t v) { uint64_t r = v; for (uint32_t s = p.shift; s < 64; s += p.shift) r = v ^ (r >> p.shift); return r & p.mask; };
-  auto inv_odd = [](uint64_t a) { uint64_t inv = a; for (int i = 0; i < 6; ++i) inv *= 2 - a * inv; return inv; };  // Newton, mod 2^64
   x = unxorshift(x);
-  x = (x * inv_odd(0xD6E8FEB86659FD93ULL)) & p.mask;
+  x = (x * inv2) & p.mask;
   x = unxorshift(x);
-  x = (x * inv_odd(0x9E3779B97F4A7C15ULL)) & p.mask;
+  x = (x * inv1) & p.mask;
   x = unxorshift(x);
   return x;
 }
@@ -146,7 +220,7 @@ __device__ __forceinline__ void ld_sector_u32_nc(const void* p, uint32_t (&s)[8]
                : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]) : "l"(p));
 }
 
-__host__ __device__ __forceinline__ uint64_t stash_slot(uint64_t h) { return (h * 0xA24BAED4963EE407ULL) >> 20; }
+__host__ __device__ __forceinline__ uint64_t stash_slot(uint64_t key) { return (key * 0xA24BAED4963EE407ULL) >> 20; }
 
 __device__ __forceinline__ ulonglong2 ld_stash_nc(const ulonglong2* p) {
   ulonglong2 r;
@@ -154,47 +228,64 @@ __device__ __forceinline__ ulonglong2 ld_stash_nc(const ulonglong2* p) {
   return r;
 }
 
-// probe the stash starting at slot i (masked by the caller or not)
-__device__ __forceinline__ uint64_t stash_lookup_from(const TableView& t, uint64_t h, uint64_t i) {
+// probe the stash for the raw k-mer key
+__device__ __forceinline__ uint64_t stash_lookup(const TableView& t, uint64_t key) {
+  uint64_t i = stash_slot(key);
   for (;;) {
     i &= t.stash_mask;
     ulonglong2 e = ld_stash_nc(t.stash + i);
-    if (e.x == h) return e.y;
+    if (e.x == key) return e.y;
     if (e.x == EMPTY64) return LOOKUP_MISS;
     ++i;
   }
 }
-__device__ __forceinline__ uint64_t stash_lookup(const TableView& t, uint64_t h) { return stash_lookup_from(t, h, stash_slot(h)); }
 
-// Resolve a bucket that has already been loaded, without following it into the stash.  Returns the value field or
-// LOOKUP_MISS; *overflow tells whether the stash has to be consulted (the bucket is full and held no match).
-__device__ __forceinline__ uint64_t bucket_resolve_local(const TableView& t, const uint64_t (&s)[4], uint64_t h, bool* overflow) {
-  const uint64_t tag = h & ((1ULL << t.tag_bits) - 1);
-  const uint64_t vmask = (1ULL << t.val_bits) - 1;
-  *overflow = false;
+__device__ __forceinline__ const uint64_t* bucket_ptr(const TableView& t, uint64_t block, uint32_t bucket) {
+  return t.slots + (block * BLOCK_BUCKETS + bucket) * BUCKET_SLOTS;
+}
+
+// Look for `tag` in one loaded bucket.  Returns the value field (kind | payload) or LOOKUP_MISS; *cont tells whether
+// the chain goes on (the bucket is full, holds no match, and some k-mer moved past it).
+__device__ __forceinline__ uint64_t bucket_resolve(const TableView& t, const uint64_t (&s)[4], uint64_t tag, bool* cont) {
+  const uint64_t vmask = (1ULL << (t.val_bits - 1)) - 1;
+  *cont = false;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     if ((s[i] >> t.val_bits) == tag && s[i] != EMPTY64) return s[i] & vmask;
-  *overflow = s[3] != EMPTY64 && t.stash_count != 0;
+  *cont = s[3] != EMPTY64 && ((s[3] >> (t.val_bits - 1)) & 1);
   return LOOKUP_MISS;
 }
 
-__device__ __forceinline__ uint64_t bucket_resolve(const TableView& t, const uint64_t (&s)[4], uint64_t h) {
-  bool overflow;
-  uint64_t v = bucket_resolve_local(t, s, h, &overflow);
-  return overflow ? stash_lookup(t, h) : v;
+// Continue a lookup past its home bucket: the same bucket of the next blocks, then the stash.
+static __device__ __noinline__ uint64_t lookup_chain(const TableView& t, const SlotAddr& a, uint64_t raw_key) {
+  const uint64_t bmask = (1ULL << t.block_bits) - 1;
+  for (uint32_t d = 1; d < CHAIN_LEN; ++d) {
+    uint64_t s[4];
+    ld_sector_nc(bucket_ptr(t, (a.block + d) & bmask, a.bucket), s);
+    bool cont;
+    uint64_t v = bucket_resolve(t, s, a.tag | ((uint64_t)d << t.hi_bits), &cont);
+    if (!cont) return v;
+  }
+  return t.stash_count ? stash_lookup(t, raw_key) : LOOKUP_MISS;
 }
 
-__device__ __forceinline__ uint64_t table_lookup(const TableView& t, uint64_t key) {
-  uint64_t h = mix_key(key, t.mix);
+// full lookup of a raw k-mer key (planes: bits [0,k) low code bits, [k,2k) high code bits)
+__device__ __forceinline__ uint64_t table_lookup(const TableView& t, uint64_t raw_key) {
+  const uint32_t kmask = (t.k >= 32) ? 0xFFFFFFFFu : ((1u << t.k) - 1);
+  const uint32_t lo = (uint32_t)raw_key & kmask, hi = (uint32_t)(raw_key >> t.k) & kmask;
+  uint32_t mh, p;
+  kmer_minimizer(t, lo, hi, &mh, &p);
+  SlotAddr a = slot_addr(t, lo, hi, mh, p);
   uint64_t s[4];
-  ld_sector_nc(t.buckets + (h >> t.tag_bits) * 4, s);
-  return bucket_resolve(t, s, h);
+  ld_sector_nc(bucket_ptr(t, a.block, a.bucket), s);
+  bool cont;
+  uint64_t v = bucket_resolve(t, s, a.tag, &cont);
+  return cont ? lookup_chain(t, a, raw_key) : v;
 }
 
-__host__ __device__ __forceinline__ uint32_t value_kind(const TableView& t, uint64_t v) { return (uint32_t)(v >> (t.val_bits - 2)) & 3u; }
+__host__ __device__ __forceinline__ uint32_t value_kind(const TableView& t, uint64_t v) { return (uint32_t)(v >> (t.val_bits - 3)) & 3u; }
 __host__ __device__ __forceinline__ uint64_t value_payload(const TableView& t, uint64_t v) {
-  return v & ((1ULL << (t.val_bits - 2)) - 1);
+  return v & ((1ULL << (t.val_bits - 3)) - 1);
 }
 // number of genomes of an inline list
 __device__ __forceinline__ uint32_t inline_count(const TableView& t, uint64_t payload) {

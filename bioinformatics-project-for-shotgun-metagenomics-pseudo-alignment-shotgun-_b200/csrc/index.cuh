@@ -33,7 +33,7 @@ struct DevBuf {
 //   pos_off[R+1]                  run -> its positions
 //   pos[N]                        positions inside the genome (ascending inside a run)
 //   genome_off[G+1]               base offsets of the genomes in the concatenated input
-//   buckets / stash / mlist       see TableView in common.cuh
+//   slots / stash / mlist         see TableView in common.cuh
 struct Index {
   int32_t k = 0;
   int32_t device = 0;
@@ -48,14 +48,16 @@ struct Index {
   bool has_first_occ = false;
   std::vector<uint64_t> h_genome_off;
   // lookup structures
-  DevBuf buckets, stash, mlist;
-  uint32_t bucket_bits = 0, tag_bits = 1, val_bits = 63, gbits = 1, n_inline = 1;
+  DevBuf slots, stash, mlist;
+  uint32_t block_bits = 0, tag_bits = 1, val_bits = 63, gbits = 1, n_inline = 1;
+  uint32_t min_len = 1;   // minimizer length m = min(k, 16)
   uint64_t stash_cap = 0;
   uint32_t stash_count = 0;
   uint64_t n_msectors = 0;
   MixParams mix{1, 1};
   // per-warp scratch of the align kernel (allocated on first use)
   DevBuf align_scratch;
+  DevBuf align_queue;   // {count u64, pad, uint32 read indices}: reads the fast kernel hands to the general kernel
   uint64_t align_scratch_warps = 0, align_scratch_stride = 0;
   // host-buffer alignment path (pa_align_batch): two chunk slots so that the H2D copy of chunk i+1 overlaps the
   // kernel of chunk i; buffers grow on demand and are kept for the next call
@@ -70,22 +72,27 @@ struct Index {
 
   TableView view() const {
     TableView t;
-    t.buckets = buckets.as<uint64_t>();
+    t.slots = slots.as<uint64_t>();
     t.stash = stash.as<ulonglong2>();
     t.mlist = mlist.as<uint32_t>();
     t.stash_mask = stash_cap ? stash_cap - 1 : 0;
     t.stash_count = stash_count;
+    t.k = (uint32_t)k;                       // k <= 0: no k-mer exists, nothing is ever looked up
+    t.m = min_len;
+    t.w = k >= 1 ? (uint32_t)k - t.m + 1 : 1;
+    t.block_bits = block_bits;
+    t.hi_bits = 2 * t.m - block_bits;
     t.tag_bits = tag_bits;
     t.val_bits = val_bits;
-    t.k = (uint32_t)k;
     t.gbits = gbits;
     t.n_inline = n_inline;
-    t.mix = mix;
+    t.mmask = (1u << t.m) - 1;
+    t.hmask = t.m >= 16 ? 0xFFFFFFFFu : ((1u << (2 * t.m)) - 1);
     return t;
   }
   size_t device_bytes() const {
     return ukeys.bytes + run_off.bytes + run_genome.bytes + pos_off.bytes + pos.bytes + genome_off.bytes + first_occ.bytes +
-           buckets.bytes + stash.bytes + mlist.bytes + align_scratch.bytes;
+           slots.bytes + stash.bytes + mlist.bytes + align_scratch.bytes + align_queue.bytes;
   }
   ~Index() {
     for (auto& sl : slot) { if (sl.stream) cudaStreamDestroy(sl.stream); if (sl.kernel_done) cudaEventDestroy(sl.kernel_done); }

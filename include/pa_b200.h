@@ -43,7 +43,7 @@ extern "C" {
 #define PA_ERR_CAPACITY (-5)    /* an output buffer is too small; the needed size is reported */
 #define PA_ERR_UNSUPPORTED (-6) /* outside the built scope (k > 31, > 2^32-2 bases, ...) -> ValueError */
 
-#define PA_ABI_VERSION 1
+#define PA_ABI_VERSION 2
 #define PA_RANK_MISS UINT64_MAX
 
 typedef struct pa_index pa_index;
@@ -52,9 +52,9 @@ typedef struct pa_index_info {
   int32_t k;
   int32_t device;
   uint32_t n_genomes;
-  uint32_t bucket_bits;     /* log2(number of 32-byte buckets of the lookup table) */
-  uint32_t tag_bits;        /* bits of the hashed k-mer stored in a slot */
-  uint32_t stash_count;     /* k-mers that overflowed their bucket */
+  uint32_t block_bits;      /* log2(number of 512-byte blocks of the minimizer-bucketed lookup table) */
+  uint32_t tag_bits;        /* bits of the k-mer stored in a slot (the rest is implied by the line) */
+  uint32_t stash_count;     /* k-mers that overflowed their bucket chain */
   uint64_t n_keys;          /* distinct k-mers            (len(KmerReference.kmers)) */
   uint64_t n_runs;          /* (k-mer, genome) pairs      (sum of inner dict sizes) */
   uint64_t n_occ;           /* k-mer occurrences          (sum of position-set sizes) */
@@ -62,6 +62,8 @@ typedef struct pa_index_info {
   uint64_t n_list_sectors;  /* 32-byte sectors holding multi-genome lists */
   uint64_t device_bytes;
   float build_encode_ms, build_sort_ms, build_rle_ms, build_table_ms; /* CUDA-event times of the last build */
+  uint32_t minimizer_len;   /* m: k-mers sharing their minimizer m-mer share a table block */
+  uint32_t reserved;
 } pa_index_info;
 
 /* thresholds of Read.pseudo_align (kmer.py:482-489); has_* = "is not None" */

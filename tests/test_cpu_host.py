@@ -26,7 +26,7 @@ def test_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in include/pa_b200.h but not exported"
     assert sorted(declared) == sorted(nat.EXPORTED_SYMBOLS)
-    assert lib.pa_abi_version() == 1
+    assert lib.pa_abi_version() == 2
 
 
 def test_encode_decode_kmers_round_trip_on_host():
