@@ -30,6 +30,8 @@ EXPORTED_SYMBOLS = [
     "pa_index_free", "pa_index_info_get", "pa_index_export", "pa_decode_kmers", "pa_encode_kmers", "pa_index_lookup",
     "pa_extsim_stats", "pa_extsim_pairwise", "pa_index_drop_genomes", "pa_align_batch", "pa_align_batch_device",
     "pa_summary_reduce_device", "pa_summary_reduce", "pa_debug_sort_pairs", "pa_debug_table_lookup",
+    "pa_records_encode_device", "pa_records_partition_device", "pa_partition_of_key", "pa_index_build_from_records_device",
+    "pa_index_csr_device", "pa_index_alloc_replica", "pa_index_finish_replica", "pa_index_build_tables",
 ]
 
 
@@ -102,6 +104,14 @@ def lib() -> ctypes.CDLL:
         "pa_summary_reduce": (i32, [vp, vp, vp, u64, u64, u64, vp, vp, vp, vp]),
         "pa_debug_sort_pairs": (i32, [vp, vp, u64, i32, i32]),
         "pa_debug_table_lookup": (i32, [vp, vp, u64, vp, vp]),
+        "pa_records_encode_device": (i32, [vp, vp, u32, u32, u32, i32, i32, vp, vp, vp, vp]),
+        "pa_records_partition_device": (i32, [vp, vp, vp, vp, u64, i32, u32, i32, vp, vp, vp]),
+        "pa_partition_of_key": (i32, [i32, u64, u32, vp]),
+        "pa_index_build_from_records_device": (i32, [vp, vp, u64, vp, u32, i32, i32, i32, vp]),
+        "pa_index_csr_device": (i32, [vp, vp, vp, vp]),
+        "pa_index_alloc_replica": (i32, [i32, u32, vp, u64, u64, u64, i32, vp]),
+        "pa_index_finish_replica": (i32, [vp]),
+        "pa_index_build_tables": (i32, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -110,9 +110,12 @@ constexpr int ENC_TILE = 4096;
 constexpr int ENC_WORDS = ENC_TILE / 32 + 2;
 
 __global__ void __launch_bounds__(ENC_THREADS)
-encode_windows(const uint8_t* __restrict__ bases, uint64_t total, const uint64_t* __restrict__ genome_off, uint32_t G,
+encode_windows(const uint8_t* __restrict__ bases, uint64_t total, uint64_t pos0, const uint64_t* __restrict__ genome_off, uint32_t G,
                int k, MixParams mix, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned long long* __restrict__ n_valid,
                unsigned int* __restrict__ bad_flag) {
+  // bases[0 .. total) is the slice of the concatenated genomes that starts at global base position pos0 (whole
+  // genomes: a multi-GPU build gives every rank a run of genomes); keys / vals are indexed like bases, vals hold
+  // GLOBAL positions
   __shared__ uint32_t s_lo[ENC_WORDS], s_hi[ENC_WORDS], s_inv[ENC_WORDS], s_brk[ENC_WORDS];
   __shared__ uint32_t s_cnt[ENC_THREADS / 32];
   const uint64_t tile_base = (uint64_t)blockIdx.x * ENC_TILE;
@@ -146,14 +149,15 @@ encode_windows(const uint8_t* __restrict__ bases, uint64_t total, const uint64_t
   __syncthreads();
   // mark the last base of every genome that ends inside this tile's span
   {
-    const uint64_t span_end = min(total, tile_base + (uint64_t)ENC_WORDS * 32);
+    const uint64_t span_beg = pos0 + tile_base;
+    const uint64_t span_end = pos0 + min(total, tile_base + (uint64_t)ENC_WORDS * 32);
     if (tile_base < total) {
-      uint32_t g0 = genome_of(genome_off, G, tile_base);
+      uint32_t g0 = genome_of(genome_off, G, span_beg);
       for (uint32_t g = g0 + tid; g < G; g += ENC_THREADS) {
         uint64_t beg = genome_off[g], end = genome_off[g + 1];
         if (beg >= span_end) break;
-        if (end == beg || end > span_end || end - 1 < tile_base) continue;
-        uint64_t r = end - 1 - tile_base;
+        if (end == beg || end > span_end || end - 1 < span_beg) continue;
+        uint64_t r = end - 1 - span_beg;
         atomicOr(&s_brk[r >> 5], 1u << (r & 31));
       }
     }
@@ -175,7 +179,7 @@ encode_windows(const uint8_t* __restrict__ bases, uint64_t total, const uint64_t
     // the bijectively hashed k-mer is the sort key: equal k-mers still group, and the sorted order is the bucket
     // order of the lookup table (and the rank partition of a multi-GPU build)
     keys[gpos] = valid ? mix_key(((uint64_t)hi << k) | lo, mix) : SENTINEL_KEY;
-    vals[gpos] = (uint32_t)gpos;
+    vals[gpos] = (uint32_t)(pos0 + gpos);
     cnt += valid;
   }
   cnt = warp_sum(cnt);
@@ -656,6 +660,35 @@ int32_t index_build_tables(Index& ix) {
   return ST_OK;
 }
 
+// K3 host side: CSR of the index from n_valid sorted (key, global position) records
+static int32_t rle_to_csr(Index& ix, const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n_valid) {
+  cudaStream_t s = ix.stream;
+  const uint32_t G = ix.n_genomes;
+  const uint64_t tiles = std::max<uint64_t>(1, (n_valid + RLE_TILE - 1) / RLE_TILE);
+  DevBuf tile_keys, tile_runs, totals;
+  PA_TRY(tile_keys.alloc((tiles + 1) * 8)); PA_TRY(tile_runs.alloc((tiles + 1) * 8)); PA_TRY(totals.alloc(16));
+  rle_count<<<(unsigned)tiles, RLE_THREADS, 0, s>>>(d_keys, d_vals, ix.genome_off.as<uint64_t>(), G, n_valid,
+                                                    tile_keys.as<uint64_t>(), tile_runs.as<uint64_t>());
+  scan_u64_single_block<<<1, 1024, 0, s>>>(tile_keys.as<uint64_t>(), tiles, totals.as<uint64_t>());
+  scan_u64_single_block<<<1, 1024, 0, s>>>(tile_runs.as<uint64_t>(), tiles, totals.as<uint64_t>() + 1);
+  uint64_t h_tot[2];
+  PA_CUDA(cudaMemcpyAsync(h_tot, totals.p, 16, cudaMemcpyDeviceToHost, s));
+  PA_CUDA(cudaStreamSynchronize(s));
+  const uint64_t U = h_tot[0], R = h_tot[1];
+  PA_TRY(ix.ukeys.alloc((U + 1) * 8)); PA_TRY(ix.run_off.alloc((U + 1) * 8));
+  PA_TRY(ix.run_genome.alloc((R + 1) * 4)); PA_TRY(ix.pos_off.alloc((R + 1) * 8)); PA_TRY(ix.pos.alloc((n_valid + 1) * 4));
+  if (n_valid)
+    rle_scatter<<<(unsigned)tiles, RLE_THREADS, 0, s>>>(d_keys, d_vals, ix.genome_off.as<uint64_t>(), G, n_valid,
+                                                        tile_keys.as<uint64_t>(), tile_runs.as<uint64_t>(), ix.ukeys.as<uint64_t>(),
+                                                        ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(),
+                                                        ix.pos_off.as<uint64_t>(), ix.pos.as<uint32_t>());
+  set_csr_tails<<<1, 1, 0, s>>>(ix.run_off.as<uint64_t>(), U, R, ix.pos_off.as<uint64_t>(), n_valid);
+  PA_CUDA(cudaGetLastError());
+  PA_CUDA(cudaStreamSynchronize(s));
+  ix.n_keys = U; ix.n_runs = R; ix.n_occ = n_valid;
+  return ST_OK;
+}
+
 int32_t index_build_from_device_bases(Index& ix, const uint8_t* d_bases) {
   cudaStream_t s = ix.stream;
   const uint64_t total = ix.total_bases;
@@ -681,7 +714,7 @@ int32_t index_build_from_device_bases(Index& ix, const uint8_t* d_bases) {
   PA_CUDA(cudaMemsetAsync(counters.p, 0, 16, s));
   PA_CUDA(cudaEventRecord(ev[0], s));
   encode_windows<<<grid_for(total, ENC_TILE), ENC_THREADS, 0, s>>>(
-      d_bases, total, ix.genome_off.as<uint64_t>(), G, k, ix.mix, keys_a.as<uint64_t>(), vals_a.as<uint32_t>(),
+      d_bases, total, 0, ix.genome_off.as<uint64_t>(), G, k, ix.mix, keys_a.as<uint64_t>(), vals_a.as<uint32_t>(),
       counters.as<unsigned long long>(), reinterpret_cast<unsigned int*>(counters.as<char>() + 8));
   PA_CUDA(cudaGetLastError());
   PA_CUDA(cudaEventRecord(ev[1], s));
@@ -702,29 +735,8 @@ int32_t index_build_from_device_bases(Index& ix, const uint8_t* d_bases) {
   keys_b.release(); vals_b.release(); sort_tmp.release();
 
   // ---- K3 ----
-  const uint64_t tiles = std::max<uint64_t>(1, (n_valid + RLE_TILE - 1) / RLE_TILE);
-  DevBuf tile_keys, tile_runs, totals;
-  PA_TRY(tile_keys.alloc((tiles + 1) * 8)); PA_TRY(tile_runs.alloc((tiles + 1) * 8)); PA_TRY(totals.alloc(16));
-  rle_count<<<(unsigned)tiles, RLE_THREADS, 0, s>>>(keys_a.as<uint64_t>(), vals_a.as<uint32_t>(), ix.genome_off.as<uint64_t>(),
-                                                    G, n_valid, tile_keys.as<uint64_t>(), tile_runs.as<uint64_t>());
-  scan_u64_single_block<<<1, 1024, 0, s>>>(tile_keys.as<uint64_t>(), tiles, totals.as<uint64_t>());
-  scan_u64_single_block<<<1, 1024, 0, s>>>(tile_runs.as<uint64_t>(), tiles, totals.as<uint64_t>() + 1);
-  uint64_t h_tot[2];
-  PA_CUDA(cudaMemcpyAsync(h_tot, totals.p, 16, cudaMemcpyDeviceToHost, s));
-  PA_CUDA(cudaStreamSynchronize(s));
-  const uint64_t U = h_tot[0], R = h_tot[1];
-  PA_TRY(ix.ukeys.alloc((U + 1) * 8)); PA_TRY(ix.run_off.alloc((U + 1) * 8));
-  PA_TRY(ix.run_genome.alloc((R + 1) * 4)); PA_TRY(ix.pos_off.alloc((R + 1) * 8)); PA_TRY(ix.pos.alloc((n_valid + 1) * 4));
-  if (n_valid)
-    rle_scatter<<<(unsigned)tiles, RLE_THREADS, 0, s>>>(keys_a.as<uint64_t>(), vals_a.as<uint32_t>(),
-                                                        ix.genome_off.as<uint64_t>(), G, n_valid, tile_keys.as<uint64_t>(),
-                                                        tile_runs.as<uint64_t>(), ix.ukeys.as<uint64_t>(),
-                                                        ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(),
-                                                        ix.pos_off.as<uint64_t>(), ix.pos.as<uint32_t>());
-  set_csr_tails<<<1, 1, 0, s>>>(ix.run_off.as<uint64_t>(), U, R, ix.pos_off.as<uint64_t>(), n_valid);
-  PA_CUDA(cudaGetLastError());
+  PA_TRY(rle_to_csr(ix, keys_a.as<uint64_t>(), vals_a.as<uint32_t>(), n_valid));
   PA_CUDA(cudaEventRecord(ev[3], s));
-  ix.n_keys = U; ix.n_runs = R; ix.n_occ = n_valid;
   keys_a.release(); vals_a.release();
 
   PA_TRY(index_build_tables(ix));
@@ -905,6 +917,88 @@ int32_t index_drop_genomes(Index& ix, const uint8_t* h_keep) {
   PA_CUDA(cudaStreamSynchronize(s));
   ix.align_scratch.release(); ix.align_scratch_warps = 0;
   return index_build_tables(ix);
+}
+
+
+// ===========================================================================
+// Multi-GPU build: every rank encodes a run of whole genomes (K1), splits its records by key
+// range (one stable counting pass on the top digit of the hashed key -- the hash is a bijective mix, so the ranges
+// carry equal load), the ranks exchange the parts (all-to-all over NVLink, done by the caller with
+// torch.distributed / NCCL), and every rank sorts and run-length encodes the key range it owns (K2, K3).
+// Records of equal keys arrive ordered by sender, i.e. by genome, and inside a sender by position, so the stable
+// sort reproduces the (genome, position) order of kmer.py:141-150.
+// ===========================================================================
+int32_t records_encode_device(const uint8_t* d_bases, uint64_t n_bases, uint64_t pos0, const uint64_t* d_genome_off,
+                              uint32_t G, int k, uint64_t* d_keys, uint32_t* d_vals, uint64_t* h_n_valid, cudaStream_t s) {
+  *h_n_valid = 0;
+  if (k <= 0 || n_bases == 0 || G == 0) return ST_OK;
+  DevBuf counters;
+  PA_TRY(counters.alloc(16));
+  PA_CUDA(cudaMemsetAsync(counters.p, 0, 16, s));
+  encode_windows<<<grid_for(n_bases, ENC_TILE), ENC_THREADS, 0, s>>>(
+      d_bases, n_bases, pos0, d_genome_off, G, k, mix_params_for_k(k), d_keys, d_vals, counters.as<unsigned long long>(),
+      reinterpret_cast<unsigned int*>(counters.as<char>() + 8));
+  PA_CUDA(cudaGetLastError());
+  unsigned long long h_cnt[2] = {0, 0};
+  PA_CUDA(cudaMemcpyAsync(h_cnt, counters.p, 16, cudaMemcpyDeviceToHost, s));
+  PA_CUDA(cudaStreamSynchronize(s));
+  if (h_cnt[1] & 0xFFFFFFFFull) { set_error("genome sequence contains a character outside ACGTN"); return ST_BAD_BASE; }
+  *h_n_valid = h_cnt[0];
+  return ST_OK;
+}
+
+// digit of the partition pass: key bits [begin, begin + 8) with begin = max(0, 2k - 7); real keys give digits below
+// 2^(2k - begin) <= 128, the all-ones sentinel of an invalid window gives 255
+void partition_geometry(int k, int* begin_bit, int* top_bits) {
+  *begin_bit = std::max(0, 2 * k - 7);
+  *top_bits = 2 * k - *begin_bit;
+}
+uint32_t partition_of_digit(uint32_t digit, int top_bits, uint32_t n_parts) { return (uint32_t)(((uint64_t)digit * n_parts) >> top_bits); }
+
+int32_t records_partition_device(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint64_t n, int k,
+                                 uint32_t n_parts, uint64_t* h_part_off /*[n_parts + 1]*/, int* in_b, cudaStream_t s) {
+  *in_b = 0;
+  for (uint32_t r = 0; r <= n_parts; ++r) h_part_off[r] = 0;
+  if (n == 0 || k <= 0) return ST_OK;
+  int begin = 0, tb = 0;
+  partition_geometry(k, &begin, &tb);
+  if (n_parts == 0 || n_parts > (1u << tb)) { set_error("partition: %u parts do not fit the %d-bit key space split", n_parts, tb); return ST_INVALID_ARG; }
+  DevBuf tmp;
+  PA_TRY(tmp.alloc(radix_sort_temp_bytes(n)));
+  PA_TRY(radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, n, begin + 8, tmp.p, tmp.bytes, s, in_b, begin));
+  // the scanned digit histogram of the pass (first 256 words of the scratch) = start of every digit's run
+  unsigned long long starts[256];
+  PA_CUDA(cudaMemcpyAsync(starts, tmp.p, sizeof(starts), cudaMemcpyDeviceToHost, s));
+  PA_CUDA(cudaStreamSynchronize(s));
+  const uint32_t n_digits = 1u << tb;
+  uint32_t d = 0;
+  for (uint32_t r = 0; r < n_parts; ++r) {
+    while (d < n_digits && partition_of_digit(d, tb, n_parts) < r) ++d;
+    h_part_off[r] = starts[d];
+  }
+  h_part_off[n_parts] = starts[n_digits];   // digits 2^tb .. 254 are empty, 255 holds the sentinels
+  return ST_OK;
+}
+
+int32_t index_build_from_records(Index& ix, uint64_t* d_keys, uint32_t* d_vals, uint64_t n, bool build_tables) {
+  cudaStream_t s = ix.stream;
+  const int k = ix.k;
+  ix.n_keys = ix.n_runs = ix.n_occ = 0;
+  if (k <= 0 || n == 0) {
+    PA_TRY(ix.ukeys.alloc(8)); PA_TRY(ix.run_off.alloc(8)); PA_TRY(ix.run_genome.alloc(4));
+    PA_TRY(ix.pos_off.alloc(8)); PA_TRY(ix.pos.alloc(4));
+    PA_CUDA(cudaMemsetAsync(ix.run_off.p, 0, 8, s)); PA_CUDA(cudaMemsetAsync(ix.pos_off.p, 0, 8, s));
+    return build_tables ? index_build_tables(ix) : ST_OK;
+  }
+  DevBuf keys_b, vals_b, sort_tmp;
+  PA_TRY(keys_b.alloc(n * 8)); PA_TRY(vals_b.alloc(n * 4));
+  PA_TRY(sort_tmp.alloc(radix_sort_temp_bytes(n)));
+  int in_b = 0;
+  PA_TRY(radix_sort_pairs(d_keys, d_vals, keys_b.as<uint64_t>(), vals_b.as<uint32_t>(), n, std::min(64, 2 * k), sort_tmp.p,
+                          sort_tmp.bytes, s, &in_b));
+  PA_TRY(rle_to_csr(ix, in_b ? keys_b.as<uint64_t>() : d_keys, in_b ? vals_b.as<uint32_t>() : d_vals, n));
+  keys_b.release(); vals_b.release(); sort_tmp.release();
+  return build_tables ? index_build_tables(ix) : ST_OK;
 }
 
 }  // namespace pa

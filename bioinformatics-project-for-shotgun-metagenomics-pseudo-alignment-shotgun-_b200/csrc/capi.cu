@@ -221,6 +221,7 @@ int32_t pa_index_export(pa_index* idx, uint64_t* keys, uint64_t* run_off, uint32
                         uint32_t* pos, uint32_t* order, uint64_t* first_occ) {
   NEED(idx, "null index");
   Index& ix = *IDX(idx);
+  NEED(!ix.align_only || (!pos_off && !pos && !order && !first_occ), "a replica index holds no positions (export the partitions instead)");
   PA_CUDA(cudaSetDevice(ix.device));
   cudaStream_t s = ix.stream;
   if (keys && ix.n_keys) PA_CUDA(cudaMemcpyAsync(keys, ix.ukeys.p, ix.n_keys * 8, cudaMemcpyDeviceToHost, s));
@@ -290,8 +291,114 @@ int32_t pa_extsim_pairwise(pa_index* idx, const uint32_t* group, uint32_t n_grou
 int32_t pa_index_drop_genomes(pa_index* idx, const uint8_t* keep) {
   NEED(idx, "null index");
   NEED(IDX(idx)->n_genomes == 0 || keep, "null keep mask");
+  NEED(!IDX(idx)->align_only, "a replica index holds no positions (drop the genomes from the partitions and re-gather)");
   PA_CUDA(cudaSetDevice(IDX(idx)->device));
   return index_drop_genomes(*IDX(idx), keep);
+}
+
+
+/* ---- multi-GPU build phases; orchestrated by multi_gpu.py over torch.distributed ---- */
+int32_t pa_records_encode_device(const uint8_t* d_bases, const uint64_t* genome_off, uint32_t n_genomes, uint32_t g_lo,
+                                 uint32_t g_hi, int32_t k, int32_t device, uint64_t* d_keys, uint32_t* d_vals,
+                                 uint64_t* n_valid, void* stream) {
+  NEED(n_valid, "null argument");
+  *n_valid = 0;
+  NEED(g_lo <= g_hi && g_hi <= n_genomes, "genome range out of bounds");
+  NEED(n_genomes == 0 || genome_off, "genome_off is null");
+  if (k > 31) { set_error("k = %d is outside the built scope (k <= 31: one k-mer per 64-bit word)", k); return PA_ERR_UNSUPPORTED; }
+  if (g_lo == g_hi) return PA_OK;
+  PA_CUDA(cudaSetDevice(device));
+  std::vector<uint64_t> off(n_genomes + 1);
+  for (uint32_t g = 0; g <= n_genomes; ++g) {
+    NEED(g == 0 || genome_off[g] >= genome_off[g - 1], "genome_off is not monotonic");
+    off[g] = genome_off[g] - genome_off[0];
+  }
+  if (off[n_genomes] >= 0xFFFFFFFFull) { set_error("index build: %llu bases exceed the 32-bit position space of this build", (unsigned long long)off[n_genomes]); return PA_ERR_UNSUPPORTED; }
+  const uint64_t n_bases = off[g_hi] - off[g_lo];
+  if (n_bases == 0) return PA_OK;
+  NEED(d_bases && d_keys && d_vals, "null device buffer");
+  NEED((reinterpret_cast<uintptr_t>(d_bases) & 15) == 0, "device bases must be 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DevBuf d_off;
+  PA_TRY(d_off.alloc(off.size() * 8));
+  PA_CUDA(cudaMemcpyAsync(d_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, s));
+  return records_encode_device(d_bases, n_bases, off[g_lo], d_off.as<uint64_t>(), n_genomes, k, d_keys, d_vals, n_valid, s);
+}
+
+int32_t pa_records_partition_device(uint64_t* d_keys, uint32_t* d_vals, uint64_t* d_keys_tmp, uint32_t* d_vals_tmp, uint64_t n,
+                                    int32_t k, uint32_t n_parts, int32_t device, uint64_t* part_off, int32_t* result_in_tmp,
+                                    void* stream) {
+  NEED(part_off && result_in_tmp && n_parts >= 1, "bad argument");
+  NEED(n == 0 || (d_keys && d_vals && d_keys_tmp && d_vals_tmp), "null device buffer");
+  PA_CUDA(cudaSetDevice(device));
+  int in_b = 0;
+  int32_t st = records_partition_device(d_keys, d_vals, d_keys_tmp, d_vals_tmp, n, k, n_parts, part_off, &in_b,
+                                        reinterpret_cast<cudaStream_t>(stream));
+  *result_in_tmp = in_b;
+  return st;
+}
+
+int32_t pa_partition_of_key(int32_t k, uint64_t hashed_key, uint32_t n_parts, uint32_t* part) {
+  NEED(part && k >= 1 && k <= 31 && n_parts >= 1, "bad argument");
+  int begin = 0, tb = 0;
+  partition_geometry(k, &begin, &tb);
+  NEED(n_parts <= (1u << tb), "too many parts for this k");
+  *part = partition_of_digit((uint32_t)((hashed_key >> begin) & 0xFF), tb, n_parts);
+  return PA_OK;
+}
+
+int32_t pa_index_build_from_records_device(uint64_t* d_keys, uint32_t* d_vals, uint64_t n, const uint64_t* genome_off,
+                                           uint32_t n_genomes, int32_t k, int32_t device, int32_t build_tables, pa_index** out) {
+  Index* ix = nullptr;
+  PA_TRY(new_index(k, n_genomes, genome_off, device, &ix));
+  if (n && (!d_keys || !d_vals)) { delete ix; set_error("null device buffer"); return PA_ERR_INVALID_ARG; }
+  if (ix->total_bases >= 0xFFFFFFFFull) { delete ix; set_error("index build: too many bases for 32-bit positions"); return PA_ERR_UNSUPPORTED; }
+  int32_t st = index_build_from_records(*ix, d_keys, d_vals, n, build_tables != 0);
+  if (st != ST_OK) { delete ix; return st; }
+  *out = reinterpret_cast<pa_index*>(ix);
+  return PA_OK;
+}
+
+int32_t pa_index_csr_device(pa_index* idx, uint64_t** d_keys, uint64_t** d_run_off, uint32_t** d_run_genome) {
+  NEED(idx, "null index");
+  Index& ix = *IDX(idx);
+  if (d_keys) *d_keys = ix.ukeys.as<uint64_t>();
+  if (d_run_off) *d_run_off = ix.run_off.as<uint64_t>();
+  if (d_run_genome) *d_run_genome = ix.run_genome.as<uint32_t>();
+  return PA_OK;
+}
+
+int32_t pa_index_alloc_replica(int32_t k, uint32_t n_genomes, const uint64_t* genome_off, uint64_t n_keys, uint64_t n_runs,
+                               uint64_t n_occ, int32_t device, pa_index** out) {
+  Index* ix = nullptr;
+  PA_TRY(new_index(k, n_genomes, genome_off, device, &ix));
+  if (n_keys >= 0xFFFFFFFFull) { delete ix; set_error("too many distinct k-mers"); return PA_ERR_UNSUPPORTED; }
+  int32_t st;
+  if ((st = ix->ukeys.alloc((n_keys + 1) * 8)) || (st = ix->run_off.alloc((n_keys + 1) * 8)) ||
+      (st = ix->run_genome.alloc((n_runs + 1) * 4)) || (st = ix->pos_off.alloc(8)) || (st = ix->pos.alloc(4))) { delete ix; return st; }
+  ix->n_keys = n_keys; ix->n_runs = n_runs; ix->n_occ = n_occ;
+  ix->align_only = true;
+  *out = reinterpret_cast<pa_index*>(ix);
+  return PA_OK;
+}
+
+int32_t pa_index_finish_replica(pa_index* idx) {
+  NEED(idx, "null index");
+  Index& ix = *IDX(idx);
+  NEED(ix.align_only, "not a replica index");
+  PA_CUDA(cudaSetDevice(ix.device));
+  PA_CUDA(cudaDeviceSynchronize());   // the caller filled the arrays on its own streams
+  const uint64_t tail = ix.n_runs;
+  PA_CUDA(cudaMemcpyAsync(ix.run_off.as<uint64_t>() + ix.n_keys, &tail, 8, cudaMemcpyHostToDevice, ix.stream));
+  PA_CUDA(cudaStreamSynchronize(ix.stream));
+  return index_build_tables(ix);
+}
+
+/* (re)build the lookup structures of an index from its CSR -- a partition built with build_tables = 0 */
+int32_t pa_index_build_tables(pa_index* idx) {
+  NEED(idx, "null index");
+  PA_CUDA(cudaSetDevice(IDX(idx)->device));
+  return index_build_tables(*IDX(idx));
 }
 
 int32_t pa_align_batch_device(pa_index* idx, const uint8_t* d_bases, const uint8_t* d_quals, const uint64_t* d_read_off,

@@ -46,6 +46,7 @@ struct Index {
   // insertion order of kmer.py:146-147 survives genome removal, kmer.py:237-243).  Materialised lazily.
   DevBuf first_occ;
   bool has_first_occ = false;
+  bool align_only = false;   // replica of a multi-GPU build: keys and genome runs only, no positions
   std::vector<uint64_t> h_genome_off;
   // lookup structures
   DevBuf slots, stash, mlist;
@@ -102,7 +103,15 @@ struct Index {
 
 // build.cu
 int32_t index_build_from_device_bases(Index& ix, const uint8_t* d_bases);
-int32_t index_build_tables(Index& ix);   // buckets / stash / mlist from the CSR
+int32_t index_build_tables(Index& ix);   // slots / stash / mlist from the CSR
+// multi-GPU build phases (see build.cu)
+int32_t records_encode_device(const uint8_t* d_bases, uint64_t n_bases, uint64_t pos0, const uint64_t* d_genome_off,
+                              uint32_t G, int k, uint64_t* d_keys, uint32_t* d_vals, uint64_t* h_n_valid, cudaStream_t s);
+int32_t records_partition_device(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint64_t n, int k,
+                                 uint32_t n_parts, uint64_t* h_part_off, int* in_b, cudaStream_t s);
+int32_t index_build_from_records(Index& ix, uint64_t* d_keys, uint32_t* d_vals, uint64_t n, bool build_tables);
+void partition_geometry(int k, int* begin_bit, int* top_bits);
+uint32_t partition_of_digit(uint32_t digit, int top_bits, uint32_t n_parts);
 int32_t index_export_order(Index& ix, uint32_t* h_order);
 int32_t index_ensure_first_occ(Index& ix);
 int32_t index_lookup_ranks(Index& ix, const uint8_t* h_kmers, uint64_t n, uint64_t* h_rank);

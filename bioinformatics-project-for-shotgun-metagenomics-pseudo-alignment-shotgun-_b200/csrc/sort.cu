@@ -33,7 +33,7 @@ constexpr uint64_t LB_FLAG_AGG = 1ULL << 62;
 constexpr uint64_t LB_FLAG_INCL = 2ULL << 62;
 constexpr uint64_t LB_COUNT_MASK = (1ULL << 62) - 1;
 
-__global__ void __launch_bounds__(SORT_THREADS) radix_histogram(const uint64_t* __restrict__ keys, uint64_t n,
+__global__ void __launch_bounds__(SORT_THREADS) radix_histogram(const uint64_t* __restrict__ keys, uint64_t n, int begin_bit,
                                                                 int n_passes, unsigned long long* __restrict__ hist) {
   __shared__ uint32_t sh[MAX_PASSES * RADIX];
   for (int i = threadIdx.x; i < n_passes * RADIX; i += SORT_THREADS) sh[i] = 0;
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_histogram(const uint64_t* 
   const uint64_t stride = (uint64_t)gridDim.x * SORT_THREADS;
   for (uint64_t i = blockIdx.x * (uint64_t)SORT_THREADS + threadIdx.x; i < n; i += stride) {
     uint64_t key = keys[i];
-    for (int p = 0; p < n_passes; ++p) atomicAdd(&sh[p * RADIX + ((key >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+    for (int p = 0; p < n_passes; ++p) atomicAdd(&sh[p * RADIX + ((key >> (begin_bit + p * RADIX_BITS)) & (RADIX - 1))], 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < n_passes * RADIX; i += SORT_THREADS)
@@ -191,12 +191,13 @@ size_t radix_sort_temp_bytes(uint64_t n) {
 }
 
 int32_t radix_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint64_t n,
-                         int end_bit, void* d_temp, size_t temp_bytes, cudaStream_t s, int* result_in_b) {
+                         int end_bit, void* d_temp, size_t temp_bytes, cudaStream_t s, int* result_in_b, int begin_bit) {
   *result_in_b = 0;
-  if (n == 0 || end_bit <= 0) return ST_OK;
   if (end_bit > 64) end_bit = 64;
+  if (begin_bit < 0) begin_bit = 0;
+  if (n == 0 || end_bit <= begin_bit) return ST_OK;
   if (temp_bytes < radix_sort_temp_bytes(n)) { set_error("radix sort: temp buffer too small"); return ST_INVALID_ARG; }
-  const int n_passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
+  const int n_passes = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
   const uint64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
   if (tiles > 0xFFFFFFFFull) { set_error("radix sort: too many tiles"); return ST_UNSUPPORTED; }
   unsigned long long* hist = reinterpret_cast<unsigned long long*>(d_temp);
@@ -214,14 +215,14 @@ int32_t radix_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, u
 
   PA_CUDA(cudaMemsetAsync(hist, 0, (size_t)MAX_PASSES * RADIX * 8, s));
   int hgrid = (int)std::min<uint64_t>((n + SORT_THREADS - 1) / SORT_THREADS, (uint64_t)sms * 8);
-  radix_histogram<<<hgrid, SORT_THREADS, 0, s>>>(keys_a, n, n_passes, hist);
+  radix_histogram<<<hgrid, SORT_THREADS, 0, s>>>(keys_a, n, begin_bit, n_passes, hist);
   radix_scan<<<n_passes, RADIX, 0, s>>>(hist);
   PA_CUDA(cudaGetLastError());
 
   uint64_t* kin = keys_a; uint32_t* vin = vals_a; uint64_t* kout = keys_b; uint32_t* vout = vals_b;
   for (int p = 0; p < n_passes; ++p) {
     PA_CUDA(cudaMemsetAsync(tile_counter, 0, 256 + (size_t)tiles * RADIX * 8, s));
-    radix_pass<<<(unsigned)tiles, SORT_THREADS, sizeof(PassSmem), s>>>(kin, vin, kout, vout, n, p * RADIX_BITS,
+    radix_pass<<<(unsigned)tiles, SORT_THREADS, sizeof(PassSmem), s>>>(kin, vin, kout, vout, n, begin_bit + p * RADIX_BITS,
                                                                        hist + (size_t)p * RADIX, lookback, tile_counter);
     PA_CUDA(cudaGetLastError());
     uint64_t* tk = kin; kin = kout; kout = tk;

@@ -7,10 +7,10 @@ namespace pa {
 // Bytes of device scratch radix_sort_pairs needs for n pairs.
 size_t radix_sort_temp_bytes(uint64_t n);
 
-// Stable LSD radix sort of n (key, value) pairs on key bits [0, end_bit).
+// Stable LSD radix sort of n (key, value) pairs on key bits [begin_bit, end_bit).
 // (keys_a, vals_a) hold the input; (keys_b, vals_b) are same-sized scratch.
 // *result_in_b tells which pair of buffers holds the sorted output.
 int32_t radix_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint64_t n,
-                         int end_bit, void* d_temp, size_t temp_bytes, cudaStream_t s, int* result_in_b);
+                         int end_bit, void* d_temp, size_t temp_bytes, cudaStream_t s, int* result_in_b, int begin_bit = 0);
 
 }  // namespace pa

@@ -1,5 +1,5 @@
 """
-multi_gpu.py -- read-sharded alignment across ranks (one process per GPU).
+multi_gpu.py -- multi-GPU paths (one process per GPU): read-sharded alignment and the hash-partitioned index build.
 
 Reads are independent units (the loop of PseudoAlignment.align_reads_from_container,
 /root/reference/src/kmer.py:616-620), so rank r aligns one contiguous block of the reads against a
@@ -8,8 +8,15 @@ replicated index and the only exchange is the summary of get_summary (kmer.py:62
     SUM  stats[4] + unique_reads[G] + ambiguous_reads[G]      (int64)
     MIN  first_seen[G] = (global read index << 22) | list position   (orders the "Summary" keys)
 
-torch.distributed is the plumbing (NCCL over NVLink on GPUs, gloo in the CPU tests).
+The index build (SURVEY.md 8(e) "Build") has one exchange step: every rank encodes a run of whole genomes, splits its
+(hashed k-mer, position) records by key range, one all-to-all moves every record to the rank that owns its range, and
+every rank sorts + run-length encodes its range (`build_partitioned`).  The align index is replicated by gathering
+the partitions' keys and genome runs into a replica whose lookup table every rank builds.  EXTSIM statistics are
+sums over disjoint key ranges: computed per partition and all-reduced.
+
+torch.distributed is the plumbing (NCCL over NVLink on GPUs; gloo with host staging in the tests).
 """
+import ctypes
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -56,3 +63,291 @@ def summary_from_accumulators(stats: Sequence[int], unique_reads: Sequence[int],
         row["unique_reads"] += int(unique_reads[g])
         row["ambiguous_reads"] += int(ambiguous_reads[g])
     return {"Statistics": statistics, "Summary": summary}
+
+
+# ---------------------------------------------------------------------------
+# hash-partitioned index build
+# ---------------------------------------------------------------------------
+def genome_shards(genome_lengths: Sequence[int], world: int) -> List[Tuple[int, int]]:
+    """Contiguous runs [g_lo, g_hi) of whole genomes per rank, balanced by bases (FASTA order is kept, so genome
+    indices ascend with the rank and equal k-mers arrive at their owner in genome order)."""
+    total = int(sum(int(x) for x in genome_lengths))
+    bounds, g, acc = [0], 0, 0
+    n = len(genome_lengths)
+    for r in range(1, world):
+        target = total * r // world
+        while g < n and acc + int(genome_lengths[g]) // 2 < target:
+            acc += int(genome_lengths[g])
+            g += 1
+        bounds.append(g)
+    bounds.append(n)
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+class _DevArray:
+    """A raw device pointer dressed as a CUDA array for torch.as_tensor (no copy)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def _as_tensor(ptr: int, n: int, typestr: str, dev):
+    import torch
+    dt = {"<i8": torch.int64, "<i4": torch.int32}[typestr]
+    if n == 0 or not ptr:
+        return torch.empty(0, dtype=dt, device=dev)
+    return torch.as_tensor(_DevArray(ptr, n, typestr), device=dev)
+
+
+def _is_nccl(group=None) -> bool:
+    import torch.distributed as dist
+    return dist.get_backend(group) == "nccl"
+
+
+def _all_to_all(out, inp, out_splits, in_splits, group=None):
+    """all_to_all_single; staged through the host when the backend cannot move device tensors (gloo)."""
+    import torch
+    import torch.distributed as dist
+    if _is_nccl(group):
+        dist.all_to_all_single(out, inp, out_splits, in_splits, group=group)
+        return
+    world = dist.get_world_size(group)
+    src = inp.cpu()
+    parts = list(torch.split(src, in_splits)) if world > 0 else []
+    got = [None] * world
+    gathered = [None] * world
+    dist.all_gather_object(gathered, [p.numpy() for p in parts], group=group)
+    rank = dist.get_rank(group)
+    for r in range(world):
+        got[r] = torch.from_numpy(gathered[r][rank].copy()) if len(gathered[r][rank]) else torch.empty(0, dtype=inp.dtype)
+    cat = torch.cat(got) if got else torch.empty(0, dtype=inp.dtype)
+    assert cat.numel() == out.numel()
+    out.copy_(cat)
+
+
+def _broadcast(t, src: int, group=None):
+    import torch.distributed as dist
+    if t.numel() == 0:
+        return
+    if _is_nccl(group):
+        dist.broadcast(t, src, group=group)
+    else:
+        c = t.cpu()
+        dist.broadcast(c, src, group=group)
+        if dist.get_rank(group) != src:
+            t.copy_(c)
+
+
+class DistributedIndex:
+    """partition = CSR of the key range this rank owns (with positions); replica = align-only index of all keys."""
+
+    def __init__(self, partition, replica, k, genome_off, rank, world, group=None):
+        self.partition, self.replica = partition, replica
+        self.k, self.genome_off, self.rank, self.world, self.group = k, genome_off, rank, world, group
+        self.timings: Dict[str, float] = {}
+
+    def close(self):
+        for ix in (self.partition, self.replica):
+            if ix is not None:
+                ix.close()
+        self.partition = self.replica = None
+
+
+def _gather_replica(partition, k: int, genome_off: np.ndarray, dev, group=None):
+    """Replicates the align index: keys / run offsets / genome runs of every partition, in key order = rank order."""
+    import torch
+    import torch.distributed as dist
+    import _native as nat
+    L = nat.lib()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    inf = partition.info()
+    sizes = torch.tensor([inf.n_keys, inf.n_runs, inf.n_occ], dtype=torch.int64)
+    all_sizes = [torch.zeros(3, dtype=torch.int64) for _ in range(world)]
+    if _is_nccl(group):
+        tmp = [t.to(dev) for t in all_sizes]
+        dist.all_gather(tmp, sizes.to(dev), group=group)
+        all_sizes = [t.cpu() for t in tmp]
+    else:
+        dist.all_gather(all_sizes, sizes, group=group)
+    U = [int(t[0]) for t in all_sizes]
+    R = [int(t[1]) for t in all_sizes]
+    N = [int(t[2]) for t in all_sizes]
+    U_off = np.concatenate([[0], np.cumsum(U)]).astype(np.int64)
+    R_off = np.concatenate([[0], np.cumsum(R)]).astype(np.int64)
+    h = ctypes.c_void_p()
+    G = len(genome_off) - 1
+    nat.check(L.pa_index_alloc_replica(int(k), G, nat._p(genome_off), int(U_off[-1]), int(R_off[-1]), int(sum(N)),
+                                       dev.index or 0, ctypes.byref(h)))
+    replica = nat.NativeIndex(h.value)
+    pk, po, pg = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    nat.check(L.pa_index_csr_device(replica.handle, ctypes.byref(pk), ctypes.byref(po), ctypes.byref(pg)))
+    r_keys = _as_tensor(pk.value, int(U_off[-1]), "<i8", dev)
+    r_off = _as_tensor(po.value, int(U_off[-1]), "<i8", dev)
+    r_gen = _as_tensor(pg.value, int(R_off[-1]), "<i4", dev)
+    nat.check(L.pa_index_csr_device(partition.handle, ctypes.byref(pk), ctypes.byref(po), ctypes.byref(pg)))
+    u0, u1, g0, g1 = int(U_off[rank]), int(U_off[rank + 1]), int(R_off[rank]), int(R_off[rank + 1])
+    if u1 > u0:
+        r_keys[u0:u1].copy_(_as_tensor(pk.value, u1 - u0, "<i8", dev))
+        r_off[u0:u1].copy_(_as_tensor(po.value, u1 - u0, "<i8", dev) + g0)   # run offsets become global
+    if g1 > g0:
+        r_gen[g0:g1].copy_(_as_tensor(pg.value, g1 - g0, "<i4", dev))
+    torch.cuda.synchronize(dev)
+    for src in range(world):
+        _broadcast(r_keys[int(U_off[src]):int(U_off[src + 1])], src, group)
+        _broadcast(r_off[int(U_off[src]):int(U_off[src + 1])], src, group)
+        _broadcast(r_gen[int(R_off[src]):int(R_off[src + 1])], src, group)
+    torch.cuda.synchronize(dev)
+    nat.check(L.pa_index_finish_replica(replica.handle))
+    return replica
+
+
+def build_partitioned(my_bases, genome_off: np.ndarray, k: int, g_range: Tuple[int, int], device: int = 0,
+                      group=None) -> DistributedIndex:
+    """Multi-GPU KmerReference build (kmer.py:135-150 across ranks).
+
+    my_bases    the genomes [g_lo, g_hi) of this rank concatenated: a uint8 numpy array or a CUDA uint8 tensor
+    genome_off  uint64 offsets of ALL genomes (G + 1 entries); positions and genome indices are global
+    g_range     (g_lo, g_hi), normally genome_shards(lengths, world)[rank]
+    """
+    import time
+    import torch
+    import torch.distributed as dist
+    import _native as nat
+    nat.require_device()
+    L = nat.lib()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device("cuda", device)
+    torch.cuda.set_device(dev)
+    genome_off = np.ascontiguousarray(genome_off, dtype=np.uint64)
+    G = len(genome_off) - 1
+    g_lo, g_hi = g_range
+    n_bases = int(genome_off[g_hi] - genome_off[g_lo])
+    if isinstance(my_bases, np.ndarray):
+        d_bases = torch.from_numpy(np.ascontiguousarray(my_bases, dtype=np.uint8)).to(dev)
+    else:
+        d_bases = my_bases
+    assert d_bases.numel() >= n_bases
+    t = {}
+    t0 = time.perf_counter()
+    keys = torch.empty(max(n_bases, 1), dtype=torch.int64, device=dev)
+    vals = torch.empty(max(n_bases, 1), dtype=torch.int32, device=dev)
+    n_valid = ctypes.c_uint64(0)
+    torch.cuda.synchronize(dev)
+    nat.check(L.pa_records_encode_device(ctypes.c_void_p(d_bases.data_ptr()), nat._p(genome_off), G, g_lo, g_hi, int(k), device,
+                                         ctypes.c_void_p(keys.data_ptr()), ctypes.c_void_p(vals.data_ptr()),
+                                         ctypes.byref(n_valid), None))
+    keys_t = torch.empty_like(keys)
+    vals_t = torch.empty_like(vals)
+    part_off = np.zeros(world + 1, dtype=np.uint64)
+    in_tmp = ctypes.c_int32(0)
+    nat.check(L.pa_records_partition_device(ctypes.c_void_p(keys.data_ptr()), ctypes.c_void_p(vals.data_ptr()),
+                                            ctypes.c_void_p(keys_t.data_ptr()), ctypes.c_void_p(vals_t.data_ptr()),
+                                            n_bases if int(k) >= 1 else 0, int(k), world, device, nat._p(part_off),
+                                            ctypes.byref(in_tmp), None))
+    if in_tmp.value:
+        keys, keys_t, vals, vals_t = keys_t, keys, vals_t, vals
+    del keys_t, vals_t
+    assert int(part_off[-1]) == n_valid.value
+    torch.cuda.synchronize(dev)
+    t["encode_partition_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    send = np.diff(part_off.astype(np.int64))
+    send_t = torch.from_numpy(send.copy())
+    recv_t = torch.empty(world, dtype=torch.int64)
+    if _is_nccl(group):
+        s_d, r_d = send_t.to(dev), recv_t.to(dev)
+        dist.all_to_all_single(r_d, s_d, group=group)
+        recv_t = r_d.cpu()
+    else:
+        _all_to_all(recv_t, send_t, [1] * world, [1] * world, group)
+    recv = [int(x) for x in recv_t.tolist()]
+    n_recv = sum(recv)
+    r_keys = torch.empty(max(n_recv, 1), dtype=torch.int64, device=dev)
+    r_vals = torch.empty(max(n_recv, 1), dtype=torch.int32, device=dev)
+    send_l = [int(x) for x in send.tolist()]
+    _all_to_all(r_keys[:n_recv], keys[:int(part_off[-1])], recv, send_l, group)
+    _all_to_all(r_vals[:n_recv], vals[:int(part_off[-1])], recv, send_l, group)
+    del keys, vals
+    torch.cuda.synchronize(dev)
+    t["exchange_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    h = ctypes.c_void_p()
+    nat.check(L.pa_index_build_from_records_device(ctypes.c_void_p(r_keys.data_ptr()), ctypes.c_void_p(r_vals.data_ptr()),
+                                                   n_recv, nat._p(genome_off), G, int(k), device, 0, ctypes.byref(h)))
+    partition = nat.NativeIndex(h.value)
+    del r_keys, r_vals
+    t["sort_rle_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    replica = _gather_replica(partition, k, genome_off, dev, group)
+    t["replicate_s"] = time.perf_counter() - t0
+    out = DistributedIndex(partition, replica, int(k), genome_off, rank, world, group)
+    out.timings = t
+    out.sent_records = int(part_off[-1])
+    out.received_records = n_recv
+    return out
+
+
+def extsim_stats_allreduce(dix: DistributedIndex, group_ids: np.ndarray, n_groups: int):
+    """_compute_genome_stats (kmer.py:152-177) over all partitions: per-class sums are additive over key ranges."""
+    import torch
+    import torch.distributed as dist
+    total, uniq = dix.partition.extsim_stats(group_ids, n_groups)
+    t = torch.from_numpy(np.concatenate([total, uniq]).astype(np.int64))
+    if _is_nccl(dix.group):
+        d = t.cuda()
+        dist.all_reduce(d, group=dix.group)
+        t = d.cpu()
+    else:
+        dist.all_reduce(t, group=dix.group)
+    a = t.numpy().astype(np.uint64)
+    return a[:n_groups], a[n_groups:]
+
+
+def extsim_pairwise_allreduce(dix: DistributedIndex, group_ids: np.ndarray, n_groups: int) -> np.ndarray:
+    """The |A & B| matrix of _apply_greedy_filter (kmer.py:206-207) summed over all partitions."""
+    import torch
+    import torch.distributed as dist
+    inter = dix.partition.extsim_pairwise(group_ids, n_groups)
+    t = torch.from_numpy(inter.astype(np.int64).reshape(-1).copy())
+    if _is_nccl(dix.group):
+        d = t.cuda()
+        dist.all_reduce(d, group=dix.group)
+        t = d.cpu()
+    else:
+        dist.all_reduce(t, group=dix.group)
+    return t.numpy().astype(np.uint64).reshape(n_groups, n_groups)
+
+
+def drop_genomes(dix: DistributedIndex, keep: np.ndarray) -> None:
+    """_remove_filtered_genomes_from_kmers (kmer.py:232-250) on every partition, then the replica is re-gathered."""
+    import torch
+    dix.partition.drop_genomes(keep)
+    keep = np.asarray(keep).astype(bool)
+    lens = np.diff(dix.genome_off.astype(np.int64))[keep]
+    dix.genome_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    dix.replica.close()
+    dev = torch.device("cuda", dix.partition.info().device)
+    dix.replica = _gather_replica(dix.partition, dix.k, dix.genome_off, dev, dix.group)
+
+
+def export_gathered(dix: DistributedIndex, dst: int = 0):
+    """CSR of the whole index on rank `dst` (dumpref / pickling): the partitions' exports concatenated in rank order
+    (= key order); `order` sorts all keys by first occurrence, i.e. the reference's dict insertion order."""
+    import torch.distributed as dist
+    ex = dix.partition.export(with_positions=True, with_order=False)
+    parts = [None] * dix.world
+    dist.all_gather_object(parts, ex, group=dix.group)
+    if dix.rank != dst:
+        return None
+    out = {"keys": np.concatenate([p["keys"] for p in parts]), "run_genome": np.concatenate([p["run_genome"] for p in parts]),
+           "pos": np.concatenate([p["pos"] for p in parts]), "first_occ": np.concatenate([p["first_occ"] for p in parts])}
+    run_off, pos_off, rb, pb = [], [], 0, 0
+    for p in parts:
+        run_off.append(p["run_off"][:-1].astype(np.uint64) + np.uint64(rb))
+        pos_off.append(p["pos_off"][:-1].astype(np.uint64) + np.uint64(pb))
+        rb += int(p["run_off"][-1])
+        pb += int(p["pos_off"][-1])
+    out["run_off"] = np.concatenate(run_off + [np.array([rb], dtype=np.uint64)])
+    out["pos_off"] = np.concatenate(pos_off + [np.array([pb], dtype=np.uint64)])
+    out["order"] = np.argsort(out["first_occ"], kind="stable").astype(np.uint32)
+    return out

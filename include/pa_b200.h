@@ -120,6 +120,38 @@ int32_t pa_extsim_pairwise(pa_index* idx, const uint32_t* group, uint32_t n_grou
 /* _remove_filtered_genomes_from_kmers + _update_genomes_list (kmer.py:232-250); keep[g] != 0 survives */
 int32_t pa_index_drop_genomes(pa_index* idx, const uint8_t* keep);
 
+/* ---- multi-GPU build (SURVEY.md 8(e) "Build: one exchange step") ------------------------------------------
+ * One process per GPU.  Rank r encodes a run of whole genomes, splits its (hashed k-mer, global position) records
+ * by key range, the ranks exchange the parts with one all-to-all (torch.distributed / NCCL over NVLink, see
+ * multi_gpu.py), and every rank sorts + run-length encodes the key range it owns into a CSR partition.  The align
+ * index is replicated: the partitions' keys and genome runs are gathered into a replica (no positions) whose lookup
+ * table every rank builds.  All buffers are caller-owned device memory; `stream` = cudaStream_t or NULL.
+ *   pa_records_encode_device        K1 over genomes [g_lo, g_hi): d_bases = those genomes concatenated (16-byte
+ *                                   aligned); writes one record per base (invalid windows get an all-ones key);
+ *                                   genome_off = offsets of ALL genomes (positions are global)
+ *   pa_records_partition_device     stable split into n_parts key ranges, invalid windows dropped; part_off[n_parts+1]
+ *                                   (host) = start of every part in the output, which is the tmp pair when
+ *                                   *result_in_tmp != 0
+ *   pa_partition_of_key             the part a hashed key (pa_encode_kmers) belongs to
+ *   pa_index_build_from_records_device   K2 + K3 over received records (sorted in place / through scratch) */
+int32_t pa_records_encode_device(const uint8_t* d_bases, const uint64_t* genome_off, uint32_t n_genomes, uint32_t g_lo,
+                                 uint32_t g_hi, int32_t k, int32_t device, uint64_t* d_keys, uint32_t* d_vals,
+                                 uint64_t* n_valid, void* stream);
+int32_t pa_records_partition_device(uint64_t* d_keys, uint32_t* d_vals, uint64_t* d_keys_tmp, uint32_t* d_vals_tmp, uint64_t n,
+                                    int32_t k, uint32_t n_parts, int32_t device, uint64_t* part_off, int32_t* result_in_tmp,
+                                    void* stream);
+int32_t pa_partition_of_key(int32_t k, uint64_t hashed_key, uint32_t n_parts, uint32_t* part);
+int32_t pa_index_build_from_records_device(uint64_t* d_keys, uint32_t* d_vals, uint64_t n, const uint64_t* genome_off,
+                                           uint32_t n_genomes, int32_t k, int32_t device, int32_t build_tables, pa_index** out);
+/* device pointers of an index's keys[n_keys], run_off[n_keys+1], run_genome[n_runs] (for the gather / to fill a replica) */
+int32_t pa_index_csr_device(pa_index* idx, uint64_t** d_keys, uint64_t** d_run_off, uint32_t** d_run_genome);
+/* replica = align-only index: allocate, fill keys / run_off (rebased) / run_genome through pa_index_csr_device,
+ * then pa_index_finish_replica builds the lookup table.  Positions stay in the partitions. */
+int32_t pa_index_alloc_replica(int32_t k, uint32_t n_genomes, const uint64_t* genome_off, uint64_t n_keys, uint64_t n_runs,
+                               uint64_t n_occ, int32_t device, pa_index** out);
+int32_t pa_index_finish_replica(pa_index* idx);
+int32_t pa_index_build_tables(pa_index* idx);
+
 /* ---- alignment: PseudoAlignment.align_reads_from_container (kmer.py:563-620) over a packed batch ---
  * bases/quals: concatenated read strings (quals may be NULL when no quality filter is on);
  * read_off[n_reads+1].  Outputs, one 64-bit word per read:

@@ -237,3 +237,45 @@ def test_shard_bounds_cover_everything_once():
             blocks = [multi_gpu.shard_bounds(n, world, r) for r in range(world)]
             assert blocks[0][0] == 0 and blocks[-1][1] == n
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+
+
+# ---------------------------------------------------------------------------
+# multi-GPU build: host-side partitioning logic (the kernels are covered by tests/test_gpu_multi.py)
+# ---------------------------------------------------------------------------
+def test_genome_shards_are_contiguous_and_balanced():
+    import multi_gpu
+    rng = np.random.default_rng(5)
+    for world in (1, 2, 3, 8):
+        for n in (0, 1, 5, 100):
+            lengths = rng.integers(1, 1000, size=n)
+            shards = multi_gpu.genome_shards(lengths, world)
+            assert len(shards) == world and shards[0][0] == 0 and shards[-1][1] == n
+            assert all(shards[i][1] == shards[i + 1][0] for i in range(world - 1))
+            if n == 100:
+                loads = [int(lengths[a:b].sum()) for a, b in shards]
+                assert max(loads) - min(loads) <= 2 * int(lengths.max())
+
+
+def test_partition_of_key_is_monotonic_and_balanced():
+    """pa_partition_of_key is pure host code: key ranges ascend with the part, and hashed k-mers spread evenly."""
+    import ctypes
+    import _native as nat
+    L = nat.lib()
+    rng = np.random.default_rng(9)
+    for k in (4, 11, 31):
+        kmers = rng.integers(0, 4, size=(20000, k))
+        flat = np.ascontiguousarray(np.frombuffer(b"ACGT", dtype=np.uint8)[kmers].reshape(-1))
+        keys = np.zeros(20000, dtype=np.uint64)
+        nat.check(L.pa_encode_kmers(k, nat._p(flat), 20000, nat._p(keys)))
+        keys = np.unique(keys)
+        for parts in (1, 2, 3, 8):
+            out = np.zeros(len(keys), dtype=np.uint32)
+            p = ctypes.c_uint32(0)
+            for i, key in enumerate(keys.tolist()):
+                nat.check(L.pa_partition_of_key(k, key, parts, ctypes.byref(p)))
+                out[i] = p.value
+            assert np.all(np.diff(out.astype(np.int64)) >= 0)          # keys are sorted ascending: parts must be too
+            assert out.max() == parts - 1 and out.min() == 0
+            if k >= 11:
+                counts = np.bincount(out, minlength=parts)
+                assert counts.max() < 1.25 * counts.mean() + 50
