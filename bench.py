@@ -249,6 +249,26 @@ def gpu_arm(args):
     inf = ix.info()
     build_kernel_ms = inf.build_encode_ms + inf.build_sort_ms + inf.build_rle_ms + inf.build_table_ms
 
+    # ---- multi-GPU build (N > 1): hash-partitioned build with one all-to-all, replica gathered on every rank ----
+    build_part = None
+    if world > 1:
+        import multi_gpu
+        lengths = np.full(G, GL, dtype=np.int64)
+        g_lo, g_hi = multi_gpu.genome_shards(lengths, world)[rank]
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        dix = multi_gpu.build_partitioned(bases[g_lo * GL:g_hi * GL], goff, k, (g_lo, g_hi), device=local)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        rinf = dix.replica.info()
+        assert (rinf.n_keys, rinf.n_runs, rinf.n_occ) == (inf.n_keys, inf.n_runs, inf.n_occ), "partitioned build differs from the single-GPU build"
+        build_part = {"kmers_per_s": inf.n_occ / float(dt.item()), "seconds": float(dt.item()), "phases_rank0": dix.timings,
+                      "records_sent_rank0": dix.sent_records, "records_received_rank0": dix.received_records,
+                      "same_sizes_as_single_gpu_build": True}
+        dix.close()
+
     # ---- reads of this rank (weak scaling: every rank aligns its own `reads` reads) ----
     rbases, rquals, roff = device_reads(torch, dev, bases, G, GL, NR, RL, seed=2000 + rank)
     words = torch.empty(NR, dtype=torch.int64, device=dev)
@@ -438,6 +458,7 @@ def gpu_arm(args):
                       "rle_ms": inf.build_rle_ms, "table_ms": inf.build_table_ms, "index_bytes": int(inf.device_bytes),
                       "stash_count": int(inf.stash_count), "block_bits": int(inf.block_bits), "minimizer_len": int(inf.minimizer_len),
                       "roofline_frac_17B": (inf.n_occ * BUILD_BYTES_PER_KMER / (build_kernel_ms * 1e-3) / 1e9 / hbm_peak) if build_kernel_ms > 0 else None},
+            "build_partitioned": build_part,
             "result": {"unique": stats_host[0], "ambiguous": stats_host[1], "unmapped": stats_host[2], "dropped": stats_host[3]},
         }
         print(json.dumps(line))

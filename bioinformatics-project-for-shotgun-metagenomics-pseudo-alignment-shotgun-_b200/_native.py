@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "pa_extsim_stats", "pa_extsim_pairwise", "pa_index_drop_genomes", "pa_align_batch", "pa_align_batch_device",
     "pa_summary_reduce_device", "pa_summary_reduce", "pa_debug_sort_pairs", "pa_debug_table_lookup",
     "pa_records_encode_device", "pa_records_partition_device", "pa_partition_of_key", "pa_index_build_from_records_device",
-    "pa_index_csr_device", "pa_index_alloc_replica", "pa_index_finish_replica", "pa_index_build_tables",
+    "pa_index_csr_device", "pa_index_alloc_replica", "pa_index_finish_replica", "pa_index_build_tables", "pa_debug_pack_reads",
 ]
 
 
@@ -112,6 +112,7 @@ def lib() -> ctypes.CDLL:
         "pa_index_alloc_replica": (i32, [i32, u32, vp, u64, u64, u64, i32, vp]),
         "pa_index_finish_replica": (i32, [vp]),
         "pa_index_build_tables": (i32, [vp]),
+        "pa_debug_pack_reads": (i32, [vp, vp, u64, vp, u64, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

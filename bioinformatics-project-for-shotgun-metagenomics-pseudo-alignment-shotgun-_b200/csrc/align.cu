@@ -140,6 +140,72 @@ __device__ __noinline__ uint64_t lookup_chain_window(const TableView& t, uint64_
   return lookup_chain(t, a, raw);
 }
 
+
+// ---------------------------------------------------------------------------
+// Read input.  ASCII: `bases` indexed with the absolute read offsets.  PACKED (host path): the host already turned
+// every read into the two bit planes the ballots below would produce (hostpack.cpp); read i of the chunk, starting
+// at base offset o, owns the words planes[w0 .. w0 + 2 nw) with w0 = 2 ((o - base0) / 32 + i), nw = ceil(L / 32):
+// nw low-plane words, then nw high-plane words.  Packed reads contain only ACGT (the host falls back to ASCII for a
+// chunk that does not), so their "invalid" plane is zero.
+// ---------------------------------------------------------------------------
+struct ReadInput {
+  const uint8_t* bases;
+  const uint32_t* planes;
+  uint64_t base0;
+};
+
+template <bool PACKED> struct Prefetch { uint32_t v[PACKED ? 1 : AL_ROUNDS + 1]; };
+
+// lane j < 5 loads low-plane word cb + j, lane 5 + j loads high-plane word cb + j (zero beyond the read)
+__device__ __forceinline__ uint32_t load_plane_words(const uint32_t* __restrict__ planes, uint64_t w0, uint32_t nw, uint32_t cb,
+                                                     uint32_t lane) {
+  const bool high = lane >= AL_ROUNDS + 1;
+  const uint32_t c = cb + (high ? lane - (AL_ROUNDS + 1) : lane);
+  return (lane < 2 * (AL_ROUNDS + 1) && c < nw) ? __ldg(planes + w0 + (high ? nw : 0u) + c) : 0u;
+}
+
+template <bool PACKED>
+__device__ __forceinline__ void prefetch_read(const ReadInput& in, bool valid, uint64_t read, uint64_t beg, uint64_t L,
+                                              uint32_t lane, Prefetch<PACKED>& p) {
+  if constexpr (PACKED) {
+    p.v[0] = valid ? load_plane_words(in.planes, 2 * ((beg - in.base0) / 32 + read), (uint32_t)((L + 31) / 32), 0, lane) : 0u;
+  } else {
+#pragma unroll
+    for (int c = 0; c <= AL_ROUNDS; ++c) {
+      const uint64_t bi = (uint64_t)(32 * c) + lane;
+      p.v[c] = (valid && bi < L) ? in.bases[beg + bi] : 0;
+    }
+  }
+}
+
+// bit planes of the AL_ROUNDS + 1 chunks of 32 bases starting at base wbase of the read
+template <bool PACKED>
+__device__ __forceinline__ void encode_planes(const ReadInput& in, const Prefetch<PACKED>& p, uint64_t read, uint64_t beg,
+                                              uint64_t L, uint64_t wbase, uint32_t lane, uint32_t (&lo)[AL_ROUNDS + 1],
+                                              uint32_t (&hi)[AL_ROUNDS + 1], uint32_t (&inv)[AL_ROUNDS + 1]) {
+  if constexpr (PACKED) {
+    uint32_t w = p.v[0];
+    if (wbase != 0)
+      w = load_plane_words(in.planes, 2 * ((beg - in.base0) / 32 + read), (uint32_t)((L + 31) / 32), (uint32_t)(wbase / 32), lane);
+#pragma unroll
+    for (int c = 0; c <= AL_ROUNDS; ++c) {
+      lo[c] = __shfl_sync(0xffffffffu, w, c);
+      hi[c] = __shfl_sync(0xffffffffu, w, AL_ROUNDS + 1 + c);
+      inv[c] = 0;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c <= AL_ROUNDS; ++c) {
+      const uint64_t bi = wbase + 32 * c + lane;
+      const uint32_t ch = wbase == 0 ? p.v[c] : (bi < L ? in.bases[beg + bi] : 0);
+      const uint32_t code = base_code(ch);
+      lo[c] = __ballot_sync(0xffffffffu, code & 1u);
+      hi[c] = __ballot_sync(0xffffffffu, code >> 1);
+      inv[c] = __ballot_sync(0xffffffffu, !is_acgt(ch));
+    }
+  }
+}
+
 struct Emit {
   uint64_t* out_word;
   uint32_t* out_list;
@@ -234,9 +300,9 @@ __device__ void decide_and_emit(const WarpScratch& ws, uint32_t nT, const AlignP
   }
 }
 
-template <bool QUAL, int MIN_BLOCKS>
+template <bool QUAL, bool PACKED, int MIN_BLOCKS>
 __global__ void __launch_bounds__(AL_THREADS, MIN_BLOCKS)
-align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals,
+align_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
              const uint64_t* __restrict__ read_off, uint64_t n_reads, AlignParams prm, Emit em,
              unsigned long long* __restrict__ counters, unsigned char* __restrict__ scratch, uint64_t scratch_stride,
              uint32_t G, uint32_t kset_cap, int gtab_in_smem, int kset_in_smem,
@@ -274,37 +340,26 @@ align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __re
   // Software pipeline over this warp's reads: the offsets of read i+2 and the first 160 bases of read i+1 are
   // requested while read i is processed, so a read never starts by waiting on its own (sequential) input.
   uint64_t nx_beg = 0, nx_end = 0;      // offsets of the next read
-  uint32_t nx_ch[AL_ROUNDS + 1];        // its first AL_ROUNDS+1 chunks of bases (one byte per lane)
+  Prefetch<PACKED> nx_ch, cur_ch;       // its first AL_ROUNDS+1 chunks of bases (one byte per lane / one plane word per lane)
   uint64_t cur_beg = 0, cur_end = 0;
-  uint32_t cur_ch[AL_ROUNDS + 1];
   uint64_t cur_read = 0, nx_read = 0;
   {
     uint64_t r0 = warp_global, r1 = warp_global + n_warps;
     if (r0 < n_items) { cur_read = queue ? queue[r0] : r0; cur_beg = read_off[cur_read]; cur_end = read_off[cur_read + 1]; }
     if (r1 < n_items) { nx_read = queue ? queue[r1] : r1; nx_beg = read_off[nx_read]; nx_end = read_off[nx_read + 1]; }
-#pragma unroll
-    for (int c = 0; c <= AL_ROUNDS; ++c) {
-      uint64_t bi = (uint64_t)(32 * c) + lane;
-      cur_ch[c] = (r0 < n_items && bi < cur_end - cur_beg) ? bases[cur_beg + bi] : 0;
-    }
+    prefetch_read<PACKED>(in, r0 < n_items, cur_read, cur_beg, cur_end - cur_beg, lane, cur_ch);
   }
 
   for (uint64_t item = warp_global; item < n_items; item += n_warps) {
     const uint64_t read = cur_read;
     const uint64_t beg = cur_beg;
     const uint64_t L = cur_end - cur_beg;
-    const uint8_t* rb = bases + beg;
     const uint8_t* rq = QUAL ? quals + beg : nullptr;
     // issue the loads of the following reads (consumed at the bottom of the loop)
     uint64_t n2_beg = 0, n2_end = 0, n2_read = 0;
     {
       const uint64_t r1 = item + n_warps, r2 = item + 2 * n_warps;
-      const uint64_t nL = nx_end - nx_beg;
-#pragma unroll
-      for (int c = 0; c <= AL_ROUNDS; ++c) {
-        uint64_t bi = (uint64_t)(32 * c) + lane;
-        nx_ch[c] = (r1 < n_items && bi < nL) ? bases[nx_beg + bi] : 0;
-      }
+      prefetch_read<PACKED>(in, r1 < n_items, nx_read, nx_beg, nx_end - nx_beg, lane, nx_ch);
       if (r2 < n_items) { n2_read = queue ? queue[r2] : r2; n2_beg = read_off[n2_read]; n2_end = read_off[n2_read + 1]; }
     }
 
@@ -326,20 +381,15 @@ align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __re
     bool done = dropped;
 
     for (uint64_t wbase = 0; wbase < W; wbase += AL_SUPER) {
-      // ---- encode AL_ROUNDS+1 chunks of 32 bases into bit planes with ballots ----
+      // ---- bit planes of AL_ROUNDS+1 chunks of 32 bases (ballots over the ASCII bases, or the host-packed words) ----
       uint32_t lo[AL_ROUNDS + 1], hi[AL_ROUNDS + 1], inv[AL_ROUNDS + 1];
       uint32_t qex[AL_ROUNDS + 1];  // exclusive quality prefix at this lane's base, relative to wbase
-      uint32_t carry = 0;
+      encode_planes<PACKED>(in, cur_ch, read, beg, L, wbase, lane, lo, hi, inv);
+      if (QUAL && prm.has_mkq) {
+        uint32_t carry = 0;
 #pragma unroll
-      for (int c = 0; c <= AL_ROUNDS; ++c) {
-        uint64_t bi = wbase + 32 * c + lane;
-        uint32_t ch = wbase == 0 ? cur_ch[c] : (bi < L ? rb[bi] : 0);
-        bool ok = is_acgt(ch);
-        uint32_t code = base_code(ch);
-        lo[c] = __ballot_sync(0xffffffffu, code & 1u);
-        hi[c] = __ballot_sync(0xffffffffu, code >> 1);
-        inv[c] = __ballot_sync(0xffffffffu, !ok);
-        if (QUAL && prm.has_mkq) {
+        for (int c = 0; c <= AL_ROUNDS; ++c) {
+          const uint64_t bi = wbase + 32 * c + lane;
           uint32_t q = bi < L ? rq[bi] : 0, incl = q;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
@@ -517,8 +567,7 @@ align_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __re
     // rotate the pipeline registers
     cur_beg = nx_beg; cur_end = nx_end; cur_read = nx_read;
     nx_beg = n2_beg; nx_end = n2_end; nx_read = n2_read;
-#pragma unroll
-    for (int c = 0; c <= AL_ROUNDS; ++c) cur_ch[c] = nx_ch[c];
+    cur_ch = nx_ch;
   }
 
   c_drop = warp_sum(c_drop); c_nq = warp_sum(c_nq); c_nr = warp_sum(c_nr);
@@ -578,9 +627,9 @@ __device__ __forceinline__ bool set_contains(const TableView& t, uint64_t val, u
   }
 }
 
-template <bool QUAL>
+template <bool QUAL, bool PACKED>
 __global__ void __launch_bounds__(FA_THREADS, PA_FAST_MINB)
-align_fast_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t* __restrict__ quals,
+align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
                   const uint64_t* __restrict__ read_off, uint64_t n_reads, AlignParams prm, uint64_t* __restrict__ out_word,
                   unsigned long long* __restrict__ counters, uint32_t* __restrict__ queue,
                   unsigned long long* __restrict__ queue_count) {
@@ -593,16 +642,12 @@ align_fast_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t*
 
   // software pipeline: offsets of read i+2 and the first 160 bases of read i+1 are requested while read i is processed
   uint64_t nx_beg = 0, nx_end = 0, cur_beg = 0, cur_end = 0;
-  uint32_t nx_ch[AL_ROUNDS + 1], cur_ch[AL_ROUNDS + 1];
+  Prefetch<PACKED> nx_ch, cur_ch;
   {
     uint64_t r0 = warp_global, r1 = warp_global + n_warps;
     if (r0 < n_reads) { cur_beg = read_off[r0]; cur_end = read_off[r0 + 1]; }
     if (r1 < n_reads) { nx_beg = read_off[r1]; nx_end = read_off[r1 + 1]; }
-#pragma unroll
-    for (int c = 0; c <= AL_ROUNDS; ++c) {
-      uint64_t bi = (uint64_t)(32 * c) + lane;
-      cur_ch[c] = (r0 < n_reads && bi < cur_end - cur_beg) ? bases[cur_beg + bi] : 0;
-    }
+    prefetch_read<PACKED>(in, r0 < n_reads, r0, cur_beg, cur_end - cur_beg, lane, cur_ch);
   }
 
   for (uint64_t read = warp_global; read < n_reads; read += n_warps) {
@@ -611,12 +656,7 @@ align_fast_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t*
     uint64_t n2_beg = 0, n2_end = 0;
     {
       const uint64_t r1 = read + n_warps, r2 = read + 2 * n_warps;
-      const uint64_t nL = nx_end - nx_beg;
-#pragma unroll
-      for (int c = 0; c <= AL_ROUNDS; ++c) {
-        uint64_t bi = (uint64_t)(32 * c) + lane;
-        nx_ch[c] = (r1 < n_reads && bi < nL) ? bases[nx_beg + bi] : 0;
-      }
+      prefetch_read<PACKED>(in, r1 < n_reads, r1, nx_beg, nx_end - nx_beg, lane, nx_ch);
       if (r2 < n_reads) { n2_beg = read_off[r2]; n2_end = read_off[r2 + 1]; }
     }
 
@@ -634,18 +674,14 @@ align_fast_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t*
     if (W > AL_SUPER) {
       defer = true;   // longer than one super-round: the general kernel loops over super-rounds
     } else if (W > 0) {
-      // ---- encode the bases into bit planes with ballots ----
+      // ---- bit planes of the read (ballots over the ASCII bases, or the host-packed words) ----
       uint32_t lo[AL_ROUNDS + 1], hi[AL_ROUNDS + 1], inv[AL_ROUNDS + 1];
       uint32_t qex[AL_ROUNDS + 1];  // exclusive quality prefix at this lane's base
-      uint32_t carry = 0;
+      encode_planes<PACKED>(in, cur_ch, read, cur_beg, L, 0, lane, lo, hi, inv);
+      if (QUAL && prm.has_mkq) {
+        uint32_t carry = 0;
 #pragma unroll
-      for (int c = 0; c <= AL_ROUNDS; ++c) {
-        const uint32_t ch = cur_ch[c];
-        const uint32_t code = base_code(ch);
-        lo[c] = __ballot_sync(0xffffffffu, code & 1u);
-        hi[c] = __ballot_sync(0xffffffffu, code >> 1);
-        inv[c] = __ballot_sync(0xffffffffu, !is_acgt(ch));
-        if (QUAL && prm.has_mkq) {
+        for (int c = 0; c <= AL_ROUNDS; ++c) {
           const uint64_t bi = 32 * c + lane;
           uint32_t q = bi < L ? rq[bi] : 0, incl = q;
 #pragma unroll
@@ -750,8 +786,7 @@ align_fast_kernel(TableView t, const uint8_t* __restrict__ bases, const uint8_t*
     }
     cur_beg = nx_beg; cur_end = nx_end;
     nx_beg = n2_beg; nx_end = n2_end;
-#pragma unroll
-    for (int c = 0; c <= AL_ROUNDS; ++c) cur_ch[c] = nx_ch[c];
+    cur_ch = nx_ch;
   }
   c_drop = warp_sum(c_drop); c_nq = warp_sum(c_nq); c_nr = warp_sum(c_nr);
   if (lane == 0) {
@@ -824,15 +859,17 @@ summary_kernel(const uint64_t* __restrict__ words, const uint32_t* __restrict__ 
 int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_quals, const uint64_t* d_read_off,
                            uint64_t n_reads, uint64_t max_read_len, const AlignParams& prm_in, uint64_t* d_words,
                            uint32_t* d_list, uint64_t list_cap, unsigned long long* d_cursor /*[2]*/,
-                           unsigned long long* d_counters /*[3]*/, cudaStream_t s, int32_t* launches) {
+                           unsigned long long* d_counters /*[3]*/, cudaStream_t s, int32_t* launches,
+                           const uint32_t* d_planes, uint64_t planes_base0) {
   if (launches) *launches = 0;
   if (n_reads == 0) return ST_OK;
   constexpr uint64_t MAX_BATCH = 1ULL << 31;   // read indices travel through the queue as uint32
   if (n_reads > MAX_BATCH) {
+    if (d_planes) { set_error("align: packed input is limited to 2^31 reads per call"); return ST_UNSUPPORTED; }
     for (uint64_t lo = 0; lo < n_reads; lo += MAX_BATCH) {
       int32_t l = 0;
       PA_TRY(align_batch_device(ix, d_bases, d_quals, d_read_off + lo, std::min(MAX_BATCH, n_reads - lo), max_read_len, prm_in,
-                                d_words + lo, d_list, list_cap, d_cursor, d_counters, s, &l));
+                                d_words + lo, d_list, list_cap, d_cursor, d_counters, s, &l, nullptr, 0));
       if (launches) *launches += l;
     }
     return ST_OK;
@@ -845,6 +882,8 @@ int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_q
   PA_CUDA(cudaGetDevice(&dev));
   PA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   TableView tv = ix.view();  // k <= 0: the kernels see no windows (kmer.py:91-92) and only apply the read-quality drop
+  const bool packed = d_planes != nullptr;
+  const ReadInput in{d_bases, d_planes, planes_base0};
 
   // ---- fast kernel over all reads; what it cannot decide goes to the queue ----
   if (ix.align_queue.bytes < 16 + n_reads * 4) PA_TRY(ix.align_queue.alloc(16 + n_reads * 4 + n_reads / 2));
@@ -852,12 +891,13 @@ int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_q
   uint32_t* q_items = reinterpret_cast<uint32_t*>(ix.align_queue.as<unsigned char>() + 16);
   PA_CUDA(cudaMemsetAsync(q_count, 0, 8, s));
   {
-    auto fk = qual ? align_fast_kernel<true> : align_fast_kernel<false>;
+    auto fk = qual ? (packed ? align_fast_kernel<true, true> : align_fast_kernel<true, false>)
+                   : (packed ? align_fast_kernel<false, true> : align_fast_kernel<false, false>);
     int occ = 1;
     PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fk, FA_THREADS, 0));
     if (occ < 1) occ = 1;
     uint64_t grid = std::min<uint64_t>((uint64_t)sms * occ, (n_reads + FA_WARPS - 1) / FA_WARPS);
-    fk<<<(unsigned)std::max<uint64_t>(grid, 1), FA_THREADS, 0, s>>>(tv, d_bases, d_quals, d_read_off, n_reads, prm, d_words,
+    fk<<<(unsigned)std::max<uint64_t>(grid, 1), FA_THREADS, 0, s>>>(tv, in, d_quals, d_read_off, n_reads, prm, d_words,
                                                                      d_counters, q_items, q_count);
     PA_CUDA(cudaGetLastError());
     if (launches) ++*launches;
@@ -873,7 +913,8 @@ int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_q
   size_t per_warp_smem = (kset_in_smem ? (size_t)kset_cap * 12 : 0) + (gtab_in_smem ? (size_t)G * 20 : 0);
   per_warp_smem = (per_warp_smem + 15) & ~(size_t)15;
   const size_t dyn_smem = per_warp_smem * AL_WARPS;
-  auto kern = qual ? align_kernel<true, 2> : align_kernel<false, 2>;
+  auto kern = qual ? (packed ? align_kernel<true, true, 2> : align_kernel<true, false, 2>)
+                   : (packed ? align_kernel<false, true, 2> : align_kernel<false, false, 2>);
   PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(dyn_smem, 1024)));
   int occ = 1;
   PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, AL_THREADS, dyn_smem));
@@ -898,7 +939,7 @@ int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_q
     }
   }
   Emit em{d_words, d_list, list_cap, d_cursor};
-  kern<<<(unsigned)grid, AL_THREADS, dyn_smem, s>>>(tv, d_bases, d_quals, d_read_off, n_reads, prm, em, d_counters,
+  kern<<<(unsigned)grid, AL_THREADS, dyn_smem, s>>>(tv, in, d_quals, d_read_off, n_reads, prm, em, d_counters,
                                                     ix.align_scratch.as<unsigned char>(), stride, G, kset_cap,
                                                     gtab_in_smem, kset_in_smem, q_items, q_count);
   PA_CUDA(cudaGetLastError());

@@ -22,7 +22,10 @@ struct AlignParams {
 int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_quals, const uint64_t* d_read_off,
                            uint64_t n_reads, uint64_t max_read_len, const AlignParams& prm, uint64_t* d_words,
                            uint32_t* d_list, uint64_t list_cap, unsigned long long* d_cursor,
-                           unsigned long long* d_counters, cudaStream_t s, int32_t* launches);
+                           unsigned long long* d_counters, cudaStream_t s, int32_t* launches,
+                           const uint32_t* d_planes = nullptr, uint64_t planes_base0 = 0);
+// d_planes != nullptr: the reads arrive as host-packed bit planes (see ReadInput in align.cu / hostpack.h) and
+// d_bases is not read
 
 int32_t summary_reduce_device(const uint64_t* d_words, const uint32_t* d_list, uint64_t n_reads, uint64_t read_index_base,
                               uint32_t G, unsigned long long* d_stats, unsigned long long* d_unique,

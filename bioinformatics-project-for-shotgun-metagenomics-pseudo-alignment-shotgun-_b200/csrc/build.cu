@@ -12,6 +12,7 @@
 #include "sort.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <vector>
 
@@ -529,8 +530,23 @@ float elapsed_ms(cudaEvent_t a, cudaEvent_t b) {
 // ===========================================================================
 // host orchestration
 // ===========================================================================
+namespace {
+struct PhaseTrace {   // PA_TRACE=1: host wall-clock of the build phases on stderr
+  bool on = getenv("PA_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void mark(const char* what, cudaStream_t s) {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[pa trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+}  // namespace
+
 int32_t index_build_tables(Index& ix) {
   cudaStream_t s = ix.stream;
+  PhaseTrace tr;
   const uint64_t U = ix.n_keys;
   const int k = ix.k < 1 ? 1 : ix.k;   // k <= 0: no k-mers at all; the geometry below only has to be benign
   ix.mix = mix_params_for_k(ix.k);
@@ -606,6 +622,7 @@ int32_t index_build_tables(Index& ix) {
     if (lb >= lb_max) { set_error("lookup table: list references do not fit (k=%d)", k); return ST_UNSUPPORTED; }
     ++lb;
   }
+  tr.mark("tables: genome sets", s);
   ix.n_msectors = n_msec;
   PA_TRY(ix.mlist.alloc(std::max<uint64_t>(n_msec, 1) * 32));
   PA_CUDA(cudaMemsetAsync(ix.mlist.p, 0xFF, ix.mlist.bytes, s));
@@ -614,6 +631,7 @@ int32_t index_build_tables(Index& ix) {
                                                      ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(),
                                                      msec_off.as<uint64_t>(), ix.mlist.as<uint32_t>());
   set_ka.release(); set_kb.release(); set_tmp.release(); flag.release(); lrank.release();
+  tr.mark("tables: set fill + frees", s);
   DevBuf ovf_count, ovf_list;
   PA_TRY(ovf_count.alloc(4));
   uint32_t ovf_cap = (uint32_t)std::min<uint64_t>(U / 4 + 4096, 0xFFFFFFF0ull);
@@ -625,7 +643,9 @@ int32_t index_build_tables(Index& ix) {
     ix.val_bits = 64 - ix.tag_bits;
     const uint64_t n_blocks = 1ULL << lb;
     PA_TRY(ix.slots.alloc(n_blocks * 512));
+    tr.mark("tables: slots alloc", s);
     PA_CUDA(cudaMemsetAsync(ix.slots.p, 0xFF, n_blocks * 512, s));
+    tr.mark("tables: slots memset", s);
     PA_CUDA(cudaMemsetAsync(ovf_count.p, 0, 4, s));
     uint32_t n_ovf = 0;
     if (U) {
@@ -636,6 +656,7 @@ int32_t index_build_tables(Index& ix) {
       PA_CUDA(cudaMemcpyAsync(&n_ovf, ovf_count.p, 4, cudaMemcpyDeviceToHost, s));
       PA_CUDA(cudaStreamSynchronize(s));
     }
+    tr.mark("tables: insert", s);
     if (n_ovf > ovf_cap) {  // pathological: grow the table instead of the stash
       if (lb >= lb_max) { set_error("lookup table: overflow list exhausted"); return ST_UNSUPPORTED; }
       ++lb;

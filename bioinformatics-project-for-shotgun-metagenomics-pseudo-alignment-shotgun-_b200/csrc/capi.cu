@@ -2,6 +2,7 @@
 // Plain pointers and sizes only; no torch types, no C++ exceptions across the ABI.
 #include "../../include/pa_b200.h"
 #include "align.cuh"
+#include "hostpack.h"
 #include "index.cuh"
 #include "sort.cuh"
 
@@ -445,44 +446,84 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
   for (auto& sl : ix.slot) {
     if (!sl.stream) PA_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
     if (!sl.kernel_done) PA_CUDA(cudaEventCreateWithFlags(&sl.kernel_done, cudaEventDisableTiming));
+    if (!sl.h2d_done) PA_CUDA(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
   }
   PA_TRY(ensure(ix.host_list, std::max<uint64_t>(list_cap, 1) * 4));
   PA_TRY(ensure(ix.host_state, 64));
   PA_CUDA(cudaMemsetAsync(ix.host_state.p, 0, 40, ix.slot[0].stream));
   PA_CUDA(cudaEventRecord(ix.slot[1].kernel_done, ix.slot[0].stream));  // "previous kernel" of chunk 0 = the memset
-  uint64_t chunk = std::min<uint64_t>(std::max<uint64_t>(n_reads / 8, 1u << 16), 1u << 21);
+  uint64_t chunk = std::min<uint64_t>(std::max<uint64_t>(n_reads / 20, 1u << 16), 1u << 20);
   if (const char* e = getenv("PA_CHUNK_READS")) { uint64_t v = strtoull(e, nullptr, 10); if (v) chunk = v; }
-  uint64_t c = 0;
+  // PA_HOST_PACK: 0 = never pack, 1 = always pack, unset / 2 = the self-balancing mix below
+  const int pack_mode = getenv("PA_HOST_PACK") ? atoi(getenv("PA_HOST_PACK")) : 2;
+  const bool use_pack = pack_mode != 0;
+
+  uint64_t c = 0, n_packed = 0;
+  double t_wait = 0, t_pack = 0, t_enq = 0;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
   for (uint64_t lo = 0; lo < n_reads; lo += chunk, ++c) {
     const uint64_t hi = std::min(n_reads, lo + chunk), n = hi - lo;
     Index::HostSlot& sl = ix.slot[c & 1];
     Index::HostSlot& prev = ix.slot[(c & 1) ^ 1];
     const uint64_t b0 = read_off[lo], nb = read_off[hi] - b0;
     uint64_t max_len = 0;
-    for (uint64_t i = lo; i < hi; ++i) {
-      NEED(read_off[i + 1] >= read_off[i], "read_off is not monotonic");
-      max_len = std::max(max_len, read_off[i + 1] - read_off[i]);
+    auto tv0 = now();
+    NEED(scan_offsets(read_off, lo, hi, &max_len, host_pack_threads()), "read_off is not monotonic");
+    t_pack += ms_since(tv0);
+    // Which way does this chunk travel?  Packing to 2-bit planes (hostpack.h) costs host time (all cores) and saves
+    // 3/4 of the link time; raw ASCII costs no host time.  Self-balancing rule: when the slot's previous chunk
+    // (c - 2) is still in flight the device side is the bottleneck and the host would only wait -- so it packs
+    // instead; when the slot is already free the host is the bottleneck and the chunk goes out as ASCII at once.
+    // A chunk with a base outside ACGT always travels as ASCII.
+    auto tp = now();
+    bool packed = false;
+    const uint64_t n_words = planes_words(nb, n);
+    const bool slot_busy = cudaStreamQuery(sl.stream) == cudaErrorNotReady;
+    (void)cudaGetLastError();
+    if (use_pack && (pack_mode == 1 || slot_busy) && ix.k >= 1 && nb) {
+      PA_CUDA(cudaEventSynchronize(sl.h2d_done));   // the staging buffer's previous transfer has left the host
+      if (sl.h_planes_words < n_words) {
+        if (sl.h_planes) { cudaFreeHost(sl.h_planes); sl.h_planes = nullptr; sl.h_planes_words = 0; }
+        const uint64_t want = n_words + n_words / 8 + 1024;
+        cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&sl.h_planes), want * 4, cudaHostAllocDefault);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); sl.h_planes = nullptr; }
+        else sl.h_planes_words = want;
+      }
+      if (sl.h_planes) packed = pack_reads_planes(bases, read_off, lo, hi, sl.h_planes, host_pack_threads());
     }
+    t_pack += ms_since(tp); tp = now();
     // slot buffers are free once the slot's previous chunk (c - 2) has finished: its stream is in order
     PA_CUDA(cudaStreamSynchronize(sl.stream));
-    PA_TRY(ensure(sl.bases, nb + 64));
+    t_wait += ms_since(tp); tp = now();
     if (need_q) PA_TRY(ensure(sl.quals, nb + 64));
     PA_TRY(ensure(sl.off, (n + 1) * 8));
     PA_TRY(ensure(sl.words, n * 8));
-    if (nb) PA_CUDA(cudaMemcpyAsync(sl.bases.p, bases + b0, nb, cudaMemcpyHostToDevice, sl.stream));
+    if (packed) {
+      PA_TRY(ensure(sl.planes, n_words * 4));
+      PA_CUDA(cudaMemcpyAsync(sl.planes.p, sl.h_planes, n_words * 4, cudaMemcpyHostToDevice, sl.stream));
+      PA_CUDA(cudaEventRecord(sl.h2d_done, sl.stream));
+    } else {
+      PA_TRY(ensure(sl.bases, nb + 64));
+      if (nb) PA_CUDA(cudaMemcpyAsync(sl.bases.p, bases + b0, nb, cudaMemcpyHostToDevice, sl.stream));
+    }
     if (need_q && nb) PA_CUDA(cudaMemcpyAsync(sl.quals.p, quals + b0, nb, cudaMemcpyHostToDevice, sl.stream));
     PA_CUDA(cudaMemcpyAsync(sl.off.p, read_off + lo, (n + 1) * 8, cudaMemcpyHostToDevice, sl.stream));
     PA_CUDA(cudaStreamWaitEvent(sl.stream, prev.kernel_done, 0));
     // the kernel indexes bases with the absolute offsets: rebase the pointers instead of rewriting the offsets
-    PA_TRY(align_batch_device(ix, sl.bases.as<uint8_t>() - b0, need_q ? sl.quals.as<uint8_t>() - b0 : nullptr,
+    PA_TRY(align_batch_device(ix, packed ? nullptr : sl.bases.as<uint8_t>() - b0, need_q ? sl.quals.as<uint8_t>() - b0 : nullptr,
                               sl.off.as<uint64_t>(), n, max_len, prm, sl.words.as<uint64_t>(), ix.host_list.as<uint32_t>(),
                               list_cap, ix.host_state.as<unsigned long long>(), ix.host_state.as<unsigned long long>() + 2,
-                              sl.stream, nullptr));
+                              sl.stream, nullptr, packed ? sl.planes.as<uint32_t>() : nullptr, b0));
+    n_packed += packed;
+    t_enq += ms_since(tp);
     PA_CUDA(cudaEventRecord(sl.kernel_done, sl.stream));
     PA_CUDA(cudaMemcpyAsync(out_words + lo, sl.words.p, n * 8, cudaMemcpyDeviceToHost, sl.stream));
   }
+  auto tq = now();
   PA_CUDA(cudaStreamSynchronize(ix.slot[0].stream));
   PA_CUDA(cudaStreamSynchronize(ix.slot[1].stream));
+  const double t_drain = ms_since(tq);
   uint64_t h_state[5];
   PA_CUDA(cudaMemcpy(h_state, ix.host_state.p, 40, cudaMemcpyDeviceToHost));
   if (list_len) *list_len = h_state[0];
@@ -496,8 +537,8 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
   }
   counters[0] += h_state[2]; counters[1] += h_state[3]; counters[2] += h_state[4];
   if (trace)
-    fprintf(stderr, "[pa_align_batch] %llu reads in %llu chunks: %.3f ms\n", (unsigned long long)n_reads,
-            (unsigned long long)c, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    fprintf(stderr, "[pa_align_batch] %llu reads in %llu chunks (%llu packed, %d pack threads; host: wait %.2f pack %.2f enqueue %.2f drain %.2f ms): %.3f ms\n", (unsigned long long)n_reads,
+            (unsigned long long)c, (unsigned long long)n_packed, host_pack_threads(), t_wait, t_pack, t_enq, t_drain, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   return PA_OK;
 }
 
@@ -560,6 +601,14 @@ int32_t pa_debug_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t n, int32_t 
   PA_CUDA(cudaDeviceSynchronize());
   PA_CUDA(cudaMemcpy(keys, in_b ? kb.p : ka.p, n * 8, cudaMemcpyDeviceToHost));
   PA_CUDA(cudaMemcpy(vals, in_b ? vb.p : va.p, n * 4, cudaMemcpyDeviceToHost));
+  return PA_OK;
+}
+
+int32_t pa_debug_pack_reads(const uint8_t* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t* planes, uint64_t planes_cap,
+                            int32_t n_threads, int32_t* all_acgt) {
+  NEED(read_off && planes && all_acgt, "null argument");
+  NEED(planes_cap >= planes_words(read_off[n_reads] - read_off[0], n_reads), "planes buffer too small");
+  *all_acgt = pack_reads_planes(bases, read_off, 0, n_reads, planes, n_threads > 0 ? n_threads : host_pack_threads()) ? 1 : 0;
   return PA_OK;
 }
 

@@ -1,0 +1,208 @@
+// hostpack.cpp -- see hostpack.h.  Plain C++ (no CUDA): AVX2 path selected at run time, scalar path otherwise.
+#include "hostpack.h"
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+namespace pa {
+
+namespace {
+
+// ---- a small persistent pool: parallel_for over [0, n_tasks) ----
+class Pool {
+ public:
+  explicit Pool(int n) : n_(n) {
+    for (int i = 0; i < n_; ++i) workers_.emplace_back([this] { run(); });
+  }
+  ~Pool() {
+    { std::lock_guard<std::mutex> g(m_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  int size() const { return n_; }
+  void parallel_for(int n_tasks, const std::function<void(int)>& fn) {
+    if (n_tasks <= 0) return;
+    std::unique_lock<std::mutex> g(m_);
+    fn_ = &fn; next_ = 0; total_ = n_tasks; pending_ = n_tasks; ++epoch_;
+    cv_.notify_all();
+    done_.wait(g, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void run() {
+    uint64_t seen = 0;
+    std::unique_lock<std::mutex> g(m_);
+    for (;;) {
+      cv_.wait(g, [&] { return stop_ || (epoch_ != seen && next_ < total_); });
+      if (stop_) return;
+      while (next_ < total_) {
+        const int task = next_++;
+        const std::function<void(int)>* fn = fn_;
+        g.unlock();
+        (*fn)(task);
+        g.lock();
+        if (--pending_ == 0) done_.notify_all();
+      }
+      seen = epoch_;
+    }
+  }
+  int n_;
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int next_ = 0, total_ = 0, pending_ = 0;
+  uint64_t epoch_ = 0;
+  bool stop_ = false;
+};
+
+Pool& pool() {
+  static Pool p(host_pack_threads());
+  return p;
+}
+
+inline bool acgt(uint8_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
+// one block of up to 32 bases -> low word, high word; returns validity
+inline bool block_scalar(const uint8_t* p, unsigned n, uint32_t* lo, uint32_t* hi) {
+  uint32_t l = 0, h = 0;
+  bool ok = true;
+  for (unsigned i = 0; i < n; ++i) {
+    const uint8_t c = p[i];
+    ok &= acgt(c);
+    l |= (uint32_t)((c >> 1) & 1u) << i;
+    h |= (uint32_t)((c >> 2) & 1u) << i;
+  }
+  *lo = l; *hi = h;
+  return ok;
+}
+
+bool pack_range_scalar(const uint8_t* bases, const uint64_t* read_off, uint64_t lo, uint64_t a, uint64_t b, uint32_t* planes) {
+  bool ok = true;
+  const uint64_t base0 = read_off[lo];
+  for (uint64_t i = a; i < b; ++i) {
+    const uint64_t o = read_off[i], L = read_off[i + 1] - o, nw = (L + 31) / 32;
+    uint32_t* w = planes + 2 * ((o - base0) / 32 + (i - lo));
+    for (uint64_t c = 0; c < nw; ++c)
+      ok &= block_scalar(bases + o + 32 * c, (unsigned)std::min<uint64_t>(32, L - 32 * c), w + c, w + nw + c);
+  }
+  return ok;
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) bool pack_range_avx2(const uint8_t* bases, const uint64_t* read_off, uint64_t lo, uint64_t a,
+                                                     uint64_t b, uint32_t* planes, uint64_t safe_end) {
+  // safe_end: one past the last base of the chunk -- full 32-byte loads must end at or before it
+  const uint64_t base0 = read_off[lo];
+  const __m256i cA = _mm256_set1_epi8('A'), cC = _mm256_set1_epi8('C'), cG = _mm256_set1_epi8('G'), cT = _mm256_set1_epi8('T');
+  uint32_t bad = 0;
+  for (uint64_t i = a; i < b; ++i) {
+    const uint64_t o = read_off[i], L = read_off[i + 1] - o, nw = (L + 31) / 32;
+    uint32_t* w = planes + 2 * ((o - base0) / 32 + (i - lo));
+    const uint8_t* p = bases + o;
+    uint64_t c = 0;
+    for (; 32 * (c + 1) <= L; ++c) {
+      const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + 32 * c));
+      const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(v, cA), _mm256_cmpeq_epi8(v, cC)),
+                                         _mm256_or_si256(_mm256_cmpeq_epi8(v, cG), _mm256_cmpeq_epi8(v, cT)));
+      bad |= ~(uint32_t)_mm256_movemask_epi8(ok);
+      w[c] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6));        // ASCII bit 1 -> bit 7 of its byte
+      w[nw + c] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5));   // ASCII bit 2 -> bit 7
+    }
+    if (c < nw) {
+      const unsigned rem = (unsigned)(L - 32 * c);   // 1 .. 31 bases in the last block
+      if (o + 32 * c + 32 <= safe_end) {
+        // the 32-byte load runs into the next read (same buffer): mask what is not ours
+        const uint32_t keep = (1u << rem) - 1;
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + 32 * c));
+        const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(v, cA), _mm256_cmpeq_epi8(v, cC)),
+                                           _mm256_or_si256(_mm256_cmpeq_epi8(v, cG), _mm256_cmpeq_epi8(v, cT)));
+        bad |= ~(uint32_t)_mm256_movemask_epi8(ok) & keep;
+        w[c] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6)) & keep;
+        w[nw + c] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5)) & keep;
+      } else {
+        uint32_t l, h;
+        if (!block_scalar(p + 32 * c, rem, &l, &h)) bad = 1;
+        w[c] = l; w[nw + c] = h;
+      }
+    }
+  }
+  return bad == 0;
+}
+#endif
+
+}  // namespace
+
+int host_pack_threads() {
+  static int n = [] {
+    if (const char* e = getenv("PA_PACK_THREADS")) { int v = atoi(e); if (v >= 1) return std::min(v, 256); }
+    unsigned hc = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(hc ? hc : 8u, 64u));
+  }();
+  return n;
+}
+
+bool scan_offsets(const uint64_t* read_off, uint64_t lo, uint64_t hi, uint64_t* max_len, int n_threads) {
+  *max_len = 0;
+  if (hi <= lo) return true;
+  const uint64_t n = hi - lo;
+  int tasks = (int)std::min<uint64_t>((uint64_t)std::max(1, n_threads), (n + 65535) / 65536);
+  if (tasks < 1) tasks = 1;
+  std::vector<uint64_t> mx(tasks, 0);
+  std::atomic<bool> ok{true};
+  auto work = [&](int t) {
+    const uint64_t a = lo + n * (uint64_t)t / tasks, b = lo + n * (uint64_t)(t + 1) / tasks;
+    uint64_t m = 0;
+    bool good = true;
+    for (uint64_t i = a; i < b; ++i) {
+      good &= read_off[i + 1] >= read_off[i];
+      m = std::max(m, read_off[i + 1] - read_off[i]);
+    }
+    mx[t] = m;
+    if (!good) ok.store(false, std::memory_order_relaxed);
+  };
+  if (tasks == 1) work(0); else pool().parallel_for(tasks, work);
+  for (uint64_t m : mx) *max_len = std::max(*max_len, m);
+  return ok.load();
+}
+
+bool pack_reads_planes(const uint8_t* bases, const uint64_t* read_off, uint64_t lo, uint64_t hi, uint32_t* planes,
+                       int n_threads) {
+  if (hi <= lo) return true;
+#if defined(__x86_64__)
+  static const bool have_avx2 = __builtin_cpu_supports("avx2");
+#else
+  static const bool have_avx2 = false;
+#endif
+  const uint64_t n = hi - lo;
+  int tasks = (int)std::min<uint64_t>((uint64_t)std::max(1, n_threads) * 4, (n + 4095) / 4096);
+  if (tasks < 1) tasks = 1;
+  std::atomic<bool> ok{true};
+  auto work = [&](int t) {
+    const uint64_t a = lo + n * (uint64_t)t / tasks, b = lo + n * (uint64_t)(t + 1) / tasks;
+    bool good;
+#if defined(__x86_64__)
+    good = have_avx2 ? pack_range_avx2(bases, read_off, lo, a, b, planes, read_off[hi]) : pack_range_scalar(bases, read_off, lo, a, b, planes);
+#else
+    good = pack_range_scalar(bases, read_off, lo, a, b, planes);
+#endif
+    if (!good) ok.store(false, std::memory_order_relaxed);
+  };
+  if (tasks == 1 || n_threads <= 1) { for (int t = 0; t < tasks; ++t) work(t); }
+  else pool().parallel_for(tasks, work);
+  return ok.load();
+}
+
+}  // namespace pa

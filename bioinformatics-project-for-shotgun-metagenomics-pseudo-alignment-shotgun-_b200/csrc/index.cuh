@@ -63,9 +63,11 @@ struct Index {
   // host-buffer alignment path (pa_align_batch): two chunk slots so that the H2D copy of chunk i+1 overlaps the
   // kernel of chunk i; buffers grow on demand and are kept for the next call
   struct HostSlot {
-    DevBuf bases, quals, off, words;
+    DevBuf bases, quals, off, words, planes;
+    uint32_t* h_planes = nullptr;      // pinned staging of the host-packed bit planes (hostpack.h)
+    uint64_t h_planes_words = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t kernel_done = nullptr;
+    cudaEvent_t kernel_done = nullptr, h2d_done = nullptr;
   } slot[2];
   DevBuf host_list, host_state;
   // timing of the last build (ms, CUDA events on `stream`)
@@ -96,7 +98,7 @@ struct Index {
            slots.bytes + stash.bytes + mlist.bytes + align_scratch.bytes + align_queue.bytes;
   }
   ~Index() {
-    for (auto& sl : slot) { if (sl.stream) cudaStreamDestroy(sl.stream); if (sl.kernel_done) cudaEventDestroy(sl.kernel_done); }
+    for (auto& sl : slot) { if (sl.stream) cudaStreamDestroy(sl.stream); if (sl.kernel_done) cudaEventDestroy(sl.kernel_done); if (sl.h2d_done) cudaEventDestroy(sl.h2d_done); if (sl.h_planes) cudaFreeHost(sl.h_planes); }
     if (stream) cudaStreamDestroy(stream);
   }
 };

@@ -186,6 +186,11 @@ int32_t pa_summary_reduce(pa_index* idx, const uint64_t* words, const uint32_t* 
 /* ---- diagnostics used by the tests ----------------------------------------------------------------- */
 /* stable LSD radix sort of (key, value) pairs on key bits [0, end_bit), host in / host out (K2) */
 int32_t pa_debug_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t n, int32_t end_bit, int32_t device);
+/* the host-side 2-bit packing of pa_align_batch (pure host code): planes needs 2 * (n_bases / 32 + n_reads + 1) words;
+ * read i owns the words from 2 * ((read_off[i] - read_off[0]) / 32 + i): ceil(L / 32) low-plane words, then as many
+ * high-plane words.  *all_acgt = 0 when a base outside ACGT was met. */
+int32_t pa_debug_pack_reads(const uint8_t* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t* planes, uint64_t planes_cap,
+                            int32_t n_threads, int32_t* all_acgt);
 /* direct table lookups (K4's lookup step): n_genomes[i] = number of genomes of k-mer i (0 = miss),
  * first_genome[i] = its smallest genome index */
 int32_t pa_debug_table_lookup(pa_index* idx, const uint8_t* kmers_ascii, uint64_t n, uint32_t* n_genomes,

@@ -279,3 +279,38 @@ def test_partition_of_key_is_monotonic_and_balanced():
             if k >= 11:
                 counts = np.bincount(out, minlength=parts)
                 assert counts.max() < 1.25 * counts.mean() + 50
+
+
+def test_host_packing_matches_a_numpy_restatement():
+    """hostpack.cpp (AVX2 or scalar, threaded) against the plane definition: bit i of word c = ASCII bit 1 / bit 2 of base 32c + i."""
+    import ctypes
+    import _native as nat
+    L = nat.lib()
+    rng = np.random.default_rng(11)
+    for trial in range(6):
+        n = int(rng.integers(1, 4000))
+        lens = rng.integers(0, 330, size=n) if trial % 2 else np.full(n, 150)
+        off = np.concatenate([[7], 7 + np.cumsum(lens)]).astype(np.uint64)      # offsets need not start at 0
+        total = int(off[-1])
+        bases = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=total)].copy()
+        bad = trial == 5
+        if bad:
+            bases[int(off[n // 2])] = ord("N")
+        cap = 2 * ((total - 7) // 32 + n + 1)
+        for threads in (1, 4):
+            planes = np.full(cap, 0xDEADBEEF, dtype=np.uint32)
+            ok = ctypes.c_int32(-1)
+            nat.check(L.pa_debug_pack_reads(nat._p(bases), nat._p(off), n, nat._p(planes), cap, threads, ctypes.byref(ok)))
+            assert ok.value == (0 if bad else 1)
+            if bad:
+                continue
+            for i in rng.choice(n, size=min(n, 200), replace=False):
+                o, ln = int(off[i]), int(lens[i])
+                nw = (ln + 31) // 32
+                w0 = 2 * ((o - 7) // 32 + int(i))
+                seq = bases[o:o + ln]
+                for c in range(nw):
+                    blk = seq[32 * c:32 * c + 32].astype(np.uint32)
+                    lo = int(sum(((int(b) >> 1) & 1) << j for j, b in enumerate(blk)))
+                    hi = int(sum(((int(b) >> 2) & 1) << j for j, b in enumerate(blk)))
+                    assert int(planes[w0 + c]) == lo and int(planes[w0 + nw + c]) == hi
