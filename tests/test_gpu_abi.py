@@ -141,6 +141,27 @@ def test_k31_moderate():
                     "params": pr, "seed": 1})
 
 
+@pytest.mark.parametrize("dense", ["2", "3", "5"])
+def test_overloaded_table_walks_chains_and_stash(dense, monkeypatch):
+    """PA_TABLE_DENSE doubles the load factor per step: buckets overflow into the next blocks (CONT) and into the stash,
+    many strain variants share minimizer and offset -- results must not change."""
+    monkeypatch.setenv("PA_TABLE_DENSE", dense)
+    genomes = synth.make_genomes(12, 30_000, seed=15, cluster_size=6, shared_frac=0.6, sub_rate=0.03, n_every=9000, n_run=11)
+    b, q, off = synth.make_reads(genomes, 3000, 150, seed=16, sub_rate=0.02, random_frac=0.05)
+    case = {"k": 31, "genomes": synth.genomes_as_pairs(genomes), "reads": synth.reads_as_triples(b, q, off),
+            "params": dict(m=1, p=1, mrq=None, mkq=None, mg=None), "seed": 2}
+    data, goff = nat.pack_strings([g[1] for g in case["genomes"]])
+    ix = nat.NativeIndex.build(data, goff, 31)
+    inf = ix.info()
+    ix.close()
+    if dense == "5":
+        assert inf.stash_count > 0, "the test is meant to reach the stash"
+    check_case(case)
+    check_case(dict(case, params=dict(m=2, p=0, mrq=None, mkq=60, mg=4)))
+    for k in (7, 13, 20):   # w = 1 (k <= 16) and w = 5: short minimizer windows
+        check_case(dict(case, k=k))
+
+
 def test_long_reads_take_the_multi_round_path():
     genomes = synth.make_genomes(5, 6000, seed=9, cluster_size=5, shared_frac=0.5, n_every=2500, n_run=5)
     b, q, off = synth.make_reads(genomes, 300, 700, seed=10, sub_rate=0.03, random_frac=0.1)
