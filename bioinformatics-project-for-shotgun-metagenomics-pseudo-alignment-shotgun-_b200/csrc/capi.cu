@@ -24,6 +24,42 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+static thread_local cudaStream_t tl_alloc_stream = nullptr;
+static thread_local int tl_alloc_depth = 0;
+cudaStream_t current_alloc_stream() { return tl_alloc_stream; }
+
+AllocScope::AllocScope(cudaStream_t s) : prev(tl_alloc_stream), outermost(tl_alloc_depth == 0) {
+  // opt-in (PA_POOL=1): measured on the B200 box the pool re-grows on every build and is slower than the driver's own
+  // reuse of freed cudaMalloc blocks (config B: 375-600 ms per build with the pool, 119-480 ms without)
+  static const bool enabled = getenv("PA_POOL") && *getenv("PA_POOL") == '1';
+  if (enabled && s) {
+    if (outermost) {   // keep freed blocks inside the pool while the build runs
+      int dev = 0; cudaMemPool_t pool = nullptr;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      (void)cudaGetLastError();
+    }
+    tl_alloc_stream = s;
+  }
+  ++tl_alloc_depth;
+}
+AllocScope::~AllocScope() {
+  --tl_alloc_depth;
+  if (outermost && tl_alloc_stream) {   // give the scratch back to the device
+    cudaStreamSynchronize(tl_alloc_stream);
+    int dev = 0; cudaMemPool_t pool = nullptr;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = 0;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      cudaMemPoolTrimTo(pool, 0);
+    }
+    (void)cudaGetLastError();
+  }
+  tl_alloc_stream = prev;
+}
+
 namespace {
 
 __global__ void debug_lookup_kernel(TableView t, MixParams mix, const uint64_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ n_genomes,
@@ -127,7 +163,8 @@ int32_t pa_index_build_device(const uint8_t* d_bases, const uint64_t* genome_off
   PA_TRY(new_index(k, n_genomes, genome_off, device, &ix));
   if (ix->total_bases && !d_bases) { delete ix; set_error("bases is null"); return PA_ERR_INVALID_ARG; }
   if ((reinterpret_cast<uintptr_t>(d_bases) & 15) != 0) { delete ix; set_error("device bases must be 16-byte aligned"); return PA_ERR_INVALID_ARG; }
-  int32_t st = index_build_from_device_bases(*ix, d_bases + (n_genomes ? genome_off[0] : 0));
+  int32_t st;
+  { AllocScope pool(ix->stream); st = index_build_from_device_bases(*ix, d_bases + (n_genomes ? genome_off[0] : 0)); }
   if (st != ST_OK) { delete ix; return st; }
   *out = reinterpret_cast<pa_index*>(ix);
   return PA_OK;
@@ -140,6 +177,7 @@ int32_t pa_index_build(const uint8_t* bases, const uint64_t* genome_off, uint32_
   if (ix->total_bases && !bases) { delete ix; set_error("bases is null"); return PA_ERR_INVALID_ARG; }
   int32_t st = ST_OK;
   {
+    AllocScope pool(ix->stream);
     DevBuf d_bases;
     st = d_bases.alloc(ix->total_bases + 64);
     if (st == ST_OK && ix->total_bases) {
@@ -154,44 +192,46 @@ int32_t pa_index_build(const uint8_t* bases, const uint64_t* genome_off, uint32_
   return PA_OK;
 }
 
+static int32_t import_fill(Index* ix, uint64_t n_keys, uint64_t n_runs, uint64_t n_occ, const uint64_t* keys,
+                           const uint64_t* run_off, const uint32_t* run_genome, const uint64_t* pos_off, const uint32_t* pos,
+                           const uint64_t* first_occ) {
+  cudaStream_t s = ix->stream;
+  PA_TRY(ix->ukeys.alloc((n_keys + 1) * 8)); PA_TRY(ix->run_off.alloc((n_keys + 1) * 8));
+  PA_TRY(ix->run_genome.alloc((n_runs + 1) * 4)); PA_TRY(ix->pos_off.alloc((n_runs + 1) * 8));
+  PA_TRY(ix->pos.alloc((n_occ + 1) * 4));
+  const uint64_t zero = 0;
+  if (n_keys) {
+    PA_CUDA(cudaMemcpyAsync(ix->ukeys.p, keys, n_keys * 8, cudaMemcpyHostToDevice, s));
+    PA_CUDA(cudaMemcpyAsync(ix->run_off.p, run_off, (n_keys + 1) * 8, cudaMemcpyHostToDevice, s));
+    PA_CUDA(cudaMemcpyAsync(ix->run_genome.p, run_genome, n_runs * 4, cudaMemcpyHostToDevice, s));
+    PA_CUDA(cudaMemcpyAsync(ix->pos_off.p, pos_off, (n_runs + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (n_occ) PA_CUDA(cudaMemcpyAsync(ix->pos.p, pos, n_occ * 4, cudaMemcpyHostToDevice, s));
+  } else {
+    PA_CUDA(cudaMemcpyAsync(ix->run_off.p, &zero, 8, cudaMemcpyHostToDevice, s));
+    PA_CUDA(cudaMemcpyAsync(ix->pos_off.p, &zero, 8, cudaMemcpyHostToDevice, s));
+  }
+  PA_CUDA(cudaStreamSynchronize(s));
+  ix->n_keys = n_keys; ix->n_runs = n_runs; ix->n_occ = n_occ;
+  if (first_occ && n_keys) {
+    PA_TRY(ix->first_occ.alloc((n_keys + 1) * 8));
+    PA_CUDA(cudaMemcpyAsync(ix->first_occ.p, first_occ, n_keys * 8, cudaMemcpyHostToDevice, s));
+    PA_CUDA(cudaStreamSynchronize(s));
+    ix->has_first_occ = true;
+  }
+  return index_build_tables(*ix);
+}
+
 int32_t pa_index_import(int32_t k, uint32_t n_genomes, const uint64_t* genome_off, uint64_t n_keys, uint64_t n_runs,
                         uint64_t n_occ, const uint64_t* keys, const uint64_t* run_off, const uint32_t* run_genome,
                         const uint64_t* pos_off, const uint32_t* pos, const uint64_t* first_occ, int32_t device,
                         pa_index** out) {
   Index* ix = nullptr;
   PA_TRY(new_index(k, n_genomes, genome_off, device, &ix));
-  auto fail = [&](int32_t st) { delete ix; return st; };
-  if (n_keys && (!keys || !run_off || !run_genome || !pos_off || !pos)) { set_error("null CSR array"); return fail(PA_ERR_INVALID_ARG); }
-  if (n_keys >= 0xFFFFFFFFull) { set_error("too many distinct k-mers"); return fail(PA_ERR_UNSUPPORTED); }
+  if (n_keys && (!keys || !run_off || !run_genome || !pos_off || !pos)) { delete ix; set_error("null CSR array"); return PA_ERR_INVALID_ARG; }
+  if (n_keys >= 0xFFFFFFFFull) { delete ix; set_error("too many distinct k-mers"); return PA_ERR_UNSUPPORTED; }
   int32_t st;
-  cudaStream_t s = ix->stream;
-  if ((st = ix->ukeys.alloc((n_keys + 1) * 8)) || (st = ix->run_off.alloc((n_keys + 1) * 8)) ||
-      (st = ix->run_genome.alloc((n_runs + 1) * 4)) || (st = ix->pos_off.alloc((n_runs + 1) * 8)) ||
-      (st = ix->pos.alloc((n_occ + 1) * 4)))
-    return fail(st);
-  cudaError_t e = cudaSuccess;
-  uint64_t zero = 0;
-  if (n_keys) {
-    e = cudaMemcpyAsync(ix->ukeys.p, keys, n_keys * 8, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ix->run_off.p, run_off, (n_keys + 1) * 8, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ix->run_genome.p, run_genome, n_runs * 4, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ix->pos_off.p, pos_off, (n_runs + 1) * 8, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess && n_occ) e = cudaMemcpyAsync(ix->pos.p, pos, n_occ * 4, cudaMemcpyHostToDevice, s);
-  } else {
-    e = cudaMemcpyAsync(ix->run_off.p, &zero, 8, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ix->pos_off.p, &zero, 8, cudaMemcpyHostToDevice, s);
-  }
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  if (e != cudaSuccess) { set_error("CSR upload failed: %s", cudaGetErrorString(e)); return fail(PA_ERR_CUDA); }
-  ix->n_keys = n_keys; ix->n_runs = n_runs; ix->n_occ = n_occ;
-  if (first_occ && n_keys) {
-    if ((st = ix->first_occ.alloc((n_keys + 1) * 8))) return fail(st);
-    e = cudaMemcpyAsync(ix->first_occ.p, first_occ, n_keys * 8, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) { set_error("first_occ upload failed: %s", cudaGetErrorString(e)); return fail(PA_ERR_CUDA); }
-    ix->has_first_occ = true;
-  }
-  if ((st = index_build_tables(*ix)) != ST_OK) return fail(st);
+  { AllocScope pool(ix->stream); st = import_fill(ix, n_keys, n_runs, n_occ, keys, run_off, run_genome, pos_off, pos, first_occ); }
+  if (st != ST_OK) { delete ix; return st; }
   *out = reinterpret_cast<pa_index*>(ix);
   return PA_OK;
 }
@@ -231,6 +271,7 @@ int32_t pa_index_export(pa_index* idx, uint64_t* keys, uint64_t* run_off, uint32
   if (pos_off) PA_CUDA(cudaMemcpyAsync(pos_off, ix.pos_off.p, (ix.n_runs + 1) * 8, cudaMemcpyDeviceToHost, s));
   if (pos && ix.n_occ) PA_CUDA(cudaMemcpyAsync(pos, ix.pos.p, ix.n_occ * 4, cudaMemcpyDeviceToHost, s));
   PA_CUDA(cudaStreamSynchronize(s));
+  AllocScope pool(ix.stream);
   if (order) PA_TRY(index_export_order(ix, order));
   if (first_occ && ix.n_keys) {
     PA_TRY(index_ensure_first_occ(ix));
@@ -294,6 +335,7 @@ int32_t pa_index_drop_genomes(pa_index* idx, const uint8_t* keep) {
   NEED(IDX(idx)->n_genomes == 0 || keep, "null keep mask");
   NEED(!IDX(idx)->align_only, "a replica index holds no positions (drop the genomes from the partitions and re-gather)");
   PA_CUDA(cudaSetDevice(IDX(idx)->device));
+  AllocScope pool(IDX(idx)->stream);
   return index_drop_genomes(*IDX(idx), keep);
 }
 
@@ -354,7 +396,8 @@ int32_t pa_index_build_from_records_device(uint64_t* d_keys, uint32_t* d_vals, u
   PA_TRY(new_index(k, n_genomes, genome_off, device, &ix));
   if (n && (!d_keys || !d_vals)) { delete ix; set_error("null device buffer"); return PA_ERR_INVALID_ARG; }
   if (ix->total_bases >= 0xFFFFFFFFull) { delete ix; set_error("index build: too many bases for 32-bit positions"); return PA_ERR_UNSUPPORTED; }
-  int32_t st = index_build_from_records(*ix, d_keys, d_vals, n, build_tables != 0);
+  int32_t st;
+  { AllocScope pool(ix->stream); st = index_build_from_records(*ix, d_keys, d_vals, n, build_tables != 0); }
   if (st != ST_OK) { delete ix; return st; }
   *out = reinterpret_cast<pa_index*>(ix);
   return PA_OK;
@@ -392,6 +435,7 @@ int32_t pa_index_finish_replica(pa_index* idx) {
   const uint64_t tail = ix.n_runs;
   PA_CUDA(cudaMemcpyAsync(ix.run_off.as<uint64_t>() + ix.n_keys, &tail, 8, cudaMemcpyHostToDevice, ix.stream));
   PA_CUDA(cudaStreamSynchronize(ix.stream));
+  AllocScope pool(ix.stream);
   return index_build_tables(ix);
 }
 
@@ -399,6 +443,7 @@ int32_t pa_index_finish_replica(pa_index* idx) {
 int32_t pa_index_build_tables(pa_index* idx) {
   NEED(idx, "null index");
   PA_CUDA(cudaSetDevice(IDX(idx)->device));
+  AllocScope pool(IDX(idx)->stream);
   return index_build_tables(*IDX(idx));
 }
 

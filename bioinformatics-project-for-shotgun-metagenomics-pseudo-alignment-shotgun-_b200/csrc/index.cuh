@@ -5,24 +5,43 @@
 
 namespace pa {
 
+// Optional stream-ordered allocation for the build paths (PA_POOL=1).  A build allocates and frees a dozen multi-GB
+// buffers; inside an AllocScope the DevBufs then come from the device's default memory pool, ordered on the scope's
+// stream (the one every kernel of the build runs on), and the scope trims the pool back when the outermost scope
+// ends.  Off by default -- it measured slower than cudaMalloc / cudaFree on the B200 box (see capi.cu).
+struct AllocScope {
+  explicit AllocScope(cudaStream_t s);
+  ~AllocScope();
+  AllocScope(const AllocScope&) = delete;
+  AllocScope& operator=(const AllocScope&) = delete;
+  cudaStream_t prev;
+  bool outermost;
+};
+cudaStream_t current_alloc_stream();   // nullptr outside a scope and unless PA_POOL=1 (off by default: see capi.cu)
+
 // Owns a device allocation; frees on destruction.
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  cudaStream_t st = nullptr;   // non-null: allocated from the pool, ordered on this stream
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
-  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  void release() {
+    if (p) { if (st) cudaFreeAsync(p, st); else cudaFree(p); }
+    p = nullptr; bytes = 0; st = nullptr;
+  }
   int32_t alloc(size_t n) {
     release();
     if (n == 0) n = 16;
-    cudaError_t e = cudaMalloc(&p, n);
-    if (e != cudaSuccess) { p = nullptr; (void)cudaGetLastError(); set_error("cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e)); return ST_NOMEM; }
-    bytes = n;
+    cudaStream_t s = current_alloc_stream();
+    cudaError_t e = s ? cudaMallocAsync(&p, n, s) : cudaMalloc(&p, n);
+    if (e != cudaSuccess) { p = nullptr; (void)cudaGetLastError(); set_error("device allocation of %zu bytes failed: %s", n, cudaGetErrorString(e)); return ST_NOMEM; }
+    bytes = n; st = s;
     return ST_OK;
   }
-  void swap(DevBuf& o) { std::swap(p, o.p); std::swap(bytes, o.bytes); }
+  void swap(DevBuf& o) { std::swap(p, o.p); std::swap(bytes, o.bytes); std::swap(st, o.st); }
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -98,6 +117,11 @@ struct Index {
            slots.bytes + stash.bytes + mlist.bytes + align_scratch.bytes + align_queue.bytes;
   }
   ~Index() {
+    // pool allocations are freed in stream order: release them while the stream still exists
+    for (DevBuf* b : {&ukeys, &run_off, &run_genome, &pos_off, &pos, &genome_off, &first_occ, &slots, &stash, &mlist,
+                      &align_scratch, &align_queue, &host_list, &host_state})
+      b->release();
+    if (stream) cudaStreamSynchronize(stream);
     for (auto& sl : slot) { if (sl.stream) cudaStreamDestroy(sl.stream); if (sl.kernel_done) cudaEventDestroy(sl.kernel_done); if (sl.h2d_done) cudaEventDestroy(sl.h2d_done); if (sl.h_planes) cudaFreeHost(sl.h_planes); }
     if (stream) cudaStreamDestroy(stream);
   }
