@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = [
     "pa_summary_reduce_device", "pa_summary_reduce", "pa_debug_sort_pairs", "pa_debug_table_lookup",
     "pa_records_encode_device", "pa_records_partition_device", "pa_partition_of_key", "pa_index_build_from_records_device",
     "pa_index_csr_device", "pa_index_alloc_replica", "pa_index_finish_replica", "pa_index_build_tables", "pa_debug_pack_reads",
+    "pa_parse_records", "pa_parsed_copy", "pa_parsed_free",
 ]
 
 
@@ -113,6 +114,9 @@ def lib() -> ctypes.CDLL:
         "pa_index_finish_replica": (i32, [vp]),
         "pa_index_build_tables": (i32, [vp]),
         "pa_debug_pack_reads": (i32, [vp, vp, u64, vp, u64, i32, vp]),
+        "pa_parse_records": (i32, [vp, u64, i32, vp, vp, vp, vp]),
+        "pa_parsed_copy": (i32, [vp, vp, vp, vp, vp, vp, vp, vp]),
+        "pa_parsed_free": (i32, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -361,3 +365,37 @@ def debug_sort_pairs(keys: np.ndarray, vals: np.ndarray, end_bit: int = 64, devi
     vals = np.ascontiguousarray(vals, dtype=np.uint32).copy()
     check(lib().pa_debug_sort_pairs(_p(keys), _p(vals), len(keys), end_bit, device))
     return keys, vals
+
+
+def parse_records_native(raw: bytes, fastq: bool):
+    """Canonical FASTA / FASTQ text -> packed arrays, or None when the text needs the regex parser (ingest.cpp).
+
+    Returns {"seq": uint8[n_bases], "qual": uint8[n_bases] | None, "off": uint64[n + 1], "name_beg", "name_len",
+    "plus_beg", "plus_len": uint64[n] ranges inside `raw`, "raw": raw}."""
+    n = len(raw)
+    buf = np.frombuffer(raw, dtype=np.uint8) if n else np.zeros(1, dtype=np.uint8)
+    h = ctypes.c_void_p()
+    canonical = ctypes.c_int32(0)
+    n_rec, n_bases = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    check(lib().pa_parse_records(_p(buf), n, int(bool(fastq)), ctypes.byref(h), ctypes.byref(canonical), ctypes.byref(n_rec),
+                                 ctypes.byref(n_bases)))
+    if not canonical.value:
+        return None
+    nr = n_rec.value
+    try:
+        seq = np.zeros(max(n_bases.value, 1), dtype=np.uint8)
+        qual = np.zeros(max(n_bases.value, 1), dtype=np.uint8) if fastq else None
+        off = np.zeros(nr + 1, dtype=np.uint64)
+        nb, nl = np.zeros(max(nr, 1), dtype=np.uint64), np.zeros(max(nr, 1), dtype=np.uint64)
+        pb, pl = (np.zeros(max(nr, 1), dtype=np.uint64), np.zeros(max(nr, 1), dtype=np.uint64)) if fastq else (None, None)
+        check(lib().pa_parsed_copy(h, _p(seq), _p(qual), _p(off), _p(nb), _p(nl), _p(pb), _p(pl)))
+    finally:
+        lib().pa_parsed_free(h)
+    return {"seq": seq[:n_bases.value], "qual": None if qual is None else qual[:n_bases.value], "off": off,
+            "name_beg": nb[:nr], "name_len": nl[:nr], "plus_beg": None if pb is None else pb[:nr],
+            "plus_len": None if pl is None else pl[:nr], "raw": raw, "n": nr}
+
+
+def parsed_names(packed) -> List[str]:
+    raw = packed["raw"]
+    return [raw[b:b + l].decode("ascii") for b, l in zip(packed["name_beg"].tolist(), packed["name_len"].tolist())]

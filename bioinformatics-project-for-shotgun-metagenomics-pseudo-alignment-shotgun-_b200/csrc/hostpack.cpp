@@ -145,6 +145,11 @@ __attribute__((target("avx2"))) bool pack_range_avx2(const uint8_t* bases, const
 
 }  // namespace
 
+void host_parallel_for(int n_tasks, const std::function<void(int)>& fn) {
+  if (n_tasks <= 1) { for (int t = 0; t < n_tasks; ++t) fn(t); return; }
+  pool().parallel_for(n_tasks, fn);
+}
+
 int host_pack_threads() {
   static int n = [] {
     if (const char* e = getenv("PA_PACK_THREADS")) { int v = atoi(e); if (v >= 1) return std::min(v, 256); }

@@ -9,6 +9,7 @@
 // (computable on both sides from the offsets alone; at most two spare words per read).
 #pragma once
 #include <cstdint>
+#include <functional>
 
 namespace pa {
 
@@ -23,6 +24,9 @@ bool pack_reads_planes(const uint8_t* bases, const uint64_t* read_off, uint64_t 
 
 // Parallel check of read_off[lo .. hi]: returns false when it is not monotonic; *max_len = longest read.
 bool scan_offsets(const uint64_t* read_off, uint64_t lo, uint64_t hi, uint64_t* max_len, int n_threads);
+
+// runs fn(0 .. n_tasks-1) on the library's worker pool (blocking)
+void host_parallel_for(int n_tasks, const std::function<void(int)>& fn);
 
 int host_pack_threads();   // worker threads available (hardware concurrency, capped; PA_PACK_THREADS overrides)
 

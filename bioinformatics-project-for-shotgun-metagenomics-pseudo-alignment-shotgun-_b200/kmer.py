@@ -153,17 +153,23 @@ class KmerReference(object):
         self._native: Optional[nat.NativeIndex] = None
         self._csr_cache = None
         self._frozen_csr = None
-        self._build_kmer_mapping(self.genomes, k)
+        packed = getattr(fasta_record_container, "packed_batch", lambda: None)()
+        self._build_kmer_mapping(self.genomes, k, packed)
         if filter_similar:
             self._filter_similar_genomes(similarity_threshold)
 
     # -- device index ------------------------------------------------------------
-    def _build_kmer_mapping(self, fasta_records: List[Record], k: int) -> None:
+    def _build_kmer_mapping(self, fasta_records: List[Record], k: int, packed=None) -> None:
         if not isinstance(k, int) or isinstance(k, bool):
             raise TypeError("k must be an int")
         if k > 31:
             raise ValueError(f"k = {k} is outside the built scope of the B200 path (k <= 31)")
-        data, off = _pack([rec["genome"] for rec in fasta_records], "genome")
+        if packed is not None and packed["n"] == len(fasta_records):
+            data, off = packed["seq"], packed["off"]      # natively parsed FASTA: no Python strings on the way
+            if data.size == 0:
+                data = np.zeros(1, dtype=np.uint8)
+        else:
+            data, off = _pack([rec["genome"] for rec in fasta_records], "genome")
         self._native = nat.NativeIndex.build(data, off, k)
         self._csr_cache = None
 
@@ -570,6 +576,13 @@ class PseudoAlignment:
     def align_reads_from_container(self, reads_container: FASTAQRecordContainer, m: int = 1, p: int = 1,
                                    min_read_quality: Optional[int] = None, min_kmer_quality: Optional[int] = None,
                                    max_genomes: Optional[int] = None) -> None:
+        packed = getattr(reads_container, "packed_batch", lambda: None)()
+        if packed is not None and len(self.reads) == 0:
+            # natively parsed FASTQ (csrc/ingest.cpp): the arrays go to the device as they are; identifiers are unique
+            # inside one container (records.py:195-198) and nothing has been filed before, so no read can collide
+            self._align_arrays(None, nat.parsed_names(packed), packed["seq"], packed["qual"], packed["off"], m, p,
+                               min_read_quality, min_kmer_quality, max_genomes)
+            return
         self._align_records(list(reads_container), m, p, min_read_quality, min_kmer_quality, max_genomes)
 
     def _align_records(self, records: List[Record], m, p, mrq, mkq, mg) -> None:
@@ -589,15 +602,30 @@ class PseudoAlignment:
             qual_bytes, qoff = _pack(quals, "quality")
             if not np.array_equal(off, qoff):
                 raise ValueError("sequence and quality lengths differ")
+        self._align_arrays(records, None, seq_bytes, qual_bytes, off, m, p, mrq, mkq, mg)
+
+    def _align_arrays(self, records: Optional[List[Record]], names: Optional[List[str]], seq_bytes, qual_bytes, off,
+                      m, p, mrq, mkq, mg) -> None:
+        """records is None for a natively parsed container (names = its identifiers, known to be collision-free)."""
+        if records is None:
+            self._set_flags(mrq, mkq, mg)
+            _check_align_args(self.kmer_reference, m, p, mrq, mkq, mg)
+            if seq_bytes.size == 0:
+                seq_bytes = np.zeros(1, dtype=np.uint8)
+            if not (mrq is not None or mkq is not None):
+                qual_bytes = None
         ref = self.kmer_reference
         words, lst, counters = ref._index().align(seq_bytes, qual_bytes, off, nat.make_params(m, p, mrq, mkq, mg))
         types, lens, payload = nat.decode_words(words)
         stored = np.nonzero(types != 0)[0]
-        ids = [records[int(i)].identifier for i in stored]
+        if records is None:
+            ids = names if len(stored) == len(names) else [names[int(i)] for i in stored]
+        else:
+            ids = [records[int(i)].identifier for i in stored]
         # duplicate identifiers: the reference raises at the first one, after filing everything before it
         seen_here: Set[str] = set()
         dup_at = None
-        for j, rid in enumerate(ids):
+        for j, rid in enumerate(ids if records is not None else ()):
             if rid in seen_here or rid in self.reads:
                 dup_at = j
                 break

@@ -8,6 +8,11 @@ FASTAQRecordContainer and the four exceptions, with the same acceptance rules
 changes here is only bookkeeping that does not scale: the reference tracks parsed
 input with one Python int per character (records.py:170-181), this version tracks
 the matched spans as intervals.
+
+Ingest fast path: canonical ASCII text is parsed natively (csrc/ingest.cpp) straight into the
+packed arrays the device path consumes; Record objects are then created lazily, only if somebody iterates the
+container.  Anything the native parser does not recognise as canonical goes through the regular expression below, so
+unusual inputs keep the reference's acceptance rules, exception types, messages and precedence.
 """
 import re
 from collections import namedtuple
@@ -17,6 +22,7 @@ import constants
 
 UNTIL_NEXT_HEADER_OR_EOF = r"(?=(?=\r?\n{section_header})|(?=(?:\r?\n)?\Z))"
 UNPARSED_SNIPPET_LEN = 20
+NATIVE_INGEST = True   # tests switch this off to compare the native parser with the regular expression
 
 
 class NoRecordsInData(Exception):
@@ -95,6 +101,59 @@ class RecordContainer(object):
         self.create_record_re_string()
         self._unique_index_values = set()
         self._records: List[Record] = []
+        self._packed = None          # natively parsed batch (see _native.parse_records_native), or None
+        self._packed_pending = False  # True while the Records of the packed batch have not been materialised
+
+    NATIVE_KIND: Optional[bool] = None   # True = FASTQ, False = FASTA, None = no native parser for this container
+
+    def _try_native(self, data: str) -> bool:
+        if not NATIVE_INGEST or type(self).NATIVE_KIND is None or self._records or self._packed is not None or not isinstance(data, str):
+            return False
+        if not data.isascii():
+            return False
+        try:
+            import _native as nat
+            packed = nat.parse_records_native(data.encode("ascii"), bool(type(self).NATIVE_KIND))
+        except ImportError:     # the library has not been built: the regex path below needs nothing native
+            return False
+        if packed is None:
+            return False
+        self._packed, self._packed_pending = packed, True
+        return True
+
+    def _materialize(self) -> None:
+        """Creates the Record objects of a natively parsed batch (lazily: the hot path never needs them)."""
+        if not self._packed_pending:
+            return
+        self._packed_pending = False
+        pk = self._packed
+        raw, off = pk["raw"], pk["off"].tolist()
+        seq = pk["seq"].tobytes().decode("ascii")
+        qual = pk["qual"].tobytes().decode("ascii") if pk["qual"] is not None else None
+        specs = type(self).SECTION_SPECIFICATIONS
+        for i, (b, l) in enumerate(zip(pk["name_beg"].tolist(), pk["name_len"].tolist())):
+            name = raw[b:b + l].decode("ascii")
+            if qual is None:
+                fields = (name, seq[off[i]:off[i + 1]])
+            else:
+                pb, pl = int(pk["plus_beg"][i]), int(pk["plus_len"][i])
+                fields = (name, seq[off[i]:off[i + 1]], raw[pb:pb + pl].decode("ascii").strip(), qual[off[i]:off[i + 1]])
+            self._records.append(Record([Section(spec.section_name, f) for spec, f in zip(specs, fields)]))
+            for spec, f in zip(specs, fields):
+                if spec.is_unique_index:
+                    self._unique_index_values.add(f)
+
+    def packed_batch(self):
+        """The natively parsed arrays when this container holds exactly that batch, else None."""
+        if self._packed is not None and (self._packed_pending or len(self._records) == self._packed["n"]):
+            return self._packed
+        return None
+
+    def __getstate__(self):
+        self._materialize()
+        state = dict(self.__dict__)
+        state["_packed"], state["_packed_pending"] = None, False
+        return state
 
     def create_record_re_string(self) -> None:
         """One lazy capture group per section, terminated by a look-ahead for the next record or the end."""
@@ -108,6 +167,9 @@ class RecordContainer(object):
         self.__re_pattern = "".join(pieces)
 
     def parse_records(self, data: str) -> None:
+        if self._try_native(data):
+            return
+        self._materialize()
         spans: List[Tuple[int, int]] = []
         for found in re.finditer(self.__re_pattern, data, flags=re.MULTILINE):
             groups = found.groups()
@@ -132,14 +194,17 @@ class RecordContainer(object):
         self._records.append(Record(sections))
 
     def __iter__(self) -> Iterator[Record]:
+        self._materialize()
         return iter(self._records)
 
     def __len__(self) -> int:
-        return len(self._records)
+        return self._packed["n"] if self._packed_pending else len(self._records)
 
 
 class FASTARecordContainer(RecordContainer):
     """'>' description line, then the genome over [ACGTN] with whitespace stripped."""
+
+    NATIVE_KIND = False
 
     SECTION_SPECIFICATIONS = (
         SectionSpecification("description", ">", True, r"\S\t ", "", False),
@@ -150,6 +215,8 @@ class FASTARecordContainer(RecordContainer):
 class FASTAQRecordContainer(RecordContainer):
     """'@' identifier (unique), sequence over [ACGT], '+' line, quality over ASCII 33..126 of equal length."""
 
+    NATIVE_KIND = True
+
     SECTION_SPECIFICATIONS = (
         SectionSpecification("identifier", "@", True, r"\S\t ", "", True),
         SectionSpecification("sequence", "", True, re.escape(constants.REAL_NUCLEOTIDES_CHARS), "", False),
@@ -159,6 +226,8 @@ class FASTAQRecordContainer(RecordContainer):
 
     def parse_records(self, data: str) -> None:
         super().parse_records(data)
+        if self._packed_pending:
+            return      # the native parser only accepts records whose two lengths agree
         for number, record in enumerate(self, start=1):
             n_seq, n_qual = len(record["sequence"]), len(record["quality_sequence"])
             if n_seq != n_qual:

@@ -183,6 +183,21 @@ int32_t pa_summary_reduce(pa_index* idx, const uint64_t* words, const uint32_t* 
                           uint64_t read_index_base, uint64_t stats[4], uint64_t* unique_reads, uint64_t* ambiguous_reads,
                           uint64_t* first_seen);
 
+/* ---- ingest: FASTA / FASTQ text -> packed arrays (records.py:141-199, 212-302; pure host code) -------------
+ * Parses the canonical form of both formats (4-line FASTQ over ACGT with qualities in ASCII 33..126; FASTA with a
+ * '>' line and ACGTN lines) into the arrays pa_index_build / pa_align_batch take.  *canonical = 0 (and *out = NULL)
+ * means the text has to go through the regex restatement of the reference's parser instead (records.py of this
+ * package), which keeps the reference's acceptance rules, exception types, messages and precedence for every
+ * unusual input (blank lines, lower case, duplicates, length mismatches, stray text ...).  ASCII text only.
+ * pa_parsed_copy: seq[n_bases], qual[n_bases] (FASTQ), seq_off[n_records + 1], name_beg / name_len[n_records] =
+ * the stripped identifier / description inside `text`; plus_beg / plus_len (FASTQ) = the text after '+'. */
+typedef struct pa_parsed pa_parsed;
+int32_t pa_parse_records(const uint8_t* text, uint64_t n, int32_t fastq, pa_parsed** out, int32_t* canonical,
+                         uint64_t* n_records, uint64_t* n_bases);
+int32_t pa_parsed_copy(pa_parsed* h, uint8_t* seq, uint8_t* qual, uint64_t* seq_off, uint64_t* name_beg, uint64_t* name_len,
+                       uint64_t* plus_beg, uint64_t* plus_len);
+int32_t pa_parsed_free(pa_parsed* h);
+
 /* ---- diagnostics used by the tests ----------------------------------------------------------------- */
 /* stable LSD radix sort of (key, value) pairs on key bits [0, end_bit), host in / host out (K2) */
 int32_t pa_debug_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t n, int32_t end_bit, int32_t device);

@@ -314,3 +314,117 @@ def test_host_packing_matches_a_numpy_restatement():
                     lo = int(sum(((int(b) >> 1) & 1) << j for j, b in enumerate(blk)))
                     hi = int(sum(((int(b) >> 2) & 1) << j for j, b in enumerate(blk)))
                     assert int(planes[w0 + c]) == lo and int(planes[w0 + nw + c]) == hi
+
+
+# ---------------------------------------------------------------------------
+# native ingest (csrc/ingest.cpp) against the regular-expression parser, and against the reference when present
+# ---------------------------------------------------------------------------
+def _random_text(rng, fastq: bool) -> str:
+    n = int(rng.integers(1, 6))
+    eol = "\r\n" if rng.random() < 0.25 else "\n"
+    out = []
+    for i in range(n):
+        name = f"rec{i}" + (" extra words" if rng.random() < 0.3 else "") + ("\t" if rng.random() < 0.1 else "")
+        L = int(rng.integers(1, 30))
+        if fastq:
+            seq = "".join(rng.choice(list("ACGT"), size=L))
+            qual = "".join(chr(int(c)) for c in rng.integers(33, 127, size=L))
+            plus = "+" + (".." if rng.random() < 0.3 else "") + ("comment" if rng.random() < 0.05 else "")
+            out.append(f"@{name}{eol}{seq}{eol}{plus}{eol}{qual}")
+        else:
+            seq = "".join(rng.choice(list("ACGTN"), size=L))
+            w = int(rng.integers(3, 12))
+            out.append(f">{name}{eol}" + eol.join(seq[j:j + w] for j in range(0, L, w)))
+    text = eol.join(out) + (eol if rng.random() < 0.7 else "")
+    # mutations that leave the canonical form (the native parser must hand these to the regex)
+    r = rng.random()
+    if r < 0.08:
+        text = text.replace("A", "a", 1)
+    elif r < 0.16:
+        text = text.replace(eol, eol + eol, 1)
+    elif r < 0.22:
+        text = " " + text
+    elif r < 0.28:
+        text = text + eol + eol
+    elif r < 0.34 and fastq:
+        text = text.replace("rec1", "rec0")            # duplicate identifier
+    elif r < 0.40 and fastq:
+        k = text.rfind(eol, 0, len(text) - 2)
+        text = text[:k + len(eol)] + text[k + len(eol) + 1:]   # quality one short
+    elif r < 0.46:
+        text = text[: max(1, len(text) // 2)]
+    elif r < 0.50:
+        text = text.replace(eol, eol + "garbage line" + eol, 1)
+    elif r < 0.54:
+        text = text + "é"
+    elif r < 0.58:
+        text = text.replace("rec0", "rec0\x0b", 1)
+    return text
+
+
+def _parse_outcome(records_module, fastq: bool, text: str):
+    c = records_module.FASTAQRecordContainer() if fastq else records_module.FASTARecordContainer()
+    names = ("identifier", "sequence", "space", "quality_sequence") if fastq else ("description", "genome")
+    try:
+        c.parse_records(text)
+    except Exception as e:   # noqa: BLE001 -- the type and the message are what is compared
+        return ("error", type(e).__name__, str(e))
+    return ("ok", [(r.identifier,) + tuple(r[n] for n in names) for r in c])
+
+
+@pytest.mark.parametrize("piece_bytes", ["1048576", "40"])
+@pytest.mark.parametrize("fastq", [True, False])
+def test_native_ingest_equals_the_regex_parser(fastq, piece_bytes, monkeypatch):
+    import records
+    import _native as nat
+    monkeypatch.setenv("PA_INGEST_PIECE_BYTES", piece_bytes)      # "40": texts are cut into up to 16 parallel pieces
+    rng = np.random.default_rng((77 if fastq else 78) + int(piece_bytes))
+    n_native = 0
+    ref_mod = None
+    if os.path.isdir("/root/reference/src"):
+        import importlib.util
+        spec_c = importlib.util.spec_from_file_location("constants", "/root/reference/src/constants.py")
+        saved = {k: sys.modules.get(k) for k in ("constants", "records")}
+        try:
+            mod_c = importlib.util.module_from_spec(spec_c); spec_c.loader.exec_module(mod_c)
+            sys.modules["constants"] = mod_c
+            spec_r = importlib.util.spec_from_file_location("ref_records", "/root/reference/src/records.py")
+            ref_mod = importlib.util.module_from_spec(spec_r); spec_r.loader.exec_module(ref_mod)
+        finally:
+            for k, v in saved.items():
+                if v is not None:
+                    sys.modules[k] = v
+    for trial in range(600):
+        text = _random_text(rng, fastq)
+        records.NATIVE_INGEST = True
+        got = _parse_outcome(records, fastq, text)
+        if text.isascii() and nat.parse_records_native(text.encode("ascii"), fastq) is not None:
+            n_native += 1
+        records.NATIVE_INGEST = False
+        try:
+            want = _parse_outcome(records, fastq, text)
+        finally:
+            records.NATIVE_INGEST = True
+        assert got == want, (text, got, want)
+        if ref_mod is not None:
+            assert got == _parse_outcome(ref_mod, fastq, text), text
+    assert 150 < n_native < 560      # both paths are exercised
+
+
+def test_native_ingest_feeds_the_packed_arrays():
+    import records
+    c = records.FASTAQRecordContainer()
+    c.parse_records("@r1 x\nACGT\n+..\nIIII\n@r2\nGG\n+\n!~\n")
+    pk = c.packed_batch()
+    assert pk is not None and pk["n"] == 2 and len(c) == 2
+    assert pk["seq"].tobytes() == b"ACGTGG" and pk["qual"].tobytes() == b"IIII!~" and pk["off"].tolist() == [0, 4, 6]
+    recs = list(c)                    # Records appear only now
+    assert [(r.identifier, r["sequence"], r["space"], r["quality_sequence"]) for r in recs] == \
+        [("r1 x", "ACGT", "..", "IIII"), ("r2", "GG", "", "!~")]
+    assert c.packed_batch() is pk
+    with pytest.raises(records.DuplicateRecordError):
+        c.parse_records("@r2\nA\n+\nI\n")           # the unique index survives the lazy path
+    f = records.FASTARecordContainer()
+    f.parse_records(">g1 d\nACGT\nNNAC\r\n>g2\nTTTT")
+    assert f.packed_batch()["seq"].tobytes() == b"ACGTNNACTTTT"
+    assert [(r.identifier, r["genome"]) for r in f] == [("g1 d", "ACGTNNAC"), ("g2", "TTTT")]
