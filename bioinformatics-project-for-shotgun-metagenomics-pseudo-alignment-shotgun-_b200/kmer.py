@@ -153,6 +153,7 @@ class KmerReference(object):
         self._native: Optional[nat.NativeIndex] = None
         self._csr_cache = None
         self._frozen_csr = None
+        self._dropped = None      # after EXTSIM: (genome strings of the ORIGINAL list, keep mask) -- see __getstate__
         packed = getattr(fasta_record_container, "packed_batch", lambda: None)()
         self._build_kmer_mapping(self.genomes, k, packed)
         if filter_similar:
@@ -174,12 +175,22 @@ class KmerReference(object):
         self._csr_cache = None
 
     def _index(self) -> nat.NativeIndex:
-        if self._native is None:  # unpickled: re-create the device index from the stored CSR
-            st = self._frozen_csr
-            if st is None:
-                raise RuntimeError("KmerReference has no index")
-            self._native = nat.NativeIndex.import_csr(self.kmer_len, st["genome_off"], st["keys"], st["run_off"],
-                                                      st["run_genome"], st["pos_off"], st["pos"], st.get("first_occ"))
+        if self._native is None:  # unpickled: re-create the device index
+            st = self.__dict__.get("_frozen_csr")
+            if st is not None:    # files written before the rebuild format: the CSR itself
+                self._native = nat.NativeIndex.import_csr(self.kmer_len, st["genome_off"], st["keys"], st["run_off"],
+                                                          st["run_genome"], st["pos_off"], st["pos"], st.get("first_occ"))
+            else:
+                # Rebuild format: the file holds the genomes, not the 40 bytes per k-mer of the
+                # CSR -- the build is deterministic and takes a fraction of a second on the device.  After EXTSIM the
+                # ORIGINAL genome list is rebuilt and the same genomes are dropped again, which also restores the
+                # dict insertion order (first occurrence over the original list, kmer.py:237-243).
+                dropped = self.__dict__.get("_dropped")
+                strings = dropped[0] if dropped is not None else [g["genome"] for g in self.genomes]
+                data, off = _pack(strings, "genome")
+                self._native = nat.NativeIndex.build(data, off, self.kmer_len)
+                if dropped is not None:
+                    self._native.drop_genomes(np.asarray(dropped[1], dtype=np.uint8))
         return self._native
 
     def _host_csr(self):
@@ -247,23 +258,18 @@ class KmerReference(object):
         kept_ids, info = self._apply_greedy_filter(self._sort_genomes_for_filtering(stats), class_info, similarity_threshold)
         keep = np.array([1 if g.identifier in kept_ids else 0 for g in self.genomes], dtype=np.uint8)
         self._index().drop_genomes(keep)  # _remove_filtered_genomes_from_kmers + renumbering
+        if not keep.all():
+            self._dropped = ([g["genome"] for g in self.genomes], keep.tolist())
         self.genomes = [g for g in self.genomes if g.identifier in kept_ids]
         self._csr_cache = None
         self.similarity_info = info
 
     # -- persistence (kmer.py:265-282) -------------------------------------------------
     def __getstate__(self):
-        state = {k: v for k, v in self.__dict__.items() if k not in ("_native", "_csr_cache", "_frozen_csr")}
-        if self._native is not None:
-            csr = self._native.export(with_order=False)
-            off = np.zeros(len(self.genomes) + 1, dtype=np.uint64)
-            if self.genomes:
-                off[1:] = np.cumsum([len(g["genome"]) for g in self.genomes])
-            state["_frozen_csr"] = {"genome_off": off, "keys": csr["keys"], "run_off": csr["run_off"],
-                                    "run_genome": csr["run_genome"], "pos_off": csr["pos_off"], "pos": csr["pos"],
-                                    "first_occ": csr["first_occ"]}
-        else:
-            state["_frozen_csr"] = self._frozen_csr
+        # the device index is not stored: _index() rebuilds it from the genomes (and the EXTSIM drop list) on demand
+        state = {k: v for k, v in self.__dict__.items() if k not in ("_native", "_csr_cache")}
+        if state.get("_frozen_csr") is None:
+            state.pop("_frozen_csr", None)
         return state
 
     def __setstate__(self, state):
@@ -272,8 +278,10 @@ class KmerReference(object):
         self._csr_cache = None
 
     def save(self, ref_file: str) -> None:
-        with gzip.open(ref_file, "wb") as f:
-            pickle.dump(self, f)
+        # gzip-pickle like the reference (kmer.py:265-271); level 1: the payload is genome text, and level 9 runs at
+        # a few MB/s for nothing
+        with gzip.open(ref_file, "wb", compresslevel=1) as f:
+            pickle.dump(self, f, protocol=pickle.HIGHEST_PROTOCOL)
 
     @classmethod
     def load(cls, ref_file: str) -> "KmerReference":
@@ -714,8 +722,8 @@ class PseudoAlignment:
         self.reads = view
 
     def save(self, align_file: str) -> None:
-        with gzip.open(align_file, "wb") as f:
-            pickle.dump(self, f)
+        with gzip.open(align_file, "wb", compresslevel=1) as f:
+            pickle.dump(self, f, protocol=pickle.HIGHEST_PROTOCOL)
 
     def __repr__(self) -> str:
         return json.dumps(self.get_summary(), indent=4)
