@@ -255,18 +255,24 @@ def gpu_arm(args):
         import multi_gpu
         lengths = np.full(G, GL, dtype=np.int64)
         g_lo, g_hi = multi_gpu.genome_shards(lengths, world)[rank]
-        torch.cuda.synchronize()
-        dist.barrier()
-        t0 = time.perf_counter()
-        dix = multi_gpu.build_partitioned(bases[g_lo * GL:g_hi * GL], goff, k, (g_lo, g_hi), device=local)
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        part_times = []
+        dix = None
+        for attempt in range(2):      # the first call also sets up the NCCL point-to-point channels
+            if dix is not None:
+                dix.close()
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            dix = multi_gpu.build_partitioned(bases[g_lo * GL:g_hi * GL], goff, k, (g_lo, g_hi), device=local)
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            part_times.append(float(dt.item()))
         rinf = dix.replica.info()
         assert (rinf.n_keys, rinf.n_runs, rinf.n_occ) == (inf.n_keys, inf.n_runs, inf.n_occ), "partitioned build differs from the single-GPU build"
-        build_part = {"kmers_per_s": inf.n_occ / float(dt.item()), "seconds": float(dt.item()), "phases_rank0": dix.timings,
-                      "records_sent_rank0": dix.sent_records, "records_received_rank0": dix.received_records,
-                      "same_sizes_as_single_gpu_build": True}
+        build_part = {"kmers_per_s": inf.n_occ / part_times[-1], "seconds": part_times[-1], "first_call_seconds": part_times[0],
+                      "phases_rank0": dix.timings, "records_sent_rank0": dix.sent_records,
+                      "records_received_rank0": dix.received_records, "same_sizes_as_single_gpu_build": True}
         dix.close()
 
     # ---- reads of this rank (weak scaling: every rank aligns its own `reads` reads) ----
