@@ -643,11 +643,14 @@ align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
   // software pipeline: offsets of read i+2 and the first 160 bases of read i+1 are requested while read i is processed
   uint64_t nx_beg = 0, nx_end = 0, cur_beg = 0, cur_end = 0;
   Prefetch<PACKED> nx_ch, cur_ch;
+  Prefetch<false> nx_q, cur_q;   // QUAL: the quality bytes travel through the same pipeline (one byte per lane per chunk)
+  const ReadInput qin{quals, nullptr, 0};
   {
     uint64_t r0 = warp_global, r1 = warp_global + n_warps;
     if (r0 < n_reads) { cur_beg = read_off[r0]; cur_end = read_off[r0 + 1]; }
     if (r1 < n_reads) { nx_beg = read_off[r1]; nx_end = read_off[r1 + 1]; }
     prefetch_read<PACKED>(in, r0 < n_reads, r0, cur_beg, cur_end - cur_beg, lane, cur_ch);
+    if (QUAL) prefetch_read<false>(qin, r0 < n_reads, r0, cur_beg, cur_end - cur_beg, lane, cur_q);
   }
 
   for (uint64_t read = warp_global; read < n_reads; read += n_warps) {
@@ -657,6 +660,7 @@ align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
     {
       const uint64_t r1 = read + n_warps, r2 = read + 2 * n_warps;
       prefetch_read<PACKED>(in, r1 < n_reads, r1, nx_beg, nx_end - nx_beg, lane, nx_ch);
+      if (QUAL) prefetch_read<false>(qin, r1 < n_reads, r1, nx_beg, nx_end - nx_beg, lane, nx_q);
       if (r2 < n_reads) { n2_beg = read_off[r2]; n2_end = read_off[r2 + 1]; }
     }
 
@@ -666,7 +670,12 @@ align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
     bool dropped = false;
     if (QUAL && prm.has_mrq) {  // Read.mean_quality() < min_read_quality  (kmer.py:587)
       uint64_t s = 0;
-      for (uint64_t i = lane; i < L; i += 32) s += rq[i];
+      if (L <= 32 * (AL_ROUNDS + 1)) {   // the prefetched bytes cover the read (bytes beyond L were loaded as 0)
+#pragma unroll
+        for (int c = 0; c <= AL_ROUNDS; ++c) s += cur_q.v[c];
+      } else {
+        for (uint64_t i = lane; i < L; i += 32) s += rq[i];
+      }
       s = warp_sum(s);
       if ((int64_t)s < prm.mrq * (int64_t)L) { dropped = true; res = 0; if (lane == 0) ++c_drop; }
     }
@@ -682,8 +691,7 @@ align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
         uint32_t carry = 0;
 #pragma unroll
         for (int c = 0; c <= AL_ROUNDS; ++c) {
-          const uint64_t bi = 32 * c + lane;
-          uint32_t q = bi < L ? rq[bi] : 0, incl = q;
+          uint32_t q = cur_q.v[c], incl = q;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
           qex[c] = carry + incl - q;
@@ -787,6 +795,7 @@ align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
     cur_beg = nx_beg; cur_end = nx_end;
     nx_beg = n2_beg; nx_end = n2_end;
     cur_ch = nx_ch;
+    if (QUAL) cur_q = nx_q;
   }
   c_drop = warp_sum(c_drop); c_nq = warp_sum(c_nq); c_nr = warp_sum(c_nr);
   if (lane == 0) {
