@@ -117,17 +117,20 @@ __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
 
 // One doubling step of the sliding minimum over the per-position m-mer hashes: entry (c, lane) stands for position
 // 32c + lane and takes the smaller of itself and the entry d positions to its right (the left one wins ties, so the
-// leftmost minimum survives).  Chunks are updated in ascending order, so every read sees pre-step values.
+// leftmost minimum survives).
 __device__ __forceinline__ void window_min_step(uint32_t (&mh)[AL_ROUNDS + 1], uint32_t (&mpos)[AL_ROUNDS + 1], uint32_t d,
                                                 uint32_t lane) {
   const uint32_t src = (lane + d) & 31;
   const bool wrap = lane + d >= 32;
+  // every chunk rotated by d lanes once; the neighbour d positions to the right is in the own chunk's rotation or,
+  // for the last d lanes, in the next chunk's
+  uint32_t rh[AL_ROUNDS + 1], rp[AL_ROUNDS + 1];
+#pragma unroll
+  for (int c = 0; c <= AL_ROUNDS; ++c) { rh[c] = __shfl_sync(0xffffffffu, mh[c], src); rp[c] = __shfl_sync(0xffffffffu, mpos[c], src); }
 #pragma unroll
   for (int c = 0; c <= AL_ROUNDS; ++c) {
-    uint32_t h_same = __shfl_sync(0xffffffffu, mh[c], src), p_same = __shfl_sync(0xffffffffu, mpos[c], src);
-    uint32_t h_next = 0xFFFFFFFFu, p_next = 0;
-    if (c < AL_ROUNDS) { h_next = __shfl_sync(0xffffffffu, mh[c + 1], src); p_next = __shfl_sync(0xffffffffu, mpos[c + 1], src); }
-    const uint32_t h2 = wrap ? h_next : h_same, p2 = wrap ? p_next : p_same;
+    const uint32_t h2 = wrap ? (c < AL_ROUNDS ? rh[c + 1] : 0xFFFFFFFFu) : rh[c];
+    const uint32_t p2 = wrap ? (c < AL_ROUNDS ? rp[c + 1] : 0u) : rp[c];
     if (h2 < mh[c]) { mh[c] = h2; mpos[c] = p2; }
   }
 }
