@@ -154,7 +154,10 @@ int host_pack_threads() {
   static int n = [] {
     if (const char* e = getenv("PA_PACK_THREADS")) { int v = atoi(e); if (v >= 1) return std::min(v, 256); }
     unsigned hc = std::thread::hardware_concurrency();
-    return (int)std::max(1u, std::min(hc ? hc : 8u, 64u));
+    if (!hc) hc = 8;
+    // one process per GPU: the ranks of a node share its cores (torchrun exports LOCAL_WORLD_SIZE)
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) { int w = atoi(e); if (w > 1) hc = std::max(1u, hc / (unsigned)w); }
+    return (int)std::max(1u, std::min(hc, 64u));
   }();
   return n;
 }
