@@ -395,7 +395,9 @@ def gpu_arm(args):
         h2d = NR * RL * (2 if need_q else 1) + (NR + 1) * 8
         d2h = NR * 8 + int(need.value) * 4 + 40
         e2e = {"value": world * NR / float(te.item()), "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": float(te.item()) * 1e3}
+               "ms_per_step": float(te.item()) * 1e3,
+               "note": "h2d = the pinned host buffers handed to pa_align_batch (ASCII bases [+ qualities] + offsets); the call "
+                       "packs chunks to 2-bit planes on the host cores before the PCIe copy when that is faster than the link"}
 
     # ---- CPU baseline + parity of the GPU path on the same bounded sample (rank 0, N = 1) ----
     cpu_baseline, parity = None, None

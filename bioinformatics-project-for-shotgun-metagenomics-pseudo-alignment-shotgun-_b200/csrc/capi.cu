@@ -502,6 +502,7 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
   // PA_HOST_PACK: 0 = never pack, 1 = always pack, unset / 2 = the self-balancing mix below
   const int pack_mode = getenv("PA_HOST_PACK") ? atoi(getenv("PA_HOST_PACK")) : 2;
   const bool use_pack = pack_mode != 0;
+  const double pack_min_gbs = getenv("PA_PACK_MIN_GBS") ? atof(getenv("PA_PACK_MIN_GBS")) : 65.0;
 
   uint64_t c = 0, n_packed = 0;
   double t_wait = 0, t_pack = 0, t_enq = 0;
@@ -526,7 +527,11 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
     const uint64_t n_words = planes_words(nb, n);
     const bool slot_busy = cudaStreamQuery(sl.stream) == cudaErrorNotReady;
     (void)cudaGetLastError();
-    if (use_pack && (pack_mode == 1 || slot_busy) && ix.k >= 1 && nb) {
+    // ... and only while the host packs clearly faster than the link moves raw ASCII (measured per chunk; a node
+    // whose ranks share few cores does not: 8 threads pack ~45 GB/s, about what PCIe 5 x16 carries)
+    if (ix.pack_rate_gbs <= 0) ix.pack_rate_gbs = 5.6 * host_pack_threads();
+    const bool pack_pays = ix.pack_rate_gbs >= pack_min_gbs;
+    if (use_pack && (pack_mode == 1 || (slot_busy && pack_pays)) && ix.k >= 1 && nb) {
       PA_CUDA(cudaEventSynchronize(sl.h2d_done));   // the staging buffer's previous transfer has left the host
       if (sl.h_planes_words < n_words) {
         if (sl.h_planes) { cudaFreeHost(sl.h_planes); sl.h_planes = nullptr; sl.h_planes_words = 0; }
@@ -535,7 +540,12 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
         if (e != cudaSuccess) { (void)cudaGetLastError(); sl.h_planes = nullptr; }
         else sl.h_planes_words = want;
       }
-      if (sl.h_planes) packed = pack_reads_planes(bases, read_off, lo, hi, sl.h_planes, host_pack_threads());
+      if (sl.h_planes) {
+        auto tk = now();
+        packed = pack_reads_planes(bases, read_off, lo, hi, sl.h_planes, host_pack_threads());
+        const double ms = ms_since(tk);
+        if (ms > 0) ix.pack_rate_gbs = 0.5 * ix.pack_rate_gbs + 0.5 * ((double)nb / ms / 1e6);
+      }
     }
     t_pack += ms_since(tp); tp = now();
     // slot buffers are free once the slot's previous chunk (c - 2) has finished: its stream is in order

@@ -89,6 +89,7 @@ struct Index {
     cudaEvent_t kernel_done = nullptr, h2d_done = nullptr;
   } slot[2];
   DevBuf host_list, host_state;
+  double pack_rate_gbs = 0;   // running estimate of the host packing rate (GB/s of ASCII), see pa_align_batch
   // timing of the last build (ms, CUDA events on `stream`)
   float t_encode_ms = 0, t_sort_ms = 0, t_rle_ms = 0, t_table_ms = 0;
 

@@ -162,6 +162,29 @@ def test_overloaded_table_walks_chains_and_stash(dense, monkeypatch):
         check_case(dict(case, k=k))
 
 
+@pytest.mark.parametrize("mode", ["1", "0"])
+def test_host_packed_reads_give_the_same_results(mode, monkeypatch):
+    """PA_HOST_PACK=1: every chunk of pa_align_batch is turned into 2-bit planes on the host and aligned by the packed
+    kernel variants (fast + general, plain + EXTQUALITY, long reads over several super-rounds); a chunk holding a base
+    outside ACGT falls back to ASCII.  PA_CHUNK_READS makes the batches span several chunks and both slots."""
+    monkeypatch.setenv("PA_HOST_PACK", mode)
+    monkeypatch.setenv("PA_CHUNK_READS", "700")
+    genomes = synth.make_genomes(6, 40_000, seed=5, cluster_size=3, shared_frac=0.35, n_every=9000, n_run=11)
+    b, q, off = synth.make_reads(genomes, 4000, 150, seed=6, sub_rate=0.02, random_frac=0.05)
+    reads = synth.reads_as_triples(b, q, off)
+    reads[1234] = (reads[1234][0], reads[1234][1][:70] + "N" + reads[1234][1][71:], reads[1234][2])   # one ASCII chunk
+    for pr in [dict(m=1, p=1, mrq=None, mkq=None, mg=None), dict(m=1, p=1, mrq=62, mkq=60, mg=1),
+               dict(m=0, p=0, mrq=None, mkq=63, mg=3)]:
+        check_case({"k": 31, "genomes": synth.genomes_as_pairs(genomes), "reads": reads, "params": pr, "seed": 1})
+    lg = synth.make_genomes(5, 6000, seed=9, cluster_size=5, shared_frac=0.5, n_every=2500, n_run=5)
+    lb, lq, loff = synth.make_reads(lg, 300, 700, seed=10, sub_rate=0.03, random_frac=0.1)
+    for k in (5, 12, 31):
+        check_case({"k": k, "genomes": synth.genomes_as_pairs(lg), "reads": synth.reads_as_triples(lb, lq, loff),
+                    "params": dict(m=2, p=0, mrq=60, mkq=61, mg=2), "seed": k})
+    for seed in range(40):   # ragged read lengths, tiny k
+        check_case(synth.fuzz_case(900 + seed))
+
+
 def test_long_reads_take_the_multi_round_path():
     genomes = synth.make_genomes(5, 6000, seed=9, cluster_size=5, shared_frac=0.5, n_every=2500, n_run=5)
     b, q, off = synth.make_reads(genomes, 300, 700, seed=10, sub_rate=0.03, random_frac=0.1)
