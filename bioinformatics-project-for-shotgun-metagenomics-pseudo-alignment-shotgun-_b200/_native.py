@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = [
     "pa_records_encode_device", "pa_records_partition_device", "pa_partition_of_key", "pa_index_build_from_records_device",
     "pa_index_csr_device", "pa_index_alloc_replica", "pa_index_finish_replica", "pa_index_build_tables", "pa_debug_pack_reads",
     "pa_parse_records", "pa_parsed_copy", "pa_parsed_free",
+    "pa_peer_alloc", "pa_peer_open", "pa_peer_close", "pa_peer_free", "pa_records_digit_counts", "pa_records_scatter_to_peers",
 ]
 
 
@@ -117,6 +118,12 @@ def lib() -> ctypes.CDLL:
         "pa_parse_records": (i32, [vp, u64, i32, vp, vp, vp, vp]),
         "pa_parsed_copy": (i32, [vp, vp, vp, vp, vp, vp, vp, vp]),
         "pa_parsed_free": (i32, [vp]),
+        "pa_peer_alloc": (i32, [u64, i32, vp, vp]),
+        "pa_peer_open": (i32, [vp, i32, vp]),
+        "pa_peer_close": (i32, [vp, i32]),
+        "pa_peer_free": (i32, [vp, i32]),
+        "pa_records_digit_counts": (i32, [vp, u64, i32, i32, vp, vp, vp, vp]),
+        "pa_records_scatter_to_peers": (i32, [vp, vp, u64, i32, i32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -600,7 +600,10 @@ align_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
 #ifndef PA_FAST_MINB
 #define PA_FAST_MINB 2
 #endif
-constexpr int FA_THREADS = 256;
+#ifndef PA_FAST_THREADS
+#define PA_FAST_THREADS 256
+#endif
+constexpr int FA_THREADS = PA_FAST_THREADS;
 constexpr int FA_WARPS = FA_THREADS / 32;
 constexpr uint32_t NO_GENOME = 0xFFFFFFFFu;
 

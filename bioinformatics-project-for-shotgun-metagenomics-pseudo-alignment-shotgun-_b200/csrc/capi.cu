@@ -447,6 +447,81 @@ int32_t pa_index_build_tables(pa_index* idx) {
   return index_build_tables(*IDX(idx));
 }
 
+/* ---- fused partition + exchange: the scatter pass of the multi-GPU build stores straight into peer memory ---- */
+int32_t pa_peer_alloc(uint64_t bytes, int32_t device, void** d_ptr, uint8_t* handle /*[64]*/) {
+  NEED(d_ptr && handle, "null argument");
+  PA_CUDA(cudaSetDevice(device));
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMalloc(%llu bytes) failed: %s", (unsigned long long)bytes, cudaGetErrorString(e)); return PA_ERR_NOMEM; }
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); cudaFree(p); set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); return PA_ERR_CUDA; }
+  memcpy(handle, &h, 64);
+  *d_ptr = p;
+  return PA_OK;
+}
+
+int32_t pa_peer_open(const uint8_t* handle /*[64]*/, int32_t device, void** d_ptr) {
+  NEED(d_ptr && handle, "null argument");
+  PA_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e)); return PA_ERR_CUDA; }
+  return PA_OK;
+}
+
+int32_t pa_peer_close(void* d_ptr, int32_t device) {
+  if (!d_ptr) return PA_OK;
+  PA_CUDA(cudaSetDevice(device));
+  PA_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return PA_OK;
+}
+
+int32_t pa_peer_free(void* d_ptr, int32_t device) {
+  if (!d_ptr) return PA_OK;
+  PA_CUDA(cudaSetDevice(device));
+  PA_CUDA(cudaFree(d_ptr));
+  return PA_OK;
+}
+
+int32_t pa_records_digit_counts(const uint64_t* d_keys, uint64_t n, int32_t k, int32_t device, uint64_t* counts /*[256]*/,
+                                int32_t* begin_bit, int32_t* top_bits, void* stream) {
+  NEED(counts && begin_bit && top_bits, "null argument");
+  NEED(k >= 1 && k <= 31, "k out of range");
+  PA_CUDA(cudaSetDevice(device));
+  partition_geometry(k, begin_bit, top_bits);
+  DevBuf tmp;
+  PA_TRY(tmp.alloc(256 * 8));
+  unsigned long long h[256];
+  PA_TRY(radix_digit_counts(d_keys, n, *begin_bit, h, tmp.p, tmp.bytes, reinterpret_cast<cudaStream_t>(stream)));
+  for (int i = 0; i < 256; ++i) counts[i] = h[i];
+  return PA_OK;
+}
+
+int32_t pa_records_scatter_to_peers(const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n, int32_t k, int32_t device,
+                                    uint64_t* const* dst_keys /*[256]*/, uint32_t* const* dst_vals /*[256]*/, void* stream) {
+  NEED(dst_keys && dst_vals, "null argument");
+  NEED(k >= 1 && k <= 31, "k out of range");
+  NEED(n == 0 || (d_keys && d_vals), "null device buffer");
+  if (n == 0) return PA_OK;
+  PA_CUDA(cudaSetDevice(device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int begin = 0, tb = 0;
+  partition_geometry(k, &begin, &tb);
+  PeerRoute h_route[256];
+  for (int d = 0; d < 256; ++d) { h_route[d].keys = dst_keys[d]; h_route[d].vals = dst_vals[d]; }
+  DevBuf d_route, tmp;
+  PA_TRY(d_route.alloc(sizeof(h_route)));
+  PA_TRY(tmp.alloc(radix_sort_temp_bytes(n)));
+  PA_CUDA(cudaMemcpyAsync(d_route.p, h_route, sizeof(h_route), cudaMemcpyHostToDevice, s));
+  PA_TRY(radix_scatter_routed(d_keys, d_vals, n, begin, d_route.as<PeerRoute>(), tmp.p, tmp.bytes, s));
+  PA_CUDA(cudaStreamSynchronize(s));   // the stores into peer memory are complete and visible when this returns
+  return PA_OK;
+}
+
 int32_t pa_align_batch_device(pa_index* idx, const uint8_t* d_bases, const uint8_t* d_quals, const uint64_t* d_read_off,
                               uint64_t n_reads, uint64_t max_read_len, const pa_align_params* params,
                               uint64_t* d_words, uint32_t* d_list, uint64_t list_cap, uint64_t* d_state, void* stream,

@@ -17,6 +17,7 @@ sums over disjoint key ranges: computed per partition and all-reduced.
 torch.distributed is the plumbing (NCCL over NVLink on GPUs; gloo with host staging in the tests).
 """
 import ctypes
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -201,13 +202,69 @@ def _gather_replica(partition, k: int, genome_off: np.ndarray, dev, group=None):
     return replica
 
 
+def _exchange_fused(L, nat, keys, vals, n_slots: int, k: int, device: int, world: int, rank: int, group):
+    """Partition + exchange in ONE pass: the stable scatter stores every record into the receive buffer of the rank
+    that owns its key range (peer memory through CUDA IPC; NVLink stores).  Returns (recv_keys_ptr, recv_vals_ptr,
+    n_recv, n_sent); the receive buffers are cudaMalloc'ed by the library (free with pa_peer_free)."""
+    import torch
+    import torch.distributed as dist
+    counts = np.zeros(256, dtype=np.uint64)
+    begin, tb = ctypes.c_int32(0), ctypes.c_int32(0)
+    nat.check(L.pa_records_digit_counts(ctypes.c_void_p(keys.data_ptr()), n_slots, int(k), device, nat._p(counts),
+                                        ctypes.byref(begin), ctypes.byref(tb), None))
+    all_counts = [None] * world
+    dist.all_gather_object(all_counts, counts.astype(np.int64), group=group)
+    all_counts = np.stack(all_counts)                                  # [sender, digit]
+    n_digits = 1 << tb.value
+    dest = (np.arange(n_digits, dtype=np.int64) * world) >> tb.value    # part of every real digit (pa_partition_of_key)
+    recv_count = [int(all_counts[:, :n_digits][:, dest == r].sum()) for r in range(world)]
+    my_k, my_v = ctypes.c_void_p(), ctypes.c_void_p()
+    hk, hv = (ctypes.c_uint8 * 64)(), (ctypes.c_uint8 * 64)()
+    nat.check(L.pa_peer_alloc(recv_count[rank] * 8, device, ctypes.byref(my_k), hk))
+    nat.check(L.pa_peer_alloc(recv_count[rank] * 4, device, ctypes.byref(my_v), hv))
+    handles = [None] * world
+    dist.all_gather_object(handles, (bytes(hk), bytes(hv)), group=group)
+    peer_k, peer_v = [0] * world, [0] * world
+    opened = []
+    for r in range(world):
+        if r == rank:
+            peer_k[r], peer_v[r] = my_k.value, my_v.value
+        else:
+            pk, pv = ctypes.c_void_p(), ctypes.c_void_p()
+            nat.check(L.pa_peer_open((ctypes.c_uint8 * 64).from_buffer_copy(handles[r][0]), device, ctypes.byref(pk)))
+            nat.check(L.pa_peer_open((ctypes.c_uint8 * 64).from_buffer_copy(handles[r][1]), device, ctypes.byref(pv)))
+            peer_k[r], peer_v[r] = pk.value, pv.value
+            opened += [pk, pv]
+    # receive layout of rank r: sender-major, digit-minor -- equal keys stay in (sender = genome run, position) order
+    dst_k = (ctypes.c_void_p * 256)()
+    dst_v = (ctypes.c_void_p * 256)()
+    for r in range(world):
+        digits = np.nonzero(dest == r)[0]
+        base = int(all_counts[:rank, :n_digits][:, dest == r].sum())
+        for d in digits.tolist():
+            dst_k[d] = peer_k[r] + base * 8
+            dst_v[d] = peer_v[r] + base * 4
+            base += int(all_counts[rank, d])
+    torch.cuda.synchronize()
+    nat.check(L.pa_records_scatter_to_peers(ctypes.c_void_p(keys.data_ptr()), ctypes.c_void_p(vals.data_ptr()), n_slots, int(k),
+                                            device, dst_k, dst_v, None))
+    dist.barrier(group=group)          # every rank's stores have landed: the receive buffers are final
+    for p in opened:
+        nat.check(L.pa_peer_close(p, device))
+    n_sent = int(all_counts[rank, :n_digits].sum())
+    return my_k, my_v, recv_count[rank], n_sent
+
+
 def build_partitioned(my_bases, genome_off: np.ndarray, k: int, g_range: Tuple[int, int], device: int = 0,
-                      group=None) -> DistributedIndex:
+                      group=None, fused: Optional[bool] = None) -> DistributedIndex:
     """Multi-GPU KmerReference build (kmer.py:135-150 across ranks).
 
     my_bases    the genomes [g_lo, g_hi) of this rank concatenated: a uint8 numpy array or a CUDA uint8 tensor
     genome_off  uint64 offsets of ALL genomes (G + 1 entries); positions and genome indices are global
     g_range     (g_lo, g_hi), normally genome_shards(lengths, world)[rank]
+    fused       True: the partition pass stores straight into the owners' receive buffers over NVLink (CUDA IPC peer
+                memory; one node).  False: partition locally, then all_to_all_single.  Default: fused (PA_FUSED_EXCHANGE=0
+                switches it off).
     """
     import time
     import torch
@@ -236,6 +293,33 @@ def build_partitioned(my_bases, genome_off: np.ndarray, k: int, g_range: Tuple[i
     nat.check(L.pa_records_encode_device(ctypes.c_void_p(d_bases.data_ptr()), nat._p(genome_off), G, g_lo, g_hi, int(k), device,
                                          ctypes.c_void_p(keys.data_ptr()), ctypes.c_void_p(vals.data_ptr()),
                                          ctypes.byref(n_valid), None))
+    if fused is None:
+        fused = os.environ.get("PA_FUSED_EXCHANGE", "1") != "0"
+    if fused and int(k) >= 1:
+        torch.cuda.synchronize(dev)
+        t["encode_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        rk, rv, n_recv, n_sent = _exchange_fused(L, nat, keys, vals, n_bases, k, device, world, rank, group)
+        assert n_sent == n_valid.value
+        del keys, vals
+        t["scatter_exchange_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        h = ctypes.c_void_p()
+        try:
+            nat.check(L.pa_index_build_from_records_device(rk, rv, n_recv, nat._p(genome_off), G, int(k), device, 0,
+                                                           ctypes.byref(h)))
+        finally:
+            L.pa_peer_free(rk, device)
+            L.pa_peer_free(rv, device)
+        partition = nat.NativeIndex(h.value)
+        t["sort_rle_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        replica = _gather_replica(partition, k, genome_off, dev, group)
+        t["replicate_s"] = time.perf_counter() - t0
+        out = DistributedIndex(partition, replica, int(k), genome_off, rank, world, group)
+        out.timings = t
+        out.sent_records, out.received_records, out.fused = n_sent, n_recv, True
+        return out
     keys_t = torch.empty_like(keys)
     vals_t = torch.empty_like(vals)
     part_off = np.zeros(world + 1, dtype=np.uint64)
@@ -284,6 +368,7 @@ def build_partitioned(my_bases, genome_off: np.ndarray, k: int, g_range: Tuple[i
     out.timings = t
     out.sent_records = int(part_off[-1])
     out.received_records = n_recv
+    out.fused = False
     return out
 
 

@@ -143,6 +143,25 @@ int32_t pa_records_partition_device(uint64_t* d_keys, uint32_t* d_vals, uint64_t
 int32_t pa_partition_of_key(int32_t k, uint64_t hashed_key, uint32_t n_parts, uint32_t* part);
 int32_t pa_index_build_from_records_device(uint64_t* d_keys, uint32_t* d_vals, uint64_t n, const uint64_t* genome_off,
                                            uint32_t n_genomes, int32_t k, int32_t device, int32_t build_tables, pa_index** out);
+/* Fused partition + exchange: instead of pa_records_partition_device + all_to_all, the stable scatter pass stores every
+ * record straight into the receive buffer of the rank that owns its key range -- peer memory mapped through CUDA IPC,
+ * the stores travel over NVLink -- so the exchange overlaps the pass tile by tile and no send buffer is written.
+ *   pa_peer_alloc / pa_peer_open / pa_peer_close / pa_peer_free   receive buffers: cudaMalloc + 64-byte IPC handle, opened
+ *                                   by the other ranks (same node)
+ *   pa_records_digit_counts         counts[256] of the partition digit = key bits [begin_bit, begin_bit + 8); digits
+ *                                   below 2^top_bits are real (part = digit * n_parts >> top_bits), 255 = invalid windows.
+ *                                   The ranks all-gather these to lay out the receive buffers (sender-major, digit-minor)
+ *   pa_records_scatter_to_peers     dst_keys[d] / dst_vals[d] = where this rank's run of digit d starts (device pointers,
+ *                                   possibly peer memory; NULL drops the digit).  Returns after the stores are complete;
+ *                                   a barrier between the ranks then makes every receive buffer final. */
+int32_t pa_peer_alloc(uint64_t bytes, int32_t device, void** d_ptr, uint8_t* handle);
+int32_t pa_peer_open(const uint8_t* handle, int32_t device, void** d_ptr);
+int32_t pa_peer_close(void* d_ptr, int32_t device);
+int32_t pa_peer_free(void* d_ptr, int32_t device);
+int32_t pa_records_digit_counts(const uint64_t* d_keys, uint64_t n, int32_t k, int32_t device, uint64_t* counts,
+                                int32_t* begin_bit, int32_t* top_bits, void* stream);
+int32_t pa_records_scatter_to_peers(const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n, int32_t k, int32_t device,
+                                    uint64_t* const* dst_keys, uint32_t* const* dst_vals, void* stream);
 /* device pointers of an index's keys[n_keys], run_off[n_keys+1], run_genome[n_runs] (for the gather / to fill a replica) */
 int32_t pa_index_csr_device(pa_index* idx, uint64_t** d_keys, uint64_t** d_run_off, uint32_t** d_run_genome);
 /* replica = align-only index: allocate, fill keys / run_off (rebased) / run_genome through pa_index_csr_device,

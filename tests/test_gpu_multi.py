@@ -31,6 +31,7 @@ torch.cuda.set_device(device)
 dist.init_process_group("nccl" if use_nccl else "gloo", rank=rank, world_size=world,
                         **({{"device_id": torch.device("cuda", device)}} if use_nccl else {{}}))
 NAMES = {{1: "UNMAPPED", 2: "UNIQUELY_MAPPED", 3: "AMBIGUOUSLY_MAPPED"}}
+FUSED = os.environ.get("PA_TEST_FUSED", "1") == "1"   # scatter into peer memory (CUDA IPC) vs partition + all_to_all
 
 def kmers_dict_from_export(ex, k):
     kmers = nat.decode_kmers(k, ex["keys"])
@@ -64,7 +65,8 @@ def run_case(case):
     g_lo, g_hi = multi_gpu.genome_shards(lengths, world)[rank]
     mine = np.zeros(int(goff[g_hi] - goff[g_lo]) + 64, dtype=np.uint8)
     mine[:int(goff[g_hi] - goff[g_lo])] = data[int(goff[g_lo]):int(goff[g_hi])]
-    dix = multi_gpu.build_partitioned(mine, goff, k, (g_lo, g_hi), device=device)
+    dix = multi_gpu.build_partitioned(mine, goff, k, (g_lo, g_hi), device=device, fused=FUSED)
+    assert dix.fused == (FUSED and k >= 1)
     o = orc.OracleReference(k, genomes)
     try:
         # every record went to exactly one owner, and keys are partitioned by range
@@ -140,14 +142,14 @@ dist.destroy_process_group()
 '''
 
 
-def _run(world, seeds, tmp_path, nccl=False):
+def _run(world, seeds, tmp_path, nccl=False, fused=True):
     script = tmp_path / "worker.py"
     script.write_text(WORKER.format(root=conftest.ROOT, pkg=conftest.PKG_DIR))
     port = 23000 + (os.getpid() * 7 + world * 131 + len(seeds)) % 4000
     procs = []
     for rank in range(world):
         env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
-                   PA_TEST_NCCL="1" if nccl else "0")
+                   PA_TEST_NCCL="1" if nccl else "0", PA_TEST_FUSED="1" if fused else "0")
         procs.append(subprocess.Popen([sys.executable, str(script), ",".join(str(s) for s in seeds)], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     outs = [p.communicate(timeout=900) for p in procs]
@@ -162,6 +164,10 @@ def test_partitioned_build_world_2_fuzz(tmp_path):
 
 def test_partitioned_build_world_3_fuzz(tmp_path):
     _run(3, list(range(6000, 6016)), tmp_path)
+
+
+def test_partitioned_build_all_to_all_exchange(tmp_path):
+    _run(2, list(range(5100, 5112)) + [-13], tmp_path, fused=False)
 
 
 def test_partitioned_build_world_2_k31(tmp_path):
