@@ -274,6 +274,7 @@ def gpu_arm(args):
                       "phases_rank0": dix.timings, "records_sent_rank0": dix.sent_records,
                       "records_received_rank0": dix.received_records, "same_sizes_as_single_gpu_build": True}
         dix.close()
+        multi_gpu.release_peer_buffers()
 
     # ---- reads of this rank (weak scaling: every rank aligns its own `reads` reads) ----
     rbases, rquals, roff = device_reads(torch, dev, bases, G, GL, NR, RL, seed=2000 + rank)

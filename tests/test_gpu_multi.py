@@ -136,6 +136,7 @@ for seed in seeds:
                 "params": dict(m=1, p=1, mrq=None, mkq=60 if seed % 2 else None, mg=2 if seed % 2 else None), "seed": -seed}}
         run_case(case)
 dist.barrier()
+multi_gpu.release_peer_buffers()
 if rank == 0:
     print("OK")
 dist.destroy_process_group()
