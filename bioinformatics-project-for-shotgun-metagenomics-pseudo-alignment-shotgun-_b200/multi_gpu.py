@@ -476,3 +476,55 @@ def export_gathered(dix: DistributedIndex, dst: int = 0):
     out["pos_off"] = np.concatenate(pos_off + [np.array([pb], dtype=np.uint64)])
     out["order"] = np.argsort(out["first_occ"], kind="stable").astype(np.uint32)
     return out
+
+
+# ---------------------------------------------------------------------------
+# read-sharded alignment, end to end
+# ---------------------------------------------------------------------------
+def align_sharded(index, bases: np.ndarray, quals: Optional[np.ndarray], read_off: np.ndarray, genome_ids: List[str],
+                  m: int = 1, p: int = 1, min_read_quality: Optional[int] = None, min_kmer_quality: Optional[int] = None,
+                  max_genomes: Optional[int] = None, group=None, gather_reads: bool = False):
+    """PseudoAlignment.align_reads_from_container + get_summary (kmer.py:600-657) across ranks.
+
+    Every rank holds the whole packed batch (bases / quals / read_off as produced by the native ingest) and a replicated
+    align index (`NativeIndex`, e.g. DistributedIndex.replica); rank r aligns the contiguous block shard_bounds(n, world, r),
+    the K8 accumulators are all-reduced, and every rank returns the reference's summary dict (key order included).
+    gather_reads=True additionally returns, on rank 0, the per-read (type, genome index list) of all reads in file order.
+    """
+    import torch
+    import torch.distributed as dist
+    import _native as nat
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
+    n = len(read_off) - 1
+    lo, hi = shard_bounds(n, world, rank)
+    params = nat.make_params(m, p, min_read_quality, min_kmer_quality, max_genomes)
+    words, lst, counters = index.align(bases, quals, read_off[lo:hi + 1], params)
+    stats, uniq, amb, first = index.summary(words, lst, read_index_base=lo)
+    G = len(genome_ids)
+    acc = torch.from_numpy(np.concatenate([stats, uniq, amb, counters]).astype(np.int64))
+    fs = torch.from_numpy(first.astype(np.uint64).view(np.int64).copy())
+    if _is_nccl(group):
+        dev = torch.device("cuda", index.info().device)
+        acc_d, fs_d = acc.to(dev), fs.to(dev)
+        allreduce_summary(acc_d, fs_d, group)
+        acc, fs = acc_d.cpu(), fs_d.cpu()
+    else:
+        allreduce_summary(acc, fs, group)
+    a = acc.numpy()
+    flags = (min_read_quality is not None, min_kmer_quality is not None, max_genomes is not None)
+    summary = summary_from_accumulators(a[:4], a[4:4 + G], a[4 + G:4 + 2 * G], fs.numpy().view(np.uint64), genome_ids, flags,
+                                        a[4 + 2 * G:4 + 2 * G + 3])
+    if not gather_reads:
+        return summary
+    types, lens, payload = nat.decode_words(words)
+    lists = [[int(payload[i])] if lens[i] == 1 else [int(x) for x in lst[int(payload[i]):int(payload[i]) + int(lens[i])]]
+             for i in range(len(words))]
+    parts = [None] * world
+    dist.all_gather_object(parts, (types.tolist(), lists), group=group)
+    if rank != 0:
+        return summary, None
+    all_types = [t for part in parts for t in part[0]]
+    all_lists = [l for part in parts for l in part[1]]
+    return summary, (all_types, all_lists)
+

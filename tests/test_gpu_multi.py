@@ -92,6 +92,18 @@ def run_case(case):
         assert got_reads == al.reads(), case.get("seed")
         assert counters == [al.filtered_quality_reads, al.filtered_quality_kmers if pr["mkq"] is not None else 0,
                             al.filtered_hr_kmers if pr["mg"] is not None else 0]
+        # read-sharded alignment end to end: summary on every rank, per-read results gathered on rank 0
+        seqs, roff = nat.pack_strings([r[1] for r in case["reads"]])
+        qls, _ = nat.pack_strings([r[2] for r in case["reads"]])
+        summary, reads = multi_gpu.align_sharded(dix.replica, seqs, qls, roff, ids, pr["m"], pr["p"], pr["mrq"], pr["mkq"],
+                                                 pr["mg"], gather_reads=True)
+        assert json.dumps(summary) == json.dumps(al.get_summary()), (summary, al.get_summary())
+        if rank == 0:
+            want_types = [int(t) for t in al.types]
+            assert reads[0] == want_types
+            for i in range(len(want_types)):
+                if want_types[i] != 0:
+                    assert reads[1][i] == [int(g) for g in al.genomes[int(al.list_off[i]):int(al.list_off[i + 1])]]
         # EXTSIM: all-reduced statistics and intersections
         classes = {{}}
         group = np.array([classes.setdefault(s, len(classes)) for s in ids], dtype=np.uint32)
