@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = [
     "pa_index_csr_device", "pa_index_alloc_replica", "pa_index_finish_replica", "pa_index_build_tables", "pa_debug_pack_reads",
     "pa_parse_records", "pa_parsed_copy", "pa_parsed_free",
     "pa_peer_alloc", "pa_peer_open", "pa_peer_close", "pa_peer_free", "pa_records_digit_counts", "pa_records_scatter_to_peers",
+    "pa_format_kmers_json", "pa_free_text",
 ]
 
 
@@ -124,6 +125,8 @@ def lib() -> ctypes.CDLL:
         "pa_peer_free": (i32, [vp, i32]),
         "pa_records_digit_counts": (i32, [vp, u64, i32, i32, vp, vp, vp, vp]),
         "pa_records_scatter_to_peers": (i32, [vp, vp, u64, i32, i32, vp, vp, vp]),
+        "pa_format_kmers_json": (i32, [i32, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]),
+        "pa_free_text": (i32, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -406,3 +409,26 @@ def parse_records_native(raw: bytes, fastq: bool):
 def parsed_names(packed) -> List[str]:
     raw = packed["raw"]
     return [raw[b:b + l].decode("ascii") for b, l in zip(packed["name_beg"].tolist(), packed["name_len"].tolist())]
+
+
+def format_kmers_json(k: int, csr, desc_class: np.ndarray, desc_json: Sequence[str], indent: int = 4, level: int = 1) -> str:
+    """The "Kmers" object of get_summary() as JSON text, written natively from an exported CSR (format.cpp)."""
+    keys = np.ascontiguousarray(csr["keys"], dtype=np.uint64)
+    n = len(keys)
+    blobs = [d.encode("ascii") for d in desc_json]       # json.dumps output is ASCII (ensure_ascii)
+    off = np.zeros(len(blobs) + 1, dtype=np.uint64)
+    if blobs:
+        off[1:] = np.cumsum([len(b) for b in blobs])
+    flat = np.frombuffer(b"".join(blobs) or b"\0", dtype=np.uint8)
+    out, out_len = ctypes.c_void_p(), ctypes.c_uint64(0)
+    arr = lambda a, t: np.ascontiguousarray(a, dtype=t) if len(a) else np.zeros(1, dtype=t)
+    check(lib().pa_format_kmers_json(int(max(k, 0)), n, _p(arr(keys, np.uint64)), _p(arr(csr["order"], np.uint32)),
+                                     _p(arr(csr["run_off"], np.uint64)), _p(arr(csr["run_genome"], np.uint32)),
+                                     _p(arr(csr["pos_off"], np.uint64)), _p(arr(csr["pos"], np.uint32)),
+                                     _p(arr(desc_class, np.uint32)), _p(flat), _p(off), int(indent), int(level),
+                                     ctypes.byref(out), ctypes.byref(out_len)))
+    try:
+        return ctypes.string_at(out, out_len.value).decode("ascii")
+    finally:
+        lib().pa_free_text(out)
+

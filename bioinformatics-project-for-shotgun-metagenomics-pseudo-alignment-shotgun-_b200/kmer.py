@@ -304,6 +304,57 @@ class KmerReference(object):
         return merged
 
     # -- summary (kmer.py:300-329) -----------------------------------------------------------
+    def summary_json(self, indent: int = 4) -> str:
+        """json.dumps(self.get_summary(), indent=indent), byte for byte, without building the nested dictionaries: the
+        "Kmers" object (all of the bulk) is written natively from the exported CSR (csrc/format.cpp), "Summary" comes
+        from array reductions.  What `main.py -t dumpref` prints."""
+        csr = self._index().export()
+        genomes = self.genomes
+        classes: Dict[str, int] = {}
+        group = np.zeros(max(len(genomes), 1), dtype=np.uint32)
+        for i, rec in enumerate(genomes):
+            group[i] = classes.setdefault(rec["description"], len(classes))
+        names = list(classes)
+        kmers_text = nat.format_kmers_json(self.kmer_len, csr, group[:max(len(genomes), 1)], [json.dumps(d) for d in names],
+                                           indent=indent, level=1)
+        summary: Dict[str, Dict[str, int]] = {}
+        n_keys = len(csr["keys"])
+        if n_keys:
+            # key order of "Summary": first appearance of a description while scanning the k-mers in insertion order
+            # and, inside a k-mer, the genomes in ascending order
+            rank_of_key = np.empty(n_keys, dtype=np.int64)
+            rank_of_key[csr["order"].astype(np.int64)] = np.arange(n_keys, dtype=np.int64)
+            runs_per_key = np.diff(csr["run_off"].astype(np.int64))
+            key_of_run = np.repeat(np.arange(n_keys, dtype=np.int64), runs_per_key)
+            cls_of_run = group[csr["run_genome"].astype(np.int64)].astype(np.int64)
+            when = rank_of_key[key_of_run] * (int(runs_per_key.max()) + 1) + (np.arange(len(key_of_run)) - csr["run_off"].astype(np.int64)[key_of_run])
+            first = np.full(len(names), np.iinfo(np.int64).max, dtype=np.int64)
+            np.minimum.at(first, cls_of_run, when)
+            total, unique = self._index().extsim_stats(group, len(names))
+            # the reference assigns total_bases at every (k-mer, genome) visit (kmer.py:315), so the value left is that
+            # of the genome of the class visited last: the last k-mer in insertion order holding the class, and its
+            # highest such genome
+            last = np.full(len(names), -1, dtype=np.int64)
+            np.maximum.at(last, cls_of_run, when)
+            order_runs = np.argsort(when, kind="stable")
+            sorted_when = when[order_runs]
+            for c in np.argsort(first, kind="stable"):
+                if first[c] == np.iinfo(np.int64).max:
+                    continue      # genomes without any valid k-mer do not appear (kmer.py:309-316)
+                run = int(order_runs[int(np.searchsorted(sorted_when, last[c]))])
+                g = int(csr["run_genome"][run])
+                summary[names[int(c)]] = {"total_bases": len(genomes[g]["genome"]), "unique_kmers": int(unique[c]),
+                                          "multi_mapping_kmers": int(total[c]) - int(unique[c])}
+        pad = " " * indent
+
+        def nested(obj) -> str:
+            return json.dumps(obj, indent=indent).replace("\n", "\n" + pad)
+
+        parts = [f'{pad}"Kmers": {kmers_text}', f'{pad}"Summary": {nested(summary)}']
+        if hasattr(self, "similarity_info"):
+            parts.append(f'{pad}"Similarity": {nested(self.similarity_info)}')
+        return "{\n" + ",\n".join(parts) + "\n}"
+
     def get_summary(self) -> Dict[str, Any]:
         csr = self._host_csr()
         genomes = self.genomes

@@ -89,7 +89,8 @@ def _load(kind, path: str):
 
 
 def dump_reference(kmer_reference: KmerReference) -> None:
-    print(json.dumps(kmer_reference.get_summary(), indent=4))
+    # the text of json.dumps(kmer_reference.get_summary(), indent=4) (main.py:127), written without the nested dicts
+    print(kmer_reference.summary_json(indent=4))
 
 
 def dump_reference_file(reference_file: str) -> None:

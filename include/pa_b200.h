@@ -217,6 +217,18 @@ int32_t pa_parsed_copy(pa_parsed* h, uint8_t* seq, uint8_t* qual, uint64_t* seq_
                        uint64_t* plus_beg, uint64_t* plus_len);
 int32_t pa_parsed_free(pa_parsed* h);
 
+/* ---- dumpref: the "Kmers" object of KmerReference.get_summary (kmer.py:300-329) as JSON text (pure host code) ----
+ * Byte for byte what json.dumps(..., indent=`indent`) prints for that object when it sits `level` levels deep: k-mers in
+ * dict insertion order (`order`), per k-mer one entry per description class in order of first appearance (the last
+ * genome of a class wins, like the dict assignment), positions ascending.  Inputs: the arrays of pa_index_export;
+ * desc_class[g] = class of genome g, desc_json = the classes' descriptions already JSON-escaped (quotes included),
+ * concatenated, desc_json_off[n_classes + 1].  *out_text is malloc'ed by the library: release with pa_free_text. */
+int32_t pa_format_kmers_json(int32_t k, uint64_t n_keys, const uint64_t* keys, const uint32_t* order, const uint64_t* run_off,
+                             const uint32_t* run_genome, const uint64_t* pos_off, const uint32_t* pos,
+                             const uint32_t* desc_class, const uint8_t* desc_json, const uint64_t* desc_json_off,
+                             int32_t indent, int32_t level, uint8_t** out_text, uint64_t* out_len);
+int32_t pa_free_text(uint8_t* p);
+
 /* ---- diagnostics used by the tests ----------------------------------------------------------------- */
 /* stable LSD radix sort of (key, value) pairs on key bits [0, end_bit), host in / host out (K2) */
 int32_t pa_debug_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t n, int32_t end_bit, int32_t device);

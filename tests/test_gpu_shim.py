@@ -40,6 +40,8 @@ def canonical_from_product(case):
         # genomes (and re-applies the EXTSIM drop), and must be indistinguishable -- dict insertion order included
         ref = pickle.loads(pickle.dumps(ref))
     index_of = {id(r): i for i, r in enumerate(ref.genomes)}
+    # the native dumpref writer must print exactly what json.dumps prints for the dictionary version
+    assert ref.summary_json(indent=4) == json.dumps(ref.get_summary(), indent=4)
     out = {"genomes": [g.identifier for g in ref.genomes],
            "kmers": [[km, [[index_of[id(r)], sorted(pos)] for r, pos in inner.items()]] for km, inner in ref.kmers.items()],
            "ref_summary_json": json.dumps(ref.get_summary())}
