@@ -203,15 +203,35 @@ constexpr int RLE_THREADS = 256;
 constexpr int RLE_ITEMS = 8;
 constexpr int RLE_TILE = RLE_THREADS * RLE_ITEMS;
 
+// genome of a global base position through the coarse map: gmap[pos >> shift] = genome of the first base of that
+// block, then a short forward walk (a block rarely holds a genome boundary) instead of a binary search per record
+struct GenomeMap {
+  const uint32_t* map;
+  uint32_t shift;
+};
+__device__ __forceinline__ uint32_t genome_at(const GenomeMap& gm, const uint64_t* __restrict__ off, uint64_t pos) {
+  uint32_t g = gm.map[pos >> gm.shift];
+  while (off[g + 1] <= pos) ++g;
+  return g;
+}
+
+__global__ void genome_map_fill(const uint64_t* __restrict__ off, uint32_t G, uint64_t total, uint32_t shift, uint32_t* __restrict__ map,
+                                uint64_t n_entries) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n_entries) return;
+  const uint64_t pos = i << shift;
+  map[i] = pos < total ? genome_of(off, G, pos) : (G ? G - 1 : 0);
+}
+
 __device__ __forceinline__ void rle_flags(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                          const uint64_t* __restrict__ genome_off, uint32_t G, uint64_t base, uint64_t n,
+                                          const uint64_t* __restrict__ genome_off, GenomeMap G, uint64_t base, uint64_t n,
                                           uint32_t (&gen)[RLE_ITEMS], uint32_t& kh_mask, uint32_t& rh_mask) {
   kh_mask = rh_mask = 0;
   uint64_t prev_key = 0; uint32_t prev_gen = 0;
   bool have_prev = false;
   if (base > 0 && base < n) {
     prev_key = keys[base - 1];
-    prev_gen = genome_of(genome_off, G, vals[base - 1]);
+    prev_gen = genome_at(G, genome_off, vals[base - 1]);
     have_prev = true;
   }
 #pragma unroll
@@ -219,7 +239,7 @@ __device__ __forceinline__ void rle_flags(const uint64_t* __restrict__ keys, con
     uint64_t i = base + j;
     if (i < n) {
       uint64_t key = keys[i];
-      uint32_t g = genome_of(genome_off, G, vals[i]);
+      uint32_t g = genome_at(G, genome_off, vals[i]);
       gen[j] = g;
       bool kh = !have_prev || key != prev_key;
       bool rh = kh || g != prev_gen;
@@ -232,7 +252,7 @@ __device__ __forceinline__ void rle_flags(const uint64_t* __restrict__ keys, con
 
 __global__ void __launch_bounds__(RLE_THREADS)
 rle_count(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint64_t* __restrict__ genome_off,
-          uint32_t G, uint64_t n, uint64_t* __restrict__ tile_keys, uint64_t* __restrict__ tile_runs) {
+          GenomeMap G, uint64_t n, uint64_t* __restrict__ tile_keys, uint64_t* __restrict__ tile_runs) {
   __shared__ uint32_t ws[2][RLE_THREADS / 32];
   const uint64_t base = (uint64_t)blockIdx.x * RLE_TILE + (uint64_t)threadIdx.x * RLE_ITEMS;
   uint32_t gen[RLE_ITEMS], kh, rh;
@@ -249,7 +269,7 @@ rle_count(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, 
 
 __global__ void __launch_bounds__(RLE_THREADS)
 rle_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint64_t* __restrict__ genome_off,
-            uint32_t G, uint64_t n, const uint64_t* __restrict__ tile_keys, const uint64_t* __restrict__ tile_runs,
+            GenomeMap G, uint64_t n, const uint64_t* __restrict__ tile_keys, const uint64_t* __restrict__ tile_runs,
             uint64_t* __restrict__ ukeys, uint64_t* __restrict__ run_off, uint32_t* __restrict__ run_genome,
             uint64_t* __restrict__ pos_off, uint32_t* __restrict__ pos) {
   __shared__ uint32_t ws[RLE_THREADS / 32];
@@ -684,10 +704,16 @@ int32_t index_build_tables(Index& ix) {
 // K3 host side: CSR of the index from n_valid sorted (key, global position) records
 static int32_t rle_to_csr(Index& ix, const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n_valid) {
   cudaStream_t s = ix.stream;
-  const uint32_t G = ix.n_genomes;
   const uint64_t tiles = std::max<uint64_t>(1, (n_valid + RLE_TILE - 1) / RLE_TILE);
-  DevBuf tile_keys, tile_runs, totals;
+  DevBuf tile_keys, tile_runs, totals, gmap;
   PA_TRY(tile_keys.alloc((tiles + 1) * 8)); PA_TRY(tile_runs.alloc((tiles + 1) * 8)); PA_TRY(totals.alloc(16));
+  const uint32_t n_genomes = ix.n_genomes;
+  const uint32_t gshift = (uint32_t)std::max<int>(0, (int)ceil_log2_u64(ix.total_bases + 1) - 20);
+  const uint64_t gentries = (ix.total_bases >> gshift) + 1;
+  PA_TRY(gmap.alloc(gentries * 4));
+  genome_map_fill<<<grid_for(gentries, 256), 256, 0, s>>>(ix.genome_off.as<uint64_t>(), n_genomes, ix.total_bases, gshift,
+                                                          gmap.as<uint32_t>(), gentries);
+  const GenomeMap G{gmap.as<uint32_t>(), gshift};
   rle_count<<<(unsigned)tiles, RLE_THREADS, 0, s>>>(d_keys, d_vals, ix.genome_off.as<uint64_t>(), G, n_valid,
                                                     tile_keys.as<uint64_t>(), tile_runs.as<uint64_t>());
   scan_u64_single_block<<<1, 1024, 0, s>>>(tile_keys.as<uint64_t>(), tiles, totals.as<uint64_t>());
