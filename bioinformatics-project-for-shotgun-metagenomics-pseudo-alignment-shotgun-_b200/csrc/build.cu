@@ -757,6 +757,8 @@ int32_t index_build_from_device_bases(Index& ix, const uint8_t* d_bases) {
   // ---- K1 ----
   DevBuf keys_a, keys_b, vals_a, vals_b, counters, sort_tmp;
   PA_TRY(keys_a.alloc(total * 8)); PA_TRY(vals_a.alloc(total * 4));
+  PA_TRY(keys_b.alloc(total * 8)); PA_TRY(vals_b.alloc(total * 4));     // allocated up front: the phase events
+  PA_TRY(sort_tmp.alloc(radix_sort_temp_bytes(total)));                  // below then bracket kernels only
   PA_TRY(counters.alloc(16));
   PA_CUDA(cudaMemsetAsync(counters.p, 0, 16, s));
   PA_CUDA(cudaEventRecord(ev[0], s));
@@ -772,8 +774,6 @@ int32_t index_build_from_device_bases(Index& ix, const uint8_t* d_bases) {
   const uint64_t n_valid = h_cnt[0];
 
   // ---- K2 ----
-  PA_TRY(keys_b.alloc(total * 8)); PA_TRY(vals_b.alloc(total * 4));
-  PA_TRY(sort_tmp.alloc(radix_sort_temp_bytes(total)));
   int in_b = 0;
   PA_TRY(radix_sort_pairs(keys_a.as<uint64_t>(), vals_a.as<uint32_t>(), keys_b.as<uint64_t>(), vals_b.as<uint32_t>(), total,
                           std::min(64, 2 * k + 1), sort_tmp.p, sort_tmp.bytes, s, &in_b));

@@ -25,7 +25,13 @@ constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_ITEMS = 16;
+#ifndef PA_SORT_ITEMS
+#define PA_SORT_ITEMS 16
+#endif
+#ifndef PA_SORT_MINB
+#define PA_SORT_MINB 3
+#endif
+constexpr int SORT_ITEMS = PA_SORT_ITEMS;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 pairs per tile
 constexpr int MAX_PASSES = 8;
 
@@ -74,7 +80,7 @@ struct PassSmem {
   uint32_t tile_id;
 };
 
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, PA_SORT_MINB)
 radix_pass(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
            uint32_t* __restrict__ vals_out, uint64_t n, int shift, const unsigned long long* __restrict__ digit_start,
            volatile unsigned long long* __restrict__ lookback, unsigned int* __restrict__ tile_counter,
