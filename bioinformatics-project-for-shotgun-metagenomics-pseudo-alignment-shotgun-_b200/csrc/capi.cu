@@ -559,25 +559,32 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
   const bool trace = getenv("PA_TRACE") != nullptr;
   auto t0 = std::chrono::steady_clock::now();
 
-  // Chunked pipeline: chunk c uses slot c & 1 (its own stream): H2D(bases, quals, offsets) -> K4 -> D2H(words).
-  // The copy engine moves chunk c+1 in while the SMs align chunk c; kernels are chained with an event because they
-  // share the index's per-warp scratch.  The list cursor and the filter counters live in one device state block
-  // shared by all chunks, so list offsets in the result words are global to the call.
+  // Chunked pipeline over N_SLOTS slots (each its own stream): chunk c uses slot c % N_SLOTS:
+  //   [2-bit packing on the host cores] -> H2D(planes | bases, quals, offsets) -> K4 -> D2H(words).
+  // The copy engines move later chunks in while the SMs align earlier ones; kernels are chained with an event
+  // because they share the queue and the per-warp scratch.  The list cursor and the filter counters live in one
+  // device state block shared by all chunks, so list offsets in the result words are global to the call.
+  constexpr int N_SLOTS = Index::N_HOST_SLOTS;
   for (auto& sl : ix.slot) {
     if (!sl.stream) PA_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
     if (!sl.kernel_done) PA_CUDA(cudaEventCreateWithFlags(&sl.kernel_done, cudaEventDisableTiming));
     if (!sl.h2d_done) PA_CUDA(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+    if (!sl.copy_beg) PA_CUDA(cudaEventCreate(&sl.copy_beg));
+    if (!sl.copy_end) PA_CUDA(cudaEventCreate(&sl.copy_end));
+    sl.copy_bytes = 0;
   }
   PA_TRY(ensure(ix.host_list, std::max<uint64_t>(list_cap, 1) * 4));
   PA_TRY(ensure(ix.host_state, 64));
   PA_CUDA(cudaMemsetAsync(ix.host_state.p, 0, 40, ix.slot[0].stream));
-  PA_CUDA(cudaEventRecord(ix.slot[1].kernel_done, ix.slot[0].stream));  // "previous kernel" of chunk 0 = the memset
+  PA_CUDA(cudaEventRecord(ix.slot[N_SLOTS - 1].kernel_done, ix.slot[0].stream));  // "previous kernel" of chunk 0 = the memset
   uint64_t chunk = std::min<uint64_t>(std::max<uint64_t>(n_reads / 20, 1u << 16), 1u << 20);
   if (const char* e = getenv("PA_CHUNK_READS")) { uint64_t v = strtoull(e, nullptr, 10); if (v) chunk = v; }
-  // PA_HOST_PACK: 0 = never pack, 1 = always pack, unset / 2 = the self-balancing mix below
+  // PA_HOST_PACK: 0 = never pack, 1 = always pack, unset / 2 = the two-resource rule below
   const int pack_mode = getenv("PA_HOST_PACK") ? atoi(getenv("PA_HOST_PACK")) : 2;
   const bool use_pack = pack_mode != 0;
-  const double pack_min_gbs = getenv("PA_PACK_MIN_GBS") ? atof(getenv("PA_PACK_MIN_GBS")) : 65.0;
+  if (ix.pack_rate_gbs <= 0) ix.pack_rate_gbs = 5.6 * host_pack_threads();
+  if (ix.link_rate_gbs <= 0) ix.link_rate_gbs = getenv("PA_LINK_GBS") ? atof(getenv("PA_LINK_GBS")) : 45.0;
+  double link_busy_until = 0;   // host-clock estimate (ms since t0) of when the queued H2D transfers end
 
   uint64_t c = 0, n_packed = 0;
   double t_wait = 0, t_pack = 0, t_enq = 0;
@@ -585,28 +592,26 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
   auto ms_since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
   for (uint64_t lo = 0; lo < n_reads; lo += chunk, ++c) {
     const uint64_t hi = std::min(n_reads, lo + chunk), n = hi - lo;
-    Index::HostSlot& sl = ix.slot[c & 1];
-    Index::HostSlot& prev = ix.slot[(c & 1) ^ 1];
+    Index::HostSlot& sl = ix.slot[c % N_SLOTS];
+    Index::HostSlot& prev = ix.slot[(c + N_SLOTS - 1) % N_SLOTS];
     const uint64_t b0 = read_off[lo], nb = read_off[hi] - b0;
     uint64_t max_len = 0;
     auto tv0 = now();
     NEED(scan_offsets(read_off, lo, hi, &max_len, host_pack_threads()), "read_off is not monotonic");
     t_pack += ms_since(tv0);
-    // Which way does this chunk travel?  Packing to 2-bit planes (hostpack.h) costs host time (all cores) and saves
-    // 3/4 of the link time; raw ASCII costs no host time.  Self-balancing rule: when the slot's previous chunk
-    // (c - 2) is still in flight the device side is the bottleneck and the host would only wait -- so it packs
-    // instead; when the slot is already free the host is the bottleneck and the chunk goes out as ASCII at once.
-    // A chunk with a base outside ACGT always travels as ASCII.
+    // Which way does this chunk travel?  Packing to 2-bit planes (hostpack.h) costs host time (all cores) and leaves
+    // a quarter of the bytes for the link; raw ASCII costs no host time.  Two resources work in parallel -- the host
+    // cores and the copy engine -- so the greedy rule is: pack while the link still has about one packing time of
+    // transfers queued (the cores would idle otherwise), else send the chunk raw at once (the link would idle).
+    // Both rates are measured as the call goes.  With 16 cores against PCIe 5 x16 this settles at ~2 packed : 1 raw;
+    // a node whose ranks share few cores settles at mostly raw.  A chunk with a base outside ACGT always travels raw.
     auto tp = now();
     bool packed = false;
     const uint64_t n_words = planes_words(nb, n);
-    const bool slot_busy = cudaStreamQuery(sl.stream) == cudaErrorNotReady;
-    (void)cudaGetLastError();
-    // ... and only while the host packs clearly faster than the link moves raw ASCII (measured per chunk; a node
-    // whose ranks share few cores does not: 8 threads pack ~45 GB/s, about what PCIe 5 x16 carries)
-    if (ix.pack_rate_gbs <= 0) ix.pack_rate_gbs = 5.6 * host_pack_threads();
-    const bool pack_pays = ix.pack_rate_gbs >= pack_min_gbs;
-    if (use_pack && (pack_mode == 1 || (slot_busy && pack_pays)) && ix.k >= 1 && nb) {
+    const double t_now = ms_since(t0);
+    const double pack_est_ms = (double)nb / (ix.pack_rate_gbs * 1e6);
+    const bool link_backed_up = (link_busy_until - t_now) >= 0.8 * pack_est_ms;
+    if (use_pack && (pack_mode == 1 || link_backed_up) && ix.k >= 1 && nb) {
       PA_CUDA(cudaEventSynchronize(sl.h2d_done));   // the staging buffer's previous transfer has left the host
       if (sl.h_planes_words < n_words) {
         if (sl.h_planes) { cudaFreeHost(sl.h_planes); sl.h_planes = nullptr; sl.h_planes_words = 0; }
@@ -623,9 +628,16 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
       }
     }
     t_pack += ms_since(tp); tp = now();
-    // slot buffers are free once the slot's previous chunk (c - 2) has finished: its stream is in order
+    // slot buffers are free once the slot's previous chunk (c - N_SLOTS) has finished: its stream is in order
     PA_CUDA(cudaStreamSynchronize(sl.stream));
     t_wait += ms_since(tp); tp = now();
+    if (sl.copy_bytes) {   // the slot's previous raw transfer has been timed: refresh the link rate
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, sl.copy_beg, sl.copy_end) == cudaSuccess && ms > 0)
+        ix.link_rate_gbs = 0.5 * ix.link_rate_gbs + 0.5 * ((double)sl.copy_bytes / ms / 1e6);
+      (void)cudaGetLastError();
+      sl.copy_bytes = 0;
+    }
     if (need_q) PA_TRY(ensure(sl.quals, nb + 64));
     PA_TRY(ensure(sl.off, (n + 1) * 8));
     PA_TRY(ensure(sl.words, n * 8));
@@ -635,10 +647,19 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
       PA_CUDA(cudaEventRecord(sl.h2d_done, sl.stream));
     } else {
       PA_TRY(ensure(sl.bases, nb + 64));
-      if (nb) PA_CUDA(cudaMemcpyAsync(sl.bases.p, bases + b0, nb, cudaMemcpyHostToDevice, sl.stream));
+      if (nb) {
+        PA_CUDA(cudaEventRecord(sl.copy_beg, sl.stream));
+        PA_CUDA(cudaMemcpyAsync(sl.bases.p, bases + b0, nb, cudaMemcpyHostToDevice, sl.stream));
+        PA_CUDA(cudaEventRecord(sl.copy_end, sl.stream));
+        sl.copy_bytes = nb;
+      }
     }
     if (need_q && nb) PA_CUDA(cudaMemcpyAsync(sl.quals.p, quals + b0, nb, cudaMemcpyHostToDevice, sl.stream));
     PA_CUDA(cudaMemcpyAsync(sl.off.p, read_off + lo, (n + 1) * 8, cudaMemcpyHostToDevice, sl.stream));
+    {
+      const double bytes = (packed ? (double)n_words * 4 : (double)nb) + (need_q ? (double)nb : 0.0) + (double)(n + 1) * 8;
+      link_busy_until = std::max(link_busy_until, ms_since(t0)) + bytes / (ix.link_rate_gbs * 1e6);
+    }
     PA_CUDA(cudaStreamWaitEvent(sl.stream, prev.kernel_done, 0));
     // the kernel indexes bases with the absolute offsets: rebase the pointers instead of rewriting the offsets
     PA_TRY(align_batch_device(ix, packed ? nullptr : sl.bases.as<uint8_t>() - b0, need_q ? sl.quals.as<uint8_t>() - b0 : nullptr,
@@ -651,8 +672,7 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
     PA_CUDA(cudaMemcpyAsync(out_words + lo, sl.words.p, n * 8, cudaMemcpyDeviceToHost, sl.stream));
   }
   auto tq = now();
-  PA_CUDA(cudaStreamSynchronize(ix.slot[0].stream));
-  PA_CUDA(cudaStreamSynchronize(ix.slot[1].stream));
+  for (auto& sl : ix.slot) PA_CUDA(cudaStreamSynchronize(sl.stream));
   const double t_drain = ms_since(tq);
   uint64_t h_state[5];
   PA_CUDA(cudaMemcpy(h_state, ix.host_state.p, 40, cudaMemcpyDeviceToHost));
@@ -667,8 +687,8 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
   }
   counters[0] += h_state[2]; counters[1] += h_state[3]; counters[2] += h_state[4];
   if (trace)
-    fprintf(stderr, "[pa_align_batch] %llu reads in %llu chunks (%llu packed, %d pack threads; host: wait %.2f pack %.2f enqueue %.2f drain %.2f ms): %.3f ms\n", (unsigned long long)n_reads,
-            (unsigned long long)c, (unsigned long long)n_packed, host_pack_threads(), t_wait, t_pack, t_enq, t_drain, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    fprintf(stderr, "[pa_align_batch] %llu reads in %llu chunks (%llu packed, %d pack threads, pack %.0f GB/s, link %.0f GB/s; host: wait %.2f pack %.2f enqueue %.2f drain %.2f ms): %.3f ms\n", (unsigned long long)n_reads,
+            (unsigned long long)c, (unsigned long long)n_packed, host_pack_threads(), ix.pack_rate_gbs, ix.link_rate_gbs, t_wait, t_pack, t_enq, t_drain, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   return PA_OK;
 }
 

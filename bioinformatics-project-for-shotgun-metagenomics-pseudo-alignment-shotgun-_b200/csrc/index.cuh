@@ -79,7 +79,7 @@ struct Index {
   DevBuf align_scratch;
   DevBuf align_queue;   // {count u64, pad, uint32 read indices}: reads the fast kernel hands to the general kernel
   uint64_t align_scratch_warps = 0, align_scratch_stride = 0;
-  // host-buffer alignment path (pa_align_batch): two chunk slots so that the H2D copy of chunk i+1 overlaps the
+  // host-buffer alignment path (pa_align_batch): chunk slots so that packing / the H2D copy of later chunks overlaps the
   // kernel of chunk i; buffers grow on demand and are kept for the next call
   struct HostSlot {
     DevBuf bases, quals, off, words, planes;
@@ -87,9 +87,13 @@ struct Index {
     uint64_t h_planes_words = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t kernel_done = nullptr, h2d_done = nullptr;
-  } slot[2];
+    cudaEvent_t copy_beg = nullptr, copy_end = nullptr;   // bracket a raw ASCII transfer: measures the link rate
+    uint64_t copy_bytes = 0;
+  } slot[4];
+  static constexpr int N_HOST_SLOTS = 4;
   DevBuf host_list, host_state;
-  double pack_rate_gbs = 0;   // running estimate of the host packing rate (GB/s of ASCII), see pa_align_batch
+  double pack_rate_gbs = 0;   // running estimates (GB/s): host packing rate of ASCII, raw H2D rate -- see pa_align_batch
+  double link_rate_gbs = 0;
   // timing of the last build (ms, CUDA events on `stream`)
   float t_encode_ms = 0, t_sort_ms = 0, t_rle_ms = 0, t_table_ms = 0;
 
@@ -123,7 +127,7 @@ struct Index {
                       &align_scratch, &align_queue, &host_list, &host_state})
       b->release();
     if (stream) cudaStreamSynchronize(stream);
-    for (auto& sl : slot) { if (sl.stream) cudaStreamDestroy(sl.stream); if (sl.kernel_done) cudaEventDestroy(sl.kernel_done); if (sl.h2d_done) cudaEventDestroy(sl.h2d_done); if (sl.h_planes) cudaFreeHost(sl.h_planes); }
+    for (auto& sl : slot) { if (sl.stream) cudaStreamDestroy(sl.stream); if (sl.kernel_done) cudaEventDestroy(sl.kernel_done); if (sl.h2d_done) cudaEventDestroy(sl.h2d_done); if (sl.copy_beg) cudaEventDestroy(sl.copy_beg); if (sl.copy_end) cudaEventDestroy(sl.copy_end); if (sl.h_planes) cudaFreeHost(sl.h_planes); }
     if (stream) cudaStreamDestroy(stream);
   }
 };
