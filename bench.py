@@ -34,7 +34,7 @@ import numpy as np  # noqa: E402
 ALG_BYTES_PLAIN = 3998      # per 150-bp read at k=31: 150 bases + 32 B x 120 lookups + 8 B result
 ALG_BYTES_QUAL = 4148       # + 150 quality bytes
 BUILD_BYTES_PER_KMER = 17   # 1 base in + 16 B record out
-RANDOM_SECTOR_PEAK_GBS = 1393.6   # measured: profiles/r01_gather_roofline.jsonl, 16 GiB table, one 256-bit load per lookup
+RANDOM_LINE_PEAK = 4.36e10        # measured: profiles/r01_gather_roofline.jsonl, 16 GiB table: distinct 128-B lines per second
 
 
 def parse_args():
@@ -456,10 +456,15 @@ def gpu_arm(args):
             "roofline": {"bound": "hbm", "kernel": "align_fast_kernel (K4)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "traffic": traffic, "kernel_ms": k4_ms, "algorithmic_bytes_per_read": alg,
-                         "random_access": {"peak": RANDOM_SECTOR_PEAK_GBS, "unit": "GB/s of 32-B sectors",
-                                           "achieved": NR * 32 * max(RL - k + 1, 0) / (k4_ms * 1e-3) / 1e9,
-                                           "frac": NR * 32 * max(RL - k + 1, 0) / (k4_ms * 1e-3) / 1e9 / RANDOM_SECTOR_PEAK_GBS,
-                                           "source": "profiles/r01_gather_roofline.jsonl"}},
+                         "random_access": {
+                             "note": "a B200 serves random table reads at a fixed rate of distinct 128-B lines; lanes of one load "
+                                     "instruction that share a line are served together (profiles/r01_locality_roofline.jsonl)",
+                             "peak_lines_per_s": RANDOM_LINE_PEAK, "unit": "128-B lines/s",
+                             "achieved_lines_per_s": (traffic / 128.0 / (k4_ms * 1e-3)) if traffic else None,
+                             "frac": (traffic / 128.0 / (k4_ms * 1e-3) / RANDOM_LINE_PEAK) if traffic else None,
+                             "window_lookups_per_s": NR * max(RL - k + 1, 0) / (k4_ms * 1e-3),
+                             "lookups_vs_one_line_per_lookup": NR * max(RL - k + 1, 0) / (k4_ms * 1e-3) / RANDOM_LINE_PEAK,
+                             "source": "profiles/r01_gather_roofline.jsonl, profiles/align_traffic.json"}},
             "cpu_baseline": cpu_baseline, "parity": parity,
             "build": {"kmers_per_s_kernels": inf.n_occ / (build_kernel_ms * 1e-3) if build_kernel_ms > 0 else None,
                       "kmers_per_s_call": inf.n_occ / min(build_times), "kmer_occurrences": int(inf.n_occ),
