@@ -459,21 +459,43 @@ __global__ void first_occurrence(const uint64_t* __restrict__ run_off, const uin
   keys[u] = genome_off[run_genome[r]] + pos[pos_off[r]];
 }
 
-// K5: per identifier class, number of distinct k-mers holding it / holding it alone.
+// K5: per identifier class, number of distinct k-mers holding it / holding it alone.  Classes are few, so every
+// block counts in shared memory first (n_groups <= EXT_SMEM_GROUPS) and adds its totals to the global counters once;
+// plain global atomics on a thousand addresses serialise in L2 (config D: 43 ms -> a few ms).
+constexpr uint32_t EXT_SMEM_GROUPS = 4096;
 __global__ void extsim_stats_kernel(const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome, uint64_t U,
-                                    const uint32_t* __restrict__ group, int dedupe,
+                                    const uint32_t* __restrict__ group, uint32_t n_groups, int dedupe,
                                     unsigned long long* __restrict__ total, unsigned long long* __restrict__ unique) {
-  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (u >= U) return;
-  uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
-  for (uint64_t j = 0; j < c; ++j) {
-    uint32_t gr = group[run_genome[r0 + j]];
-    bool first = true;
-    if (dedupe)
-      for (uint64_t i = 0; i < j && first; ++i) first = group[run_genome[r0 + i]] != gr;
-    if (!first) continue;
-    atomicAdd(&total[gr], 1ULL);
-    if (c == 1) atomicAdd(&unique[gr], 1ULL);
+  __shared__ uint32_t s_total[EXT_SMEM_GROUPS], s_unique[EXT_SMEM_GROUPS];
+  const bool in_smem = n_groups <= EXT_SMEM_GROUPS;
+  if (in_smem) {
+    for (uint32_t i = threadIdx.x; i < n_groups; i += blockDim.x) { s_total[i] = 0; s_unique[i] = 0; }
+    __syncthreads();
+  }
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; u < U; u += stride) {
+    uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
+    for (uint64_t j = 0; j < c; ++j) {
+      uint32_t gr = group[run_genome[r0 + j]];
+      bool first = true;
+      if (dedupe)
+        for (uint64_t i = 0; i < j && first; ++i) first = group[run_genome[r0 + i]] != gr;
+      if (!first) continue;
+      if (in_smem) {
+        atomicAdd(&s_total[gr], 1u);
+        if (c == 1) atomicAdd(&s_unique[gr], 1u);
+      } else {
+        atomicAdd(&total[gr], 1ULL);
+        if (c == 1) atomicAdd(&unique[gr], 1ULL);
+      }
+    }
+  }
+  if (in_smem) {
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_groups; i += blockDim.x) {
+      if (s_total[i]) atomicAdd(&total[i], (unsigned long long)s_total[i]);
+      if (s_unique[i]) atomicAdd(&unique[i], (unsigned long long)s_unique[i]);
+    }
   }
 }
 
@@ -869,10 +891,16 @@ int32_t index_extsim_stats(Index& ix, const uint32_t* h_group, uint32_t n_groups
   size_t nb = (size_t)std::max<uint32_t>(n_groups, 1) * 8;
   PA_TRY(d_out.alloc(nb * 2));
   PA_CUDA(cudaMemsetAsync(d_out.p, 0, nb * 2, s));
-  if (ix.n_keys)
-    extsim_stats_kernel<<<grid_for(ix.n_keys, 256), 256, 0, s>>>(
-        ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(), ix.n_keys, d_group.as<uint32_t>(), dedupe,
+  if (ix.n_keys) {
+    int dev = 0, sms = 148;
+    PA_CUDA(cudaGetDevice(&dev));
+    PA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // persistent grid: a block's shared counters (uint32) cannot overflow below 2^32 k-mers per block
+    const unsigned grid = (unsigned)std::min<uint64_t>(grid_for(ix.n_keys, 256), (uint64_t)sms * 8);
+    extsim_stats_kernel<<<grid, 256, 0, s>>>(
+        ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(), ix.n_keys, d_group.as<uint32_t>(), n_groups, dedupe,
         d_out.as<unsigned long long>(), d_out.as<unsigned long long>() + std::max<uint32_t>(n_groups, 1));
+  }
   PA_CUDA(cudaGetLastError());
   if (n_groups) {
     PA_CUDA(cudaMemcpyAsync(h_total, d_out.p, (size_t)n_groups * 8, cudaMemcpyDeviceToHost, s));
