@@ -24,40 +24,39 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
-static thread_local cudaStream_t tl_alloc_stream = nullptr;
-static thread_local int tl_alloc_depth = 0;
-cudaStream_t current_alloc_stream() { return tl_alloc_stream; }
+// ---- scratch reuse inside a build (see AllocScope in index.cuh) ----
+static thread_local int tl_scope_depth = 0;
+static thread_local std::vector<std::pair<void*, size_t>>* tl_parked = nullptr;
 
-AllocScope::AllocScope(cudaStream_t s) : prev(tl_alloc_stream), outermost(tl_alloc_depth == 0) {
-  // opt-in (PA_POOL=1): measured on the B200 box the pool re-grows on every build and is slower than the driver's own
-  // reuse of freed cudaMalloc blocks (config B: 375-600 ms per build with the pool, 119-480 ms without)
-  static const bool enabled = getenv("PA_POOL") && *getenv("PA_POOL") == '1';
-  if (enabled && s) {
-    if (outermost) {   // keep freed blocks inside the pool while the build runs
-      int dev = 0; cudaMemPool_t pool = nullptr;
-      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t keep = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-      }
-      (void)cudaGetLastError();
-    }
-    tl_alloc_stream = s;
-  }
-  ++tl_alloc_depth;
+AllocScope::AllocScope(cudaStream_t) : outermost(tl_scope_depth == 0) {
+  static const bool disabled = getenv("PA_NO_CACHE") && *getenv("PA_NO_CACHE") == '1';
+  if (outermost && !disabled) tl_parked = new std::vector<std::pair<void*, size_t>>();
+  ++tl_scope_depth;
 }
 AllocScope::~AllocScope() {
-  --tl_alloc_depth;
-  if (outermost && tl_alloc_stream) {   // give the scratch back to the device
-    cudaStreamSynchronize(tl_alloc_stream);
-    int dev = 0; cudaMemPool_t pool = nullptr;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t keep = 0;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-      cudaMemPoolTrimTo(pool, 0);
-    }
-    (void)cudaGetLastError();
+  --tl_scope_depth;
+  if (outermost && tl_parked) {
+    for (auto& b : *tl_parked) cudaFree(b.first);
+    delete tl_parked;
+    tl_parked = nullptr;
   }
-  tl_alloc_stream = prev;
+}
+bool scope_take(size_t bytes, void** p, size_t* got) {
+  if (!tl_parked || bytes < (1u << 20)) return false;       // small buffers are not worth the bookkeeping
+  size_t best = SIZE_MAX; int at = -1;
+  for (int i = 0; i < (int)tl_parked->size(); ++i) {
+    const size_t sz = (*tl_parked)[i].second;
+    if (sz >= bytes && sz <= bytes + bytes / 2 + (64u << 20) && sz < best) { best = sz; at = i; }
+  }
+  if (at < 0) return false;
+  *p = (*tl_parked)[at].first; *got = best;
+  tl_parked->erase(tl_parked->begin() + at);
+  return true;
+}
+bool scope_park(void* p, size_t bytes) {
+  if (!tl_parked || bytes < (1u << 20)) return false;
+  tl_parked->push_back({p, bytes});
+  return true;
 }
 
 namespace {

@@ -5,43 +5,46 @@
 
 namespace pa {
 
-// Optional stream-ordered allocation for the build paths (PA_POOL=1).  A build allocates and frees a dozen multi-GB
-// buffers; inside an AllocScope the DevBufs then come from the device's default memory pool, ordered on the scope's
-// stream (the one every kernel of the build runs on), and the scope trims the pool back when the outermost scope
-// ends.  Off by default -- it measured slower than cudaMalloc / cudaFree on the B200 box (see capi.cu).
+// Scratch reuse inside a build.  A build allocates and frees a dozen multi-GB buffers, and cudaMalloc / cudaFree of
+// that size map / unmap memory and synchronise the device: measured on the B200 boxes that is tens of ms per call and
+// occasionally hundreds.  Inside an AllocScope (one per public build entry point; everything in it runs on the one
+// stream of the index) a released DevBuf is parked instead of freed and the next allocation that fits takes it over --
+// stream order makes the hand-over safe -- so e.g. the CSR arrays land in the sort's double buffers.  What is still
+// parked when the outermost scope ends is freed.  PA_NO_CACHE=1 switches the reuse off.
+// (A stream-ordered cudaMallocAsync pool was tried first and measured slower: it re-grows on every build.)
 struct AllocScope {
   explicit AllocScope(cudaStream_t s);
   ~AllocScope();
   AllocScope(const AllocScope&) = delete;
   AllocScope& operator=(const AllocScope&) = delete;
-  cudaStream_t prev;
   bool outermost;
 };
-cudaStream_t current_alloc_stream();   // nullptr outside a scope and unless PA_POOL=1 (off by default: see capi.cu)
+bool scope_take(size_t bytes, void** p, size_t* got);   // a parked block of >= bytes (and not absurdly larger), if any
+bool scope_park(void* p, size_t bytes);                 // false outside a scope: the caller frees
 
 // Owns a device allocation; frees on destruction.
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
-  cudaStream_t st = nullptr;   // non-null: allocated from the pool, ordered on this stream
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) { if (st) cudaFreeAsync(p, st); else cudaFree(p); }
-    p = nullptr; bytes = 0; st = nullptr;
+    if (p && !scope_park(p, bytes)) cudaFree(p);
+    p = nullptr; bytes = 0;
   }
   int32_t alloc(size_t n) {
     release();
     if (n == 0) n = 16;
-    cudaStream_t s = current_alloc_stream();
-    cudaError_t e = s ? cudaMallocAsync(&p, n, s) : cudaMalloc(&p, n);
-    if (e != cudaSuccess) { p = nullptr; (void)cudaGetLastError(); set_error("device allocation of %zu bytes failed: %s", n, cudaGetErrorString(e)); return ST_NOMEM; }
-    bytes = n; st = s;
+    size_t got = 0;
+    if (scope_take(n, &p, &got)) { bytes = got; return ST_OK; }
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) { p = nullptr; (void)cudaGetLastError(); set_error("cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e)); return ST_NOMEM; }
+    bytes = n;
     return ST_OK;
   }
-  void swap(DevBuf& o) { std::swap(p, o.p); std::swap(bytes, o.bytes); std::swap(st, o.st); }
+  void swap(DevBuf& o) { std::swap(p, o.p); std::swap(bytes, o.bytes); }
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -122,7 +125,6 @@ struct Index {
            slots.bytes + stash.bytes + mlist.bytes + align_scratch.bytes + align_queue.bytes;
   }
   ~Index() {
-    // pool allocations are freed in stream order: release them while the stream still exists
     for (DevBuf* b : {&ukeys, &run_off, &run_genome, &pos_off, &pos, &genome_off, &first_occ, &slots, &stash, &mlist,
                       &align_scratch, &align_queue, &host_list, &host_state})
       b->release();
