@@ -223,30 +223,38 @@ __global__ void genome_map_fill(const uint64_t* __restrict__ off, uint32_t G, ui
   map[i] = pos < total ? genome_of(off, G, pos) : (G ? G - 1 : 0);
 }
 
+// Head flags of one warp's 256 consecutive records, striped: lane l holds records warp_base + 32 j + l (j = 0..7), so
+// every load and -- after compaction -- every store of a warp instruction touches consecutive addresses (the first
+// version gave each thread 8 consecutive records: its stores were 64 bytes apart and the kernel was bound by L2
+// transactions, profiles/r01_rle_scatter_ncu.json).  kh / rh = ballot masks of key heads / (key, genome) heads.
 __device__ __forceinline__ void rle_flags(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                          const uint64_t* __restrict__ genome_off, GenomeMap G, uint64_t base, uint64_t n,
-                                          uint32_t (&gen)[RLE_ITEMS], uint32_t& kh_mask, uint32_t& rh_mask) {
-  kh_mask = rh_mask = 0;
-  uint64_t prev_key = 0; uint32_t prev_gen = 0;
-  bool have_prev = false;
-  if (base > 0 && base < n) {
-    prev_key = keys[base - 1];
-    prev_gen = genome_at(G, genome_off, vals[base - 1]);
-    have_prev = true;
+                                          const uint64_t* __restrict__ genome_off, GenomeMap G, uint64_t warp_base, uint64_t n,
+                                          uint32_t lane, uint64_t (&key)[RLE_ITEMS], uint32_t (&gen)[RLE_ITEMS],
+                                          uint32_t (&kh)[RLE_ITEMS], uint32_t (&rh)[RLE_ITEMS]) {
+  uint64_t carry_key = 0; uint32_t carry_gen = 0;   // record just before the current row (lane 31 of the previous row)
+  bool have_carry = false;
+  if (warp_base > 0 && warp_base < n) {
+    carry_key = keys[warp_base - 1];
+    carry_gen = genome_at(G, genome_off, vals[warp_base - 1]);
+    have_carry = true;
   }
 #pragma unroll
   for (int j = 0; j < RLE_ITEMS; ++j) {
-    uint64_t i = base + j;
-    if (i < n) {
-      uint64_t key = keys[i];
-      uint32_t g = genome_at(G, genome_off, vals[i]);
-      gen[j] = g;
-      bool kh = !have_prev || key != prev_key;
-      bool rh = kh || g != prev_gen;
-      kh_mask |= (uint32_t)kh << j;
-      rh_mask |= (uint32_t)rh << j;
-      prev_key = key; prev_gen = g; have_prev = true;
-    }
+    const uint64_t i = warp_base + (uint64_t)j * 32 + lane;
+    const bool ok = i < n;
+    key[j] = ok ? keys[i] : 0;
+    gen[j] = ok ? genome_at(G, genome_off, vals[i]) : 0;
+    uint64_t pk = __shfl_up_sync(0xffffffffu, key[j], 1);
+    uint32_t pg = __shfl_up_sync(0xffffffffu, gen[j], 1);
+    bool have_prev = true;
+    if (lane == 0) { pk = carry_key; pg = carry_gen; have_prev = have_carry; }
+    const bool k_head = ok && (!have_prev || key[j] != pk);
+    const bool r_head = ok && (k_head || gen[j] != pg);
+    kh[j] = __ballot_sync(0xffffffffu, k_head);
+    rh[j] = __ballot_sync(0xffffffffu, r_head);
+    carry_key = __shfl_sync(0xffffffffu, key[j], 31);
+    carry_gen = __shfl_sync(0xffffffffu, gen[j], 31);
+    have_carry = true;
   }
 }
 
@@ -254,11 +262,14 @@ __global__ void __launch_bounds__(RLE_THREADS)
 rle_count(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint64_t* __restrict__ genome_off,
           GenomeMap G, uint64_t n, uint64_t* __restrict__ tile_keys, uint64_t* __restrict__ tile_runs) {
   __shared__ uint32_t ws[2][RLE_THREADS / 32];
-  const uint64_t base = (uint64_t)blockIdx.x * RLE_TILE + (uint64_t)threadIdx.x * RLE_ITEMS;
-  uint32_t gen[RLE_ITEMS], kh, rh;
-  rle_flags(keys, vals, genome_off, G, base, n, gen, kh, rh);
-  uint32_t a = warp_sum((uint32_t)__popc(kh)), b = warp_sum((uint32_t)__popc(rh));
-  if ((threadIdx.x & 31) == 0) { ws[0][threadIdx.x >> 5] = a; ws[1][threadIdx.x >> 5] = b; }
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t warp_base = (uint64_t)blockIdx.x * RLE_TILE + (uint64_t)warp * (32 * RLE_ITEMS);
+  uint64_t key[RLE_ITEMS]; uint32_t gen[RLE_ITEMS], kh[RLE_ITEMS], rh[RLE_ITEMS];
+  rle_flags(keys, vals, genome_off, G, warp_base, n, lane, key, gen, kh, rh);
+  uint32_t a = 0, b = 0;
+#pragma unroll
+  for (int j = 0; j < RLE_ITEMS; ++j) { a += __popc(kh[j]); b += __popc(rh[j]); }
+  if (lane == 0) { ws[0][warp] = a; ws[1][warp] = b; }
   __syncthreads();
   if (threadIdx.x == 0) {
     uint64_t ta = 0, tb = 0;
@@ -272,25 +283,33 @@ rle_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals
             GenomeMap G, uint64_t n, const uint64_t* __restrict__ tile_keys, const uint64_t* __restrict__ tile_runs,
             uint64_t* __restrict__ ukeys, uint64_t* __restrict__ run_off, uint32_t* __restrict__ run_genome,
             uint64_t* __restrict__ pos_off, uint32_t* __restrict__ pos) {
-  __shared__ uint32_t ws[RLE_THREADS / 32];
-  const uint64_t base = (uint64_t)blockIdx.x * RLE_TILE + (uint64_t)threadIdx.x * RLE_ITEMS;
-  uint32_t gen[RLE_ITEMS], kh, rh;
-  rle_flags(keys, vals, genome_off, G, base, n, gen, kh, rh);
-  uint32_t tot;
-  uint64_t kr = tile_keys[blockIdx.x] + block_exclusive_scan<RLE_THREADS, uint32_t>(__popc(kh), tot, ws);
-  uint64_t rr = tile_runs[blockIdx.x] + block_exclusive_scan<RLE_THREADS, uint32_t>(__popc(rh), tot, ws);
+  __shared__ uint32_t ws[2][RLE_THREADS / 32];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t warp_base = (uint64_t)blockIdx.x * RLE_TILE + (uint64_t)warp * (32 * RLE_ITEMS);
+  uint64_t key[RLE_ITEMS]; uint32_t gen[RLE_ITEMS], kh[RLE_ITEMS], rh[RLE_ITEMS];
+  rle_flags(keys, vals, genome_off, G, warp_base, n, lane, key, gen, kh, rh);
+  uint32_t a = 0, b = 0;
+#pragma unroll
+  for (int j = 0; j < RLE_ITEMS; ++j) { a += __popc(kh[j]); b += __popc(rh[j]); }
+  if (lane == 0) { ws[0][warp] = a; ws[1][warp] = b; }
+  __syncthreads();
+  uint64_t kr = tile_keys[blockIdx.x], rr = tile_runs[blockIdx.x];   // first key / run index of this warp
+  for (uint32_t w = 0; w < warp; ++w) { kr += ws[0][w]; rr += ws[1][w]; }
+  const uint32_t lt = (1u << lane) - 1;
 #pragma unroll
   for (int j = 0; j < RLE_ITEMS; ++j) {
-    uint64_t i = base + j;
+    const uint64_t i = warp_base + (uint64_t)j * 32 + lane;
     if (i < n) {
-      if ((rh >> j) & 1) {
-        if ((kh >> j) & 1) { ukeys[kr] = keys[i]; run_off[kr] = rr; ++kr; }
-        run_genome[rr] = gen[j];
-        pos_off[rr] = i;
-        ++rr;
+      if ((rh[j] >> lane) & 1) {
+        const uint64_t r = rr + __popc(rh[j] & lt);
+        if ((kh[j] >> lane) & 1) { const uint64_t q = kr + __popc(kh[j] & lt); ukeys[q] = key[j]; run_off[q] = r; }
+        run_genome[r] = gen[j];
+        pos_off[r] = i;
       }
       pos[i] = (uint32_t)((uint64_t)vals[i] - genome_off[gen[j]]);
     }
+    kr += __popc(kh[j]);
+    rr += __popc(rh[j]);
   }
 }
 
