@@ -11,6 +11,8 @@
 #include <thread>
 #include <vector>
 
+#include <unistd.h>
+
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -69,8 +71,13 @@ class Pool {
 };
 
 Pool& pool() {
-  static Pool p(host_pack_threads());
-  return p;
+  // worker threads do not survive fork(): a child process gets a pool of its own (the parent's object is left alone)
+  static Pool* p = nullptr;
+  static pid_t owner = 0;
+  static std::mutex guard;
+  std::lock_guard<std::mutex> g(guard);
+  if (!p || owner != getpid()) { p = new Pool(host_pack_threads()); owner = getpid(); }
+  return *p;
 }
 
 inline bool acgt(uint8_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
