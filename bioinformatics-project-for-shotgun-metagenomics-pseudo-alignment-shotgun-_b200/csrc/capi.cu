@@ -589,8 +589,11 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
   double t_wait = 0, t_pack = 0, t_enq = 0;
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms_since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
-  for (uint64_t lo = 0; lo < n_reads; lo += chunk, ++c) {
-    const uint64_t hi = std::min(n_reads, lo + chunk), n = hi - lo;
+  const bool fixed_chunk = getenv("PA_CHUNK_READS") != nullptr;
+  for (uint64_t lo = 0, step = 0; lo < n_reads; lo += step, ++c) {
+    // the last chunks are halved: what is left in flight when the host has enqueued everything is the tail of the call
+    step = (!fixed_chunk && n_reads - lo <= 2 * chunk && chunk >= (1u << 17)) ? chunk / 2 : chunk;
+    const uint64_t hi = std::min(n_reads, lo + step), n = hi - lo;
     Index::HostSlot& sl = ix.slot[c % N_SLOTS];
     Index::HostSlot& prev = ix.slot[(c + N_SLOTS - 1) % N_SLOTS];
     const uint64_t b0 = read_off[lo], nb = read_off[hi] - b0;
