@@ -61,6 +61,11 @@ bool scope_park(void* p, size_t bytes) {
 
 namespace {
 
+__global__ void fill_offsets_kernel(uint64_t* __restrict__ off, uint64_t n, uint64_t first, uint64_t len) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) off[i] = first + i * len;
+}
+
 __global__ void debug_lookup_kernel(TableView t, MixParams mix, const uint64_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ n_genomes,
                                     uint32_t* __restrict__ first_genome) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -597,9 +602,9 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
     Index::HostSlot& sl = ix.slot[c % N_SLOTS];
     Index::HostSlot& prev = ix.slot[(c + N_SLOTS - 1) % N_SLOTS];
     const uint64_t b0 = read_off[lo], nb = read_off[hi] - b0;
-    uint64_t max_len = 0;
+    uint64_t max_len = 0, min_len = 0;
     auto tv0 = now();
-    NEED(scan_offsets(read_off, lo, hi, &max_len, host_pack_threads()), "read_off is not monotonic");
+    NEED(scan_offsets(read_off, lo, hi, &max_len, &min_len, host_pack_threads()), "read_off is not monotonic");
     t_pack += ms_since(tv0);
     // Which way does this chunk travel?  Packing to 2-bit planes (hostpack.h) costs host time (all cores) and leaves
     // a quarter of the bytes for the link; raw ASCII costs no host time.  Two resources work in parallel -- the host
@@ -657,9 +662,15 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
       }
     }
     if (need_q && nb) PA_CUDA(cudaMemcpyAsync(sl.quals.p, quals + b0, nb, cudaMemcpyHostToDevice, sl.stream));
-    PA_CUDA(cudaMemcpyAsync(sl.off.p, read_off + lo, (n + 1) * 8, cudaMemcpyHostToDevice, sl.stream));
+    if (min_len == max_len) {   // fixed-length reads (the usual FASTQ): the offsets are an arithmetic sequence, no copy
+      fill_offsets_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, sl.stream>>>(sl.off.as<uint64_t>(), n + 1, b0, max_len);
+      PA_CUDA(cudaGetLastError());
+    } else {
+      PA_CUDA(cudaMemcpyAsync(sl.off.p, read_off + lo, (n + 1) * 8, cudaMemcpyHostToDevice, sl.stream));
+    }
     {
-      const double bytes = (packed ? (double)n_words * 4 : (double)nb) + (need_q ? (double)nb : 0.0) + (double)(n + 1) * 8;
+      const double bytes = (packed ? (double)n_words * 4 : (double)nb) + (need_q ? (double)nb : 0.0) +
+                           (min_len == max_len ? 0.0 : (double)(n + 1) * 8);
       link_busy_until = std::max(link_busy_until, ms_since(t0)) + bytes / (ix.link_rate_gbs * 1e6);
     }
     PA_CUDA(cudaStreamWaitEvent(sl.stream, prev.kernel_done, 0));

@@ -169,27 +169,30 @@ int host_pack_threads() {
   return n;
 }
 
-bool scan_offsets(const uint64_t* read_off, uint64_t lo, uint64_t hi, uint64_t* max_len, int n_threads) {
-  *max_len = 0;
+bool scan_offsets(const uint64_t* read_off, uint64_t lo, uint64_t hi, uint64_t* max_len, uint64_t* min_len, int n_threads) {
+  *max_len = 0; *min_len = 0;
   if (hi <= lo) return true;
   const uint64_t n = hi - lo;
   int tasks = (int)std::min<uint64_t>((uint64_t)std::max(1, n_threads), (n + 65535) / 65536);
   if (tasks < 1) tasks = 1;
-  std::vector<uint64_t> mx(tasks, 0);
+  std::vector<uint64_t> mx(tasks, 0), mn(tasks, UINT64_MAX);
   std::atomic<bool> ok{true};
   auto work = [&](int t) {
     const uint64_t a = lo + n * (uint64_t)t / tasks, b = lo + n * (uint64_t)(t + 1) / tasks;
-    uint64_t m = 0;
+    uint64_t m = 0, s = UINT64_MAX;
     bool good = true;
     for (uint64_t i = a; i < b; ++i) {
       good &= read_off[i + 1] >= read_off[i];
-      m = std::max(m, read_off[i + 1] - read_off[i]);
+      const uint64_t len = read_off[i + 1] - read_off[i];
+      m = std::max(m, len); s = std::min(s, len);
     }
-    mx[t] = m;
+    mx[t] = m; mn[t] = s;
     if (!good) ok.store(false, std::memory_order_relaxed);
   };
   if (tasks == 1) work(0); else pool().parallel_for(tasks, work);
-  for (uint64_t m : mx) *max_len = std::max(*max_len, m);
+  uint64_t s = UINT64_MAX;
+  for (int t = 0; t < tasks; ++t) { *max_len = std::max(*max_len, mx[t]); s = std::min(s, mn[t]); }
+  *min_len = s == UINT64_MAX ? 0 : s;
   return ok.load();
 }
 

@@ -22,8 +22,8 @@ inline uint64_t planes_words(uint64_t n_bases, uint64_t n_reads) { return 2 * (n
 bool pack_reads_planes(const uint8_t* bases, const uint64_t* read_off, uint64_t lo, uint64_t hi, uint32_t* planes,
                        int n_threads);
 
-// Parallel check of read_off[lo .. hi]: returns false when it is not monotonic; *max_len = longest read.
-bool scan_offsets(const uint64_t* read_off, uint64_t lo, uint64_t hi, uint64_t* max_len, int n_threads);
+// Parallel check of read_off[lo .. hi]: returns false when it is not monotonic; *max_len / *min_len = longest / shortest read.
+bool scan_offsets(const uint64_t* read_off, uint64_t lo, uint64_t hi, uint64_t* max_len, uint64_t* min_len, int n_threads);
 
 // runs fn(0 .. n_tasks-1) on the library's worker pool (blocking)
 void host_parallel_for(int n_tasks, const std::function<void(int)>& fn);
