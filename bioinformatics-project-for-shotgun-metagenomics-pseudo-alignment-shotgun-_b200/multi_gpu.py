@@ -253,23 +253,46 @@ def _exchange_fused(L, nat, keys, vals, n_slots: int, k: int, device: int, world
         cap = [c + c // 16 + 1024 for c in recv_count]
         my_k, my_v = ctypes.c_void_p(), ctypes.c_void_p()
         hk, hv = (ctypes.c_uint8 * 64)(), (ctypes.c_uint8 * 64)()
-        nat.check(L.pa_peer_alloc(cap[rank] * 8, device, ctypes.byref(my_k), hk))
-        nat.check(L.pa_peer_alloc(cap[rank] * 4, device, ctypes.byref(my_v), hv))
-        tm["alloc_s"] = time.perf_counter() - t0; t0 = time.perf_counter()
-        handles = [None] * world
-        dist.all_gather_object(handles, (bytes(hk), bytes(hv)), group=group)
-        tm["gather_handles_s"] = time.perf_counter() - t0; t0 = time.perf_counter()
         peer_k, peer_v = [0] * world, [0] * world
         opened = []
-        for r in range(world):
-            if r == rank:
-                peer_k[r], peer_v[r] = my_k.value, my_v.value
-            else:
-                pk, pv = ctypes.c_void_p(), ctypes.c_void_p()
-                nat.check(L.pa_peer_open((ctypes.c_uint8 * 64).from_buffer_copy(handles[r][0]), device, ctypes.byref(pk)))
-                nat.check(L.pa_peer_open((ctypes.c_uint8 * 64).from_buffer_copy(handles[r][1]), device, ctypes.byref(pv)))
-                peer_k[r], peer_v[r] = pk.value, pv.value
-                opened += [pk, pv]
+        problem = "peer mapping switched off (PA_TEST_NO_IPC)" if os.environ.get("PA_TEST_NO_IPC") == "1" and rank == world - 1 else None
+        try:
+            if problem:
+                raise RuntimeError(problem)
+            nat.check(L.pa_peer_alloc(cap[rank] * 8, device, ctypes.byref(my_k), hk))
+            nat.check(L.pa_peer_alloc(cap[rank] * 4, device, ctypes.byref(my_v), hv))
+        except (RuntimeError, MemoryError) as e:
+            problem = str(e)
+        tm["alloc_s"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        handles = [None] * world
+        dist.all_gather_object(handles, None if problem else (bytes(hk), bytes(hv)), group=group)
+        tm["gather_handles_s"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        if problem is None and all(h is not None for h in handles):
+            try:
+                for r in range(world):
+                    if r == rank:
+                        peer_k[r], peer_v[r] = my_k.value, my_v.value
+                    else:
+                        pk, pv = ctypes.c_void_p(), ctypes.c_void_p()
+                        nat.check(L.pa_peer_open((ctypes.c_uint8 * 64).from_buffer_copy(handles[r][0]), device, ctypes.byref(pk)))
+                        opened.append(pk)
+                        nat.check(L.pa_peer_open((ctypes.c_uint8 * 64).from_buffer_copy(handles[r][1]), device, ctypes.byref(pv)))
+                        opened.append(pv)
+                        peer_k[r], peer_v[r] = pk.value, pv.value
+            except RuntimeError as e:       # no peer mapping on this system (containers without IPC, no P2P path ...)
+                problem = str(e)
+        elif problem is None:
+            problem = "a peer could not allocate its receive buffer"
+        verdicts = [None] * world
+        dist.all_gather_object(verdicts, problem, group=group)   # all ranks take the same way out
+        if any(v is not None for v in verdicts):
+            for p in opened:
+                L.pa_peer_close(p, device)
+            if my_k.value:
+                L.pa_peer_free(my_k, device)
+            if my_v.value:
+                L.pa_peer_free(my_v, device)
+            return None, next(v for v in verdicts if v is not None)
         ent = {"cap": cap, "my_k": my_k, "my_v": my_v, "peer_k": peer_k, "peer_v": peer_v, "opened": opened}
         _PEER_CACHE[key] = ent
     else:
@@ -340,7 +363,12 @@ def build_partitioned(my_bases, genome_off: np.ndarray, k: int, g_range: Tuple[i
         torch.cuda.synchronize(dev)
         t["encode_s"] = time.perf_counter() - t0
         t0 = time.perf_counter()
-        rk, rv, n_recv, n_sent, t["scatter_exchange_phases"] = _exchange_fused(L, nat, keys, vals, n_bases, k, device, world, rank, group)
+        res = _exchange_fused(L, nat, keys, vals, n_bases, k, device, world, rank, group)
+        if res[0] is None:
+            t["fused_exchange_unavailable"] = res[1]      # every rank got the same verdict: use the all-to-all path
+            fused = False
+    if fused and int(k) >= 1:
+        rk, rv, n_recv, n_sent, t["scatter_exchange_phases"] = res
         assert n_sent == n_valid.value
         del keys, vals
         t["scatter_exchange_s"] = time.perf_counter() - t0

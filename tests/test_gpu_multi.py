@@ -66,7 +66,10 @@ def run_case(case):
     mine = np.zeros(int(goff[g_hi] - goff[g_lo]) + 64, dtype=np.uint8)
     mine[:int(goff[g_hi] - goff[g_lo])] = data[int(goff[g_lo]):int(goff[g_hi])]
     dix = multi_gpu.build_partitioned(mine, goff, k, (g_lo, g_hi), device=device, fused=FUSED)
-    assert dix.fused == (FUSED and k >= 1)
+    if os.environ.get("PA_TEST_NO_IPC") == "1" and FUSED and k >= 1:
+        assert not dix.fused and "fused_exchange_unavailable" in dix.timings    # every rank fell back together
+    else:
+        assert dix.fused == (FUSED and k >= 1) or "fused_exchange_unavailable" in dix.timings
     o = orc.OracleReference(k, genomes)
     try:
         # every record went to exactly one owner, and keys are partitioned by range
@@ -155,14 +158,15 @@ dist.destroy_process_group()
 '''
 
 
-def _run(world, seeds, tmp_path, nccl=False, fused=True):
+def _run(world, seeds, tmp_path, nccl=False, fused=True, no_ipc=False):
     script = tmp_path / "worker.py"
     script.write_text(WORKER.format(root=conftest.ROOT, pkg=conftest.PKG_DIR))
     port = 23000 + (os.getpid() * 7 + world * 131 + len(seeds)) % 4000
     procs = []
     for rank in range(world):
         env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
-                   PA_TEST_NCCL="1" if nccl else "0", PA_TEST_FUSED="1" if fused else "0")
+                   PA_TEST_NCCL="1" if nccl else "0", PA_TEST_FUSED="1" if fused else "0",
+                   PA_TEST_NO_IPC="1" if no_ipc else "0")
         procs.append(subprocess.Popen([sys.executable, str(script), ",".join(str(s) for s in seeds)], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     outs = [p.communicate(timeout=900) for p in procs]
@@ -177,6 +181,10 @@ def test_partitioned_build_world_2_fuzz(tmp_path):
 
 def test_partitioned_build_world_3_fuzz(tmp_path):
     _run(3, list(range(6000, 6016)), tmp_path)
+
+
+def test_partitioned_build_falls_back_when_peer_mapping_fails(tmp_path):
+    _run(3, [5200, 5201, 5202, -15], tmp_path, no_ipc=True)
 
 
 def test_partitioned_build_all_to_all_exchange(tmp_path):
