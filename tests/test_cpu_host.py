@@ -428,3 +428,45 @@ def test_native_ingest_feeds_the_packed_arrays():
     f.parse_records(">g1 d\nACGT\nNNAC\r\n>g2\nTTTT")
     assert f.packed_batch()["seq"].tobytes() == b"ACGTNNACTTTT"
     assert [(r.identifier, r["genome"]) for r in f] == [("g1 d", "ACGTNNAC"), ("g2", "TTTT")]
+
+
+def test_native_dumpref_writer_against_json_dumps():
+    """format.cpp on a hand-made CSR (pure host code): byte-identical to json.dumps(indent=4) of the dictionary that
+    kmer.py:300-329 builds, including descriptions that need escaping and genomes sharing a description."""
+    import _native as nat
+    rng = np.random.default_rng(21)
+    for k in (1, 5, 31):
+        n = 40 if k > 1 else 4
+        kmers = sorted({"".join(rng.choice(list("ACGT"), size=k)) for _ in range(n)})
+        flat = np.frombuffer("".join(kmers).encode(), dtype=np.uint8).copy()
+        keys = np.zeros(len(kmers), dtype=np.uint64)
+        nat.check(nat.lib().pa_encode_kmers(k, nat._p(flat), len(kmers), nat._p(keys)))
+        srt = np.argsort(keys)
+        keys, kmers = keys[srt], [kmers[i] for i in srt]
+        descs = ['g "zero"', "tab\there", "g\\two", 'g "zero"', "ünï"]          # genomes 0 and 3 share a description
+        cls = {}
+        group = np.array([cls.setdefault(d, len(cls)) for d in descs], dtype=np.uint32)
+        run_off, run_genome, pos_off, pos = [0], [], [0], []
+        for _ in kmers:
+            gs = sorted(rng.choice(len(descs), size=int(rng.integers(1, len(descs) + 1)), replace=False).tolist())
+            for g in gs:
+                run_genome.append(g)
+                pos += sorted(rng.choice(1000, size=int(rng.integers(1, 4)), replace=False).tolist())
+                pos_off.append(len(pos))
+            run_off.append(len(run_genome))
+        order = rng.permutation(len(kmers)).astype(np.uint32)
+        csr = {"keys": keys, "order": order, "run_off": np.array(run_off, np.uint64), "run_genome": np.array(run_genome, np.uint32),
+               "pos_off": np.array(pos_off, np.uint64), "pos": np.array(pos, np.uint32)}
+        assert nat.decode_kmers(k, keys) == kmers
+        want = {}
+        for u in order.tolist():
+            inner = {}
+            for r in range(run_off[u], run_off[u + 1]):
+                inner[descs[run_genome[r]]] = pos[pos_off[r]:pos_off[r + 1]]
+            want[kmers[u]] = inner
+        got = nat.format_kmers_json(k, csr, group, [json.dumps(d) for d in cls], indent=4, level=1)
+        ref = json.dumps({"Kmers": want}, indent=4)
+        assert "{\n    \"Kmers\": " + got + "\n}" == ref
+    empty = {"keys": np.zeros(0, np.uint64), "order": np.zeros(0, np.uint32), "run_off": np.zeros(1, np.uint64),
+             "run_genome": np.zeros(0, np.uint32), "pos_off": np.zeros(1, np.uint64), "pos": np.zeros(0, np.uint32)}
+    assert nat.format_kmers_json(3, empty, np.zeros(1, np.uint32), [], indent=4, level=1) == "{}"
