@@ -200,9 +200,11 @@ bool pack_reads_planes(const uint8_t* bases, const uint64_t* read_off, uint64_t 
                        int n_threads) {
   if (hi <= lo) return true;
 #if defined(__x86_64__)
-  static const bool have_avx2 = __builtin_cpu_supports("avx2");
+  static const bool cpu_avx2 = __builtin_cpu_supports("avx2");
+  const char* scalar = getenv("PA_PACK_SCALAR");   // tests: force the portable path
+  const bool have_avx2 = cpu_avx2 && !(scalar && *scalar == '1');
 #else
-  static const bool have_avx2 = false;
+  const bool have_avx2 = false;
 #endif
   const uint64_t n = hi - lo;
   int tasks = (int)std::min<uint64_t>((uint64_t)std::max(1, n_threads) * 4, (n + 4095) / 4096);

@@ -281,10 +281,13 @@ def test_partition_of_key_is_monotonic_and_balanced():
                 assert counts.max() < 1.25 * counts.mean() + 50
 
 
-def test_host_packing_matches_a_numpy_restatement():
-    """hostpack.cpp (AVX2 or scalar, threaded) against the plane definition: bit i of word c = ASCII bit 1 / bit 2 of base 32c + i."""
+@pytest.mark.parametrize("scalar", ["0", "1"])
+def test_host_packing_matches_a_numpy_restatement(scalar, monkeypatch):
+    """hostpack.cpp (AVX2 and the portable scalar path, threaded) against the plane definition: bit i of word c = ASCII
+    bit 1 / bit 2 of base 32c + i."""
     import ctypes
     import _native as nat
+    monkeypatch.setenv("PA_PACK_SCALAR", scalar)
     L = nat.lib()
     rng = np.random.default_rng(11)
     for trial in range(6):
