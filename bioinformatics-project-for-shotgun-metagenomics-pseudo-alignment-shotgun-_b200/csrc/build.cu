@@ -519,25 +519,169 @@ __global__ void extsim_stats_kernel(const uint64_t* __restrict__ run_off, const 
 }
 
 // K6: inter[a][b] += 1 for every pair of classes sharing a distinct k-mer (diagonal = total).
-// One warp per k-mer; lanes split the c*c pairs.
-__global__ void extsim_pairwise_kernel(const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome, uint64_t U,
-                                       const uint32_t* __restrict__ group, uint32_t n_groups, int dedupe,
-                                       unsigned long long* __restrict__ inter) {
-  uint64_t u = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
-  if (u >= U) return;
-  const uint32_t lane = threadIdx.x & 31;
-  uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
-  for (uint64_t t = lane; t < c * c; t += 32) {
-    uint64_t a = t / c, b = t % c;
-    uint32_t ga = group[run_genome[r0 + a]], gb = group[run_genome[r0 + b]];
-    if (dedupe) {
-      bool fa = true, fb = true;
-      for (uint64_t i = 0; i < a && fa; ++i) fa = group[run_genome[r0 + i]] != ga;
-      for (uint64_t i = 0; i < b && fb; ++i) fb = group[run_genome[r0 + i]] != gb;
-      if (!fa || !fb) continue;
-    }
-    atomicAdd(&inter[(size_t)ga * n_groups + gb], 1ULL);
+//
+// Counting pair by pair costs sum(c^2) atomics on a few thousand hot cells (config D: 6x10^9; measured 45-67 ms however
+// they are issued: warp or thread per k-mer, 32 or 64 bits, private copies of the matrix).  Near-duplicate genomes make
+// the same class list recur millions of times, so the pass counts *lists* first: (a) every k-mer adds one to the
+// counter of its list in a hash table keyed by a 64-bit hash of the list (one atomic per k-mer instead of c^2);
+// (b) every k-mer compares its list with the table entry's representative - a hash collision between different lists
+// sets a flag and the whole pass is redone pair by pair, so the result never depends on the hash; (c) one thread per
+// table entry adds the entry's count to the cells of its pairs.  K-mers whose probe window is full (more distinct lists
+// than the table holds) and lists longer than EXT_PAIR_SMALL (taken by the whole warp) are counted pair by pair.
+// Cells are (min, max) in 32 bits (a count is at most n_keys < 2^32); extsim_pairwise_mirror widens and mirrors.
+constexpr uint32_t EXT_PAIR_SMALL = 16;
+constexpr uint32_t EXT_PAIR_THREADS = 256;
+constexpr uint32_t EXT_SET_PROBES = 16;
+
+struct SetTable {
+  unsigned long long* key;   // 0 = empty
+  uint32_t* rep;             // smallest k-mer index that holds the list
+  uint32_t* count;
+  uint32_t mask;             // entries - 1 (0: no table, count pair by pair)
+  uint32_t weak_hash;        // tests: every list hashes alike, which must end in the pair-by-pair redo
+};
+
+// class list of k-mer [r0, r0+c) into the caller's shared-memory column; returns its length
+__device__ __forceinline__ uint32_t class_list(const uint32_t* __restrict__ run_genome, const uint32_t* __restrict__ group,
+                                               uint64_t r0, uint32_t c, int dedupe, uint32_t (*col)[EXT_PAIR_THREADS]) {
+  uint32_t n = 0;
+  for (uint32_t j = 0; j < c; ++j) {
+    const uint32_t gr = group[run_genome[r0 + j]];
+    bool first = true;
+    if (dedupe)
+      for (uint32_t i = 0; i < n && first; ++i) first = col[i][threadIdx.x] != gr;
+    if (first) col[n++][threadIdx.x] = gr;
   }
+  return n;
+}
+
+__device__ __forceinline__ unsigned long long class_list_hash(const SetTable& t, uint32_t n, uint32_t (*col)[EXT_PAIR_THREADS]) {
+  if (t.weak_hash) return 1;
+  unsigned long long h = 0x243F6A8885A308D3ULL + n;
+  for (uint32_t i = 0; i < n; ++i) {
+    h = (h ^ col[i][threadIdx.x]) * 0x9E3779B97F4A7C15ULL;
+    h ^= h >> 29;
+  }
+  return h ? h : 1;
+}
+
+__device__ __forceinline__ void add_pairs(uint32_t n, uint32_t (*col)[EXT_PAIR_THREADS], uint32_t n_groups, uint32_t by,
+                                          uint32_t* __restrict__ tri) {
+  for (uint32_t a = 0; a < n; ++a) {
+    const uint32_t ga = col[a][threadIdx.x];
+    for (uint32_t b = a; b < n; ++b) {
+      const uint32_t gb = col[b][threadIdx.x];
+      atomicAdd(&tri[(size_t)min(ga, gb) * n_groups + max(ga, gb)], by);
+    }
+  }
+}
+
+// slot of `h` in the probe window, claiming an empty one when `claim`; -1 if the window holds other lists only
+__device__ __forceinline__ int64_t set_slot(const SetTable& t, unsigned long long h, bool claim) {
+  uint32_t at = (uint32_t)(h >> 20) & t.mask;
+  for (uint32_t i = 0; i < EXT_SET_PROBES; ++i, at = (at + 1) & t.mask) {
+    unsigned long long cur = t.key[at];
+    if (cur == 0 && claim) cur = atomicCAS(&t.key[at], 0ULL, h), cur = cur ? cur : h;
+    if (cur == h) return at;
+    if (cur == 0) return -1;   // (only without claim) never inserted
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(EXT_PAIR_THREADS)
+extsim_pairwise_kernel(const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome, uint64_t U,
+                       const uint32_t* __restrict__ group, uint32_t n_groups, int dedupe, SetTable sets,
+                       uint32_t* __restrict__ tri) {
+  __shared__ uint32_t s_class[EXT_PAIR_SMALL][EXT_PAIR_THREADS];
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t base = blockIdx.x * (uint64_t)blockDim.x; base < U; base += stride) {   // uniform per block
+    const uint64_t u = base + threadIdx.x;
+    uint64_t r0 = 0, c = 0;
+    if (u < U) { r0 = run_off[u]; c = run_off[u + 1] - r0; }
+    if (c <= EXT_PAIR_SMALL) {
+      const uint32_t n = class_list(run_genome, group, r0, (uint32_t)c, dedupe, s_class);
+      int64_t at = -1;
+      if (n >= 2 && sets.mask) at = set_slot(sets, class_list_hash(sets, n, s_class), true);
+      if (at >= 0) {
+        if (sets.rep[at] > (uint32_t)u) atomicMin(&sets.rep[at], (uint32_t)u);
+        atomicAdd(&sets.count[at], 1u);
+      } else {
+        add_pairs(n, s_class, n_groups, 1u, tri);
+      }
+    }
+    unsigned big = __ballot_sync(0xFFFFFFFFu, c > EXT_PAIR_SMALL);
+    while (big) {
+      const int src = __ffs(big) - 1;
+      big &= big - 1;
+      const uint64_t wr0 = __shfl_sync(0xFFFFFFFFu, r0, src), wc = __shfl_sync(0xFFFFFFFFu, c, src);
+      for (uint64_t t = lane; t < wc * wc; t += 32) {
+        uint64_t a = t / wc, b = t % wc;
+        if (a > b) continue;
+        uint32_t ga = group[run_genome[wr0 + a]], gb = group[run_genome[wr0 + b]];
+        if (dedupe) {
+          bool fa = true, fb = true;
+          for (uint64_t i = 0; i < a && fa; ++i) fa = group[run_genome[wr0 + i]] != ga;
+          for (uint64_t i = 0; i < b && fb; ++i) fb = group[run_genome[wr0 + i]] != gb;
+          if (!fa || !fb) continue;
+        }
+        atomicAdd(&tri[(size_t)min(ga, gb) * n_groups + max(ga, gb)], 1u);
+      }
+    }
+  }
+}
+
+// K6 (b): a k-mer counted through the table must hold exactly the representative's list.
+__global__ void __launch_bounds__(EXT_PAIR_THREADS)
+extsim_sets_verify(const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome, uint64_t U,
+                   const uint32_t* __restrict__ group, int dedupe, SetTable sets, uint32_t* __restrict__ collision) {
+  __shared__ uint32_t s_class[EXT_PAIR_SMALL][EXT_PAIR_THREADS];
+  const uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  const uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
+  if (c < 2 || c > EXT_PAIR_SMALL) return;
+  const uint32_t n = class_list(run_genome, group, r0, (uint32_t)c, dedupe, s_class);
+  if (n < 2) return;
+  const int64_t at = set_slot(sets, class_list_hash(sets, n, s_class), false);
+  if (at < 0) return;                       // was counted pair by pair
+  const uint32_t rep = sets.rep[at];
+  if (rep == (uint32_t)u) return;
+  // walk the representative's list; its distinct classes so far equal mine so far, so mine serve as its seen-set
+  const uint64_t q0 = run_off[rep], qc = run_off[rep + 1] - q0;
+  uint32_t m = 0;
+  bool same = true;
+  for (uint64_t j = 0; j < qc && same; ++j) {
+    const uint32_t gr = group[run_genome[q0 + j]];
+    bool first = true;
+    if (dedupe)
+      for (uint32_t i = 0; i < m && first; ++i) first = s_class[i][threadIdx.x] != gr;
+    if (!first) continue;
+    same = m < n && s_class[m][threadIdx.x] == gr;
+    ++m;
+  }
+  if (!same || m != n) atomicOr(collision, 1u);
+}
+
+// K6 (c): one thread per table entry adds the entry's count to the cells of its pairs.
+__global__ void __launch_bounds__(EXT_PAIR_THREADS)
+extsim_sets_flush(const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome,
+                  const uint32_t* __restrict__ group, uint32_t n_groups, int dedupe, SetTable sets,
+                  uint32_t* __restrict__ tri) {
+  __shared__ uint32_t s_class[EXT_PAIR_SMALL][EXT_PAIR_THREADS];
+  const uint64_t at = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (at > sets.mask || sets.key[at] == 0) return;
+  const uint32_t rep = sets.rep[at];
+  const uint64_t r0 = run_off[rep], c = run_off[rep + 1] - r0;
+  const uint32_t n = class_list(run_genome, group, r0, (uint32_t)c, dedupe, s_class);
+  add_pairs(n, s_class, n_groups, sets.count[at], tri);
+}
+
+// The matrix is symmetric: K6 counts cell (min, max) in 32 bits (a count is at most n_keys < 2^32); widen and mirror.
+__global__ void extsim_pairwise_mirror(const uint32_t* __restrict__ tri, uint32_t n_groups, unsigned long long* __restrict__ inter) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= (uint64_t)n_groups * n_groups) return;
+  const uint32_t a = (uint32_t)(i / n_groups), b = (uint32_t)(i % n_groups);
+  inter[i] = tri[(size_t)min(a, b) * n_groups + max(a, b)];
 }
 
 // K7 (a): per distinct k-mer, how many runs / positions survive the keep mask.
@@ -934,13 +1078,55 @@ int32_t index_extsim_pairwise(Index& ix, const uint32_t* h_group, uint32_t n_gro
   DevBuf d_group, d_out;
   int dedupe = 0;
   PA_TRY(upload_groups(ix, h_group, n_groups, d_group, &dedupe));
-  size_t nb = std::max<size_t>((size_t)n_groups * n_groups, 1) * 8;
-  PA_TRY(d_out.alloc(nb));
-  PA_CUDA(cudaMemsetAsync(d_out.p, 0, nb, s));
-  if (ix.n_keys)
-    extsim_pairwise_kernel<<<grid_for(ix.n_keys * 32, 256), 256, 0, s>>>(
-        ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(), ix.n_keys, d_group.as<uint32_t>(), n_groups, dedupe,
-        d_out.as<unsigned long long>());
+  const size_t cells = std::max<size_t>((size_t)n_groups * n_groups, 1);
+  DevBuf d_tri, d_sets;
+  PA_TRY(d_out.alloc(cells * 8));
+  PA_TRY(d_tri.alloc(cells * 4));
+  // table of class lists: 2^20 entries (16 MB: stays in L2); PA_K6_SETS=0 counts pair by pair
+  uint32_t entries = 1u << 20;
+  if (const char* e = getenv("PA_K6_SETS")) entries = (uint32_t)atoi(e);
+  if (entries & (entries - 1)) { set_error("PA_K6_SETS must be a power of two"); return ST_INVALID_ARG; }
+  if (ix.n_keys >= 0xFFFFFFFFull) entries = 0;   // representatives are 32-bit k-mer indices
+  SetTable sets{nullptr, nullptr, nullptr, 0, 0};
+  if (const char* e = getenv("PA_K6_WEAK_HASH")) sets.weak_hash = *e == '1';
+  uint32_t* d_collision = nullptr;
+  if (entries) {
+    PA_TRY(d_sets.alloc((size_t)entries * 16 + 16));
+    sets.key = d_sets.as<unsigned long long>();
+    sets.rep = (uint32_t*)(sets.key + entries);
+    sets.count = sets.rep + entries;
+    d_collision = sets.count + entries;
+    sets.mask = entries - 1;
+  }
+  const unsigned grid = (unsigned)grid_for(ix.n_keys, EXT_PAIR_THREADS);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    PA_CUDA(cudaMemsetAsync(d_tri.p, 0, cells * 4, s));
+    if (sets.mask) {
+      PA_CUDA(cudaMemsetAsync(sets.key, 0, (size_t)entries * 8, s));
+      PA_CUDA(cudaMemsetAsync(sets.rep, 0xFF, (size_t)entries * 4, s));
+      PA_CUDA(cudaMemsetAsync(sets.count, 0, (size_t)entries * 4 + 16, s));
+    }
+    if (!ix.n_keys) break;
+    extsim_pairwise_kernel<<<grid, EXT_PAIR_THREADS, 0, s>>>(
+        ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(), ix.n_keys, d_group.as<uint32_t>(), n_groups, dedupe, sets,
+        d_tri.as<uint32_t>());
+    PA_CUDA(cudaGetLastError());
+    if (!sets.mask) break;
+    extsim_sets_verify<<<grid, EXT_PAIR_THREADS, 0, s>>>(
+        ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(), ix.n_keys, d_group.as<uint32_t>(), dedupe, sets, d_collision);
+    PA_CUDA(cudaGetLastError());
+    uint32_t collision = 0;
+    PA_CUDA(cudaMemcpyAsync(&collision, d_collision, 4, cudaMemcpyDeviceToHost, s));
+    PA_CUDA(cudaStreamSynchronize(s));
+    if (collision) { sets.mask = 0; continue; }   // two lists under one hash: count pair by pair instead
+    extsim_sets_flush<<<(unsigned)grid_for(entries, EXT_PAIR_THREADS), EXT_PAIR_THREADS, 0, s>>>(
+        ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(), d_group.as<uint32_t>(), n_groups, dedupe, sets,
+        d_tri.as<uint32_t>());
+    PA_CUDA(cudaGetLastError());
+    break;
+  }
+  if (n_groups)
+    extsim_pairwise_mirror<<<grid_for(cells, 256), 256, 0, s>>>(d_tri.as<uint32_t>(), n_groups, d_out.as<unsigned long long>());
   PA_CUDA(cudaGetLastError());
   if (n_groups) PA_CUDA(cudaMemcpyAsync(h_inter, d_out.p, (size_t)n_groups * n_groups * 8, cudaMemcpyDeviceToHost, s));
   PA_CUDA(cudaStreamSynchronize(s));

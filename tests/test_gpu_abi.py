@@ -250,6 +250,50 @@ def test_extsim_kernels_against_oracle():
             ix.close()
 
 
+@pytest.mark.parametrize("env", [{}, {"PA_K6_SETS": "0"}, {"PA_K6_SETS": "4"}, {"PA_K6_WEAK_HASH": "1"}])
+def test_extsim_pairwise_paths(env, monkeypatch):
+    """K6 counts class lists through a hash table; without the table, with a table far too small (probe windows full) and with
+    a hash under which all lists collide (detected, then redone pair by pair) the matrix must be the same."""
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    for seed in list(range(7100, 7115)) + list(range(10_100, 10_115)):
+        case = synth.fuzz_case(seed, dup_ids=seed >= 10_000)
+        o = orc.OracleReference(case["k"], case["genomes"])
+        ix = build_native(case)
+        try:
+            classes = {}
+            group = np.array([classes.setdefault(g[0], len(classes)) for g in case["genomes"]], dtype=np.uint32)
+            n = len(classes)
+            oi = np.zeros(n * n, np.uint64)
+            orc.lib().orc_extsim_pairwise(o._h, orc._ptr(group), n, orc._ptr(oi))
+            assert np.array_equal(ix.extsim_pairwise(group, n).reshape(-1), oi)
+        finally:
+            ix.close()
+
+
+def test_extsim_pairwise_long_genome_lists():
+    """k-mers shared by more genomes than a thread takes alone (the warp-cooperative branch of K6), with and without repeated
+    identifier classes."""
+    rng = np.random.default_rng(77)
+    genomes = [(f"g{g}", "".join("ACGT"[int(x)] for x in rng.integers(0, 4, int(rng.integers(30, 400))))) for g in range(45)]
+    for k in (3, 5):
+        o = orc.OracleReference(k, genomes)
+        ix = build_native({"k": k, "genomes": genomes})
+        try:
+            for n, group in ((45, np.arange(45, dtype=np.uint32)), (7, (np.arange(45) % 7).astype(np.uint32)),
+                             (20, rng.integers(0, 20, 45).astype(np.uint32))):
+                total, uniq = ix.extsim_stats(group, n)
+                inter = ix.extsim_pairwise(group, n)
+                L = orc.lib()
+                ot = np.zeros(n, np.uint64); ou = np.zeros(n, np.uint64); oi = np.zeros(n * n, np.uint64)
+                L.orc_extsim_stats(o._h, orc._ptr(group), n, orc._ptr(ot), orc._ptr(ou))
+                L.orc_extsim_pairwise(o._h, orc._ptr(group), n, orc._ptr(oi))
+                assert np.array_equal(total, ot) and np.array_equal(uniq, ou)
+                assert np.array_equal(inter.reshape(-1), oi)
+        finally:
+            ix.close()
+
+
 def test_bad_genome_character_is_rejected():
     data, off = nat.pack_strings(["ACGTNNACGT", "ACGXACGT"])
     with pytest.raises(ValueError):

@@ -75,6 +75,10 @@ def main():
     group = np.arange(G, dtype=np.uint32)
     t0 = time.perf_counter(); total, uniq = ix.extsim_stats(group, G); t_stats = time.perf_counter() - t0
     t0 = time.perf_counter(); inter = ix.extsim_pairwise(group, G); t_pair = time.perf_counter() - t0
+    pair_ts = [t_pair]
+    for _ in range(3):
+        t0 = time.perf_counter(); ix.extsim_pairwise(group, G); pair_ts.append(time.perf_counter() - t0)
+    t_pair = min(pair_ts)
     t0 = time.perf_counter(); keep, dropped = greedy(total, uniq, inter, [L] * G, a.threshold); t_greedy = time.perf_counter() - t0
     t0 = time.perf_counter(); ix.drop_genomes(keep); t_drop = time.perf_counter() - t0
     inf2 = ix.info()
