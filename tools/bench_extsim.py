@@ -57,6 +57,7 @@ def main():
     ap.add_argument("--sub", type=float, default=0.01)
     ap.add_argument("--threshold", type=float, default=0.5)
     ap.add_argument("-k", type=int, default=31)
+    ap.add_argument("--builds", type=int, default=3, help="build this many times, report the fastest")
     a = ap.parse_args()
     import torch
     import _native as nat
@@ -68,9 +69,15 @@ def main():
     bases = cluster_genomes(torch, dev, G, L, a.cluster, a.sub, seed=7)
     goff = (np.arange(G + 1, dtype=np.uint64) * np.uint64(L)).astype(np.uint64)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    ix = nat.NativeIndex.build_device(bases.data_ptr(), goff, a.k)
-    t_build = time.perf_counter() - t0
+    builds = []
+    ix = None
+    for _ in range(a.builds):        # the first build of a process pays module loading and the first large allocations
+        if ix is not None:
+            ix.close()
+        t0 = time.perf_counter()
+        ix = nat.NativeIndex.build_device(bases.data_ptr(), goff, a.k)
+        builds.append(time.perf_counter() - t0)
+    t_build = min(builds)
     inf = ix.info()
     group = np.arange(G, dtype=np.uint32)
     t0 = time.perf_counter(); total, uniq = ix.extsim_stats(group, G); t_stats = time.perf_counter() - t0
@@ -85,7 +92,7 @@ def main():
     print(json.dumps({
         "workload": f"configs[3]: {G} genomes x {L} bp in clusters of {a.cluster} ({100 * (1 - a.sub):.0f} % identity), k={a.k}, threshold {a.threshold}",
         "kmer_occurrences": int(inf.n_occ), "distinct_kmers": int(inf.n_keys), "key_genome_pairs": int(inf.n_runs),
-        "build_s": t_build, "build_kmers_per_s": inf.n_occ / t_build,
+        "build_s": t_build, "build_s_all": [round(t, 4) for t in builds], "build_kmers_per_s": inf.n_occ / t_build,
         "build_kernels_ms": {"encode": inf.build_encode_ms, "sort": inf.build_sort_ms, "csr": inf.build_rle_ms, "table": inf.build_table_ms},
         "extsim_stats_s": t_stats, "extsim_pairwise_s": t_pair, "greedy_host_s": t_greedy, "drop_genomes_s": t_drop,
         "table": {"block_bits": int(inf.block_bits), "stash_count": int(inf.stash_count), "set_sectors": int(inf.n_list_sectors),
