@@ -127,6 +127,13 @@ def test_fuzz_small_k_against_oracle(block):
         check_case(synth.fuzz_case(seed))
 
 
+def test_summary_global_counter_path(monkeypatch):
+    """K8 counts per genome in shared memory; indexes with more genomes than the shared counters hold use global atomics."""
+    monkeypatch.setenv("PA_SUMMARY_GLOBAL", "1")
+    for seed in range(8000, 8040):
+        check_case(synth.fuzz_case(seed))
+
+
 def test_fuzz_wider_k():
     for seed in range(5000, 5080):
         check_case(synth.fuzz_case(seed, k_range=(9, 31), max_genomes=8))
