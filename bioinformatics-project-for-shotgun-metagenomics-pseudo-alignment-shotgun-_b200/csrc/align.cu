@@ -115,24 +115,30 @@ __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
 }
 
 
-// One doubling step of the sliding minimum over the per-position m-mer hashes: entry (c, lane) stands for position
-// 32c + lane and takes the smaller of itself and the entry d positions to its right (the left one wins ties, so the
-// leftmost minimum survives).
-__device__ __forceinline__ void window_min_step(uint32_t (&mh)[AL_ROUNDS + 1], uint32_t (&mpos)[AL_ROUNDS + 1], uint32_t d,
-                                                uint32_t lane) {
+// One doubling step of the sliding minimum over the per-position minimizer keys.  Entry (c, lane) stands for position
+// 32c + lane and holds (order << 4 | offset of the best candidate seen so far, relative to this position); it takes the
+// smaller of itself and the entry d positions to its right, whose offset grows by d (offsets stay below w <= 16, so the
+// addition never reaches the order bits).  Equal orders compare by offset: the leftmost candidate wins, as in
+// kmer_minimizer.
+__device__ __forceinline__ void window_min_step(uint32_t (&key)[AL_ROUNDS + 1], uint32_t d, uint32_t lane) {
   const uint32_t src = (lane + d) & 31;
   const bool wrap = lane + d >= 32;
   // every chunk rotated by d lanes once; the neighbour d positions to the right is in the own chunk's rotation or,
   // for the last d lanes, in the next chunk's
-  uint32_t rh[AL_ROUNDS + 1], rp[AL_ROUNDS + 1];
+  uint32_t rk[AL_ROUNDS + 1];
 #pragma unroll
-  for (int c = 0; c <= AL_ROUNDS; ++c) { rh[c] = __shfl_sync(0xffffffffu, mh[c], src); rp[c] = __shfl_sync(0xffffffffu, mpos[c], src); }
+  for (int c = 0; c <= AL_ROUNDS; ++c) rk[c] = __shfl_sync(0xffffffffu, key[c], src);
 #pragma unroll
   for (int c = 0; c <= AL_ROUNDS; ++c) {
-    const uint32_t h2 = wrap ? (c < AL_ROUNDS ? rh[c + 1] : 0xFFFFFFFFu) : rh[c];
-    const uint32_t p2 = wrap ? (c < AL_ROUNDS ? rp[c + 1] : 0u) : rp[c];
-    if (h2 < mh[c]) { mh[c] = h2; mpos[c] = p2; }
+    if (c < AL_ROUNDS) key[c] = min(key[c], (wrap ? rk[c + 1] : rk[c]) + d);
+    else if (!wrap) key[c] = min(key[c], rk[c] + d);
   }
+}
+
+// minimizer (full hash, offset) of the window whose planes are wl / wh, from its slid key
+__device__ __forceinline__ void window_minimizer(const TableView& t, uint32_t key, uint32_t wl, uint32_t* mhash, uint32_t* p) {
+  *p = key & 15u;
+  *mhash = ((key >> 4) << t.hdrop) | ((wl >> *p) & ((1u << t.hdrop) - 1));
 }
 
 // rare continuation of a lookup whose home bucket was full, without a match, and has CONT set (kept out of line:
@@ -401,19 +407,18 @@ align_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
         }
       }
       // ---- minimizers: hash of the m-mer at every base position, sliding minimum over the w candidates ----
-      uint32_t mh[AL_ROUNDS + 1], mpos[AL_ROUNDS + 1];
+      uint32_t mkey[AL_ROUNDS + 1], mh[AL_ROUNDS], mpos[AL_ROUNDS];
 #pragma unroll
       for (int c = 0; c <= AL_ROUNDS; ++c) {
         const uint32_t nl = c < AL_ROUNDS ? lo[c + 1] : 0u, nh = c < AL_ROUNDS ? hi[c + 1] : 0u;
         const uint32_t xl = __funnelshift_r(lo[c], nl, lane) & t.mmask;
         const uint32_t xh = __funnelshift_r(hi[c], nh, lane) & t.mmask;
-        mh[c] = mmer_hash((xh << t.m) | xl, t.hmask, t.m);
-        mpos[c] = 32 * c + lane;
+        mkey[c] = mmer_order((xh << t.m) | xl, t) << 4;
       }
       {
         uint32_t span = 1;
-        for (; 2 * span <= t.w; span <<= 1) window_min_step(mh, mpos, span, lane);
-        if (t.w > span) window_min_step(mh, mpos, t.w - span, lane);   // two overlapping spans cover the w candidates
+        for (; 2 * span <= t.w; span <<= 1) window_min_step(mkey, span, lane);
+        if (t.w > span) window_min_step(mkey, t.w - span, lane);   // two overlapping spans cover the w candidates
       }
       // ---- per window: quality filter, block / bucket / tag, one sector load ----
       uint64_t raw[AL_ROUNDS], tag[AL_ROUNDS];
@@ -437,7 +442,7 @@ align_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
         uint32_t wi = __funnelshift_r(inv[r], inv[r + 1], lane) & kmask;
         look[r] = exists && !qf && wi == 0;
         raw[r] = ((uint64_t)wh << k) | wl;
-        mpos[r] -= 32 * r + lane;   // minimizer offset inside the window, 0 .. w-1
+        window_minimizer(t, mkey[r], wl, &mh[r], &mpos[r]);   // full hash and offset inside the window, 0 .. w-1
         const SlotAddr a = slot_addr(t, wl, wh, mh[r], mpos[r]);
         tag[r] = a.tag;
         if (look[r]) ld_sector_nc(bucket_ptr(t, a.block, a.bucket), sector[r]);
@@ -705,19 +710,18 @@ align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
         }
       }
       // ---- minimizers ----
-      uint32_t mh[AL_ROUNDS + 1], mpos[AL_ROUNDS + 1];
+      uint32_t mkey[AL_ROUNDS + 1], mh[AL_ROUNDS], mpos[AL_ROUNDS];
 #pragma unroll
       for (int c = 0; c <= AL_ROUNDS; ++c) {
         const uint32_t nl = c < AL_ROUNDS ? lo[c + 1] : 0u, nh = c < AL_ROUNDS ? hi[c + 1] : 0u;
         const uint32_t xl = __funnelshift_r(lo[c], nl, lane) & t.mmask;
         const uint32_t xh = __funnelshift_r(hi[c], nh, lane) & t.mmask;
-        mh[c] = mmer_hash((xh << t.m) | xl, t.hmask, t.m);
-        mpos[c] = 32 * c + lane;
+        mkey[c] = mmer_order((xh << t.m) | xl, t) << 4;
       }
       {
         uint32_t span = 1;
-        for (; 2 * span <= t.w; span <<= 1) window_min_step(mh, mpos, span, lane);
-        if (t.w > span) window_min_step(mh, mpos, t.w - span, lane);
+        for (; 2 * span <= t.w; span <<= 1) window_min_step(mkey, span, lane);
+        if (t.w > span) window_min_step(mkey, t.w - span, lane);
       }
       // ---- per window: quality filter, block / bucket / tag, one sector load ----
       uint64_t tag[AL_ROUNDS];
@@ -739,7 +743,7 @@ align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
         const uint32_t wl = __funnelshift_r(lo[r], lo[r + 1], lane) & kmask;
         const uint32_t wh = __funnelshift_r(hi[r], hi[r + 1], lane) & kmask;
         const uint32_t wi = __funnelshift_r(inv[r], inv[r + 1], lane) & kmask;
-        mpos[r] -= s;   // minimizer offset inside the window, 0 .. w-1
+        window_minimizer(t, mkey[r], wl, &mh[r], &mpos[r]);   // full hash and offset inside the window, 0 .. w-1
         const SlotAddr a = slot_addr(t, wl, wh, mh[r], mpos[r]);
         tag[r] = a.tag;
         if (exists && !qf && wi == 0) { look |= 1u << r; ld_sector_nc(bucket_ptr(t, a.block, a.bucket), sector[r]); }

@@ -137,7 +137,9 @@ struct TableView {
   uint32_t gbits;      // bits per genome id inside an inline list
   uint32_t n_inline;   // longest inline list (1 = inline lists unused)
   uint32_t mmask;      // 2^m - 1
-  uint32_t hmask;      // 2^(2m) - 1
+  uint32_t hdrop;      // low bits of an m-mer that stay raw in its hash: max(0, 2m - 28)
+  uint32_t ymask;      // 2^(2m - hdrop) - 1: the mixed part of the hash, also the minimizer order
+  uint32_t yshift;     // xorshift distance of the mix: half of its width
 };
 
 enum : uint32_t { KIND_MLIST = 0, KIND_INLINE = 2, KIND_SPECIFIC = 3 };
@@ -145,14 +147,21 @@ enum : uint32_t { KIND_MLIST = 0, KIND_INLINE = 2, KIND_SPECIFIC = 3 };
 constexpr uint32_t MINIMIZER_MAX = 16;
 __host__ __device__ __forceinline__ uint32_t minimizer_len_for_k(int k) { return k < 1 ? 1u : (k > (int)MINIMIZER_MAX ? MINIMIZER_MAX : (uint32_t)k); }
 
-// bijective hash of an m-mer (2m <= 32 bits): xorshift and odd multiplication mod 2^(2m) are invertible
-__host__ __device__ __forceinline__ uint32_t mmer_hash(uint32_t x, uint32_t hmask, uint32_t m) {
-  x ^= x >> m;
-  x = (x * 0x7FEB352DU) & hmask;
-  x ^= x >> m;
-  x = (x * 0x846CA68BU) & hmask;
-  x ^= x >> m;
-  return x;
+// Hash of an m-mer x (2m <= 32 bits), bijective: the upper 2m - hdrop bits of x go through an invertible xorshift /
+// odd-multiplication mix (`mmer_order`), the low hdrop bits stay raw.  Minimizers are ordered by the mixed part alone: it
+// has at most 28 bits, so the align kernel slides (order << 4 | offset) through one 32-bit shuffle per step and rebuilds the
+// full hash from the winner's offset with a shift and a mask.
+__host__ __device__ __forceinline__ uint32_t mmer_order(uint32_t x, const TableView& t) {
+  uint32_t y = x >> t.hdrop;
+  y ^= y >> t.yshift;
+  y = (y * 0x7FEB352DU) & t.ymask;
+  y ^= y >> t.yshift;
+  y = (y * 0x846CA68BU) & t.ymask;
+  y ^= y >> t.yshift;
+  return y;
+}
+__host__ __device__ __forceinline__ uint32_t mmer_hash(uint32_t x, const TableView& t) {
+  return (mmer_order(x, t) << t.hdrop) | (x & ((1u << t.hdrop) - 1));
 }
 
 struct SlotAddr {
@@ -181,11 +190,11 @@ __host__ __device__ __forceinline__ SlotAddr slot_addr(const TableView& t, uint3
 __host__ __device__ __forceinline__ void kmer_minimizer(const TableView& t, uint32_t lo, uint32_t hi, uint32_t* mhash, uint32_t* p) {
   uint32_t best = 0xFFFFFFFFu, bp = 0;
   for (uint32_t j = 0; j < t.w; ++j) {
-    uint32_t x = (((hi >> j) & t.mmask) << t.m) | ((lo >> j) & t.mmask);
-    uint32_t h = mmer_hash(x, t.hmask, t.m);
-    if (j == 0 || h < best) { best = h; bp = j; }
+    const uint32_t y = mmer_order((((hi >> j) & t.mmask) << t.m) | ((lo >> j) & t.mmask), t);
+    if (j == 0 || y < best) { best = y; bp = j; }
   }
-  *mhash = best; *p = bp;
+  *mhash = (best << t.hdrop) | ((lo >> bp) & ((1u << t.hdrop) - 1));
+  *p = bp;
 }
 
 // inverse of mix_key (decoding exported keys back into k-mer strings; the table build un-hashes the CSR keys)

@@ -117,7 +117,9 @@ struct Index {
     t.gbits = gbits;
     t.n_inline = n_inline;
     t.mmask = (1u << t.m) - 1;
-    t.hmask = t.m >= 16 ? 0xFFFFFFFFu : ((1u << (2 * t.m)) - 1);
+    t.hdrop = 2 * t.m > 28 ? 2 * t.m - 28 : 0;
+    t.ymask = (1u << (2 * t.m - t.hdrop)) - 1;
+    t.yshift = (2 * t.m - t.hdrop + 1) / 2;
     return t;
   }
   size_t device_bytes() const {
