@@ -457,7 +457,7 @@ def gpu_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args),
             "e2e": e2e, "gpu_launches": launches["n"],
             "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "kernel": "align_fast_kernel (K4)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": ("align_fast_kernel (K4)" if args.extquality else "align_fast_split_kernel (K4)"), "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "traffic": traffic, "kernel_ms": k4_ms, "algorithmic_bytes_per_read": alg,
                          "random_access": {

@@ -815,6 +815,227 @@ align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// K4 fast kernel, staggered (PA_FAST_SPLIT=1).  ncu attributes a fifth of the samples of the kernel above to the tag
+// compare waiting for its sector: a warp issues its 128 loads and needs them a few instructions later.  Here the body
+// is cut into three stages -- A: planes, minimizer keys (no table access); B: addresses + sector loads; C: resolve +
+// rules -- and run as B(i), A(i+1), C(i): the ~500 instructions of the next read's stage A execute while the sectors of
+// read i are in flight, with only A's result (planes + five keys per lane) carried from one iteration to the next.
+// ---------------------------------------------------------------------------
+#ifndef PA_FAST_SPLIT
+#define PA_FAST_SPLIT 1
+#endif
+
+template <bool QUAL>
+struct FrontState {
+  uint32_t lo[AL_ROUNDS + 1], hi[AL_ROUNDS + 1], inv[AL_ROUNDS + 1];   // bit planes of the read (warp-uniform)
+  uint32_t mkey[AL_ROUNDS + 1];                                        // slid minimizer keys
+  uint32_t qex[QUAL ? AL_ROUNDS + 1 : 1];                              // exclusive quality prefix at this lane's base
+  uint32_t W;                                                          // windows to look up (0: none)
+  bool dropped, defer;
+};
+
+template <bool QUAL, bool PACKED>
+__device__ __forceinline__ void fast_stage_a(const TableView& t, const AlignParams& prm, const ReadInput& in,
+                                             const uint8_t* __restrict__ quals, const Prefetch<PACKED>& ch,
+                                             const Prefetch<false>& q, uint64_t read, uint64_t beg, uint64_t L, uint32_t lane,
+                                             FrontState<QUAL>& f, unsigned long long& c_drop) {
+  const int k = (int)t.k;
+  f.dropped = false; f.defer = false; f.W = 0;
+  if (QUAL && prm.has_mrq) {  // Read.mean_quality() < min_read_quality  (kmer.py:587)
+    uint64_t s = 0;
+    if (L <= 32 * (AL_ROUNDS + 1)) {   // the prefetched bytes cover the read (bytes beyond L were loaded as 0)
+#pragma unroll
+      for (int c = 0; c <= AL_ROUNDS; ++c) s += q.v[c];
+    } else {
+      const uint8_t* rq = quals + beg;
+      for (uint64_t i = lane; i < L; i += 32) s += rq[i];
+    }
+    s = warp_sum(s);
+    if ((int64_t)s < prm.mrq * (int64_t)L) { f.dropped = true; if (lane == 0) ++c_drop; }
+  }
+  const uint64_t W = (!f.dropped && k >= 1 && L >= (uint64_t)k) ? L - k + 1 : 0;  // kmer.py:91-92
+  if (W > AL_SUPER) { f.defer = true; return; }   // longer than one super-round: the general kernel loops over super-rounds
+  if (W == 0) return;
+  f.W = (uint32_t)W;
+  encode_planes<PACKED>(in, ch, read, beg, L, 0, lane, f.lo, f.hi, f.inv);
+  if (QUAL && prm.has_mkq) {
+    uint32_t carry = 0;
+#pragma unroll
+    for (int c = 0; c <= AL_ROUNDS; ++c) {
+      uint32_t qq = q.v[c], incl = qq;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+      f.qex[QUAL ? c : 0] = carry + incl - qq;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c <= AL_ROUNDS; ++c) {
+    const uint32_t nl = c < AL_ROUNDS ? f.lo[c + 1] : 0u, nh = c < AL_ROUNDS ? f.hi[c + 1] : 0u;
+    const uint32_t xl = __funnelshift_r(f.lo[c], nl, lane) & t.mmask;
+    const uint32_t xh = __funnelshift_r(f.hi[c], nh, lane) & t.mmask;
+    f.mkey[c] = mmer_order((xh << t.m) | xl, t) << 4;
+  }
+  uint32_t span = 1;
+  for (; 2 * span <= t.w; span <<= 1) window_min_step(f.mkey, span, lane);
+  if (t.w > span) window_min_step(f.mkey, t.w - span, lane);
+}
+
+template <bool QUAL, bool PACKED>
+__global__ void __launch_bounds__(FA_THREADS, PA_FAST_MINB)
+align_fast_split_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
+                        const uint64_t* __restrict__ read_off, uint64_t n_reads, AlignParams prm, uint64_t* __restrict__ out_word,
+                        unsigned long long* __restrict__ counters, uint32_t* __restrict__ queue,
+                        unsigned long long* __restrict__ queue_count) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp_global = (uint64_t)blockIdx.x * FA_WARPS + (threadIdx.x >> 5);
+  const uint64_t n_warps = (uint64_t)gridDim.x * FA_WARPS;
+  const int k = (int)t.k;
+  const uint32_t kmask = (k >= 1 && k < 32) ? ((1u << k) - 1) : 0u;
+  unsigned long long c_drop = 0, c_nq = 0, c_nr = 0;  // per-lane partial counters
+  const ReadInput qin{quals, nullptr, 0};
+
+  // input pipeline: while read i is resolved, stage A runs on read i+1 (bases requested one iteration earlier), the
+  // bases of read i+2 and the offsets of read i+3 are requested
+  uint64_t nx_beg = 0, nx_end = 0, n2_beg = 0, n2_end = 0;
+  Prefetch<PACKED> nx_ch;
+  Prefetch<false> nx_q;
+  FrontState<QUAL> cur;
+  {
+    const uint64_t r0 = warp_global, r1 = r0 + n_warps, r2 = r0 + 2 * n_warps;
+    uint64_t beg0 = 0, end0 = 0;
+    if (r0 < n_reads) { beg0 = read_off[r0]; end0 = read_off[r0 + 1]; }
+    if (r1 < n_reads) { nx_beg = read_off[r1]; nx_end = read_off[r1 + 1]; }
+    if (r2 < n_reads) { n2_beg = read_off[r2]; n2_end = read_off[r2 + 1]; }
+    Prefetch<PACKED> ch0;
+    Prefetch<false> q0;
+    prefetch_read<PACKED>(in, r0 < n_reads, r0, beg0, end0 - beg0, lane, ch0);
+    if (QUAL) prefetch_read<false>(qin, r0 < n_reads, r0, beg0, end0 - beg0, lane, q0);
+    prefetch_read<PACKED>(in, r1 < n_reads, r1, nx_beg, nx_end - nx_beg, lane, nx_ch);
+    if (QUAL) prefetch_read<false>(qin, r1 < n_reads, r1, nx_beg, nx_end - nx_beg, lane, nx_q);
+    if (r0 < n_reads) fast_stage_a<QUAL, PACKED>(t, prm, in, quals, ch0, q0, r0, beg0, end0 - beg0, lane, cur, c_drop);
+  }
+
+  for (uint64_t read = warp_global; read < n_reads; read += n_warps) {
+    // ---- stage B: per window quality filter, block / bucket / tag, one sector load ----
+    uint64_t tag[AL_ROUNDS];
+    uint64_t sector[AL_ROUNDS][4];
+    uint32_t look = 0;   // bit r: window r of this lane is looked up
+    uint32_t read_nq = 0, read_nr = 0;
+    if (cur.W) {
+#pragma unroll
+      for (int r = 0; r < AL_ROUNDS; ++r) {
+        const uint32_t s = 32 * r + lane;
+        const bool exists = s < cur.W;
+        bool qf = false;
+        if (QUAL && prm.has_mkq) {  // kmer_quality(start, k) < min_kmer_quality, before the lookup (kmer.py:420-422)
+          const uint32_t tl = lane + k;
+          const uint32_t p_a = __shfl_sync(0xffffffffu, cur.qex[QUAL ? r : 0], tl & 31);
+          const uint32_t p_b = __shfl_sync(0xffffffffu, cur.qex[QUAL ? r + 1 : 0], tl & 31);
+          const uint32_t end = tl < 32 ? p_a : p_b;
+          qf = exists && ((int64_t)(end - cur.qex[QUAL ? r : 0]) < prm.mkq * (int64_t)k);
+          read_nq += qf;
+        }
+        const uint32_t wl = __funnelshift_r(cur.lo[r], cur.lo[r + 1], lane) & kmask;
+        const uint32_t wh = __funnelshift_r(cur.hi[r], cur.hi[r + 1], lane) & kmask;
+        const uint32_t wi = __funnelshift_r(cur.inv[r], cur.inv[r + 1], lane) & kmask;
+        uint32_t mh, mp;
+        window_minimizer(t, cur.mkey[r], wl, &mh, &mp);
+        const SlotAddr a = slot_addr(t, wl, wh, mh, mp);
+        tag[r] = a.tag;
+        if (exists && !qf && wi == 0) { look |= 1u << r; ld_sector_nc(bucket_ptr(t, a.block, a.bucket), sector[r]); }
+      }
+    }
+
+    // ---- stage A of the next read, inputs of the reads after it ----
+    FrontState<QUAL> nx;
+    nx.W = 0; nx.dropped = false; nx.defer = false;
+    {
+      const uint64_t r1 = read + n_warps, r2 = read + 2 * n_warps, r3 = read + 3 * n_warps;
+      Prefetch<PACKED> n2_ch;
+      Prefetch<false> n2_q;
+      prefetch_read<PACKED>(in, r2 < n_reads, r2, n2_beg, n2_end - n2_beg, lane, n2_ch);
+      if (QUAL) prefetch_read<false>(qin, r2 < n_reads, r2, n2_beg, n2_end - n2_beg, lane, n2_q);
+      uint64_t n3_beg = 0, n3_end = 0;
+      if (r3 < n_reads) { n3_beg = read_off[r3]; n3_end = read_off[r3 + 1]; }
+      if (r1 < n_reads) fast_stage_a<QUAL, PACKED>(t, prm, in, quals, nx_ch, nx_q, r1, nx_beg, nx_end - nx_beg, lane, nx, c_drop);
+      nx_ch = n2_ch;
+      if (QUAL) nx_q = n2_q;
+      nx_beg = n2_beg; nx_end = n2_end;
+      n2_beg = n3_beg; n2_end = n3_end;
+    }
+
+    // ---- stage C: resolve and classify ----
+    uint64_t res = cur.dropped ? 0 : make_word(1, 0, 0);   // UNMAPPED unless decided otherwise
+    bool defer = cur.defer;
+    if (cur.W) {
+      uint32_t mine = NO_GENOME, l_filtered = 0;
+      bool same = true;
+      uint64_t multi[AL_ROUNDS];   // kept multi-genome values of this lane (LOOKUP_MISS = none)
+#pragma unroll
+      for (int r = 0; r < AL_ROUNDS; ++r) {
+        multi[r] = LOOKUP_MISS;
+        if (!((look >> r) & 1)) continue;
+        bool cont;
+        uint64_t v = bucket_resolve(t, sector[r], tag[r], &cont);
+        if (cont) {
+          const uint32_t wl = __funnelshift_r(cur.lo[r], cur.lo[r + 1], lane) & kmask;
+          const uint32_t wh = __funnelshift_r(cur.hi[r], cur.hi[r + 1], lane) & kmask;
+          uint32_t mh, mp;
+          window_minimizer(t, cur.mkey[r], wl, &mh, &mp);
+          v = lookup_chain_window(t, ((uint64_t)wh << k) | wl, mh, mp);
+        }
+        if (v == LOOKUP_MISS) continue;
+        const uint32_t kind = value_kind(t, v);
+        if (prm.has_mg) {  // max-genomes filter, per occurrence (kmer.py:425-427)
+          uint32_t c = 1;
+          if (kind == KIND_INLINE) c = inline_count(t, value_payload(t, v));
+          else if (kind == KIND_MLIST) c = (prm.mg <= (int64_t)t.n_inline) ? t.n_inline + 1 : mlist_count(t.mlist, value_payload(t, v));
+          if ((int64_t)c > prm.mg) { ++l_filtered; continue; }
+        }
+        if (kind == KIND_SPECIFIC) {
+          const uint32_t g = (uint32_t)value_payload(t, v);
+          if (mine == NO_GENOME) mine = g; else same &= (g == mine);
+        } else {
+          multi[r] = v;
+        }
+      }
+      read_nr += l_filtered;
+      const uint32_t have = __ballot_sync(0xffffffffu, mine != NO_GENOME);
+      const bool l_multi = (multi[0] & multi[1] & multi[2] & multi[3]) != LOOKUP_MISS;
+      const bool w_multi = __any_sync(0xffffffffu, l_multi);
+      if (have == 0) {
+        res = make_word(w_multi ? 3 : 1, 0, 0);
+      } else {
+        const uint32_t g0 = __shfl_sync(0xffffffffu, mine, __ffs(have) - 1);
+        bool ok = same && (mine == NO_GENOME || mine == g0);
+        if (w_multi && prm.p >= 0) {
+#pragma unroll
+          for (int r = 0; r < AL_ROUNDS; ++r)
+            if (multi[r] != LOOKUP_MISS) ok = ok && set_contains(t, multi[r], g0);
+        }
+        if (__all_sync(0xffffffffu, ok)) res = make_word(2, 1, g0); else defer = true;
+      }
+    }
+    if (defer) {
+      if (lane == 0) queue[atomicAdd(queue_count, 1ULL)] = (uint32_t)read;
+    } else {
+      if (lane == 0) out_word[read] = res;
+      c_nq += read_nq;
+      c_nr += read_nr;
+    }
+    cur = nx;
+  }
+  c_drop = warp_sum(c_drop); c_nq = warp_sum(c_nq); c_nr = warp_sum(c_nr);
+  if (lane == 0) {
+    if (c_drop) atomicAdd(counters + 0, c_drop);
+    if (c_nq) atomicAdd(counters + 1, c_nq);
+    if (c_nr) atomicAdd(counters + 2, c_nr);
+  }
+}
+
 __global__ void scratch_init(unsigned char* scratch, uint64_t n_warps, uint64_t stride, uint32_t G, uint32_t kset_cap,
                              int gtab_in_smem, int kset_in_smem) {
   uint64_t w = blockIdx.x;
@@ -923,8 +1144,15 @@ int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_q
   uint32_t* q_items = reinterpret_cast<uint32_t*>(ix.align_queue.as<unsigned char>() + 16);
   PA_CUDA(cudaMemsetAsync(q_count, 0, 8, s));
   {
+#if PA_FAST_SPLIT
+    // the staggered kernel wins without quality filters (15.4 -> 15.0 ms per 10^7 reads); with them its extra state
+    // spills (20.1 -> 30.1 ms), so EXTQUALITY keeps the plain order of stages
+    auto fk = qual ? (packed ? align_fast_kernel<true, true> : align_fast_kernel<true, false>)
+                   : (packed ? align_fast_split_kernel<false, true> : align_fast_split_kernel<false, false>);
+#else
     auto fk = qual ? (packed ? align_fast_kernel<true, true> : align_fast_kernel<true, false>)
                    : (packed ? align_fast_kernel<false, true> : align_fast_kernel<false, false>);
+#endif
     int occ = 1;
     PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fk, FA_THREADS, 0));
     if (occ < 1) occ = 1;
