@@ -454,7 +454,7 @@ align_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
         val[r] = LOOKUP_MISS;
         if (look[r]) {
           bool cont;
-          val[r] = bucket_resolve(t, sector[r], tag[r], &cont);
+          val[r] = bucket_resolve_home(t, sector[r], tag[r], &cont);
           if (cont) val[r] = lookup_chain_window(t, raw[r], mh[r], mpos[r]);
         }
       }
@@ -757,7 +757,7 @@ align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
         multi[r] = LOOKUP_MISS;
         if (!((look >> r) & 1)) continue;
         bool cont;
-        uint64_t v = bucket_resolve(t, sector[r], tag[r], &cont);
+        uint64_t v = bucket_resolve_home(t, sector[r], tag[r], &cont);
         if (cont) {
           const uint32_t wl = __funnelshift_r(lo[r], lo[r + 1], lane) & kmask;
           const uint32_t wh = __funnelshift_r(hi[r], hi[r + 1], lane) & kmask;
@@ -979,7 +979,7 @@ align_fast_split_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ q
         multi[r] = LOOKUP_MISS;
         if (!((look >> r) & 1)) continue;
         bool cont;
-        uint64_t v = bucket_resolve(t, sector[r], tag[r], &cont);
+        uint64_t v = bucket_resolve_home(t, sector[r], tag[r], &cont);
         if (cont) {
           const uint32_t wl = __funnelshift_r(cur.lo[r], cur.lo[r + 1], lane) & kmask;
           const uint32_t wh = __funnelshift_r(cur.hi[r], cur.hi[r + 1], lane) & kmask;

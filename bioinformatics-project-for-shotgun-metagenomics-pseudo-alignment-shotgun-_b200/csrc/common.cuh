@@ -265,6 +265,21 @@ __device__ __forceinline__ uint64_t bucket_resolve(const TableView& t, const uin
   return LOOKUP_MISS;
 }
 
+// The same for a k-mer's home bucket (chain distance 0), branch-free.  There the chain field of `tag` is 00, so an empty
+// slot (all ones) can never equal it and needs no test of its own; at most one slot matches.
+__device__ __forceinline__ uint64_t bucket_resolve_home(const TableView& t, const uint64_t (&s)[4], uint64_t tag, bool* cont) {
+  uint64_t hit = 0;
+  bool found = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool m = (s[i] >> t.val_bits) == tag;
+    hit = m ? s[i] : hit;
+    found |= m;
+  }
+  *cont = !found && s[3] != EMPTY64 && ((s[3] >> (t.val_bits - 1)) & 1);
+  return found ? (hit & (((uint64_t)1 << (t.val_bits - 1)) - 1)) : LOOKUP_MISS;
+}
+
 // Continue a lookup past its home bucket: the same bucket of the next blocks, then the stash.
 static __device__ __noinline__ uint64_t lookup_chain(const TableView& t, const SlotAddr& a, uint64_t raw_key) {
   const uint64_t bmask = (1ULL << t.block_bits) - 1;
