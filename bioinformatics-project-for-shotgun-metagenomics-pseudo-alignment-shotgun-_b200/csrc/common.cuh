@@ -156,8 +156,6 @@ __host__ __device__ __forceinline__ uint32_t mmer_order(uint32_t x, const TableV
   y ^= y >> t.yshift;
   y = (y * 0x7FEB352DU) & t.ymask;
   y ^= y >> t.yshift;
-  y = (y * 0x846CA68BU) & t.ymask;
-  y ^= y >> t.yshift;
   return y;
 }
 __host__ __device__ __forceinline__ uint32_t mmer_hash(uint32_t x, const TableView& t) {
