@@ -173,8 +173,9 @@ __host__ __device__ __forceinline__ SlotAddr slot_addr(const TableView& t, uint3
   SlotAddr a;
   const uint32_t km = t.k - t.m;                     // bases outside the minimizer
   const uint32_t below = (1u << p) - 1;              // p <= 15
-  const uint32_t rl = (lo & below) | ((lo >> (p + t.m)) << p);   // p + m <= k <= 31
-  const uint32_t rh = (hi & below) | ((hi >> (p + t.m)) << p);
+  // drop the m bits at [p, p+m): bits below p stay, bit j >= p comes from bit j+m -- a bit select between x and x >> m
+  const uint32_t rl = (lo & below) | ((lo >> t.m) & ~below);   // p + m <= k <= 31
+  const uint32_t rh = (hi & below) | ((hi >> t.m) & ~below);
   const uint32_t rest = (rh << km) | rl;             // 2(k-m) <= 30 bits
   a.block = mhash & (uint32_t)((1ULL << t.block_bits) - 1);
   const uint64_t mh = (uint64_t)mhash >> t.block_bits;
