@@ -699,14 +699,18 @@ align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
       uint32_t qex[AL_ROUNDS + 1];  // exclusive quality prefix at this lane's base
       encode_planes<PACKED>(in, cur_ch, read, cur_beg, L, 0, lane, lo, hi, inv);
       if (QUAL && prm.has_mkq) {
+        // warp prefix scans of two chunks per register: a 16-bit field holds the sum of 160 bytes
         uint32_t carry = 0;
 #pragma unroll
-        for (int c = 0; c <= AL_ROUNDS; ++c) {
-          uint32_t q = cur_q.v[c], incl = q;
+        for (int c = 0; c <= AL_ROUNDS; c += 2) {
+          const uint32_t q0 = cur_q.v[c], q1 = c + 1 <= AL_ROUNDS ? cur_q.v[c + 1 <= AL_ROUNDS ? c + 1 : c] : 0u;
+          uint32_t incl = q0 | (q1 << 16);
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-          qex[c] = carry + incl - q;
-          carry += __shfl_sync(0xffffffffu, incl, 31);
+          const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+          qex[c] = carry + (incl & 0xFFFFu) - q0;
+          carry += tot & 0xFFFFu;
+          if (c + 1 <= AL_ROUNDS) { qex[c + 1 <= AL_ROUNDS ? c + 1 : c] = carry + (incl >> 16) - q1; carry += tot >> 16; }
         }
       }
       // ---- minimizers ----
