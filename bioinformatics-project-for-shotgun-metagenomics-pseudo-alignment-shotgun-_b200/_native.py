@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "pa_extsim_stats", "pa_extsim_pairwise", "pa_index_drop_genomes", "pa_align_batch", "pa_align_batch_device",
     "pa_summary_reduce_device", "pa_summary_reduce", "pa_debug_sort_pairs", "pa_debug_table_lookup",
     "pa_records_encode_device", "pa_records_partition_device", "pa_partition_of_key", "pa_index_build_from_records_device",
-    "pa_index_csr_device", "pa_index_alloc_replica", "pa_index_finish_replica", "pa_index_build_tables", "pa_debug_pack_reads",
+    "pa_index_csr_device", "pa_index_alloc_replica", "pa_index_finish_replica", "pa_index_build_tables", "pa_debug_pack_reads", "pa_debug_minimizer",
     "pa_parse_records", "pa_parsed_copy", "pa_parsed_free",
     "pa_peer_alloc", "pa_peer_open", "pa_peer_close", "pa_peer_free", "pa_records_digit_counts", "pa_records_scatter_to_peers",
     "pa_format_kmers_json", "pa_free_text",
@@ -116,6 +116,7 @@ def lib() -> ctypes.CDLL:
         "pa_index_finish_replica": (i32, [vp]),
         "pa_index_build_tables": (i32, [vp]),
         "pa_debug_pack_reads": (i32, [vp, vp, u64, vp, u64, i32, vp]),
+        "pa_debug_minimizer": (i32, [i32, vp, u64, vp, vp]),
         "pa_parse_records": (i32, [vp, u64, i32, vp, vp, vp, vp]),
         "pa_parsed_copy": (i32, [vp, vp, vp, vp, vp, vp, vp, vp]),
         "pa_parsed_free": (i32, [vp]),

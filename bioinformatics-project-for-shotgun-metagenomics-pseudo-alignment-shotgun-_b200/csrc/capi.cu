@@ -775,6 +775,21 @@ int32_t pa_debug_pack_reads(const uint8_t* bases, const uint64_t* read_off, uint
   return PA_OK;
 }
 
+int32_t pa_debug_minimizer(int32_t k, const uint8_t* kmers_ascii, uint64_t n, uint32_t* mhash, uint32_t* offset) {
+  NEED(k >= 1 && k <= 31, "k out of range");
+  NEED(n == 0 || (kmers_ascii && mhash && offset), "null argument");
+  TableView t{};
+  minimizer_params(t, k);
+  const uint32_t kmask = (1u << k) - 1;
+  for (uint64_t i = 0; i < n; ++i) {
+    bool ok;
+    const uint64_t raw = encode_kmer_host(kmers_ascii + i * (uint64_t)k, k, &ok);
+    NEED(ok, "k-mer with a base outside ACGT");
+    kmer_minimizer(t, (uint32_t)raw & kmask, (uint32_t)(raw >> k) & kmask, &mhash[i], &offset[i]);
+  }
+  return PA_OK;
+}
+
 int32_t pa_debug_table_lookup(pa_index* idx, const uint8_t* kmers_ascii, uint64_t n, uint32_t* n_genomes,
                               uint32_t* first_genome) {
   NEED(idx, "null index");

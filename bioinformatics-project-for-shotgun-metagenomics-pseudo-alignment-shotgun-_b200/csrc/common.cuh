@@ -147,6 +147,17 @@ enum : uint32_t { KIND_MLIST = 0, KIND_INLINE = 2, KIND_SPECIFIC = 3 };
 constexpr uint32_t MINIMIZER_MAX = 16;
 __host__ __device__ __forceinline__ uint32_t minimizer_len_for_k(int k) { return k < 1 ? 1u : (k > (int)MINIMIZER_MAX ? MINIMIZER_MAX : (uint32_t)k); }
 
+// the minimizer fields of a TableView (k, m, w, mmask and the split of the m-mer hash) for a k-mer length
+__host__ __device__ __forceinline__ void minimizer_params(TableView& t, int k) {
+  t.k = (uint32_t)k;                       // k <= 0: no k-mer exists, nothing is ever looked up
+  t.m = minimizer_len_for_k(k);
+  t.w = k >= 1 ? (uint32_t)k - t.m + 1 : 1;
+  t.mmask = (1u << t.m) - 1;
+  t.hdrop = 2 * t.m > 28 ? 2 * t.m - 28 : 0;
+  t.ymask = (1u << (2 * t.m - t.hdrop)) - 1;
+  t.yshift = (2 * t.m - t.hdrop + 1) / 2;
+}
+
 // Hash of an m-mer x (2m <= 32 bits), bijective: the upper 2m - hdrop bits of x go through an invertible xorshift /
 // odd-multiplication mix (`mmer_order`), the low hdrop bits stay raw.  Minimizers are ordered by the mixed part alone: it
 // has at most 28 bits, so the align kernel slides (order << 4 | offset) through one 32-bit shuffle per step and rebuilds the

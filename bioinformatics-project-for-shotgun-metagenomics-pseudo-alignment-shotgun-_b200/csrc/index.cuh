@@ -107,19 +107,13 @@ struct Index {
     t.mlist = mlist.as<uint32_t>();
     t.stash_mask = stash_cap ? stash_cap - 1 : 0;
     t.stash_count = stash_count;
-    t.k = (uint32_t)k;                       // k <= 0: no k-mer exists, nothing is ever looked up
-    t.m = min_len;
-    t.w = k >= 1 ? (uint32_t)k - t.m + 1 : 1;
+    minimizer_params(t, k);
     t.block_bits = block_bits;
     t.hi_bits = 2 * t.m - block_bits;
     t.tag_bits = tag_bits;
     t.val_bits = val_bits;
     t.gbits = gbits;
     t.n_inline = n_inline;
-    t.mmask = (1u << t.m) - 1;
-    t.hdrop = 2 * t.m > 28 ? 2 * t.m - 28 : 0;
-    t.ymask = (1u << (2 * t.m - t.hdrop)) - 1;
-    t.yshift = (2 * t.m - t.hdrop + 1) / 2;
     return t;
   }
   size_t device_bytes() const {

@@ -237,6 +237,9 @@ int32_t pa_debug_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t n, int32_t 
  * high-plane words.  *all_acgt = 0 when a base outside ACGT was met. */
 int32_t pa_debug_pack_reads(const uint8_t* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t* planes, uint64_t planes_cap,
                             int32_t n_threads, int32_t* all_acgt);
+/* minimizer of each k-mer (pure host code, the function the table build and K4 share): mhash = bijective hash of its m-mer,
+ * m = min(k, 16); offset = position of that m-mer inside the k-mer (leftmost among equal orders) */
+int32_t pa_debug_minimizer(int32_t k, const uint8_t* kmers_ascii, uint64_t n, uint32_t* mhash, uint32_t* offset);
 /* direct table lookups (K4's lookup step): n_genomes[i] = number of genomes of k-mer i (0 = miss),
  * first_genome[i] = its smallest genome index */
 int32_t pa_debug_table_lookup(pa_index* idx, const uint8_t* kmers_ascii, uint64_t n, uint32_t* n_genomes,

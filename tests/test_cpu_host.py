@@ -473,3 +473,65 @@ def test_native_dumpref_writer_against_json_dumps():
     empty = {"keys": np.zeros(0, np.uint64), "order": np.zeros(0, np.uint32), "run_off": np.zeros(1, np.uint64),
              "run_genome": np.zeros(0, np.uint32), "pos_off": np.zeros(1, np.uint64), "pos": np.zeros(0, np.uint32)}
     assert nat.format_kmers_json(3, empty, np.zeros(1, np.uint32), [], indent=4, level=1) == "{}"
+
+
+def _minimizer_restated(kmer):
+    """The definition in DESIGN.md §3: m = min(k,16); the m-mer x at offset j is (high plane << m) | low plane with bit i =
+    base j+i; hdrop = max(0, 2m-28); order(x) = xorshift-multiply-xorshift of x >> hdrop on 2m-hdrop bits; the minimizer is the
+    leftmost m-mer of smallest order and its hash is order << hdrop | low hdrop bits of x."""
+    k = len(kmer)
+    m = min(k, 16)
+    code = {"A": 0, "C": 1, "T": 2, "G": 3}
+    hdrop = max(0, 2 * m - 28)
+    ybits = 2 * m - hdrop
+    ymask, yshift = (1 << ybits) - 1, (ybits + 1) // 2
+    best = None
+    for j in range(k - m + 1):
+        lo = sum((code[c] & 1) << i for i, c in enumerate(kmer[j:j + m]))
+        hi = sum((code[c] >> 1) << i for i, c in enumerate(kmer[j:j + m]))
+        x = (hi << m) | lo
+        y = x >> hdrop
+        y ^= y >> yshift
+        y = (y * 0x7FEB352D) & ymask
+        y ^= y >> yshift
+        if best is None or y < best[0]:
+            best = (y, j, x)
+    y, j, x = best
+    return (y << hdrop) | (x & ((1 << hdrop) - 1)), j
+
+
+def test_minimizer_hash_is_a_bijection_and_matches_its_definition():
+    """Block, bucket and tag identify a k-mer only if the m-mer hash is a bijection: exhaustive for m <= 8, and for m = 16 on
+    m-mers that differ only in the bits the hash keeps raw / only in the mixed bits.  The minimizer (hash, offset) of random
+    k-mers equals the restated definition, ties included (low-complexity k-mers)."""
+    import itertools
+    import _native as nat
+    L = nat.lib()
+
+    def native(kmers, k):
+        flat = np.frombuffer("".join(kmers).encode(), dtype=np.uint8).copy()
+        mh = np.zeros(len(kmers), np.uint32); off = np.zeros(len(kmers), np.uint32)
+        assert L.pa_debug_minimizer(k, nat._p(flat), len(kmers), nat._p(mh), nat._p(off)) == 0
+        return mh, off
+
+    for k in (1, 2, 5, 8):   # k <= 16: the k-mer is its own m-mer
+        kmers = ["".join(p) for p in itertools.product("ACGT", repeat=k)]
+        mh, off = native(kmers, k)
+        assert len(set(mh.tolist())) == 4 ** k and int(mh.max()) < 4 ** k and not off.any()
+    rng = np.random.default_rng(5)
+    base = "".join(rng.choice(list("ACGT"), size=16))
+    variants = {base}
+    for _ in range(4000):
+        s = list(base)
+        for pos in rng.integers(0, 16, size=int(rng.integers(1, 4))):
+            s[int(pos)] = "ACGT"[int(rng.integers(0, 4))]
+        variants.add("".join(s))
+    variants = sorted(variants)
+    mh, _ = native(variants, 16)
+    assert len(set(mh.tolist())) == len(variants)
+    for k in (3, 15, 16, 17, 24, 31):
+        kmers = ["".join(rng.choice(list("ACGT"), size=k)) for _ in range(300)]
+        kmers += ["A" * k, "AC" * (k // 2) + "A" * (k % 2), "ACG" * (k // 3) + "T" * (k % 3), "T" * (k - 1) + "G"]
+        mh, off = native(kmers, k)
+        for s, h, o in zip(kmers, mh, off):
+            assert (int(h), int(o)) == _minimizer_restated(s), (k, s)
