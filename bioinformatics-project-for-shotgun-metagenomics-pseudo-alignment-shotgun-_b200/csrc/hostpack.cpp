@@ -113,7 +113,11 @@ __attribute__((target("avx2"))) bool pack_range_avx2(const uint8_t* bases, const
                                                      uint64_t b, uint32_t* planes, uint64_t safe_end) {
   // safe_end: one past the last base of the chunk -- full 32-byte loads must end at or before it
   const uint64_t base0 = read_off[lo];
-  const __m256i cA = _mm256_set1_epi8('A'), cC = _mm256_set1_epi8('C'), cG = _mm256_set1_epi8('G'), cT = _mm256_set1_epi8('T');
+  // validity by table: pshufb indexes with the low nibble of a byte (and yields 0 for bytes >= 0x80); only A, C, G, T
+  // find themselves at their own nibble ('A' 0x41 -> 1, 'C' 0x43 -> 3, 'T' 0x54 -> 4, 'G' 0x47 -> 7)
+  const __m256i lut = _mm256_setr_epi8(-1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1,
+                                       -1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1);
+  __m256i all_ok = _mm256_set1_epi8(-1);   // AND of the per-byte validity of every full block
   uint32_t bad = 0;
   for (uint64_t i = a; i < b; ++i) {
     const uint64_t o = read_off[i], L = read_off[i + 1] - o, nw = (L + 31) / 32;
@@ -122,9 +126,7 @@ __attribute__((target("avx2"))) bool pack_range_avx2(const uint8_t* bases, const
     uint64_t c = 0;
     for (; 32 * (c + 1) <= L; ++c) {
       const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + 32 * c));
-      const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(v, cA), _mm256_cmpeq_epi8(v, cC)),
-                                         _mm256_or_si256(_mm256_cmpeq_epi8(v, cG), _mm256_cmpeq_epi8(v, cT)));
-      bad |= ~(uint32_t)_mm256_movemask_epi8(ok);
+      all_ok = _mm256_and_si256(all_ok, _mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, v), v));
       w[c] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6));        // ASCII bit 1 -> bit 7 of its byte
       w[nw + c] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5));   // ASCII bit 2 -> bit 7
     }
@@ -134,8 +136,7 @@ __attribute__((target("avx2"))) bool pack_range_avx2(const uint8_t* bases, const
         // the 32-byte load runs into the next read (same buffer): mask what is not ours
         const uint32_t keep = (1u << rem) - 1;
         const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + 32 * c));
-        const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(v, cA), _mm256_cmpeq_epi8(v, cC)),
-                                           _mm256_or_si256(_mm256_cmpeq_epi8(v, cG), _mm256_cmpeq_epi8(v, cT)));
+        const __m256i ok = _mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, v), v);
         bad |= ~(uint32_t)_mm256_movemask_epi8(ok) & keep;
         w[c] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6)) & keep;
         w[nw + c] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5)) & keep;
@@ -146,6 +147,7 @@ __attribute__((target("avx2"))) bool pack_range_avx2(const uint8_t* bases, const
       }
     }
   }
+  bad |= ~(uint32_t)_mm256_movemask_epi8(all_ok);
   return bad == 0;
 }
 #endif

@@ -290,15 +290,16 @@ def test_host_packing_matches_a_numpy_restatement(scalar, monkeypatch):
     monkeypatch.setenv("PA_PACK_SCALAR", scalar)
     L = nat.lib()
     rng = np.random.default_rng(11)
-    for trial in range(6):
-        n = int(rng.integers(1, 4000))
+    for trial in range(40):
+        n = int(rng.integers(1, 4000)) if trial < 6 else int(rng.integers(1, 60))
         lens = rng.integers(0, 330, size=n) if trial % 2 else np.full(n, 150)
         off = np.concatenate([[7], 7 + np.cumsum(lens)]).astype(np.uint64)      # offsets need not start at 0
         total = int(off[-1])
         bases = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=total)].copy()
-        bad = trial == 5
-        if bad:
-            bases[int(off[n // 2])] = ord("N")
+        bad = trial in (4, 5) or trial >= 10
+        if bad:   # one byte outside ACGT anywhere (full blocks and tails): same low nibble as a base, lower case, >= 0x80, NUL
+            where = int(off[n // 2]) if trial == 5 else int(rng.integers(7, total))
+            bases[where] = [ord("N"), ord("Q"), ord("D"), ord("a"), 0xC1, 0xD4, 0x00, 0xFF, ord("S"), ord("W")][int(rng.integers(0, 10))]
         cap = 2 * ((total - 7) // 32 + n + 1)
         for threads in (1, 4):
             planes = np.full(cap, 0xDEADBEEF, dtype=np.uint32)
