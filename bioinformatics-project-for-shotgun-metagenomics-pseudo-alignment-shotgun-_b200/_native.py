@@ -378,27 +378,39 @@ def debug_sort_pairs(keys: np.ndarray, vals: np.ndarray, end_bit: int = 64, devi
     return keys, vals
 
 
-def parse_records_native(raw: bytes, fastq: bool):
-    """Canonical FASTA / FASTQ text -> packed arrays, or None when the text needs the regex parser (ingest.cpp).
+def parse_records_native(raw, fastq: bool):
+    """Canonical FASTA / FASTQ text (an ASCII str, parsed in place, or bytes) -> packed arrays, or None when the text needs the regex parser (ingest.cpp).
 
     Returns {"seq": uint8[n_bases], "qual": uint8[n_bases] | None, "off": uint64[n + 1], "name_beg", "name_len",
     "plus_beg", "plus_len": uint64[n] ranges inside `raw`, "raw": raw}."""
     n = len(raw)
-    buf = np.frombuffer(raw, dtype=np.uint8) if n else np.zeros(1, dtype=np.uint8)
+    if isinstance(raw, str):
+        # an ASCII str is stored one byte per character: parse its buffer in place instead of encoding a copy
+        # (the caller checked isascii(); `raw` stays referenced by the result, which keeps the buffer alive)
+        size = ctypes.c_ssize_t(0)
+        as_utf8 = ctypes.pythonapi.PyUnicode_AsUTF8AndSize
+        as_utf8.restype, as_utf8.argtypes = ctypes.c_void_p, [ctypes.py_object, ctypes.POINTER(ctypes.c_ssize_t)]
+        ptr = as_utf8(raw, ctypes.byref(size))
+        if not ptr or size.value != n:
+            raise ValueError("parse_records_native: the text is not ASCII")
+        text_ptr = ctypes.c_void_p(ptr)
+    else:
+        buf = np.frombuffer(raw, dtype=np.uint8) if n else np.zeros(1, dtype=np.uint8)
+        text_ptr = _p(buf)
     h = ctypes.c_void_p()
     canonical = ctypes.c_int32(0)
     n_rec, n_bases = ctypes.c_uint64(0), ctypes.c_uint64(0)
-    check(lib().pa_parse_records(_p(buf), n, int(bool(fastq)), ctypes.byref(h), ctypes.byref(canonical), ctypes.byref(n_rec),
+    check(lib().pa_parse_records(text_ptr, n, int(bool(fastq)), ctypes.byref(h), ctypes.byref(canonical), ctypes.byref(n_rec),
                                  ctypes.byref(n_bases)))
     if not canonical.value:
         return None
     nr = n_rec.value
     try:
-        seq = np.zeros(max(n_bases.value, 1), dtype=np.uint8)
-        qual = np.zeros(max(n_bases.value, 1), dtype=np.uint8) if fastq else None
+        seq = np.empty(max(n_bases.value, 1), dtype=np.uint8)     # pa_parsed_copy fills every element it reports
+        qual = np.empty(max(n_bases.value, 1), dtype=np.uint8) if fastq else None
         off = np.zeros(nr + 1, dtype=np.uint64)
-        nb, nl = np.zeros(max(nr, 1), dtype=np.uint64), np.zeros(max(nr, 1), dtype=np.uint64)
-        pb, pl = (np.zeros(max(nr, 1), dtype=np.uint64), np.zeros(max(nr, 1), dtype=np.uint64)) if fastq else (None, None)
+        nb, nl = np.empty(max(nr, 1), dtype=np.uint64), np.empty(max(nr, 1), dtype=np.uint64)
+        pb, pl = (np.empty(max(nr, 1), dtype=np.uint64), np.empty(max(nr, 1), dtype=np.uint64)) if fastq else (None, None)
         check(lib().pa_parsed_copy(h, _p(seq), _p(qual), _p(off), _p(nb), _p(nl), _p(pb), _p(pl)))
     finally:
         lib().pa_parsed_free(h)
@@ -407,8 +419,16 @@ def parse_records_native(raw: bytes, fastq: bool):
             "plus_len": None if pl is None else pl[:nr], "raw": raw, "n": nr}
 
 
+def parsed_text(raw, beg: int, length: int) -> str:
+    """A byte range of the parsed text (`raw` is the ASCII str that was parsed, or bytes)."""
+    piece = raw[beg:beg + length]
+    return piece if isinstance(piece, str) else piece.decode("ascii")
+
+
 def parsed_names(packed) -> List[str]:
     raw = packed["raw"]
+    if isinstance(raw, str):
+        return [raw[b:b + l] for b, l in zip(packed["name_beg"].tolist(), packed["name_len"].tolist())]
     return [raw[b:b + l].decode("ascii") for b, l in zip(packed["name_beg"].tolist(), packed["name_len"].tolist())]
 
 

@@ -113,7 +113,7 @@ class RecordContainer(object):
             return False
         try:
             import _native as nat
-            packed = nat.parse_records_native(data.encode("ascii"), bool(type(self).NATIVE_KIND))
+            packed = nat.parse_records_native(data, bool(type(self).NATIVE_KIND))
         except ImportError:     # the library has not been built: the regex path below needs nothing native
             return False
         if packed is None:
@@ -126,18 +126,19 @@ class RecordContainer(object):
         if not self._packed_pending:
             return
         self._packed_pending = False
+        import _native as nat
         pk = self._packed
         raw, off = pk["raw"], pk["off"].tolist()
         seq = pk["seq"].tobytes().decode("ascii")
         qual = pk["qual"].tobytes().decode("ascii") if pk["qual"] is not None else None
         specs = type(self).SECTION_SPECIFICATIONS
         for i, (b, l) in enumerate(zip(pk["name_beg"].tolist(), pk["name_len"].tolist())):
-            name = raw[b:b + l].decode("ascii")
+            name = nat.parsed_text(raw, b, l)
             if qual is None:
                 fields = (name, seq[off[i]:off[i + 1]])
             else:
                 pb, pl = int(pk["plus_beg"][i]), int(pk["plus_len"][i])
-                fields = (name, seq[off[i]:off[i + 1]], raw[pb:pb + pl].decode("ascii").strip(), qual[off[i]:off[i + 1]])
+                fields = (name, seq[off[i]:off[i + 1]], nat.parsed_text(raw, pb, pl).strip(), qual[off[i]:off[i + 1]])
             self._records.append(Record([Section(spec.section_name, f) for spec, f in zip(specs, fields)]))
             for spec, f in zip(specs, fields):
                 if spec.is_unique_index:
