@@ -20,7 +20,7 @@ import gzip
 import json
 import pickle
 from collections import namedtuple
-from collections.abc import Mapping
+from collections.abc import Mapping, Sequence
 from enum import Enum
 from typing import Any, Dict, Iterator, List, Optional, Set, Tuple, Union
 
@@ -547,6 +547,33 @@ class _Batch:
                 "genomes_mapped_to": [self.genome_ids[int(g)] for g in self.genome_idx[lo:hi]]}
 
 
+class _LazyIds(Sequence):
+    """Identifiers of the stored reads of a natively parsed batch: cut out of the parsed text on first use (a summary
+    never needs them; 10^7 Python strings take seconds)."""
+
+    def __init__(self, packed, stored, n_total: int) -> None:
+        self._packed = packed
+        self._stored = None if len(stored) == n_total else stored
+        self._n = len(stored)
+        self._list: Optional[List[str]] = None
+
+    def _get(self) -> List[str]:
+        if self._list is None:
+            names = nat.parsed_names(self._packed)
+            self._list = names if self._stored is None else [names[int(i)] for i in self._stored]
+            self._packed = self._stored = None
+        return self._list
+
+    def __len__(self) -> int:
+        return self._n
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+    def __iter__(self):
+        return iter(self._get())
+
+
 class _ReadsView(Mapping):
     """Dict-shaped view of PseudoAlignment.reads: {read id: {"mapping_type", "genomes_mapped_to"}} in insertion order.
     Device batches stay as arrays; reads added one at a time (add_read) are kept as plain entries."""
@@ -639,7 +666,7 @@ class PseudoAlignment:
         if packed is not None and len(self.reads) == 0:
             # natively parsed FASTQ (csrc/ingest.cpp): the arrays go to the device as they are; identifiers are unique
             # inside one container (records.py:195-198) and nothing has been filed before, so no read can collide
-            self._align_arrays(None, nat.parsed_names(packed), packed["seq"], packed["qual"], packed["off"], m, p,
+            self._align_arrays(None, packed, packed["seq"], packed["qual"], packed["off"], m, p,
                                min_read_quality, min_kmer_quality, max_genomes)
             return
         self._align_records(list(reads_container), m, p, min_read_quality, min_kmer_quality, max_genomes)
@@ -663,9 +690,10 @@ class PseudoAlignment:
                 raise ValueError("sequence and quality lengths differ")
         self._align_arrays(records, None, seq_bytes, qual_bytes, off, m, p, mrq, mkq, mg)
 
-    def _align_arrays(self, records: Optional[List[Record]], names: Optional[List[str]], seq_bytes, qual_bytes, off,
+    def _align_arrays(self, records: Optional[List[Record]], names, seq_bytes, qual_bytes, off,
                       m, p, mrq, mkq, mg) -> None:
-        """records is None for a natively parsed container (names = its identifiers, known to be collision-free)."""
+        """records is None for a natively parsed container (names = its packed batch; its identifiers are known to be
+        collision-free and are only cut out of the text when somebody looks at `reads`)."""
         if records is None:
             self._set_flags(mrq, mkq, mg)
             _check_align_args(self.kmer_reference, m, p, mrq, mkq, mg)
@@ -678,7 +706,7 @@ class PseudoAlignment:
         types, lens, payload = nat.decode_words(words)
         stored = np.nonzero(types != 0)[0]
         if records is None:
-            ids = names if len(stored) == len(names) else [names[int(i)] for i in stored]
+            ids = _LazyIds(names, stored, int(names["n"]))
         else:
             ids = [records[int(i)].identifier for i in stored]
         # duplicate identifiers: the reference raises at the first one, after filing everything before it
