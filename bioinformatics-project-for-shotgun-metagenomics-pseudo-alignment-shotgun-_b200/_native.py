@@ -27,13 +27,14 @@ RANK_MISS = 0xFFFFFFFFFFFFFFFF
 
 EXPORTED_SYMBOLS = [
     "pa_abi_version", "pa_last_error", "pa_device_count", "pa_index_build", "pa_index_build_device", "pa_index_import",
-    "pa_index_free", "pa_index_info_get", "pa_index_export", "pa_decode_kmers", "pa_encode_kmers", "pa_index_lookup",
+    "pa_index_free", "pa_index_info_get", "pa_index_export", "pa_decode_kmers", "pa_encode_kmers", "pa_index_lookup", "pa_index_entries", "pa_index_checksum",
     "pa_extsim_stats", "pa_extsim_pairwise", "pa_index_drop_genomes", "pa_align_batch", "pa_align_batch_device",
     "pa_summary_reduce_device", "pa_summary_reduce", "pa_debug_sort_pairs", "pa_debug_table_lookup",
-    "pa_records_encode_device", "pa_records_partition_device", "pa_partition_of_key", "pa_index_build_from_records_device",
-    "pa_index_csr_device", "pa_index_alloc_replica", "pa_index_finish_replica", "pa_index_build_tables", "pa_debug_pack_reads", "pa_debug_minimizer",
+    "pa_comm_unique_id", "pa_comm_init", "pa_comm_init_callbacks", "pa_comm_free", "pa_comm_info", "pa_comm_allreduce_summary",
+    "pa_comm_allreduce_host", "pa_comm_allgather_host", "pa_comm_barrier", "pa_index_build_partitioned", "pa_index_rebuild_replica", "pa_genome_shard",
+    "pa_build_exchange", "pa_build_timings", "pa_partition_of_kmer",
+    "pa_debug_pack_reads", "pa_debug_minimizer",
     "pa_parse_records", "pa_parsed_copy", "pa_parsed_free",
-    "pa_peer_alloc", "pa_peer_open", "pa_peer_close", "pa_peer_free", "pa_records_digit_counts", "pa_records_scatter_to_peers",
     "pa_format_kmers_json", "pa_free_text",
 ]
 
@@ -45,11 +46,12 @@ class NativeLibraryMissing(ImportError):
 class IndexInfo(ctypes.Structure):
     _fields_ = [
         ("k", ctypes.c_int32), ("device", ctypes.c_int32), ("n_genomes", ctypes.c_uint32),
-        ("block_bits", ctypes.c_uint32), ("tag_bits", ctypes.c_uint32), ("stash_count", ctypes.c_uint32),
+        ("blocks_per_digit", ctypes.c_uint32), ("tag_bits", ctypes.c_uint32), ("stash_count", ctypes.c_uint32),
         ("n_keys", ctypes.c_uint64), ("n_runs", ctypes.c_uint64), ("n_occ", ctypes.c_uint64),
         ("total_bases", ctypes.c_uint64), ("n_list_sectors", ctypes.c_uint64), ("device_bytes", ctypes.c_uint64),
         ("build_encode_ms", ctypes.c_float), ("build_sort_ms", ctypes.c_float), ("build_rle_ms", ctypes.c_float),
-        ("build_table_ms", ctypes.c_float), ("minimizer_len", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
+        ("build_table_ms", ctypes.c_float), ("minimizer_len", ctypes.c_uint32), ("digit_bits", ctypes.c_uint32),
+        ("n_blocks", ctypes.c_uint64), ("table_bytes", ctypes.c_uint64), ("align_only", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
     ]
 
 
@@ -98,6 +100,8 @@ def lib() -> ctypes.CDLL:
         "pa_decode_kmers": (i32, [i32, vp, u64, vp]),
         "pa_encode_kmers": (i32, [i32, vp, u64, vp]),
         "pa_index_lookup": (i32, [vp, vp, u64, vp]),
+        "pa_index_entries": (i32, [vp, vp, u64, vp, vp, u64, vp, vp, u64, vp, vp]),
+        "pa_index_checksum": (i32, [vp, vp]),
         "pa_extsim_stats": (i32, [vp, vp, u32, vp, vp]),
         "pa_extsim_pairwise": (i32, [vp, vp, u32, vp]),
         "pa_index_drop_genomes": (i32, [vp, vp]),
@@ -107,25 +111,26 @@ def lib() -> ctypes.CDLL:
         "pa_summary_reduce": (i32, [vp, vp, vp, u64, u64, u64, vp, vp, vp, vp]),
         "pa_debug_sort_pairs": (i32, [vp, vp, u64, i32, i32]),
         "pa_debug_table_lookup": (i32, [vp, vp, u64, vp, vp]),
-        "pa_records_encode_device": (i32, [vp, vp, u32, u32, u32, i32, i32, vp, vp, vp, vp]),
-        "pa_records_partition_device": (i32, [vp, vp, vp, vp, u64, i32, u32, i32, vp, vp, vp]),
-        "pa_partition_of_key": (i32, [i32, u64, u32, vp]),
-        "pa_index_build_from_records_device": (i32, [vp, vp, u64, vp, u32, i32, i32, i32, vp]),
-        "pa_index_csr_device": (i32, [vp, vp, vp, vp]),
-        "pa_index_alloc_replica": (i32, [i32, u32, vp, u64, u64, u64, i32, vp]),
-        "pa_index_finish_replica": (i32, [vp]),
-        "pa_index_build_tables": (i32, [vp]),
+        "pa_comm_unique_id": (i32, [vp]),
+        "pa_comm_init": (i32, [i32, i32, vp, i32, vp]),
+        "pa_comm_init_callbacks": (i32, [i32, i32, i32, vp, vp]),
+        "pa_comm_free": (i32, [vp]),
+        "pa_comm_info": (i32, [vp, vp, vp, vp, vp]),
+        "pa_comm_allreduce_summary": (i32, [vp, vp, u64, vp, u64, vp]),
+        "pa_comm_allreduce_host": (i32, [vp, vp, u64, i32]),
+        "pa_comm_allgather_host": (i32, [vp, vp, vp, u64]),
+        "pa_comm_barrier": (i32, [vp]),
+        "pa_index_build_partitioned": (i32, [vp, vp, vp, u32, u32, u32, i32, i32, u32, u32, vp, vp]),
+        "pa_index_rebuild_replica": (i32, [vp, vp, vp]),
+        "pa_genome_shard": (i32, [vp, u32, i32, i32, vp, vp]),
+        "pa_build_exchange": (i32, [vp, vp, vp, vp, u64, vp, vp, vp, vp]),
+        "pa_build_timings": (i32, [vp, vp]),
+        "pa_partition_of_kmer": (i32, [i32, vp, u32, vp]),
         "pa_debug_pack_reads": (i32, [vp, vp, u64, vp, u64, i32, vp]),
         "pa_debug_minimizer": (i32, [i32, vp, u64, vp, vp]),
         "pa_parse_records": (i32, [vp, u64, i32, vp, vp, vp, vp]),
         "pa_parsed_copy": (i32, [vp, vp, vp, vp, vp, vp, vp, vp]),
         "pa_parsed_free": (i32, [vp]),
-        "pa_peer_alloc": (i32, [u64, i32, vp, vp]),
-        "pa_peer_open": (i32, [vp, i32, vp]),
-        "pa_peer_close": (i32, [vp, i32]),
-        "pa_peer_free": (i32, [vp, i32]),
-        "pa_records_digit_counts": (i32, [vp, u64, i32, i32, vp, vp, vp, vp]),
-        "pa_records_scatter_to_peers": (i32, [vp, vp, u64, i32, i32, vp, vp, vp]),
         "pa_format_kmers_json": (i32, [i32, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]),
         "pa_free_text": (i32, [vp]),
     }
@@ -191,6 +196,35 @@ def decode_words(words: np.ndarray):
     lens = ((words >> np.uint64(40)) & np.uint64(0x3FFFFF)).astype(np.int64)
     payload = (words & np.uint64(0xFFFFFFFFFF)).astype(np.int64)
     return types, lens, payload
+
+
+def flatten_results(words: np.ndarray, lst: np.ndarray):
+    """Result words (+ the side list) of pa_align_batch[_device] -> (types uint8[n], lens int32[n], flat genome indices
+    uint32[sum lens]) in read order: independent of where the list cursor put a list."""
+    words = np.ascontiguousarray(words, dtype=np.uint64)
+    types, lens, payload = decode_words(words)
+    off = np.zeros(len(words) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    flat = np.zeros(int(off[-1]), dtype=np.uint32)
+    single = lens == 1
+    flat[off[:-1][single]] = payload[single]
+    for i in np.nonzero(lens > 1)[0]:
+        flat[off[i]:off[i + 1]] = lst[payload[i]:payload[i] + lens[i]]
+    return types, lens.astype(np.int32), flat
+
+
+def canonical_words(types: np.ndarray, lens: np.ndarray, flat: np.ndarray):
+    """The inverse: result words whose lists sit in `flat` in read order (what K8, pa_summary_reduce, reads)."""
+    lens64 = np.asarray(lens, dtype=np.int64)
+    off = np.zeros(len(lens64) + 1, dtype=np.int64)
+    np.cumsum(lens64, out=off[1:])
+    payload = off[:-1].astype(np.uint64)
+    payload[lens64 == 0] = 0
+    single = lens64 == 1
+    if single.any():
+        payload[single] = np.asarray(flat, dtype=np.uint64)[off[:-1][single]]
+    words = (np.asarray(types, dtype=np.uint64) << np.uint64(62)) | (lens64.astype(np.uint64) << np.uint64(40)) | payload
+    return words, np.ascontiguousarray(flat, dtype=np.uint32)
 
 
 class NativeIndex:
@@ -292,6 +326,32 @@ class NativeIndex:
                 rank[np.asarray(good, dtype=np.int64)] = sub
         return rank[:n]
 
+    def checksum(self) -> np.ndarray:
+        """Order-independent content checksum of the CSR (additive over the partitions of a multi-GPU build)."""
+        out = np.zeros(4, dtype=np.uint64)
+        check(lib().pa_index_checksum(self.handle, _p(out)))
+        return out
+
+    def entries(self, ranks: Sequence[int]):
+        """CSR entries of the k-mers at `ranks` (no misses): (run_off[n+1], run_genome, pos_off, pos) -- only these k-mers
+        leave the device."""
+        ranks = np.ascontiguousarray(ranks, dtype=np.uint64)
+        n = len(ranks)
+        run_off = np.zeros(n + 1, dtype=np.uint64)
+        rt, pt = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        run_cap, pos_cap = max(4 * n, 16), max(16 * n, 64)
+        while True:
+            run_genome = np.zeros(run_cap, dtype=np.uint32)
+            pos_off = np.zeros(run_cap + 1, dtype=np.uint64)
+            pos = np.zeros(pos_cap, dtype=np.uint32)
+            st = lib().pa_index_entries(self.handle, _p(ranks if n else np.zeros(1, np.uint64)), n, _p(run_off), _p(run_genome),
+                                        run_cap, _p(pos_off), _p(pos), pos_cap, ctypes.byref(rt), ctypes.byref(pt))
+            if st == PA_ERR_CAPACITY:
+                run_cap, pos_cap = max(run_cap, int(rt.value)), max(pos_cap, int(pt.value))
+                continue
+            check(st)
+            return run_off, run_genome[:rt.value], pos_off[:rt.value + 1], pos[:pt.value]
+
     def table_lookup(self, kmers: Sequence[str]):
         k = self.info().k
         n = len(kmers)
@@ -357,6 +417,190 @@ class NativeIndex:
                                       _p(lst if len(lst) else np.zeros(1, np.uint32)), len(words), len(lst),
                                       int(read_index_base), _p(stats), _p(uniq), _p(amb), _p(first)))
         return stats, uniq[:G], amb[:G], first[:G]
+
+
+PA_BUILD_TABLE_ONLY = 1
+PA_BUILD_HOST_BASES = 2
+_ALLGATHER_CB = ctypes.CFUNCTYPE(ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64)
+
+
+class _CommCallbacks(ctypes.Structure):
+    _fields_ = [("user", ctypes.c_void_p), ("allgather", _ALLGATHER_CB)]
+
+
+class Comm:
+    """Owns one pa_comm handle: one process per GPU on one node (include/pa_b200.h "communicator").
+
+    Comm.nccl(...)        NCCL transport (the product path): rank 0 calls Comm.unique_id() and hands the 128 bytes to all
+    Comm.callbacks(...)   any host all-gather as the control plane (tests over gloo); device data travels through CUDA IPC
+    Comm.from_torch(...)  either of the two from an initialised torch.distributed process group
+    """
+
+    def __init__(self, handle: int, keep=None):
+        self._h = ctypes.c_void_p(handle)
+        self._keep = keep          # callback objects must outlive the handle
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (ctypes.c_uint8 * 128)()
+        check(lib().pa_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def nccl(cls, n_ranks: int, rank: int, unique_id: bytes, device: int) -> "Comm":
+        require_device()
+        h = ctypes.c_void_p()
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(lib().pa_comm_init(n_ranks, rank, buf, device, ctypes.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def callbacks(cls, n_ranks: int, rank: int, device: int, allgather) -> "Comm":
+        """allgather(data: bytes) -> list of every rank's bytes (equal lengths), in rank order.
+        device < 0: host-only communicator (host collectives only; no CUDA device needed)."""
+        if device >= 0:
+            require_device()
+
+        def _cb(_user, p_in, p_out, nbytes):
+            try:
+                parts = allgather(ctypes.string_at(p_in, nbytes))
+                blob = b"".join(parts)
+                if len(blob) != nbytes * n_ranks:
+                    return 2
+                ctypes.memmove(p_out, blob, len(blob))
+                return 0
+            except Exception:      # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        fn = _ALLGATHER_CB(_cb)
+        cbs = _CommCallbacks(None, fn)
+        h = ctypes.c_void_p()
+        check(lib().pa_comm_init_callbacks(n_ranks, rank, device, ctypes.byref(cbs), ctypes.byref(h)))
+        return cls(h.value, keep=(fn, cbs))
+
+    @classmethod
+    def from_torch(cls, device: int, group=None) -> "Comm":
+        import torch
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if dist.get_backend(group) == "nccl":
+            box = [cls.unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group,
+                                       device=torch.device("cuda", device))
+            return cls.nccl(world, rank, box[0], device)
+
+        def allgather(data: bytes):
+            mine = torch.frombuffer(bytearray(data), dtype=torch.uint8)
+            out = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(out, mine, group=group)
+            return [bytes(t.numpy().tobytes()) for t in out]
+
+        return cls.callbacks(world, rank, device, allgather)
+
+    @property
+    def handle(self) -> ctypes.c_void_p:
+        if self._h is None:
+            raise RuntimeError("communicator already freed")
+        return self._h
+
+    def close(self) -> None:
+        if self._h is not None and self._h.value and _lib is not None:
+            _lib.pa_comm_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        n, r, d, nc = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        check(lib().pa_comm_info(self.handle, ctypes.byref(n), ctypes.byref(r), ctypes.byref(d), ctypes.byref(nc)))
+        return {"n_ranks": n.value, "rank": r.value, "device": d.value, "nccl": bool(nc.value)}
+
+    def barrier(self) -> None:
+        check(lib().pa_comm_barrier(self.handle))
+
+    def allgather_bytes(self, data: bytes) -> List[bytes]:
+        """Every rank's `data` (any lengths), in rank order."""
+        n = self.info()["n_ranks"]
+        sizes = np.zeros(n, dtype=np.uint64)
+        mine = np.array([len(data)], dtype=np.uint64)
+        check(lib().pa_comm_allgather_host(self.handle, _p(mine), _p(sizes), 8))
+        mx = int(sizes.max()) if n else 0
+        if mx == 0:
+            return [b""] * n
+        pad = np.zeros(mx, dtype=np.uint8)
+        pad[:len(data)] = np.frombuffer(data, dtype=np.uint8)
+        out = np.zeros(mx * n, dtype=np.uint8)
+        check(lib().pa_comm_allgather_host(self.handle, _p(pad), _p(out), mx))
+        return [out[r * mx:r * mx + int(sizes[r])].tobytes() for r in range(n)]
+
+    def allgather_array(self, a: np.ndarray) -> List[np.ndarray]:
+        a = np.ascontiguousarray(a)
+        return [np.frombuffer(b, dtype=a.dtype) for b in self.allgather_bytes(a.tobytes())]
+
+    def allreduce_host(self, values: np.ndarray, take_min: bool = False) -> np.ndarray:
+        v = np.ascontiguousarray(values, dtype=np.uint64).copy()
+        check(lib().pa_comm_allreduce_host(self.handle, _p(v), v.size, 1 if take_min else 0))
+        return v
+
+    def allreduce_summary(self, d_sum_ptr: int, n_sum: int, d_min_ptr: int, n_min: int, stream_ptr: int = 0) -> None:
+        check(lib().pa_comm_allreduce_summary(self.handle, ctypes.c_void_p(d_sum_ptr), n_sum, ctypes.c_void_p(d_min_ptr), n_min,
+                                              ctypes.c_void_p(stream_ptr) if stream_ptr else None))
+
+
+def genome_shard(genome_off: np.ndarray, n_ranks: int, rank: int) -> Tuple[int, int]:
+    genome_off = np.ascontiguousarray(genome_off, dtype=np.uint64)
+    lo, hi = ctypes.c_uint32(), ctypes.c_uint32()
+    check(lib().pa_genome_shard(_p(genome_off), len(genome_off) - 1, n_ranks, rank, ctypes.byref(lo), ctypes.byref(hi)))
+    return lo.value, hi.value
+
+
+def build_partitioned(comm: Optional[Comm], bases, genome_off: np.ndarray, g_range: Tuple[int, int], k: int, device: int = 0,
+                      table_only: bool = False, n_rounds: int = 0):
+    """pa_index_build_partitioned.  bases: the genomes [g_lo, g_hi) concatenated -- a uint8 numpy array (host) or an int
+    (device pointer).  Returns (partition or None, replica) as NativeIndex objects."""
+    require_device()
+    genome_off = np.ascontiguousarray(genome_off, dtype=np.uint64)
+    flags = PA_BUILD_TABLE_ONLY if table_only else 0
+    keep = None
+    if isinstance(bases, (int, np.integer)):
+        ptr = ctypes.c_void_p(int(bases))
+    else:
+        keep = _u8(bases)
+        if keep.size == 0:
+            keep = np.zeros(1, dtype=np.uint8)
+        ptr = _p(keep)
+        flags |= PA_BUILD_HOST_BASES
+    hp, hr = ctypes.c_void_p(), ctypes.c_void_p()
+    check(lib().pa_index_build_partitioned(comm.handle if comm is not None else None, ptr, _p(genome_off), len(genome_off) - 1,
+                                           int(g_range[0]), int(g_range[1]), int(k), device, flags, int(n_rounds),
+                                           None if table_only else ctypes.byref(hp), ctypes.byref(hr)))
+    return (NativeIndex(hp.value) if hp.value else None), NativeIndex(hr.value)
+
+
+def rebuild_replica(comm: Optional[Comm], partition: "NativeIndex") -> "NativeIndex":
+    hr = ctypes.c_void_p()
+    check(lib().pa_index_rebuild_replica(comm.handle if comm is not None else None, partition.handle, ctypes.byref(hr)))
+    return NativeIndex(hr.value)
+
+
+def build_timings(replica: "NativeIndex") -> dict:
+    ms = (ctypes.c_float * 8)()
+    check(lib().pa_build_timings(replica.handle, ms))
+    names = ["encode_count_ms", "scatter_exchange_ms", "sort_ms", "csr_ms", "table_slice_ms", "table_gather_ms", "total_ms"]
+    return {n: float(ms[i]) for i, n in enumerate(names)}
+
+
+def partition_of_kmer(k: int, kmer: str, n_parts: int) -> int:
+    b = np.frombuffer(kmer.encode("latin-1"), dtype=np.uint8).copy()
+    out = ctypes.c_uint32()
+    check(lib().pa_partition_of_kmer(int(k), _p(b), int(n_parts), ctypes.byref(out)))
+    return out.value
 
 
 def decode_kmers(k: int, keys: np.ndarray) -> List[str]:

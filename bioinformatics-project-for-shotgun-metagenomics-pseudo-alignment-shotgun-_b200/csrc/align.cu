@@ -138,7 +138,7 @@ __device__ __forceinline__ void window_min_step(uint32_t (&key)[AL_ROUNDS + 1], 
 // minimizer (full hash, offset) of the window whose planes are wl / wh, from its slid key
 __device__ __forceinline__ void window_minimizer(const TableView& t, uint32_t key, uint32_t wl, uint32_t* mhash, uint32_t* p) {
   *p = key & 15u;
-  *mhash = ((key >> 4) << t.hdrop) | ((wl >> *p) & ((1u << t.hdrop) - 1));
+  *mhash = hash_from_order(key >> 4, wl >> *p, t);
 }
 
 // rare continuation of a lookup whose home bucket was full, without a match, and has CONT set (kept out of line:
@@ -146,7 +146,7 @@ __device__ __forceinline__ void window_minimizer(const TableView& t, uint32_t ke
 __device__ __noinline__ uint64_t lookup_chain_window(const TableView& t, uint64_t raw, uint32_t mhash, uint32_t p) {
   const uint32_t kmask = (t.k >= 32) ? 0xFFFFFFFFu : ((1u << t.k) - 1);
   const SlotAddr a = slot_addr(t, (uint32_t)raw & kmask, (uint32_t)(raw >> t.k) & kmask, mhash, p);
-  return lookup_chain(t, a, raw);
+  return lookup_chain(t, a, mhash, raw);
 }
 
 
@@ -527,11 +527,14 @@ align_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
         // self.kmers[kmer] = ...: a repeated k-mer keeps the position of its first kept occurrence (kmer.py:429)
         const uint32_t pos = (uint32_t)(wbase + 32 * r + lane);
         uint32_t sl = ((((uint32_t)raw[r] ^ (uint32_t)(raw[r] >> 31)) * 0x9E3779B1u) >> 7) & ws.kset_mask;
-        for (;;) {
+        uint32_t probes = 0;
+        for (;; ++probes) {
+          if (probes > ws.kset_mask) break;   // set full: a read longer than the declared max_read_len (flagged below)
           unsigned long long old = atomicCAS(ws.kset_key + sl, (unsigned long long)EMPTY64, (unsigned long long)raw[r]);
           if (old == EMPTY64 || old == raw[r]) break;
           sl = (sl + 1) & ws.kset_mask;
         }
+        if (probes > ws.kset_mask) { atomicExch(em.cursor + 1, 2ULL); kept[r] = false; continue; }
         atomicMin(ws.kset_pos + sl, pos);
         slot[r] = sl;
       }

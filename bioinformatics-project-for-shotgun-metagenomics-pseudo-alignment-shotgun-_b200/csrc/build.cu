@@ -10,6 +10,7 @@
 #include "index.cuh"
 #include "scan.cuh"
 #include "sort.cuh"
+#include "table.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -113,12 +114,14 @@ constexpr int ENC_WORDS = ENC_TILE / 32 + 2;
 __global__ void __launch_bounds__(ENC_THREADS)
 encode_windows(const uint8_t* __restrict__ bases, uint64_t total, uint64_t pos0, const uint64_t* __restrict__ genome_off, uint32_t G,
                int k, MixParams mix, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned long long* __restrict__ n_valid,
-               unsigned int* __restrict__ bad_flag) {
-  // bases[0 .. total) is the slice of the concatenated genomes that starts at global base position pos0 (whole
-  // genomes: a multi-GPU build gives every rank a run of genomes); keys / vals are indexed like bases, vals hold
-  // GLOBAL positions
+               unsigned int* __restrict__ bad_flag, EncodeOpts opt) {
+  // bases[0 .. total) is the slice of the concatenated genomes that starts at global base position pos0 (a multi-GPU
+  // build gives every rank a run of genomes, a streamed build walks them chunk by chunk); keys / vals are indexed like
+  // bases, vals hold GLOBAL positions (or genome indices: opt.vals_are_genomes).  Only windows starting before
+  // opt.emit_total are emitted: the k - 1 bases beyond it are the overlap into the next chunk.
   __shared__ uint32_t s_lo[ENC_WORDS], s_hi[ENC_WORDS], s_inv[ENC_WORDS], s_brk[ENC_WORDS];
   __shared__ uint32_t s_cnt[ENC_THREADS / 32];
+  __shared__ uint32_t s_g0;
   const uint64_t tile_base = (uint64_t)blockIdx.x * ENC_TILE;
   const int tid = threadIdx.x;
   bool bad = false;
@@ -154,6 +157,7 @@ encode_windows(const uint8_t* __restrict__ bases, uint64_t total, uint64_t pos0,
     const uint64_t span_end = pos0 + min(total, tile_base + (uint64_t)ENC_WORDS * 32);
     if (tile_base < total) {
       uint32_t g0 = genome_of(genome_off, G, span_beg);
+      if (tid == 0) s_g0 = g0;
       for (uint32_t g = g0 + tid; g < G; g += ENC_THREADS) {
         uint64_t beg = genome_off[g], end = genome_off[g + 1];
         if (beg >= span_end) break;
@@ -165,22 +169,40 @@ encode_windows(const uint8_t* __restrict__ bases, uint64_t total, uint64_t pos0,
   }
   __syncthreads();
   const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1);
+  TableView mt;                   // only the minimizer fields are used (owner of a record = f(digit of its minimizer))
+  minimizer_params(mt, k);
+  const uint32_t tb = digit_bits_for_k(k);
   uint32_t cnt = 0;
+  uint32_t g_walk = (tile_base < total) ? s_g0 : 0;
 #pragma unroll 4
   for (int j = 0; j < ENC_TILE / ENC_THREADS; ++j) {
     uint32_t s = j * ENC_THREADS + tid;
     uint64_t gpos = tile_base + s;
-    if (gpos >= total) break;
+    if (gpos >= opt.emit_total) break;
     uint32_t w = s >> 5, b = s & 31;
     uint32_t lo = __funnelshift_r(s_lo[w], s_lo[w + 1], b) & kmask;
     uint32_t hi = __funnelshift_r(s_hi[w], s_hi[w + 1], b) & kmask;
     uint32_t inv = __funnelshift_r(s_inv[w], s_inv[w + 1], b) & kmask;
     uint32_t brk = __funnelshift_r(s_brk[w], s_brk[w + 1], b) & (kmask >> 1);
     bool valid = (inv | brk) == 0 && gpos + (uint64_t)k <= total;
-    // the bijectively hashed k-mer is the sort key: equal k-mers still group, and the sorted order is the bucket
-    // order of the lookup table (and the rank partition of a multi-GPU build)
+    // the bijectively hashed k-mer is the sort key: equal k-mers still group
     keys[gpos] = valid ? mix_key(((uint64_t)hi << k) | lo, mix) : SENTINEL_KEY;
-    vals[gpos] = (uint32_t)(pos0 + gpos);
+    if (opt.vals_are_genomes) {
+      while (g_walk + 1 < G && genome_off[g_walk + 1] <= pos0 + gpos) ++g_walk;
+      vals[gpos] = g_walk;
+    } else {
+      vals[gpos] = (uint32_t)(pos0 + gpos);
+    }
+    if (opt.owner) {
+      uint32_t own = 255;
+      if (valid) {
+        uint32_t mh, mp;
+        kmer_minimizer(mt, lo, hi, &mh, &mp);
+        const uint32_t part = (uint32_t)(((uint64_t)(mh >> mt.dshift) * opt.n_parts) >> tb);
+        if (part % opt.n_rounds == opt.round) own = part / opt.n_rounds;
+      }
+      opt.owner[gpos] = (uint8_t)own;
+    }
     cnt += valid;
   }
   cnt = warp_sum(cnt);
@@ -227,6 +249,7 @@ __global__ void genome_map_fill(const uint64_t* __restrict__ off, uint32_t G, ui
 // every load and -- after compaction -- every store of a warp instruction touches consecutive addresses (the first
 // version gave each thread 8 consecutive records: its stores were 64 bytes apart and the kernel was bound by L2
 // transactions, profiles/r01_rle_scatter_ncu.json).  kh / rh = ballot masks of key heads / (key, genome) heads.
+template <bool GEN>   // GEN: vals hold genome indices already (table-only builds), else global positions
 __device__ __forceinline__ void rle_flags(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                           const uint64_t* __restrict__ genome_off, GenomeMap G, uint64_t warp_base, uint64_t n,
                                           uint32_t lane, uint64_t (&key)[RLE_ITEMS], uint32_t (&gen)[RLE_ITEMS],
@@ -235,7 +258,7 @@ __device__ __forceinline__ void rle_flags(const uint64_t* __restrict__ keys, con
   bool have_carry = false;
   if (warp_base > 0 && warp_base < n) {
     carry_key = keys[warp_base - 1];
-    carry_gen = genome_at(G, genome_off, vals[warp_base - 1]);
+    carry_gen = GEN ? vals[warp_base - 1] : genome_at(G, genome_off, vals[warp_base - 1]);
     have_carry = true;
   }
 #pragma unroll
@@ -243,7 +266,7 @@ __device__ __forceinline__ void rle_flags(const uint64_t* __restrict__ keys, con
     const uint64_t i = warp_base + (uint64_t)j * 32 + lane;
     const bool ok = i < n;
     key[j] = ok ? keys[i] : 0;
-    gen[j] = ok ? genome_at(G, genome_off, vals[i]) : 0;
+    gen[j] = ok ? (GEN ? vals[i] : genome_at(G, genome_off, vals[i])) : 0;
     uint64_t pk = __shfl_up_sync(0xffffffffu, key[j], 1);
     uint32_t pg = __shfl_up_sync(0xffffffffu, gen[j], 1);
     bool have_prev = true;
@@ -258,6 +281,7 @@ __device__ __forceinline__ void rle_flags(const uint64_t* __restrict__ keys, con
   }
 }
 
+template <bool GEN>
 __global__ void __launch_bounds__(RLE_THREADS)
 rle_count(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint64_t* __restrict__ genome_off,
           GenomeMap G, uint64_t n, uint64_t* __restrict__ tile_keys, uint64_t* __restrict__ tile_runs) {
@@ -265,7 +289,7 @@ rle_count(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t warp_base = (uint64_t)blockIdx.x * RLE_TILE + (uint64_t)warp * (32 * RLE_ITEMS);
   uint64_t key[RLE_ITEMS]; uint32_t gen[RLE_ITEMS], kh[RLE_ITEMS], rh[RLE_ITEMS];
-  rle_flags(keys, vals, genome_off, G, warp_base, n, lane, key, gen, kh, rh);
+  rle_flags<GEN>(keys, vals, genome_off, G, warp_base, n, lane, key, gen, kh, rh);
   uint32_t a = 0, b = 0;
 #pragma unroll
   for (int j = 0; j < RLE_ITEMS; ++j) { a += __popc(kh[j]); b += __popc(rh[j]); }
@@ -278,6 +302,7 @@ rle_count(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, 
   }
 }
 
+template <bool GEN>
 __global__ void __launch_bounds__(RLE_THREADS)
 rle_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint64_t* __restrict__ genome_off,
             GenomeMap G, uint64_t n, const uint64_t* __restrict__ tile_keys, const uint64_t* __restrict__ tile_runs,
@@ -287,7 +312,7 @@ rle_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t warp_base = (uint64_t)blockIdx.x * RLE_TILE + (uint64_t)warp * (32 * RLE_ITEMS);
   uint64_t key[RLE_ITEMS]; uint32_t gen[RLE_ITEMS], kh[RLE_ITEMS], rh[RLE_ITEMS];
-  rle_flags(keys, vals, genome_off, G, warp_base, n, lane, key, gen, kh, rh);
+  rle_flags<GEN>(keys, vals, genome_off, G, warp_base, n, lane, key, gen, kh, rh);
   uint32_t a = 0, b = 0;
 #pragma unroll
   for (int j = 0; j < RLE_ITEMS; ++j) { a += __popc(kh[j]); b += __popc(rh[j]); }
@@ -304,9 +329,9 @@ rle_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals
         const uint64_t r = rr + __popc(rh[j] & lt);
         if ((kh[j] >> lane) & 1) { const uint64_t q = kr + __popc(kh[j] & lt); ukeys[q] = key[j]; run_off[q] = r; }
         run_genome[r] = gen[j];
-        pos_off[r] = i;
+        if (!GEN) pos_off[r] = i;
       }
-      pos[i] = (uint32_t)((uint64_t)vals[i] - genome_off[gen[j]]);
+      if (!GEN) pos[i] = (uint32_t)((uint64_t)vals[i] - genome_off[gen[j]]);
     }
     kr += __popc(kh[j]);
     rr += __popc(rh[j]);
@@ -320,135 +345,7 @@ __global__ void iota_u32(uint32_t* v, uint64_t n) {
 
 __global__ void set_csr_tails(uint64_t* run_off, uint64_t U, uint64_t R, uint64_t* pos_off, uint64_t N) {
   run_off[U] = R;
-  pos_off[R] = N;
-}
-
-// ===========================================================================
-// lookup table construction from the CSR
-// ===========================================================================
-// ---- genome sets of the k-mers with more than n_inline genomes, de-duplicated ("colour sets") ----------------
-// Related genomes share long runs of k-mers, so the number of DISTINCT genome sets is tiny next to the number of
-// k-mers carrying them (config B: a few hundred sets for 10^7 k-mers).  Storing each set once keeps mlist inside
-// L1/L2 and keeps the slot payload (a sector index) short.
-//   long_flags    flag[u] = 1 when k-mer u has more than n_inline genomes
-//   set_hash_keys (hash of the genome list, u) for every flagged k-mer, compacted by the scan of the flags
-//   [radix sort by hash]
-//   set_heads     an entry opens a new set unless its list equals its sorted predecessor's (hash AND content)
-//   set_assign    msec_off[u] = first sector of the k-mer's set; heads write their list into mlist
-__global__ void long_flags(const uint64_t* __restrict__ run_off, uint64_t U, uint32_t n_inline, uint32_t* __restrict__ flag) {
-  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (u >= U) return;
-  flag[u] = (run_off[u + 1] - run_off[u]) > n_inline ? 1u : 0u;
-}
-
-__global__ void set_hash_keys(const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome, uint64_t U,
-                              const uint32_t* __restrict__ flag, const uint64_t* __restrict__ rank,
-                              uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (u >= U || !flag[u]) return;
-  uint64_t h = 0xCBF29CE484222325ULL;
-  for (uint64_t r = run_off[u]; r < run_off[u + 1]; ++r) { h ^= run_genome[r]; h *= 0x100000001B3ULL; h ^= h >> 29; }
-  keys[rank[u]] = h;
-  vals[rank[u]] = (uint32_t)u;
-}
-
-__global__ void set_heads(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t n,
-                          const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome,
-                          uint32_t* __restrict__ head_secs) {
-  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t u = vals[i], r0 = run_off[u], c = run_off[u + 1] - r0;
-  bool head = true;
-  if (i > 0 && keys[i] == keys[i - 1]) {
-    const uint64_t v = vals[i - 1], q0 = run_off[v];
-    if (run_off[v + 1] - q0 == c) {
-      head = false;
-      for (uint64_t j = 0; j < c && !head; ++j) head = run_genome[r0 + j] != run_genome[q0 + j];
-    }
-  }
-  head_secs[i] = head ? (uint32_t)((c + MLIST_SECTOR - 1) / MLIST_SECTOR) : 0u;
-}
-
-__global__ void set_assign(const uint32_t* __restrict__ vals, uint64_t n, const uint32_t* __restrict__ head_secs,
-                           const uint64_t* __restrict__ sec_off, const uint64_t* __restrict__ run_off,
-                           const uint32_t* __restrict__ run_genome, uint64_t* __restrict__ msec_off,
-                           uint32_t* __restrict__ mlist) {
-  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t u = vals[i], r0 = run_off[u], c = run_off[u + 1] - r0;
-  const uint64_t secs = (c + MLIST_SECTOR - 1) / MLIST_SECTOR;
-  if (head_secs[i]) {
-    msec_off[u] = sec_off[i];
-    uint32_t* dst = mlist + sec_off[i] * MLIST_SECTOR;
-    for (uint64_t j = 0; j < c; ++j) dst[j] = run_genome[r0 + j] | (j + 1 == c ? LIST_END : 0u);
-  } else {
-    msec_off[u] = sec_off[i] - secs;   // sec_off is an exclusive scan: the set of the nearest head before i ends at sec_off[i]
-  }
-}
-
-// value field of a distinct k-mer with c genomes rg[0..c) (ascending); see TableView in common.cuh
-__device__ __forceinline__ uint64_t entry_value(const TableView& t, uint64_t c, const uint32_t* __restrict__ rg, uint64_t msec) {
-  const uint32_t kshift = t.val_bits - 3;
-  if (c == 1) return ((uint64_t)KIND_SPECIFIC << kshift) | rg[0];
-  if (c <= t.n_inline) {
-    uint64_t v = 0;
-    for (uint32_t i = 0; i < t.n_inline; ++i) v |= (uint64_t)rg[i < c ? i : c - 1] << (i * t.gbits);
-    return ((uint64_t)KIND_INLINE << kshift) | v;
-  }
-  return ((uint64_t)KIND_MLIST << kshift) | msec;
-}
-
-// One thread per distinct k-mer: un-hash the CSR key, find its minimizer, and claim the first free slot of its bucket
-// with atomicCAS -- in the home block or, when that bucket is full, in the same bucket of the next blocks, setting
-// CONT on the last slot of every bucket it passes (readers only go on from a full bucket that has CONT).  Slots of a
-// bucket fill in order, so "last slot taken" means "bucket full".  K-mers that find no free slot within CHAIN_LEN
-// blocks are collected for the stash (the last bucket of their chain then has CONT set, which sends readers there).
-__global__ void table_insert(const uint64_t* __restrict__ ukeys, const uint64_t* __restrict__ run_off,
-                             const uint32_t* __restrict__ run_genome, const uint64_t* __restrict__ msec_off, uint64_t U,
-                             TableView t, MixParams mix, unsigned long long* __restrict__ slots,
-                             unsigned int* __restrict__ ovf_count, uint32_t* __restrict__ ovf_list, uint32_t ovf_cap) {
-  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (u >= U) return;
-  const uint64_t raw = unmix_key(ukeys[u], mix);
-  const uint32_t kmask = (t.k >= 32) ? 0xFFFFFFFFu : ((1u << t.k) - 1);
-  const uint32_t lo = (uint32_t)raw & kmask, hi = (uint32_t)(raw >> t.k) & kmask;
-  uint32_t mh, p;
-  kmer_minimizer(t, lo, hi, &mh, &p);
-  const SlotAddr a = slot_addr(t, lo, hi, mh, p);
-  const uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
-  const unsigned long long value = entry_value(t, c, run_genome + r0, msec_off[u]);
-  const unsigned long long cont_bit = 1ULL << (t.val_bits - 1);
-  const uint64_t bmask = (1ULL << t.block_bits) - 1;
-  for (uint32_t d = 0; d < CHAIN_LEN; ++d) {
-    unsigned long long* b = slots + (((a.block + d) & bmask) * BLOCK_BUCKETS + a.bucket) * BUCKET_SLOTS;
-    const unsigned long long word = ((a.tag | ((uint64_t)d << t.hi_bits)) << t.val_bits) | value;
-    for (uint32_t i = 0; i < BUCKET_SLOTS; ++i)
-      if (atomicCAS(b + i, (unsigned long long)EMPTY64, word) == EMPTY64) return;
-    atomicOr(b + BUCKET_SLOTS - 1, cont_bit);
-  }
-  uint32_t at = atomicAdd(ovf_count, 1u);
-  if (at < ovf_cap) ovf_list[at] = (uint32_t)u;
-}
-
-__global__ void stash_insert(const uint64_t* __restrict__ ukeys, const uint64_t* __restrict__ run_off,
-                             const uint32_t* __restrict__ run_genome, const uint64_t* __restrict__ msec_off,
-                             const uint32_t* __restrict__ ovf_list, uint32_t n_ovf, TableView t, MixParams mix,
-                             unsigned long long* __restrict__ stash /* {raw key, value} pairs */, uint64_t stash_mask) {
-  uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i0 >= n_ovf) return;
-  uint64_t u = ovf_list[i0];
-  uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
-  uint64_t raw = unmix_key(ukeys[u], mix);
-  uint64_t value = entry_value(t, c, run_genome + r0, msec_off[u]);
-  uint64_t i = stash_slot(raw);
-  for (;;) {
-    i &= stash_mask;
-    if (atomicCAS(&stash[2 * i], (unsigned long long)EMPTY64, (unsigned long long)raw) == EMPTY64) {
-      stash[2 * i + 1] = value;
-      return;
-    }
-    ++i;
-  }
+  if (pos_off) pos_off[R] = N;
 }
 
 // ===========================================================================
@@ -465,6 +362,34 @@ __global__ void lookup_ranks(const uint64_t* __restrict__ ukeys, uint64_t U, con
     if (ukeys[mid] < key) lo = mid + 1; else hi = mid;
   }
   rank[i] = (key != SENTINEL_KEY && lo < U && ukeys[lo] == key) ? lo : LOOKUP_MISS;
+}
+
+// Content checksum of a CSR: four sums modulo 2^64 over {k-mers, (k-mer, genome) pairs, (k-mer, genome, position)
+// triples, k-mer count}.  Order-independent and additive over disjoint key sets, so the checksums of the partitions
+// of a multi-GPU build add up to the checksum of the single-GPU index exactly when the contents agree.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return x;
+}
+__global__ void __launch_bounds__(256)
+csr_checksum_kernel(const uint64_t* __restrict__ ukeys, const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome,
+                    const uint64_t* __restrict__ pos_off, const uint32_t* __restrict__ pos, uint64_t U, int with_pos,
+                    unsigned long long* __restrict__ out) {
+  unsigned long long a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; u < U; u += stride) {
+    const unsigned long long key = ukeys[u];
+    a0 += mix64(key ^ 0x243F6A8885A308D3ULL);
+    a3 += 1;
+    for (uint64_t r = run_off[u]; r < run_off[u + 1]; ++r) {
+      const unsigned long long g = run_genome[r];
+      a1 += mix64(key * 3 + g);
+      if (with_pos)
+        for (uint64_t q = pos_off[r]; q < pos_off[r + 1]; ++q) a2 += mix64(key * 5 + ((g << 32) | pos[q]));
+    }
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out, a0); atomicAdd(out + 1, a1); atomicAdd(out + 2, a2); atomicAdd(out + 3, a3); }
 }
 
 // first occurrence of each distinct k-mer as a global base position: the dict
@@ -749,175 +674,66 @@ struct PhaseTrace {   // PA_TRACE=1: host wall-clock of the build phases on stde
 };
 }  // namespace
 
-int32_t index_build_tables(Index& ix) {
-  cudaStream_t s = ix.stream;
-  PhaseTrace tr;
-  const uint64_t U = ix.n_keys;
-  const int k = ix.k < 1 ? 1 : ix.k;   // k <= 0: no k-mers at all; the geometry below only has to be benign
-  ix.mix = mix_params_for_k(ix.k);
-  ix.slots.release(); ix.stash.release(); ix.mlist.release();
-  ix.stash_cap = 0; ix.stash_count = 0; ix.n_msectors = 0;
-  // Table geometry (see TableView in common.cuh).  tag = 2(k-m) + CHAIN_BITS + (2m - line_bits) bits; the value field
-  // (val_bits = 64 - tag_bits) must hold the CONT bit + 2 kind bits + a genome id (with the all-ones id left unused so that no slot
-  // equals EMPTY64) + any mlist sector index.
-  const uint32_t G = ix.n_genomes;
-  const uint32_t m = minimizer_len_for_k(k);
-  const int64_t tag_fixed = 2 * ((int64_t)k - m) + CHAIN_BITS + 2 * m;   // tag_bits = tag_fixed - block_bits
-  const uint32_t gb = std::max(1u, ceil_log2_u64(G));
-  const uint32_t need_spec = std::max(1u, ceil_log2_u64((uint64_t)G + 1));
-  const int64_t lb_max = 2 * m;   // the block index comes out of the 2m hash bits
-  // load factor over the slots: in (1/8, 1/4] (99.6 % of the k-mers in their home bucket; simulated and measured),
-  // halved while the table would take more than a third of the free device memory
-  size_t free_b = 0, total_b = 0;
-  PA_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  int64_t lb = 0;
-  {
-    const char* dense = getenv("PA_TABLE_DENSE");
-    int shift = dense && *dense ? atoi(dense) : 0;      // tuning knob: +1 doubles the load factor, -1 halves it
-    lb = (int64_t)ceil_log2_u64((U * 4 + 63) / 64) - shift;
-    while (lb > 0 && (512ull << lb) > free_b / 3) --lb;
-    if (lb < 0) lb = 0;
-  }
-  lb = std::max<int64_t>(lb, tag_fixed - 61 + need_spec);
-  lb = std::max<int64_t>(std::min<int64_t>(lb, lb_max), 0);
-  DevBuf flag, lrank, msec_off, tile_sums, d_total, set_ka, set_kb, set_va, set_vb, set_tmp, head_secs, sec_off;
-  PA_TRY(flag.alloc((U + 1) * 4));
-  PA_TRY(lrank.alloc((U + 1) * 8));
-  PA_TRY(msec_off.alloc((U + 1) * 8));
-  PA_TRY(tile_sums.alloc((scan_tiles(U) + 1) * 8));
-  PA_TRY(d_total.alloc(8));
-  uint64_t n_msec = 0, n_long = 0;
-  uint32_t* set_vals = nullptr;   // k-mers with long lists, sorted by set
-  for (;;) {
-    const int64_t T = tag_fixed - lb;
-    const int64_t P = 64 - T - 3;
-    if (P < (int64_t)need_spec) {
-      if (lb >= lb_max) { set_error("lookup table: genome ids do not fit (k=%d, G=%u)", k, G); return ST_UNSUPPORTED; }
-      ++lb; continue;
-    }
-    uint32_t n_in = std::min<uint32_t>(4, (uint32_t)P / gb);
-    if (n_in < 2) n_in = 1;
-    ix.gbits = gb; ix.n_inline = n_in;
-    n_msec = 0; n_long = 0;
-    if (U) {
-      long_flags<<<grid_for(U, 256), 256, 0, s>>>(ix.run_off.as<uint64_t>(), U, n_in, flag.as<uint32_t>());
-      PA_TRY(exclusive_scan_u32(flag.as<uint32_t>(), lrank.as<uint64_t>(), U, tile_sums.as<uint64_t>(), d_total.as<uint64_t>(), s));
-      PA_CUDA(cudaMemcpyAsync(&n_long, d_total.p, 8, cudaMemcpyDeviceToHost, s));
-      PA_CUDA(cudaStreamSynchronize(s));
-    }
-    if (n_long) {
-      PA_TRY(set_ka.alloc(n_long * 8)); PA_TRY(set_kb.alloc(n_long * 8)); PA_TRY(set_va.alloc(n_long * 4)); PA_TRY(set_vb.alloc(n_long * 4));
-      PA_TRY(set_tmp.alloc(radix_sort_temp_bytes(n_long)));
-      PA_TRY(head_secs.alloc(n_long * 4)); PA_TRY(sec_off.alloc(n_long * 8));
-      set_hash_keys<<<grid_for(U, 256), 256, 0, s>>>(ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(), U, flag.as<uint32_t>(),
-                                                      lrank.as<uint64_t>(), set_ka.as<uint64_t>(), set_va.as<uint32_t>());
-      int in_b = 0;
-      PA_TRY(radix_sort_pairs(set_ka.as<uint64_t>(), set_va.as<uint32_t>(), set_kb.as<uint64_t>(), set_vb.as<uint32_t>(), n_long, 64,
-                              set_tmp.p, set_tmp.bytes, s, &in_b));
-      const uint64_t* skeys = in_b ? set_kb.as<uint64_t>() : set_ka.as<uint64_t>();
-      set_vals = in_b ? set_vb.as<uint32_t>() : set_va.as<uint32_t>();
-      set_heads<<<grid_for(n_long, 256), 256, 0, s>>>(skeys, set_vals, n_long, ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(),
-                                                      head_secs.as<uint32_t>());
-      if (scan_tiles(n_long) > scan_tiles(U)) PA_TRY(tile_sums.alloc((scan_tiles(n_long) + 1) * 8));
-      PA_TRY(exclusive_scan_u32(head_secs.as<uint32_t>(), sec_off.as<uint64_t>(), n_long, tile_sums.as<uint64_t>(), d_total.as<uint64_t>(), s));
-      PA_CUDA(cudaMemcpyAsync(&n_msec, d_total.p, 8, cudaMemcpyDeviceToHost, s));
-      PA_CUDA(cudaStreamSynchronize(s));
-    }
-    if ((int64_t)ceil_log2_u64(n_msec + 1) <= P) break;
-    if (lb >= lb_max) { set_error("lookup table: list references do not fit (k=%d)", k); return ST_UNSUPPORTED; }
-    ++lb;
-  }
-  tr.mark("tables: genome sets", s);
-  ix.n_msectors = n_msec;
-  PA_TRY(ix.mlist.alloc(std::max<uint64_t>(n_msec, 1) * 32));
-  PA_CUDA(cudaMemsetAsync(ix.mlist.p, 0xFF, ix.mlist.bytes, s));
-  if (n_long)
-    set_assign<<<grid_for(n_long, 256), 256, 0, s>>>(set_vals, n_long, head_secs.as<uint32_t>(), sec_off.as<uint64_t>(),
-                                                     ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(),
-                                                     msec_off.as<uint64_t>(), ix.mlist.as<uint32_t>());
-  set_ka.release(); set_kb.release(); set_tmp.release(); flag.release(); lrank.release();
-  tr.mark("tables: set fill + frees", s);
-  DevBuf ovf_count, ovf_list;
-  PA_TRY(ovf_count.alloc(4));
-  uint32_t ovf_cap = (uint32_t)std::min<uint64_t>(U / 4 + 4096, 0xFFFFFFF0ull);
-  PA_TRY(ovf_list.alloc((size_t)ovf_cap * 4));
-  for (;;) {
-    ix.min_len = m;
-    ix.block_bits = (uint32_t)lb;
-    ix.tag_bits = (uint32_t)(tag_fixed - lb);
-    ix.val_bits = 64 - ix.tag_bits;
-    const uint64_t n_blocks = 1ULL << lb;
-    PA_TRY(ix.slots.alloc(n_blocks * 512));
-    tr.mark("tables: slots alloc", s);
-    PA_CUDA(cudaMemsetAsync(ix.slots.p, 0xFF, n_blocks * 512, s));
-    tr.mark("tables: slots memset", s);
-    PA_CUDA(cudaMemsetAsync(ovf_count.p, 0, 4, s));
-    uint32_t n_ovf = 0;
-    if (U) {
-      table_insert<<<grid_for(U, 256), 256, 0, s>>>(ix.ukeys.as<uint64_t>(), ix.run_off.as<uint64_t>(),
-                                                     ix.run_genome.as<uint32_t>(), msec_off.as<uint64_t>(), U, ix.view(),
-                                                     ix.mix, ix.slots.as<unsigned long long>(), ovf_count.as<unsigned int>(),
-                                                     ovf_list.as<uint32_t>(), ovf_cap);
-      PA_CUDA(cudaMemcpyAsync(&n_ovf, ovf_count.p, 4, cudaMemcpyDeviceToHost, s));
-      PA_CUDA(cudaStreamSynchronize(s));
-    }
-    tr.mark("tables: insert", s);
-    if (n_ovf > ovf_cap) {  // pathological: grow the table instead of the stash
-      if (lb >= lb_max) { set_error("lookup table: overflow list exhausted"); return ST_UNSUPPORTED; }
-      ++lb;
-      continue;
-    }
-    ix.stash_count = n_ovf;
-    if (n_ovf) {
-      uint64_t cap = 16;
-      while (cap < (uint64_t)n_ovf * 2) cap <<= 1;
-      ix.stash_cap = cap;
-      PA_TRY(ix.stash.alloc(cap * 16));
-      PA_CUDA(cudaMemsetAsync(ix.stash.p, 0xFF, cap * 16, s));
-      stash_insert<<<grid_for(n_ovf, 256), 256, 0, s>>>(ix.ukeys.as<uint64_t>(), ix.run_off.as<uint64_t>(),
-                                                         ix.run_genome.as<uint32_t>(), msec_off.as<uint64_t>(),
-                                                         ovf_list.as<uint32_t>(), n_ovf, ix.view(), ix.mix,
-                                                         ix.stash.as<unsigned long long>(), cap - 1);
-    }
-    break;
-  }
-  PA_CUDA(cudaGetLastError());
-  PA_CUDA(cudaStreamSynchronize(s));
-  return ST_OK;
-}
-
-// K3 host side: CSR of the index from n_valid sorted (key, global position) records
-static int32_t rle_to_csr(Index& ix, const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n_valid) {
+// K3 host side: CSR of the index from n_valid sorted (key, global position) records -- or (key, genome index) records,
+// which give the keys and genome runs only (no positions: table-only builds)
+int32_t rle_to_csr(Index& ix, const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n_valid, bool vals_are_genomes) {
   cudaStream_t s = ix.stream;
   const uint64_t tiles = std::max<uint64_t>(1, (n_valid + RLE_TILE - 1) / RLE_TILE);
   DevBuf tile_keys, tile_runs, totals, gmap;
   PA_TRY(tile_keys.alloc((tiles + 1) * 8)); PA_TRY(tile_runs.alloc((tiles + 1) * 8)); PA_TRY(totals.alloc(16));
   const uint32_t n_genomes = ix.n_genomes;
-  const uint32_t gshift = (uint32_t)std::max<int>(0, (int)ceil_log2_u64(ix.total_bases + 1) - 20);
-  const uint64_t gentries = (ix.total_bases >> gshift) + 1;
-  PA_TRY(gmap.alloc(gentries * 4));
-  genome_map_fill<<<grid_for(gentries, 256), 256, 0, s>>>(ix.genome_off.as<uint64_t>(), n_genomes, ix.total_bases, gshift,
-                                                          gmap.as<uint32_t>(), gentries);
-  const GenomeMap G{gmap.as<uint32_t>(), gshift};
-  rle_count<<<(unsigned)tiles, RLE_THREADS, 0, s>>>(d_keys, d_vals, ix.genome_off.as<uint64_t>(), G, n_valid,
-                                                    tile_keys.as<uint64_t>(), tile_runs.as<uint64_t>());
+  GenomeMap G{nullptr, 0};
+  if (!vals_are_genomes) {
+    const uint32_t gshift = (uint32_t)std::max<int>(0, (int)ceil_log2_u64(ix.total_bases + 1) - 20);
+    const uint64_t gentries = (ix.total_bases >> gshift) + 1;
+    PA_TRY(gmap.alloc(gentries * 4));
+    genome_map_fill<<<grid_for(gentries, 256), 256, 0, s>>>(ix.genome_off.as<uint64_t>(), n_genomes, ix.total_bases, gshift,
+                                                            gmap.as<uint32_t>(), gentries);
+    G = GenomeMap{gmap.as<uint32_t>(), gshift};
+  }
+  if (vals_are_genomes)
+    rle_count<true><<<(unsigned)tiles, RLE_THREADS, 0, s>>>(d_keys, d_vals, ix.genome_off.as<uint64_t>(), G, n_valid,
+                                                            tile_keys.as<uint64_t>(), tile_runs.as<uint64_t>());
+  else
+    rle_count<false><<<(unsigned)tiles, RLE_THREADS, 0, s>>>(d_keys, d_vals, ix.genome_off.as<uint64_t>(), G, n_valid,
+                                                             tile_keys.as<uint64_t>(), tile_runs.as<uint64_t>());
   scan_u64_single_block<<<1, 1024, 0, s>>>(tile_keys.as<uint64_t>(), tiles, totals.as<uint64_t>());
   scan_u64_single_block<<<1, 1024, 0, s>>>(tile_runs.as<uint64_t>(), tiles, totals.as<uint64_t>() + 1);
   uint64_t h_tot[2];
   PA_CUDA(cudaMemcpyAsync(h_tot, totals.p, 16, cudaMemcpyDeviceToHost, s));
   PA_CUDA(cudaStreamSynchronize(s));
   const uint64_t U = h_tot[0], R = h_tot[1];
+  if (U >= 0xFFFFFFFFull) { set_error("index build: more than 2^32 - 2 distinct k-mers in one partition"); return ST_UNSUPPORTED; }
   PA_TRY(ix.ukeys.alloc((U + 1) * 8)); PA_TRY(ix.run_off.alloc((U + 1) * 8));
-  PA_TRY(ix.run_genome.alloc((R + 1) * 4)); PA_TRY(ix.pos_off.alloc((R + 1) * 8)); PA_TRY(ix.pos.alloc((n_valid + 1) * 4));
-  if (n_valid)
-    rle_scatter<<<(unsigned)tiles, RLE_THREADS, 0, s>>>(d_keys, d_vals, ix.genome_off.as<uint64_t>(), G, n_valid,
-                                                        tile_keys.as<uint64_t>(), tile_runs.as<uint64_t>(), ix.ukeys.as<uint64_t>(),
-                                                        ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(),
-                                                        ix.pos_off.as<uint64_t>(), ix.pos.as<uint32_t>());
-  set_csr_tails<<<1, 1, 0, s>>>(ix.run_off.as<uint64_t>(), U, R, ix.pos_off.as<uint64_t>(), n_valid);
+  PA_TRY(ix.run_genome.alloc((R + 1) * 4));
+  if (vals_are_genomes) { PA_TRY(ix.pos_off.alloc(8)); PA_TRY(ix.pos.alloc(4)); }
+  else { PA_TRY(ix.pos_off.alloc((R + 1) * 8)); PA_TRY(ix.pos.alloc((n_valid + 1) * 4)); }
+  if (n_valid) {
+    if (vals_are_genomes)
+      rle_scatter<true><<<(unsigned)tiles, RLE_THREADS, 0, s>>>(d_keys, d_vals, ix.genome_off.as<uint64_t>(), G, n_valid,
+                                                                tile_keys.as<uint64_t>(), tile_runs.as<uint64_t>(), ix.ukeys.as<uint64_t>(),
+                                                                ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(),
+                                                                ix.pos_off.as<uint64_t>(), ix.pos.as<uint32_t>());
+    else
+      rle_scatter<false><<<(unsigned)tiles, RLE_THREADS, 0, s>>>(d_keys, d_vals, ix.genome_off.as<uint64_t>(), G, n_valid,
+                                                                 tile_keys.as<uint64_t>(), tile_runs.as<uint64_t>(), ix.ukeys.as<uint64_t>(),
+                                                                 ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(),
+                                                                 ix.pos_off.as<uint64_t>(), ix.pos.as<uint32_t>());
+  }
+  set_csr_tails<<<1, 1, 0, s>>>(ix.run_off.as<uint64_t>(), U, R, vals_are_genomes ? nullptr : ix.pos_off.as<uint64_t>(), n_valid);
   PA_CUDA(cudaGetLastError());
   PA_CUDA(cudaStreamSynchronize(s));
   ix.n_keys = U; ix.n_runs = R; ix.n_occ = n_valid;
+  return ST_OK;
+}
+
+int32_t encode_slice(const uint8_t* d_bases, uint64_t total, uint64_t pos0, const uint64_t* d_genome_off, uint32_t G, int k,
+                     uint64_t* d_keys, uint32_t* d_vals, const EncodeOpts& opt, unsigned long long* d_counters, cudaStream_t s) {
+  if (k <= 0 || total == 0 || G == 0 || opt.emit_total == 0) return ST_OK;
+  encode_windows<<<grid_for(std::min(total, opt.emit_total), ENC_TILE), ENC_THREADS, 0, s>>>(
+      d_bases, total, pos0, d_genome_off, G, k, mix_params_for_k(k), d_keys, d_vals, d_counters,
+      reinterpret_cast<unsigned int*>(d_counters + 1), opt);
+  PA_CUDA(cudaGetLastError());
   return ST_OK;
 }
 
@@ -947,10 +763,8 @@ int32_t index_build_from_device_bases(Index& ix, const uint8_t* d_bases) {
   PA_TRY(counters.alloc(16));
   PA_CUDA(cudaMemsetAsync(counters.p, 0, 16, s));
   PA_CUDA(cudaEventRecord(ev[0], s));
-  encode_windows<<<grid_for(total, ENC_TILE), ENC_THREADS, 0, s>>>(
-      d_bases, total, 0, ix.genome_off.as<uint64_t>(), G, k, ix.mix, keys_a.as<uint64_t>(), vals_a.as<uint32_t>(),
-      counters.as<unsigned long long>(), reinterpret_cast<unsigned int*>(counters.as<char>() + 8));
-  PA_CUDA(cudaGetLastError());
+  PA_TRY(encode_slice(d_bases, total, 0, ix.genome_off.as<uint64_t>(), G, k, keys_a.as<uint64_t>(), vals_a.as<uint32_t>(),
+                      EncodeOpts{total, nullptr, 1, 1, 0, 0}, counters.as<unsigned long long>(), s));
   PA_CUDA(cudaEventRecord(ev[1], s));
   unsigned long long h_cnt[2] = {0, 0};
   PA_CUDA(cudaMemcpyAsync(h_cnt, counters.p, 16, cudaMemcpyDeviceToHost, s));
@@ -967,7 +781,7 @@ int32_t index_build_from_device_bases(Index& ix, const uint8_t* d_bases) {
   keys_b.release(); vals_b.release(); sort_tmp.release();
 
   // ---- K3 ----
-  PA_TRY(rle_to_csr(ix, keys_a.as<uint64_t>(), vals_a.as<uint32_t>(), n_valid));
+  PA_TRY(rle_to_csr(ix, keys_a.as<uint64_t>(), vals_a.as<uint32_t>(), n_valid, false));
   PA_CUDA(cudaEventRecord(ev[3], s));
   keys_a.release(); vals_a.release();
 
@@ -1008,6 +822,25 @@ int32_t index_export_order(Index& ix, uint32_t* h_order) {
   PA_TRY(radix_sort_pairs(ka.as<uint64_t>(), va.as<uint32_t>(), kb.as<uint64_t>(), vb.as<uint32_t>(), U, 64, tmp.p,
                           tmp.bytes, s, &in_b));
   PA_CUDA(cudaMemcpyAsync(h_order, in_b ? vb.p : va.p, U * 4, cudaMemcpyDeviceToHost, s));
+  PA_CUDA(cudaStreamSynchronize(s));
+  return ST_OK;
+}
+
+int32_t index_checksum(Index& ix, uint64_t h_out[4]) {
+  cudaStream_t s = ix.stream;
+  DevBuf d;
+  PA_TRY(d.alloc(32));
+  PA_CUDA(cudaMemsetAsync(d.p, 0, 32, s));
+  if (ix.n_keys) {
+    int dev = 0, sms = 148;
+    PA_CUDA(cudaGetDevice(&dev));
+    PA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const unsigned grid = (unsigned)std::min<uint64_t>(grid_for(ix.n_keys, 256), (uint64_t)sms * 16);
+    csr_checksum_kernel<<<grid, 256, 0, s>>>(ix.ukeys.as<uint64_t>(), ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(),
+                                             ix.pos_off.as<uint64_t>(), ix.pos.as<uint32_t>(), ix.n_keys, 1, d.as<unsigned long long>());
+    PA_CUDA(cudaGetLastError());
+  }
+  PA_CUDA(cudaMemcpyAsync(h_out, d.p, 32, cudaMemcpyDeviceToHost, s));
   PA_CUDA(cudaStreamSynchronize(s));
   return ST_OK;
 }
@@ -1196,89 +1029,8 @@ int32_t index_drop_genomes(Index& ix, const uint8_t* h_keep) {
   PA_CUDA(cudaMemcpyAsync(ix.genome_off.p, new_off.data(), new_off.size() * 8, cudaMemcpyHostToDevice, s));
   PA_CUDA(cudaStreamSynchronize(s));
   ix.align_scratch.release(); ix.align_scratch_warps = 0;
-  return index_build_tables(ix);
+  return ix.no_tables ? ST_OK : index_build_tables(ix);
 }
 
-
-// ===========================================================================
-// Multi-GPU build: every rank encodes a run of whole genomes (K1), splits its records by key
-// range (one stable counting pass on the top digit of the hashed key -- the hash is a bijective mix, so the ranges
-// carry equal load), the ranks exchange the parts (all-to-all over NVLink, done by the caller with
-// torch.distributed / NCCL), and every rank sorts and run-length encodes the key range it owns (K2, K3).
-// Records of equal keys arrive ordered by sender, i.e. by genome, and inside a sender by position, so the stable
-// sort reproduces the (genome, position) order of kmer.py:141-150.
-// ===========================================================================
-int32_t records_encode_device(const uint8_t* d_bases, uint64_t n_bases, uint64_t pos0, const uint64_t* d_genome_off,
-                              uint32_t G, int k, uint64_t* d_keys, uint32_t* d_vals, uint64_t* h_n_valid, cudaStream_t s) {
-  *h_n_valid = 0;
-  if (k <= 0 || n_bases == 0 || G == 0) return ST_OK;
-  DevBuf counters;
-  PA_TRY(counters.alloc(16));
-  PA_CUDA(cudaMemsetAsync(counters.p, 0, 16, s));
-  encode_windows<<<grid_for(n_bases, ENC_TILE), ENC_THREADS, 0, s>>>(
-      d_bases, n_bases, pos0, d_genome_off, G, k, mix_params_for_k(k), d_keys, d_vals, counters.as<unsigned long long>(),
-      reinterpret_cast<unsigned int*>(counters.as<char>() + 8));
-  PA_CUDA(cudaGetLastError());
-  unsigned long long h_cnt[2] = {0, 0};
-  PA_CUDA(cudaMemcpyAsync(h_cnt, counters.p, 16, cudaMemcpyDeviceToHost, s));
-  PA_CUDA(cudaStreamSynchronize(s));
-  if (h_cnt[1] & 0xFFFFFFFFull) { set_error("genome sequence contains a character outside ACGTN"); return ST_BAD_BASE; }
-  *h_n_valid = h_cnt[0];
-  return ST_OK;
-}
-
-// digit of the partition pass: key bits [begin, begin + 8) with begin = max(0, 2k - 7); real keys give digits below
-// 2^(2k - begin) <= 128, the all-ones sentinel of an invalid window gives 255
-void partition_geometry(int k, int* begin_bit, int* top_bits) {
-  *begin_bit = std::max(0, 2 * k - 7);
-  *top_bits = 2 * k - *begin_bit;
-}
-uint32_t partition_of_digit(uint32_t digit, int top_bits, uint32_t n_parts) { return (uint32_t)(((uint64_t)digit * n_parts) >> top_bits); }
-
-int32_t records_partition_device(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint64_t n, int k,
-                                 uint32_t n_parts, uint64_t* h_part_off /*[n_parts + 1]*/, int* in_b, cudaStream_t s) {
-  *in_b = 0;
-  for (uint32_t r = 0; r <= n_parts; ++r) h_part_off[r] = 0;
-  if (n == 0 || k <= 0) return ST_OK;
-  int begin = 0, tb = 0;
-  partition_geometry(k, &begin, &tb);
-  if (n_parts == 0 || n_parts > (1u << tb)) { set_error("partition: %u parts do not fit the %d-bit key space split", n_parts, tb); return ST_INVALID_ARG; }
-  DevBuf tmp;
-  PA_TRY(tmp.alloc(radix_sort_temp_bytes(n)));
-  PA_TRY(radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, n, begin + 8, tmp.p, tmp.bytes, s, in_b, begin));
-  // the scanned digit histogram of the pass (first 256 words of the scratch) = start of every digit's run
-  unsigned long long starts[256];
-  PA_CUDA(cudaMemcpyAsync(starts, tmp.p, sizeof(starts), cudaMemcpyDeviceToHost, s));
-  PA_CUDA(cudaStreamSynchronize(s));
-  const uint32_t n_digits = 1u << tb;
-  uint32_t d = 0;
-  for (uint32_t r = 0; r < n_parts; ++r) {
-    while (d < n_digits && partition_of_digit(d, tb, n_parts) < r) ++d;
-    h_part_off[r] = starts[d];
-  }
-  h_part_off[n_parts] = starts[n_digits];   // digits 2^tb .. 254 are empty, 255 holds the sentinels
-  return ST_OK;
-}
-
-int32_t index_build_from_records(Index& ix, uint64_t* d_keys, uint32_t* d_vals, uint64_t n, bool build_tables) {
-  cudaStream_t s = ix.stream;
-  const int k = ix.k;
-  ix.n_keys = ix.n_runs = ix.n_occ = 0;
-  if (k <= 0 || n == 0) {
-    PA_TRY(ix.ukeys.alloc(8)); PA_TRY(ix.run_off.alloc(8)); PA_TRY(ix.run_genome.alloc(4));
-    PA_TRY(ix.pos_off.alloc(8)); PA_TRY(ix.pos.alloc(4));
-    PA_CUDA(cudaMemsetAsync(ix.run_off.p, 0, 8, s)); PA_CUDA(cudaMemsetAsync(ix.pos_off.p, 0, 8, s));
-    return build_tables ? index_build_tables(ix) : ST_OK;
-  }
-  DevBuf keys_b, vals_b, sort_tmp;
-  PA_TRY(keys_b.alloc(n * 8)); PA_TRY(vals_b.alloc(n * 4));
-  PA_TRY(sort_tmp.alloc(radix_sort_temp_bytes(n)));
-  int in_b = 0;
-  PA_TRY(radix_sort_pairs(d_keys, d_vals, keys_b.as<uint64_t>(), vals_b.as<uint32_t>(), n, std::min(64, 2 * k), sort_tmp.p,
-                          sort_tmp.bytes, s, &in_b));
-  PA_TRY(rle_to_csr(ix, in_b ? keys_b.as<uint64_t>() : d_keys, in_b ? vals_b.as<uint32_t>() : d_vals, n));
-  keys_b.release(); vals_b.release(); sort_tmp.release();
-  return build_tables ? index_build_tables(ix) : ST_OK;
-}
 
 }  // namespace pa

@@ -5,6 +5,7 @@
 #include "hostpack.h"
 #include "index.cuh"
 #include "sort.cuh"
+#include "table.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -254,7 +255,9 @@ int32_t pa_index_info_get(pa_index* idx, pa_index_info* info) {
   Index& ix = *IDX(idx);
   memset(info, 0, sizeof(*info));
   info->k = ix.k; info->device = ix.device; info->n_genomes = ix.n_genomes;
-  info->block_bits = ix.block_bits; info->minimizer_len = ix.min_len; info->tag_bits = ix.tag_bits; info->stash_count = ix.stash_count;
+  info->blocks_per_digit = ix.bpd; info->digit_bits = digit_bits_for_k(ix.k); info->n_blocks = ix.n_blocks();
+  info->table_bytes = ix.slots.bytes + ix.stash.bytes + ix.mlist.bytes; info->align_only = ix.align_only ? 1 : 0;
+  info->minimizer_len = ix.min_len; info->tag_bits = ix.tag_bits; info->stash_count = ix.stash_count;
   info->n_keys = ix.n_keys; info->n_runs = ix.n_runs; info->n_occ = ix.n_occ; info->total_bases = ix.total_bases;
   info->n_list_sectors = ix.n_msectors; info->device_bytes = ix.device_bytes();
   info->build_encode_ms = ix.t_encode_ms; info->build_sort_ms = ix.t_sort_ms;
@@ -266,7 +269,7 @@ int32_t pa_index_export(pa_index* idx, uint64_t* keys, uint64_t* run_off, uint32
                         uint32_t* pos, uint32_t* order, uint64_t* first_occ) {
   NEED(idx, "null index");
   Index& ix = *IDX(idx);
-  NEED(!ix.align_only || (!pos_off && !pos && !order && !first_occ), "a replica index holds no positions (export the partitions instead)");
+  NEED(!ix.align_only, "a table-only index holds no CSR (export the partitions instead)");
   PA_CUDA(cudaSetDevice(ix.device));
   cudaStream_t s = ix.stream;
   if (keys && ix.n_keys) PA_CUDA(cudaMemcpyAsync(keys, ix.ukeys.p, ix.n_keys * 8, cudaMemcpyDeviceToHost, s));
@@ -283,6 +286,13 @@ int32_t pa_index_export(pa_index* idx, uint64_t* keys, uint64_t* run_off, uint32
     PA_CUDA(cudaStreamSynchronize(s));
   }
   return PA_OK;
+}
+
+int32_t pa_index_checksum(pa_index* idx, uint64_t sums[4]) {
+  NEED(idx && sums, "null argument");
+  NEED(!IDX(idx)->align_only, "a table-only index holds no CSR");
+  PA_CUDA(cudaSetDevice(IDX(idx)->device));
+  return index_checksum(*IDX(idx), sums);
 }
 
 int32_t pa_decode_kmers(int32_t k, const uint64_t* keys, uint64_t n, uint8_t* ascii) {
@@ -314,14 +324,63 @@ int32_t pa_encode_kmers(int32_t k, const uint8_t* ascii, uint64_t n, uint64_t* k
 int32_t pa_index_lookup(pa_index* idx, const uint8_t* kmers_ascii, uint64_t n, uint64_t* rank) {
   NEED(idx, "null index");
   NEED(n == 0 || (kmers_ascii && rank), "null argument");
+  NEED(!IDX(idx)->align_only, "a table-only index holds no CSR (look the k-mer up in the partitions instead)");
   PA_CUDA(cudaSetDevice(IDX(idx)->device));
   return index_lookup_ranks(*IDX(idx), kmers_ascii, n, rank);
+}
+
+int32_t pa_index_entries(pa_index* idx, const uint64_t* ranks, uint64_t n, uint64_t* run_off, uint32_t* run_genome,
+                         uint64_t run_cap, uint64_t* pos_off, uint32_t* pos, uint64_t pos_cap, uint64_t* run_total,
+                         uint64_t* pos_total) {
+  NEED(idx && run_total && pos_total, "null argument");
+  NEED(n == 0 || (ranks && run_off), "null argument");
+  Index& ix = *IDX(idx);
+  NEED(!ix.align_only, "a table-only index holds no CSR (fetch the entries from the partitions instead)");
+  PA_CUDA(cudaSetDevice(ix.device));
+  cudaStream_t s = ix.stream;
+  // a handful of k-mers at a time (one read's windows at most): plain small copies, no kernel
+  std::vector<uint64_t> r01(2 * n), p_lo(n, 0);
+  uint64_t runs = 0, npos = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    NEED(ranks[i] < ix.n_keys, "rank out of range");
+    PA_CUDA(cudaMemcpyAsync(&r01[2 * i], ix.run_off.as<uint64_t>() + ranks[i], 16, cudaMemcpyDeviceToHost, s));
+  }
+  PA_CUDA(cudaStreamSynchronize(s));
+  std::vector<std::vector<uint64_t>> poffs(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint64_t c = r01[2 * i + 1] - r01[2 * i];
+    poffs[i].resize(c + 1);
+    PA_CUDA(cudaMemcpyAsync(poffs[i].data(), ix.pos_off.as<uint64_t>() + r01[2 * i], (c + 1) * 8, cudaMemcpyDeviceToHost, s));
+    run_off[i] = runs;
+    runs += c;
+  }
+  if (n) run_off[n] = runs;
+  PA_CUDA(cudaStreamSynchronize(s));
+  for (uint64_t i = 0; i < n; ++i) npos += poffs[i].back() - poffs[i].front();
+  *run_total = runs; *pos_total = npos;
+  if (runs > run_cap || npos > pos_cap || !run_genome || !pos_off || !pos) {
+    if (runs == 0 && npos == 0) return PA_OK;
+    set_error("entries: %llu runs / %llu positions needed", (unsigned long long)runs, (unsigned long long)npos);
+    return PA_ERR_CAPACITY;
+  }
+  uint64_t at_r = 0, at_p = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint64_t c = r01[2 * i + 1] - r01[2 * i], np_i = poffs[i].back() - poffs[i].front();
+    if (c) PA_CUDA(cudaMemcpyAsync(run_genome + at_r, ix.run_genome.as<uint32_t>() + r01[2 * i], c * 4, cudaMemcpyDeviceToHost, s));
+    if (np_i) PA_CUDA(cudaMemcpyAsync(pos + at_p, ix.pos.as<uint32_t>() + poffs[i].front(), np_i * 4, cudaMemcpyDeviceToHost, s));
+    for (uint64_t j = 0; j < c; ++j) pos_off[at_r + j] = at_p + (poffs[i][j] - poffs[i].front());
+    at_r += c; at_p += np_i;
+  }
+  pos_off[at_r] = at_p;
+  PA_CUDA(cudaStreamSynchronize(s));
+  return PA_OK;
 }
 
 int32_t pa_extsim_stats(pa_index* idx, const uint32_t* group, uint32_t n_groups, uint64_t* total, uint64_t* unique) {
   NEED(idx, "null index");
   NEED(IDX(idx)->n_genomes == 0 || group, "null group map");
   NEED(n_groups == 0 || (total && unique), "null output");
+  NEED(!IDX(idx)->align_only, "a table-only index holds no CSR (EXTSIM runs on the partitions)");
   PA_CUDA(cudaSetDevice(IDX(idx)->device));
   return index_extsim_stats(*IDX(idx), group, n_groups, total, unique);
 }
@@ -330,6 +389,7 @@ int32_t pa_extsim_pairwise(pa_index* idx, const uint32_t* group, uint32_t n_grou
   NEED(idx, "null index");
   NEED(IDX(idx)->n_genomes == 0 || group, "null group map");
   NEED(n_groups == 0 || inter, "null output");
+  NEED(!IDX(idx)->align_only, "a table-only index holds no CSR (EXTSIM runs on the partitions)");
   PA_CUDA(cudaSetDevice(IDX(idx)->device));
   return index_extsim_pairwise(*IDX(idx), group, n_groups, inter);
 }
@@ -337,194 +397,12 @@ int32_t pa_extsim_pairwise(pa_index* idx, const uint32_t* group, uint32_t n_grou
 int32_t pa_index_drop_genomes(pa_index* idx, const uint8_t* keep) {
   NEED(idx, "null index");
   NEED(IDX(idx)->n_genomes == 0 || keep, "null keep mask");
-  NEED(!IDX(idx)->align_only, "a replica index holds no positions (drop the genomes from the partitions and re-gather)");
+  NEED(!IDX(idx)->align_only, "a table-only index holds no CSR (drop the genomes from the partitions, then pa_index_rebuild_replica)");
   PA_CUDA(cudaSetDevice(IDX(idx)->device));
   AllocScope pool(IDX(idx)->stream);
   return index_drop_genomes(*IDX(idx), keep);
 }
 
-
-/* ---- multi-GPU build phases; orchestrated by multi_gpu.py over torch.distributed ---- */
-int32_t pa_records_encode_device(const uint8_t* d_bases, const uint64_t* genome_off, uint32_t n_genomes, uint32_t g_lo,
-                                 uint32_t g_hi, int32_t k, int32_t device, uint64_t* d_keys, uint32_t* d_vals,
-                                 uint64_t* n_valid, void* stream) {
-  NEED(n_valid, "null argument");
-  *n_valid = 0;
-  NEED(g_lo <= g_hi && g_hi <= n_genomes, "genome range out of bounds");
-  NEED(n_genomes == 0 || genome_off, "genome_off is null");
-  if (k > 31) { set_error("k = %d is outside the built scope (k <= 31: one k-mer per 64-bit word)", k); return PA_ERR_UNSUPPORTED; }
-  if (g_lo == g_hi) return PA_OK;
-  PA_CUDA(cudaSetDevice(device));
-  std::vector<uint64_t> off(n_genomes + 1);
-  for (uint32_t g = 0; g <= n_genomes; ++g) {
-    NEED(g == 0 || genome_off[g] >= genome_off[g - 1], "genome_off is not monotonic");
-    off[g] = genome_off[g] - genome_off[0];
-  }
-  if (off[n_genomes] >= 0xFFFFFFFFull) { set_error("index build: %llu bases exceed the 32-bit position space of this build", (unsigned long long)off[n_genomes]); return PA_ERR_UNSUPPORTED; }
-  const uint64_t n_bases = off[g_hi] - off[g_lo];
-  if (n_bases == 0) return PA_OK;
-  NEED(d_bases && d_keys && d_vals, "null device buffer");
-  NEED((reinterpret_cast<uintptr_t>(d_bases) & 15) == 0, "device bases must be 16-byte aligned");
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  DevBuf d_off;
-  PA_TRY(d_off.alloc(off.size() * 8));
-  PA_CUDA(cudaMemcpyAsync(d_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, s));
-  return records_encode_device(d_bases, n_bases, off[g_lo], d_off.as<uint64_t>(), n_genomes, k, d_keys, d_vals, n_valid, s);
-}
-
-int32_t pa_records_partition_device(uint64_t* d_keys, uint32_t* d_vals, uint64_t* d_keys_tmp, uint32_t* d_vals_tmp, uint64_t n,
-                                    int32_t k, uint32_t n_parts, int32_t device, uint64_t* part_off, int32_t* result_in_tmp,
-                                    void* stream) {
-  NEED(part_off && result_in_tmp && n_parts >= 1, "bad argument");
-  NEED(n == 0 || (d_keys && d_vals && d_keys_tmp && d_vals_tmp), "null device buffer");
-  PA_CUDA(cudaSetDevice(device));
-  int in_b = 0;
-  int32_t st = records_partition_device(d_keys, d_vals, d_keys_tmp, d_vals_tmp, n, k, n_parts, part_off, &in_b,
-                                        reinterpret_cast<cudaStream_t>(stream));
-  *result_in_tmp = in_b;
-  return st;
-}
-
-int32_t pa_partition_of_key(int32_t k, uint64_t hashed_key, uint32_t n_parts, uint32_t* part) {
-  NEED(part && k >= 1 && k <= 31 && n_parts >= 1, "bad argument");
-  int begin = 0, tb = 0;
-  partition_geometry(k, &begin, &tb);
-  NEED(n_parts <= (1u << tb), "too many parts for this k");
-  *part = partition_of_digit((uint32_t)((hashed_key >> begin) & 0xFF), tb, n_parts);
-  return PA_OK;
-}
-
-int32_t pa_index_build_from_records_device(uint64_t* d_keys, uint32_t* d_vals, uint64_t n, const uint64_t* genome_off,
-                                           uint32_t n_genomes, int32_t k, int32_t device, int32_t build_tables, pa_index** out) {
-  Index* ix = nullptr;
-  PA_TRY(new_index(k, n_genomes, genome_off, device, &ix));
-  if (n && (!d_keys || !d_vals)) { delete ix; set_error("null device buffer"); return PA_ERR_INVALID_ARG; }
-  if (ix->total_bases >= 0xFFFFFFFFull) { delete ix; set_error("index build: too many bases for 32-bit positions"); return PA_ERR_UNSUPPORTED; }
-  int32_t st;
-  { AllocScope pool(ix->stream); st = index_build_from_records(*ix, d_keys, d_vals, n, build_tables != 0); }
-  if (st != ST_OK) { delete ix; return st; }
-  *out = reinterpret_cast<pa_index*>(ix);
-  return PA_OK;
-}
-
-int32_t pa_index_csr_device(pa_index* idx, uint64_t** d_keys, uint64_t** d_run_off, uint32_t** d_run_genome) {
-  NEED(idx, "null index");
-  Index& ix = *IDX(idx);
-  if (d_keys) *d_keys = ix.ukeys.as<uint64_t>();
-  if (d_run_off) *d_run_off = ix.run_off.as<uint64_t>();
-  if (d_run_genome) *d_run_genome = ix.run_genome.as<uint32_t>();
-  return PA_OK;
-}
-
-int32_t pa_index_alloc_replica(int32_t k, uint32_t n_genomes, const uint64_t* genome_off, uint64_t n_keys, uint64_t n_runs,
-                               uint64_t n_occ, int32_t device, pa_index** out) {
-  Index* ix = nullptr;
-  PA_TRY(new_index(k, n_genomes, genome_off, device, &ix));
-  if (n_keys >= 0xFFFFFFFFull) { delete ix; set_error("too many distinct k-mers"); return PA_ERR_UNSUPPORTED; }
-  int32_t st;
-  if ((st = ix->ukeys.alloc((n_keys + 1) * 8)) || (st = ix->run_off.alloc((n_keys + 1) * 8)) ||
-      (st = ix->run_genome.alloc((n_runs + 1) * 4)) || (st = ix->pos_off.alloc(8)) || (st = ix->pos.alloc(4))) { delete ix; return st; }
-  ix->n_keys = n_keys; ix->n_runs = n_runs; ix->n_occ = n_occ;
-  ix->align_only = true;
-  *out = reinterpret_cast<pa_index*>(ix);
-  return PA_OK;
-}
-
-int32_t pa_index_finish_replica(pa_index* idx) {
-  NEED(idx, "null index");
-  Index& ix = *IDX(idx);
-  NEED(ix.align_only, "not a replica index");
-  PA_CUDA(cudaSetDevice(ix.device));
-  PA_CUDA(cudaDeviceSynchronize());   // the caller filled the arrays on its own streams
-  const uint64_t tail = ix.n_runs;
-  PA_CUDA(cudaMemcpyAsync(ix.run_off.as<uint64_t>() + ix.n_keys, &tail, 8, cudaMemcpyHostToDevice, ix.stream));
-  PA_CUDA(cudaStreamSynchronize(ix.stream));
-  AllocScope pool(ix.stream);
-  return index_build_tables(ix);
-}
-
-/* (re)build the lookup structures of an index from its CSR -- a partition built with build_tables = 0 */
-int32_t pa_index_build_tables(pa_index* idx) {
-  NEED(idx, "null index");
-  PA_CUDA(cudaSetDevice(IDX(idx)->device));
-  AllocScope pool(IDX(idx)->stream);
-  return index_build_tables(*IDX(idx));
-}
-
-/* ---- fused partition + exchange: the scatter pass of the multi-GPU build stores straight into peer memory ---- */
-int32_t pa_peer_alloc(uint64_t bytes, int32_t device, void** d_ptr, uint8_t* handle /*[64]*/) {
-  NEED(d_ptr && handle, "null argument");
-  PA_CUDA(cudaSetDevice(device));
-  void* p = nullptr;
-  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
-  if (e != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMalloc(%llu bytes) failed: %s", (unsigned long long)bytes, cudaGetErrorString(e)); return PA_ERR_NOMEM; }
-  cudaIpcMemHandle_t h;
-  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  e = cudaIpcGetMemHandle(&h, p);
-  if (e != cudaSuccess) { (void)cudaGetLastError(); cudaFree(p); set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); return PA_ERR_CUDA; }
-  memcpy(handle, &h, 64);
-  *d_ptr = p;
-  return PA_OK;
-}
-
-int32_t pa_peer_open(const uint8_t* handle /*[64]*/, int32_t device, void** d_ptr) {
-  NEED(d_ptr && handle, "null argument");
-  PA_CUDA(cudaSetDevice(device));
-  cudaIpcMemHandle_t h;
-  memcpy(&h, handle, 64);
-  cudaError_t e = cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess);
-  if (e != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e)); return PA_ERR_CUDA; }
-  return PA_OK;
-}
-
-int32_t pa_peer_close(void* d_ptr, int32_t device) {
-  if (!d_ptr) return PA_OK;
-  PA_CUDA(cudaSetDevice(device));
-  PA_CUDA(cudaIpcCloseMemHandle(d_ptr));
-  return PA_OK;
-}
-
-int32_t pa_peer_free(void* d_ptr, int32_t device) {
-  if (!d_ptr) return PA_OK;
-  PA_CUDA(cudaSetDevice(device));
-  PA_CUDA(cudaFree(d_ptr));
-  return PA_OK;
-}
-
-int32_t pa_records_digit_counts(const uint64_t* d_keys, uint64_t n, int32_t k, int32_t device, uint64_t* counts /*[256]*/,
-                                int32_t* begin_bit, int32_t* top_bits, void* stream) {
-  NEED(counts && begin_bit && top_bits, "null argument");
-  NEED(k >= 1 && k <= 31, "k out of range");
-  PA_CUDA(cudaSetDevice(device));
-  partition_geometry(k, begin_bit, top_bits);
-  DevBuf tmp;
-  PA_TRY(tmp.alloc(256 * 8));
-  unsigned long long h[256];
-  PA_TRY(radix_digit_counts(d_keys, n, *begin_bit, h, tmp.p, tmp.bytes, reinterpret_cast<cudaStream_t>(stream)));
-  for (int i = 0; i < 256; ++i) counts[i] = h[i];
-  return PA_OK;
-}
-
-int32_t pa_records_scatter_to_peers(const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n, int32_t k, int32_t device,
-                                    uint64_t* const* dst_keys /*[256]*/, uint32_t* const* dst_vals /*[256]*/, void* stream) {
-  NEED(dst_keys && dst_vals, "null argument");
-  NEED(k >= 1 && k <= 31, "k out of range");
-  NEED(n == 0 || (d_keys && d_vals), "null device buffer");
-  if (n == 0) return PA_OK;
-  PA_CUDA(cudaSetDevice(device));
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  int begin = 0, tb = 0;
-  partition_geometry(k, &begin, &tb);
-  PeerRoute h_route[256];
-  for (int d = 0; d < 256; ++d) { h_route[d].keys = dst_keys[d]; h_route[d].vals = dst_vals[d]; }
-  DevBuf d_route, tmp;
-  PA_TRY(d_route.alloc(sizeof(h_route)));
-  PA_TRY(tmp.alloc(radix_sort_temp_bytes(n)));
-  PA_CUDA(cudaMemcpyAsync(d_route.p, h_route, sizeof(h_route), cudaMemcpyHostToDevice, s));
-  PA_TRY(radix_scatter_routed(d_keys, d_vals, n, begin, d_route.as<PeerRoute>(), tmp.p, tmp.bytes, s));
-  PA_CUDA(cudaStreamSynchronize(s));   // the stores into peer memory are complete and visible when this returns
-  return PA_OK;
-}
 
 int32_t pa_align_batch_device(pa_index* idx, const uint8_t* d_bases, const uint8_t* d_quals, const uint64_t* d_read_off,
                               uint64_t n_reads, uint64_t max_read_len, const pa_align_params* params,
@@ -534,6 +412,7 @@ int32_t pa_align_batch_device(pa_index* idx, const uint8_t* d_bases, const uint8
   NEED(n_reads == 0 || (d_bases && d_read_off && d_words && d_state), "null device buffer");
   NEED(params->m >= 0, "m must be bigger than or equal to 0");
   Index& ix = *IDX(idx);
+  NEED(!ix.no_tables, "a partition holds no lookup table: align against the replica");
   PA_CUDA(cudaSetDevice(ix.device));
   AlignParams prm = clamp_params(params);
   cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : ix.stream;
@@ -556,6 +435,7 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
   if (n_reads == 0) return PA_OK;
   NEED(bases && read_off && out_words && counters, "null host buffer");
   Index& ix = *IDX(idx);
+  NEED(!ix.no_tables, "a partition holds no lookup table: align against the replica");
   PA_CUDA(cudaSetDevice(ix.device));
   const bool need_q = params->has_min_read_quality || params->has_min_kmer_quality;
   NEED(!need_q || quals, "quality filters requested without quality data");
@@ -690,6 +570,7 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
   uint64_t h_state[5];
   PA_CUDA(cudaMemcpy(h_state, ix.host_state.p, 40, cudaMemcpyDeviceToHost));
   if (list_len) *list_len = h_state[0];
+  if (h_state[1] == 2) { set_error("align: a read is longer than the length the batch was sized for"); return PA_ERR_INVALID_ARG; }
   if (h_state[0] > list_cap) {
     set_error("out_list too small: %llu entries needed", (unsigned long long)h_state[0]);
     return PA_ERR_CAPACITY;
@@ -796,6 +677,7 @@ int32_t pa_debug_table_lookup(pa_index* idx, const uint8_t* kmers_ascii, uint64_
   NEED(n == 0 || (kmers_ascii && n_genomes && first_genome), "null argument");
   if (n == 0) return PA_OK;
   Index& ix = *IDX(idx);
+  NEED(!ix.no_tables, "a partition holds no lookup table: query the replica");
   PA_CUDA(cudaSetDevice(ix.device));
   if (ix.k < 1 || ix.n_keys == 0) { for (uint64_t i = 0; i < n; ++i) { n_genomes[i] = 0; first_genome[i] = 0xFFFFFFFFu; } return PA_OK; }
   std::vector<uint64_t> q(n);

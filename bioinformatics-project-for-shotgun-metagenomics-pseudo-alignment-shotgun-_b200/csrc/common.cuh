@@ -99,11 +99,15 @@ __host__ __device__ __forceinline__ uint64_t mix_key(uint64_t x, const MixParams
 //   minimizer of a k-mer = its m-mer (m = min(k, 16), w = k-m+1 <= 16 candidates) with the smallest bijective
 //   2m-bit hash, leftmost on ties; consecutive windows share their minimizer (8.5 windows on average at w = 16,
 //   27 % of the groups have all 16), and inside a group the minimizer offset p takes consecutive values.
-//   block  = low block_bits of the minimizer hash    (one block = 16 buckets = 512 bytes = 4 lines)
-//   bucket = (p + hash >> block_bits) & 15           (one bucket = one 32-byte sector = 4 slots of 8 bytes)
+//   digit  = top digit_bits (<= 8) of the minimizer hash: the unit of ownership of a multi-GPU build (rank r owns a
+//            contiguous range of digits, i.e. a contiguous slice of the table) and the range a chain stays inside
+//   block  = (hash * blocks_per_digit) >> (2m - digit_bits)   -- any number of blocks per digit, so the load factor
+//            is what was asked for and not a power of two away from it (one block = 16 buckets = 512 bytes = 4 lines)
+//   bucket = (p + hash) & 15                        (one bucket = one 32-byte sector = 4 slots of 8 bytes)
 //            -- a group of consecutive windows reads consecutive sectors: 32 windows touch ~12 lines instead of 32
-//   tag    = [k-mer without the minimizer's bases : 2(k-m)] [chain distance d : 2] [hash >> block_bits]
-//            -- block, bucket and tag identify the k-mer exactly (no false positives)
+//   tag    = [k-mer without the minimizer's bases : 2(k-m)] [chain distance d : 2] [low hi_bits of the hash]
+//            -- the hashes that share a block are consecutive integers, fewer than 2^hi_bits of them, so block,
+//            bucket and tag identify the k-mer exactly (no false positives)
 //   word   = tag | CONT | kind (2 bits) | payload
 //     KIND_SPECIFIC  k-mer of exactly one genome, payload = genome id
 //     KIND_INLINE    2..n_inline genomes packed in the payload, gbits each, ascending;
@@ -111,10 +115,9 @@ __host__ __device__ __forceinline__ uint64_t mix_key(uint64_t x, const MixParams
 //     KIND_MLIST     longer lists: payload = first 32-byte sector of the (de-duplicated) genome set in mlist
 // The four slots of a bucket absorb the k-mers of other minimizers that hash to the same block and the strain
 // variants that share minimizer and offset; a k-mer whose bucket is full moves to the same bucket of the next
-// block (d = 1..3, then the stash) and sets CONT on the last slot of every bucket it passed.  A lookup reads ONE
-// sector and goes on only when that bucket is full, has no match AND has CONT set (0.4 % of the lookups at the
-// default load factor), so a miss costs one sector too.  The stash holds {raw k-mer key, value} pairs with linear
-// probing.
+// block of its digit (d = 1..3, wrapping inside the digit's blocks, then the stash) and sets CONT on the last slot of
+// every bucket it passed.  A lookup reads ONE sector and goes on only when that bucket is full, has no match AND has
+// CONT set, so a miss costs one sector too.  The stash holds {raw k-mer key, value} pairs with linear probing.
 // ---------------------------------------------------------------------------
 constexpr uint32_t BLOCK_BUCKETS = 16;
 constexpr uint32_t BUCKET_SLOTS = 4;
@@ -130,8 +133,10 @@ struct TableView {
   uint32_t k;
   uint32_t m;          // minimizer length
   uint32_t w;          // minimizer candidates per k-mer = k - m + 1 (1..16)
-  uint32_t block_bits;
-  uint32_t hi_bits;    // 2m - block_bits: bits of the minimizer hash kept in the tag
+  uint32_t bpd;        // blocks per digit (>= 1); the table has bpd << digit_bits blocks
+  uint32_t dshift;     // 2m - digit_bits: hash bits below the digit
+  uint32_t hi_bits;    // low bits of the minimizer hash kept in the tag: 2^hi_bits >= hashes per block
+  uint32_t hmask;      // 2^hi_bits - 1
   uint32_t tag_bits;   // 2(k-m) + CHAIN_BITS + hi_bits
   uint32_t val_bits;   // 64 - tag_bits = CONT bit + 2 kind bits + payload
   uint32_t gbits;      // bits per genome id inside an inline list
@@ -145,7 +150,10 @@ struct TableView {
 enum : uint32_t { KIND_MLIST = 0, KIND_INLINE = 2, KIND_SPECIFIC = 3 };
 
 constexpr uint32_t MINIMIZER_MAX = 16;
+constexpr uint32_t DIGIT_BITS_MAX = 8;
 __host__ __device__ __forceinline__ uint32_t minimizer_len_for_k(int k) { return k < 1 ? 1u : (k > (int)MINIMIZER_MAX ? MINIMIZER_MAX : (uint32_t)k); }
+// digit of a minimizer hash = its top digit_bits: ownership unit of the multi-GPU build, range of a chain
+__host__ __device__ __forceinline__ uint32_t digit_bits_for_k(int k) { const uint32_t b = 2 * minimizer_len_for_k(k); return b < DIGIT_BITS_MAX ? b : DIGIT_BITS_MAX; }
 
 // the minimizer fields of a TableView (k, m, w, mmask and the split of the m-mer hash) for a k-mer length
 __host__ __device__ __forceinline__ void minimizer_params(TableView& t, int k) {
@@ -156,12 +164,21 @@ __host__ __device__ __forceinline__ void minimizer_params(TableView& t, int k) {
   t.hdrop = 2 * t.m > 28 ? 2 * t.m - 28 : 0;
   t.ymask = (1u << (2 * t.m - t.hdrop)) - 1;
   t.yshift = (2 * t.m - t.hdrop + 1) / 2;
+  t.dshift = 2 * t.m - digit_bits_for_k(k);
 }
 
-// Hash of an m-mer x (2m <= 32 bits), bijective: the upper 2m - hdrop bits of x go through an invertible xorshift /
-// odd-multiplication mix (`mmer_order`), the low hdrop bits stay raw.  Minimizers are ordered by the mixed part alone: it
-// has at most 28 bits, so the align kernel slides (order << 4 | offset) through one 32-bit shuffle per step and rebuilds the
-// full hash from the winner's offset with a shift and a mask.
+// Two bijective functions of an m-mer x (2m <= 32 bits):
+//   mmer_order  the upper 2m - hdrop bits of x through an invertible xorshift / odd-multiplication mix.  Minimizers are
+//               ordered by it alone: it has at most 28 bits, so the align kernel slides (order << 4 | offset) through one
+//               32-bit shuffle per step.
+//   mmer_hash   addresses the table: [low hdrop bits of x, raw][order * odd constant mod 2^(2m - hdrop)].
+//               The minimizer of a k-mer is the SMALLEST order among its candidates, so the orders of minimizers crowd
+//               near zero and their top bits are nearly constant; the (Fibonacci) multiplication spreads exactly such a
+//               range evenly over its top bits.  The raw bits sit on top, where the table block and the owner rank are
+//               selected: m-mers that differ only in those bits share their order, so a substitution there (strain
+//               variants) keeps the minimizer in place -- with the raw bits below, all variants of a minimizer would
+//               crowd into one block (measured: 48x the stash entries, K4 21 % slower).
+constexpr uint32_t MMER_SPREAD = 0x9E3779B1u;
 __host__ __device__ __forceinline__ uint32_t mmer_order(uint32_t x, const TableView& t) {
   uint32_t y = x >> t.hdrop;
   y ^= y >> t.yshift;
@@ -169,8 +186,12 @@ __host__ __device__ __forceinline__ uint32_t mmer_order(uint32_t x, const TableV
   y ^= y >> t.yshift;
   return y;
 }
+// hash from the order and the raw m-mer bits (the align kernel holds the order of the winning candidate)
+__host__ __device__ __forceinline__ uint32_t hash_from_order(uint32_t order, uint32_t x_low, const TableView& t) {
+  return ((x_low & ((1u << t.hdrop) - 1)) << (2 * t.m - t.hdrop)) | ((order * MMER_SPREAD) & t.ymask);
+}
 __host__ __device__ __forceinline__ uint32_t mmer_hash(uint32_t x, const TableView& t) {
-  return (mmer_order(x, t) << t.hdrop) | (x & ((1u << t.hdrop) - 1));
+  return hash_from_order(mmer_order(x, t), x, t);
 }
 
 struct SlotAddr {
@@ -188,10 +209,9 @@ __host__ __device__ __forceinline__ SlotAddr slot_addr(const TableView& t, uint3
   const uint32_t rl = (lo & below) | ((lo >> t.m) & ~below);   // p + m <= k <= 31
   const uint32_t rh = (hi & below) | ((hi >> t.m) & ~below);
   const uint32_t rest = (rh << km) | rl;             // 2(k-m) <= 30 bits
-  a.block = mhash & (uint32_t)((1ULL << t.block_bits) - 1);
-  const uint64_t mh = (uint64_t)mhash >> t.block_bits;
-  a.tag = ((uint64_t)rest << (CHAIN_BITS + t.hi_bits)) | mh;
-  a.bucket = (p + (uint32_t)mh) & (BLOCK_BUCKETS - 1);
+  a.block = ((uint64_t)mhash * t.bpd) >> t.dshift;
+  a.tag = ((uint64_t)rest << (CHAIN_BITS + t.hi_bits)) | (mhash & t.hmask);
+  a.bucket = (p + mhash) & (BLOCK_BUCKETS - 1);
   return a;
 }
 
@@ -203,7 +223,7 @@ __host__ __device__ __forceinline__ void kmer_minimizer(const TableView& t, uint
     const uint32_t y = mmer_order((((hi >> j) & t.mmask) << t.m) | ((lo >> j) & t.mmask), t);
     if (j == 0 || y < best) { best = y; bp = j; }
   }
-  *mhash = (best << t.hdrop) | ((lo >> bp) & ((1u << t.hdrop) - 1));
+  *mhash = hash_from_order(best, lo >> bp, t);
   *p = bp;
 }
 
@@ -291,11 +311,19 @@ __device__ __forceinline__ uint64_t bucket_resolve_home(const TableView& t, cons
 }
 
 // Continue a lookup past its home bucket: the same bucket of the next blocks, then the stash.
-static __device__ __noinline__ uint64_t lookup_chain(const TableView& t, const SlotAddr& a, uint64_t raw_key) {
-  const uint64_t bmask = (1ULL << t.block_bits) - 1;
+// block at chain distance d (< CHAIN_LEN) of a home block: the next blocks of the same digit, wrapping inside the
+// digit; mhash = the minimizer hash the home block came from (its top bits are the digit: no division here)
+__host__ __device__ __forceinline__ uint64_t chain_block(const TableView& t, uint64_t home, uint32_t d, uint32_t mhash) {
+  const uint64_t first = (uint64_t)(mhash >> t.dshift) * t.bpd;
+  uint64_t local = home - first + d;
+  while (local >= t.bpd) local -= t.bpd;
+  return first + local;
+}
+
+static __device__ __noinline__ uint64_t lookup_chain(const TableView& t, const SlotAddr& a, uint32_t mhash, uint64_t raw_key) {
   for (uint32_t d = 1; d < CHAIN_LEN; ++d) {
     uint64_t s[4];
-    ld_sector_nc(bucket_ptr(t, (a.block + d) & bmask, a.bucket), s);
+    ld_sector_nc(bucket_ptr(t, chain_block(t, a.block, d, mhash), a.bucket), s);
     bool cont;
     uint64_t v = bucket_resolve(t, s, a.tag | ((uint64_t)d << t.hi_bits), &cont);
     if (!cont) return v;
@@ -314,7 +342,7 @@ __device__ __forceinline__ uint64_t table_lookup(const TableView& t, uint64_t ra
   ld_sector_nc(bucket_ptr(t, a.block, a.bucket), s);
   bool cont;
   uint64_t v = bucket_resolve(t, s, a.tag, &cont);
-  return cont ? lookup_chain(t, a, raw_key) : v;
+  return cont ? lookup_chain(t, a, mh, raw_key) : v;
 }
 
 __host__ __device__ __forceinline__ uint32_t value_kind(const TableView& t, uint64_t v) { return (uint32_t)(v >> (t.val_bits - 3)) & 3u; }

@@ -35,6 +35,9 @@ class Pool {
   int size() const { return n_; }
   void parallel_for(int n_tasks, const std::function<void(int)>& fn) {
     if (n_tasks <= 0) return;
+    // one job at a time: the job state below (fn_, next_, total_, pending_) is shared, and ctypes callers run without
+    // the GIL, so two threads (one per GPU, say) may arrive together -- the second waits for the first job to drain
+    std::lock_guard<std::mutex> one_job(job_);
     std::unique_lock<std::mutex> g(m_);
     fn_ = &fn; next_ = 0; total_ = n_tasks; pending_ = n_tasks; ++epoch_;
     cv_.notify_all();
@@ -62,7 +65,7 @@ class Pool {
   }
   int n_;
   std::vector<std::thread> workers_;
-  std::mutex m_;
+  std::mutex m_, job_;
   std::condition_variable cv_, done_;
   const std::function<void(int)>* fn_ = nullptr;
   int next_ = 0, total_ = 0, pending_ = 0;

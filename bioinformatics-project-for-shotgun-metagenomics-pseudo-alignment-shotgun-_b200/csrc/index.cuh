@@ -68,11 +68,13 @@ struct Index {
   // insertion order of kmer.py:146-147 survives genome removal, kmer.py:237-243).  Materialised lazily.
   DevBuf first_occ;
   bool has_first_occ = false;
-  bool align_only = false;   // replica of a multi-GPU build: keys and genome runs only, no positions
+  bool align_only = false;   // table-only index (replica of a partitioned build, streamed build): no CSR at all
+  bool no_tables = false;    // partition of a partitioned build: CSR only, the lookup table lives in the replica
+  float t_dist_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // phases of the partitioned build that produced this replica
   std::vector<uint64_t> h_genome_off;
   // lookup structures
   DevBuf slots, stash, mlist;
-  uint32_t block_bits = 0, tag_bits = 1, val_bits = 63, gbits = 1, n_inline = 1;
+  uint32_t bpd = 1, hi_bits = 0, tag_bits = 1, val_bits = 63, gbits = 1, n_inline = 1;   // table geometry, see TableView
   uint32_t min_len = 1;   // minimizer length m = min(k, 16)
   uint64_t stash_cap = 0;
   uint32_t stash_count = 0;
@@ -108,14 +110,16 @@ struct Index {
     t.stash_mask = stash_cap ? stash_cap - 1 : 0;
     t.stash_count = stash_count;
     minimizer_params(t, k);
-    t.block_bits = block_bits;
-    t.hi_bits = 2 * t.m - block_bits;
+    t.bpd = bpd;
+    t.hi_bits = hi_bits;
+    t.hmask = hi_bits >= 32 ? 0xFFFFFFFFu : ((1u << hi_bits) - 1);
     t.tag_bits = tag_bits;
     t.val_bits = val_bits;
     t.gbits = gbits;
     t.n_inline = n_inline;
     return t;
   }
+  uint64_t n_blocks() const { return (uint64_t)bpd << digit_bits_for_k(k); }
   size_t device_bytes() const {
     return ukeys.bytes + run_off.bytes + run_genome.bytes + pos_off.bytes + pos.bytes + genome_off.bytes + first_occ.bytes +
            slots.bytes + stash.bytes + mlist.bytes + align_scratch.bytes + align_queue.bytes;
@@ -130,18 +134,24 @@ struct Index {
   }
 };
 
+// K1 options (build.cu: encode_windows)
+struct EncodeOpts {
+  uint64_t emit_total;        // windows starting at or beyond this base of the slice are left to the next chunk
+  uint8_t* owner;             // [total] out: rank that owns the record (255: invalid window / another round); null: not partitioned
+  uint32_t n_parts, n_rounds, round;   // part = (digit of the minimizer * n_parts) >> digit_bits; owner = part / n_rounds, in round part % n_rounds
+  uint32_t vals_are_genomes;  // vals = genome index instead of global position (table-only builds: no 2^32-base limit)
+};
+
 // build.cu
 int32_t index_build_from_device_bases(Index& ix, const uint8_t* d_bases);
-int32_t index_build_tables(Index& ix);   // slots / stash / mlist from the CSR
-// multi-GPU build phases (see build.cu)
-int32_t records_encode_device(const uint8_t* d_bases, uint64_t n_bases, uint64_t pos0, const uint64_t* d_genome_off,
-                              uint32_t G, int k, uint64_t* d_keys, uint32_t* d_vals, uint64_t* h_n_valid, cudaStream_t s);
-int32_t records_partition_device(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint64_t n, int k,
-                                 uint32_t n_parts, uint64_t* h_part_off, int* in_b, cudaStream_t s);
-int32_t index_build_from_records(Index& ix, uint64_t* d_keys, uint32_t* d_vals, uint64_t n, bool build_tables);
-void partition_geometry(int k, int* begin_bit, int* top_bits);
-uint32_t partition_of_digit(uint32_t digit, int top_bits, uint32_t n_parts);
+// K1 over a slice of the concatenated genomes (see encode_windows); *h_n_valid += valid windows emitted
+int32_t encode_slice(const uint8_t* d_bases, uint64_t total, uint64_t pos0, const uint64_t* d_genome_off, uint32_t G, int k,
+                     uint64_t* d_keys, uint32_t* d_vals, const EncodeOpts& opt, unsigned long long* d_counters /*[2]: valid, bad*/,
+                     cudaStream_t s);
+// K3: CSR of `ix` from n sorted records (vals = global positions, or genome indices without positions)
+int32_t rle_to_csr(Index& ix, const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n, bool vals_are_genomes);
 int32_t index_export_order(Index& ix, uint32_t* h_order);
+int32_t index_checksum(Index& ix, uint64_t h_out[4]);
 int32_t index_ensure_first_occ(Index& ix);
 int32_t index_lookup_ranks(Index& ix, const uint8_t* h_kmers, uint64_t n, uint64_t* h_rank);
 int32_t index_extsim_stats(Index& ix, const uint32_t* h_group, uint32_t n_groups, uint64_t* h_total, uint64_t* h_unique);

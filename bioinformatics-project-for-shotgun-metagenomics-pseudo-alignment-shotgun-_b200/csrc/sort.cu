@@ -83,11 +83,7 @@ struct PassSmem {
 __global__ void __launch_bounds__(SORT_THREADS, PA_SORT_MINB)
 radix_pass(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
            uint32_t* __restrict__ vals_out, uint64_t n, int shift, const unsigned long long* __restrict__ digit_start,
-           volatile unsigned long long* __restrict__ lookback, unsigned int* __restrict__ tile_counter,
-           const PeerRoute* __restrict__ route) {
-  // route != nullptr: the pass is the scatter step of the multi-GPU build -- the run of digit d does not go to
-  // keys_out / vals_out but to route[d] (peer memory of the rank that owns the digit's key range, mapped through CUDA
-  // IPC; stores travel over NVLink), or nowhere when route[d].keys is null (the sentinel digit)
+           volatile unsigned long long* __restrict__ lookback, unsigned int* __restrict__ tile_counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PassSmem& sm = *reinterpret_cast<PassSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -187,17 +183,8 @@ radix_pass(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     uint64_t kk = sm.keys[i];
     uint32_t d = (uint32_t)((kk >> shift) & (RADIX - 1));
     uint64_t dst = (uint64_t)(sm.adjust[d] + (int64_t)i);
-    if (route) {
-      const PeerRoute rt = route[d];
-      if (rt.keys) {
-        const uint64_t j = dst - digit_start[d];   // position inside this sender's run of digit d
-        rt.keys[j] = kk;
-        rt.vals[j] = sm.vals[i];
-      }
-    } else {
-      keys_out[dst] = kk;
-      vals_out[dst] = sm.vals[i];
-    }
+    keys_out[dst] = kk;
+    vals_out[dst] = sm.vals[i];
   }
 }
 
@@ -223,11 +210,9 @@ int32_t radix_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, u
   unsigned int* tile_counter = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(d_temp) + (size_t)MAX_PASSES * RADIX * 8);
   unsigned long long* lookback = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(tile_counter) + 256);
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    PA_CUDA(cudaFuncSetAttribute(radix_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)));
-    attr_set = true;
-  }
+  // the opt-in to more than 48 KB of dynamic shared memory is per device: set it on every call (a process may build on
+  // several devices)
+  PA_CUDA(cudaFuncSetAttribute(radix_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)));
   int dev = 0, sms = 148;
   PA_CUDA(cudaGetDevice(&dev));
   PA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -242,60 +227,12 @@ int32_t radix_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, u
   for (int p = 0; p < n_passes; ++p) {
     PA_CUDA(cudaMemsetAsync(tile_counter, 0, 256 + (size_t)tiles * RADIX * 8, s));
     radix_pass<<<(unsigned)tiles, SORT_THREADS, sizeof(PassSmem), s>>>(kin, vin, kout, vout, n, begin_bit + p * RADIX_BITS,
-                                                                       hist + (size_t)p * RADIX, lookback, tile_counter, nullptr);
+                                                                       hist + (size_t)p * RADIX, lookback, tile_counter);
     PA_CUDA(cudaGetLastError());
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
   }
   *result_in_b = (n_passes & 1);
-  return ST_OK;
-}
-
-// counts of the 256 values of key bits [begin_bit, begin_bit + 8) (host output)
-int32_t radix_digit_counts(const uint64_t* keys, uint64_t n, int begin_bit, unsigned long long* h_counts /*[256]*/, void* d_temp,
-                           size_t temp_bytes, cudaStream_t s) {
-  for (int i = 0; i < RADIX; ++i) h_counts[i] = 0;
-  if (n == 0) return ST_OK;
-  if (temp_bytes < (size_t)RADIX * 8) { set_error("radix counts: temp buffer too small"); return ST_INVALID_ARG; }
-  int dev = 0, sms = 148;
-  PA_CUDA(cudaGetDevice(&dev));
-  PA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  unsigned long long* hist = reinterpret_cast<unsigned long long*>(d_temp);
-  PA_CUDA(cudaMemsetAsync(hist, 0, (size_t)RADIX * 8, s));
-  int hgrid = (int)std::min<uint64_t>((n + SORT_THREADS - 1) / SORT_THREADS, (uint64_t)sms * 8);
-  radix_histogram<<<hgrid, SORT_THREADS, 0, s>>>(keys, n, begin_bit, 1, hist);
-  PA_CUDA(cudaGetLastError());
-  PA_CUDA(cudaMemcpyAsync(h_counts, hist, (size_t)RADIX * 8, cudaMemcpyDeviceToHost, s));
-  PA_CUDA(cudaStreamSynchronize(s));
-  return ST_OK;
-}
-
-// one stable pass on key bits [begin_bit, begin_bit + 8) whose output runs go to d_route[digit] (see radix_pass)
-int32_t radix_scatter_routed(const uint64_t* keys, const uint32_t* vals, uint64_t n, int begin_bit, const PeerRoute* d_route,
-                             void* d_temp, size_t temp_bytes, cudaStream_t s) {
-  if (n == 0) return ST_OK;
-  if (temp_bytes < radix_sort_temp_bytes(n)) { set_error("radix scatter: temp buffer too small"); return ST_INVALID_ARG; }
-  const uint64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
-  if (tiles > 0xFFFFFFFFull) { set_error("radix scatter: too many tiles"); return ST_UNSUPPORTED; }
-  unsigned long long* hist = reinterpret_cast<unsigned long long*>(d_temp);
-  unsigned int* tile_counter = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(d_temp) + (size_t)MAX_PASSES * RADIX * 8);
-  unsigned long long* lookback = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(tile_counter) + 256);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PA_CUDA(cudaFuncSetAttribute(radix_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)));
-    attr_set = true;
-  }
-  int dev = 0, sms = 148;
-  PA_CUDA(cudaGetDevice(&dev));
-  PA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  PA_CUDA(cudaMemsetAsync(hist, 0, (size_t)MAX_PASSES * RADIX * 8, s));
-  int hgrid = (int)std::min<uint64_t>((n + SORT_THREADS - 1) / SORT_THREADS, (uint64_t)sms * 8);
-  radix_histogram<<<hgrid, SORT_THREADS, 0, s>>>(keys, n, begin_bit, 1, hist);
-  radix_scan<<<1, RADIX, 0, s>>>(hist);
-  PA_CUDA(cudaMemsetAsync(tile_counter, 0, 256 + (size_t)tiles * RADIX * 8, s));
-  radix_pass<<<(unsigned)tiles, SORT_THREADS, sizeof(PassSmem), s>>>(keys, vals, nullptr, nullptr, n, begin_bit, hist, lookback,
-                                                                     tile_counter, d_route);
-  PA_CUDA(cudaGetLastError());
   return ST_OK;
 }
 

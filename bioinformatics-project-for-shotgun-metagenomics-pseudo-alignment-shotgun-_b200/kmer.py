@@ -105,31 +105,50 @@ class _KmerMap(Mapping):
             out[genomes[int(csr["run_genome"][r])]] = set(csr["pos"][int(csr["pos_off"][r]):int(csr["pos_off"][r + 1])].tolist())
         return out
 
+    def lookup_many(self, kmers: List[str]) -> List[Optional[Dict[Record, Set[int]]]]:
+        """{Record: positions} of each k-mer, None when absent.  Only the looked-up entries leave the device
+        (pa_index_lookup + pa_index_entries): the reference answers a lookup in O(1), so must this."""
+        owner = self._owner
+        k = owner.kmer_len
+        out: List[Optional[Dict[Record, Set[int]]]] = [None] * len(kmers)
+        good = [i for i, km in enumerate(kmers) if isinstance(km, str) and len(km) == k and k >= 1]
+        if not good:
+            return out
+        if owner._dist is not None:      # partitioned index: the merged host CSR (collective, cached) + binary search
+            csr = owner._host_csr()
+            keys = owner._hashed_keys([kmers[i] for i in good])
+            at = np.searchsorted(csr["keys"], keys)
+            for i, a, key in zip(good, at.tolist(), keys.tolist()):
+                if a < len(csr["keys"]) and int(csr["keys"][a]) == key and key != nat.RANK_MISS:
+                    out[i] = self._entry(csr, a)
+            return out
+        ranks = owner._index().lookup([kmers[i] for i in good])
+        hit = [j for j, r in enumerate(ranks.tolist()) if r != nat.RANK_MISS]
+        if hit:
+            run_off, run_genome, pos_off, pos = owner._index().entries(ranks[hit])
+            small = {"run_off": run_off, "run_genome": run_genome, "pos_off": pos_off, "pos": pos}
+            for n, j in enumerate(hit):
+                out[good[j]] = self._entry(small, n)
+        return out
+
     def __len__(self) -> int:
-        return int(self._owner._index().info().n_keys)
+        return int(self._owner._index().info().n_keys)   # a replica reports the totals of all partitions
 
     def __iter__(self) -> Iterator[str]:
-        csr = self._owner._host_csr()
-        return iter(csr["kmers_in_order"])
+        return iter(self._owner._kmers_in_order())
 
     def __contains__(self, kmer) -> bool:
-        return self._rank(kmer) is not None
-
-    def _rank(self, kmer) -> Optional[int]:
-        if not isinstance(kmer, str) or len(kmer) != self._owner.kmer_len or self._owner.kmer_len < 1:
-            return None
-        rank = int(self._owner._index().lookup([kmer])[0])
-        return None if rank == nat.RANK_MISS else rank
+        return self.lookup_many([kmer])[0] is not None
 
     def __getitem__(self, kmer: str) -> Dict[Record, Set[int]]:
-        u = self._rank(kmer)
-        if u is None:
+        entry = self.lookup_many([kmer])[0]
+        if entry is None:
             raise KeyError(kmer)
-        return self._entry(self._owner._host_csr(), u)
+        return entry
 
     def items(self):
         csr = self._owner._host_csr()
-        return [(km, self._entry(csr, int(u))) for km, u in zip(csr["kmers_in_order"], csr["order"])]
+        return [(km, self._entry(csr, int(u))) for km, u in zip(self._owner._kmers_in_order(), csr["order"])]
 
     def values(self):
         return [v for _, v in self.items()]
@@ -151,6 +170,7 @@ class KmerReference(object):
         self.genomes: List[Record] = list(fasta_record_container)
         self.kmer_len: int = k
         self._native: Optional[nat.NativeIndex] = None
+        self._dist = None         # multi_gpu.DistributedIndex when the process is one of several ranks (multi_gpu.init)
         self._csr_cache = None
         self._frozen_csr = None
         self._dropped = None      # after EXTSIM: (genome strings of the ORIGINAL list, keep mask) -- see __getstate__
@@ -171,8 +191,32 @@ class KmerReference(object):
                 data = np.zeros(1, dtype=np.uint8)
         else:
             data, off = _pack([rec["genome"] for rec in fasta_records], "genome")
-        self._native = nat.NativeIndex.build(data, off, k)
+        self._build_index(data, off, k)
+
+    def _build_index(self, data, off, k: int) -> None:
+        """One GPU: pa_index_build.  Several ranks (multi_gpu.init() was called, e.g. main.py under torchrun): the
+        partitioned build -- every rank encodes its share of the genomes, owns a key range, and holds the whole lookup
+        table; same results, byte for byte."""
+        import multi_gpu
+        ctx = multi_gpu.context()
         self._csr_cache = None
+        if ctx is None:
+            self._native = nat.NativeIndex.build(data, off, k)
+            self._dist = None
+        else:
+            self._dist = multi_gpu.build_partitioned(ctx["comm"], data, off, k, device=ctx["device"])
+            self._native = self._dist.replica
+
+    def _csr_index(self):
+        """What answers the CSR questions (EXTSIM statistics, genome removal): the index itself, or its partitions."""
+        self._index()
+        return self._dist if self._dist is not None else self._native
+
+    def _hashed_keys(self, kmers: List[str]) -> np.ndarray:
+        flat = np.frombuffer("".join(kmers).encode("latin-1", "replace"), dtype=np.uint8).copy()
+        keys = np.zeros(max(len(kmers), 1), dtype=np.uint64)
+        nat.check(nat.lib().pa_encode_kmers(self.kmer_len, nat._p(flat), len(kmers), nat._p(keys)))
+        return keys[:len(kmers)]
 
     def _index(self) -> nat.NativeIndex:
         if self._native is None:  # unpickled: re-create the device index
@@ -188,19 +232,26 @@ class KmerReference(object):
                 dropped = self.__dict__.get("_dropped")
                 strings = dropped[0] if dropped is not None else [g["genome"] for g in self.genomes]
                 data, off = _pack(strings, "genome")
-                self._native = nat.NativeIndex.build(data, off, self.kmer_len)
+                self._build_index(data, off, self.kmer_len)
                 if dropped is not None:
-                    self._native.drop_genomes(np.asarray(dropped[1], dtype=np.uint8))
+                    self._csr_index().drop_genomes(np.asarray(dropped[1], dtype=np.uint8))
+                    if self._dist is not None:
+                        self._native = self._dist.replica
         return self._native
 
     def _host_csr(self):
+        """The whole CSR on the host (iteration, items, get_summary, dumpref) -- never needed by a point lookup."""
         if self._csr_cache is None:
-            ix = self._index()
-            csr = ix.export()
+            self._index()
+            self._csr_cache = self._dist.export_gathered() if self._dist is not None else self._native.export()
+        return self._csr_cache
+
+    def _kmers_in_order(self) -> List[str]:
+        csr = self._host_csr()
+        if "kmers_in_order" not in csr:
             kmers = nat.decode_kmers(max(self.kmer_len, 0), csr["keys"])
             csr["kmers_in_order"] = [kmers[int(u)] for u in csr["order"]]
-            self._csr_cache = csr
-        return self._csr_cache
+        return csr["kmers_in_order"]
 
     @property
     def kmers(self) -> _KmerMap:
@@ -216,7 +267,7 @@ class KmerReference(object):
 
     def _compute_genome_stats(self):
         classes, group = self._identifier_classes()
-        total, unique = self._index().extsim_stats(group, len(classes))
+        total, unique = self._csr_index().extsim_stats(group, len(classes))
         stats: Dict[str, Dict[str, Union[int, float]]] = {}
         for order, genome in enumerate(self.genomes):
             c = classes[genome.identifier]
@@ -231,7 +282,7 @@ class KmerReference(object):
     def _apply_greedy_filter(self, sorted_genomes, class_info, similarity_threshold: float):
         classes, group, total = class_info
         n = len(classes)
-        inter = self._index().extsim_pairwise(group, n)  # integer |A & B| for every pair, from the device
+        inter = self._csr_index().extsim_pairwise(group, n)  # integer |A & B| for every pair, from the device
         kept: List[str] = []
         info: Dict[str, Dict[str, Union[str, int, float]]] = {}
         for genome_id, stats in sorted_genomes:
@@ -257,7 +308,9 @@ class KmerReference(object):
         stats, class_info = self._compute_genome_stats()
         kept_ids, info = self._apply_greedy_filter(self._sort_genomes_for_filtering(stats), class_info, similarity_threshold)
         keep = np.array([1 if g.identifier in kept_ids else 0 for g in self.genomes], dtype=np.uint8)
-        self._index().drop_genomes(keep)  # _remove_filtered_genomes_from_kmers + renumbering
+        self._csr_index().drop_genomes(keep)  # _remove_filtered_genomes_from_kmers + renumbering
+        if self._dist is not None:
+            self._native = self._dist.replica
         if not keep.all():
             self._dropped = ([g["genome"] for g in self.genomes], keep.tolist())
         self.genomes = [g for g in self.genomes if g.identifier in kept_ids]
@@ -267,7 +320,7 @@ class KmerReference(object):
     # -- persistence (kmer.py:265-282) -------------------------------------------------
     def __getstate__(self):
         # the device index is not stored: _index() rebuilds it from the genomes (and the EXTSIM drop list) on demand
-        state = {k: v for k, v in self.__dict__.items() if k not in ("_native", "_csr_cache")}
+        state = {k: v for k, v in self.__dict__.items() if k not in ("_native", "_csr_cache", "_dist")}
         if state.get("_frozen_csr") is None:
             state.pop("_frozen_csr", None)
         return state
@@ -275,6 +328,7 @@ class KmerReference(object):
     def __setstate__(self, state):
         self.__dict__.update(state)
         self._native = None
+        self._dist = None
         self._csr_cache = None
 
     def save(self, ref_file: str) -> None:
@@ -290,10 +344,11 @@ class KmerReference(object):
 
     # -- lookups (kmer.py:284-298, 331-351) ----------------------------------------------
     def __getitem__(self, kmer: str) -> Optional[Dict[Record, Set[int]]]:
-        return self.kmers.get(kmer, None)
+        return self.kmers.lookup_many([kmer])[0]
 
     def get_kmer_references(self, kmer: str) -> Dict[Record, Set[int]]:
-        return self.kmers.get(kmer, {})
+        entry = self.kmers.lookup_many([kmer])[0]
+        return {} if entry is None else entry
 
     def get_kmer_and_reverse_references(self, kmer: str) -> Dict[Record, Set[int]]:
         merged = {genome: set(positions) for genome, positions in self.get_kmer_references(kmer).items()}
@@ -308,7 +363,7 @@ class KmerReference(object):
         """json.dumps(self.get_summary(), indent=indent), byte for byte, without building the nested dictionaries: the
         "Kmers" object (all of the bulk) is written natively from the exported CSR (csrc/format.cpp), "Summary" comes
         from array reductions.  What `main.py -t dumpref` prints."""
-        csr = self._index().export()
+        csr = self._host_csr()
         genomes = self.genomes
         classes: Dict[str, int] = {}
         group = np.zeros(max(len(genomes), 1), dtype=np.uint32)
@@ -330,7 +385,7 @@ class KmerReference(object):
             when = rank_of_key[key_of_run] * (int(runs_per_key.max()) + 1) + (np.arange(len(key_of_run)) - csr["run_off"].astype(np.int64)[key_of_run])
             first = np.full(len(names), np.iinfo(np.int64).max, dtype=np.int64)
             np.minimum.at(first, cls_of_run, when)
-            total, unique = self._index().extsim_stats(group, len(names))
+            total, unique = self._csr_index().extsim_stats(group, len(names))
             # the reference assigns total_bases at every (k-mer, genome) visit (kmer.py:315), so the value left is that
             # of the genome of the class visited last: the last k-mer in insertion order holding the class, and its
             # highest such genome
@@ -361,7 +416,7 @@ class KmerReference(object):
         run_off, run_genome, pos_off, pos = csr["run_off"], csr["run_genome"], csr["pos_off"], csr["pos"]
         kmer_details: Dict[str, Dict[str, List[int]]] = {}
         summary: Dict[str, Dict[str, int]] = {}
-        for km, u in zip(csr["kmers_in_order"], csr["order"]):
+        for km, u in zip(self._kmers_in_order(), csr["order"]):
             u = int(u)
             inner: Dict[str, List[int]] = {}
             for r in range(int(run_off[u]), int(run_off[u + 1])):
@@ -376,7 +431,7 @@ class KmerReference(object):
             group = np.zeros(max(len(genomes), 1), dtype=np.uint32)
             for i, rec in enumerate(genomes):
                 group[i] = classes.setdefault(rec["description"], len(classes))
-            total, unique = self._index().extsim_stats(group, len(classes))
+            total, unique = self._csr_index().extsim_stats(group, len(classes))
             for desc, entry in summary.items():
                 c = classes[desc]
                 entry["unique_kmers"] = int(unique[c])
@@ -451,13 +506,9 @@ class Read:
             candidates.append(kmer)
         if not candidates:
             return
-        ranks = kmer_reference._index().lookup(candidates)
-        view = kmer_reference.kmers
-        csr = kmer_reference._host_csr()
-        for kmer, rank in zip(candidates, ranks):
-            if int(rank) == nat.RANK_MISS:
+        for kmer, refs in zip(candidates, kmer_reference.kmers.lookup_many(candidates)):
+            if refs is None:
                 continue
-            refs = view._entry(csr, int(rank))
             if max_genomes is not None and len(refs) > max_genomes:
                 self.num_redundant_kmers += 1
                 continue
@@ -506,7 +557,9 @@ class Read:
         if min_read_quality is not None and self.mean_quality() < min_read_quality:
             return ReadMappingType.UNMAPPED
         seq, off = _pack([self.__raw_read], "read")
-        qual, _ = _pack([self.__quality_scores], "quality")
+        qual, qoff = _pack([self.__quality_scores], "quality")
+        if min_kmer_quality is not None and not np.array_equal(off, qoff):
+            raise ValueError("sequence and quality lengths differ")   # the kernel reads one quality byte per base
         words, lst, counters = kmer_reference._index().align(
             seq, qual, off, nat.make_params(m, p, None, min_kmer_quality, max_genomes))
         types, lens, payload = nat.decode_words(words)
@@ -528,9 +581,11 @@ class Read:
 # PseudoAlignment
 # ---------------------------------------------------------------------------
 class _Batch:
-    """Per-read results of one device batch, array-backed (stored reads only)."""
+    """Per-read results of one device batch, array-backed: `types` / `list_off` / `genome_idx` cover the STORED reads
+    (a read dropped by min_read_quality is not stored, kmer.py:587-589); `words` / `lst` are canonical result words of
+    the whole batch (dropped reads included) for K8."""
 
-    __slots__ = ("ids", "types", "list_off", "genome_idx", "genome_ids", "words", "lst", "first_index")
+    __slots__ = ("ids", "types", "list_off", "genome_idx", "genome_ids", "words", "lst")
 
     def __init__(self, ids, types, list_off, genome_idx, genome_ids, words, lst):
         self.ids = ids                  # identifiers of the stored reads, in order
@@ -538,7 +593,7 @@ class _Batch:
         self.list_off = list_off        # int64[n+1] into genome_idx
         self.genome_idx = genome_idx    # genome indices (into genome_ids)
         self.genome_ids = genome_ids    # identifier of every genome of the reference at alignment time
-        self.words = words              # raw result words of the whole batch (dropped reads included), for K8
+        self.words = words              # canonical result words of the whole batch, for K8
         self.lst = lst
 
     def entry(self, i: int) -> Dict[str, Any]:
@@ -546,23 +601,77 @@ class _Batch:
         return {"mapping_type": _TYPE_BY_CODE[int(self.types[i])],
                 "genomes_mapped_to": [self.genome_ids[int(g)] for g in self.genome_idx[lo:hi]]}
 
+    # the pickle (.aln, kmer.py:659-665) holds the arrays, not one Python dict per read
+    def __getstate__(self):
+        ids = self.ids if isinstance(self.ids, _LazyIds) else _LazyIds.from_list(list(self.ids))
+        return {"ids": ids, "types": self.types, "list_off": self.list_off, "genome_idx": self.genome_idx,
+                "genome_ids": self.genome_ids, "words": self.words, "lst": self.lst}
+
+    def __setstate__(self, state):
+        for name in self.__slots__:
+            setattr(self, name, state[name])
+
 
 class _LazyIds(Sequence):
-    """Identifiers of the stored reads of a natively parsed batch: cut out of the parsed text on first use (a summary
-    never needs them; 10^7 Python strings take seconds)."""
+    """Identifiers of the stored reads of a batch as one byte blob + offsets; the Python strings are cut on first use (a
+    summary never needs them; 10^7 Python strings take seconds).  For a natively parsed FASTQ (csrc/ingest.cpp) the blob is
+    gathered from the parsed text with array operations only."""
 
     def __init__(self, packed, stored, n_total: int) -> None:
         self._packed = packed
         self._stored = None if len(stored) == n_total else stored
         self._n = len(stored)
+        self._blob: Optional[bytes] = None
+        self._off: Optional[np.ndarray] = None
         self._list: Optional[List[str]] = None
+
+    @classmethod
+    def from_list(cls, names: List[str]) -> "_LazyIds":
+        self = cls.__new__(cls)
+        self._packed = self._stored = None
+        self._n = len(names)
+        enc = [s.encode("utf-8") for s in names]
+        self._blob = b"".join(enc)
+        self._off = np.concatenate([[0], np.cumsum([len(e) for e in enc], dtype=np.int64)]).astype(np.int64)
+        self._list = list(names)
+        return self
+
+    def _compact(self) -> None:
+        """(blob, offsets) of the stored identifiers, without building a Python string per read."""
+        if self._blob is not None:
+            return
+        pk = self._packed
+        beg, ln = pk["name_beg"].astype(np.int64), pk["name_len"].astype(np.int64)
+        if self._stored is not None:
+            beg, ln = beg[self._stored], ln[self._stored]
+        raw = pk["raw"]
+        text = np.frombuffer(raw.encode("ascii") if isinstance(raw, str) else raw, dtype=np.uint8)
+        off = np.zeros(len(ln) + 1, dtype=np.int64)
+        np.cumsum(ln, out=off[1:])
+        total = int(off[-1])
+        idx = np.repeat(beg - off[:-1], ln) + np.arange(total, dtype=np.int64)
+        self._blob, self._off = text[idx].tobytes(), off
+        self._packed = self._stored = None
 
     def _get(self) -> List[str]:
         if self._list is None:
-            names = nat.parsed_names(self._packed)
-            self._list = names if self._stored is None else [names[int(i)] for i in self._stored]
-            self._packed = self._stored = None
+            self._compact()
+            text, off = self._blob.decode("utf-8"), self._off
+            if len(text) == len(self._blob):     # ASCII: byte offsets are character offsets
+                o = off.tolist()
+                self._list = [text[o[i]:o[i + 1]] for i in range(self._n)]
+            else:
+                o = off.tolist()
+                self._list = [self._blob[o[i]:o[i + 1]].decode("utf-8") for i in range(self._n)]
         return self._list
+
+    def __getstate__(self):
+        self._compact()
+        return {"n": self._n, "blob": self._blob, "off": self._off}
+
+    def __setstate__(self, state):
+        self._packed = self._stored = self._list = None
+        self._n, self._blob, self._off = state["n"], state["blob"], state["off"]
 
     def __len__(self) -> int:
         return self._n
@@ -702,8 +811,25 @@ class PseudoAlignment:
             if not (mrq is not None or mkq is not None):
                 qual_bytes = None
         ref = self.kmer_reference
-        words, lst, counters = ref._index().align(seq_bytes, qual_bytes, off, nat.make_params(m, p, mrq, mkq, mg))
-        types, lens, payload = nat.decode_words(words)
+        import multi_gpu
+        ctx = multi_gpu.context()
+        params = nat.make_params(m, p, mrq, mkq, mg)
+        if ctx is None:
+            words, lst, counters = ref._index().align(seq_bytes, qual_bytes, off, params)
+            types_all, lens_all, flat = nat.flatten_results(words, lst)
+        else:
+            # reads are independent units (kmer.py:616-620): rank r aligns one contiguous block against its replica of the
+            # index; the per-read arrays are gathered so that `reads`, save() and get_summary() agree on every rank
+            comm, n_reads = ctx["comm"], len(off) - 1
+            lo, hi = multi_gpu.shard_bounds(n_reads, ctx["world"], ctx["rank"])
+            w, l, c = ref._index().align(seq_bytes, qual_bytes, np.ascontiguousarray(off[lo:hi + 1]), params)
+            t, ln, fl = nat.flatten_results(w, l)
+            types_all = np.concatenate(comm.allgather_array(t))
+            lens_all = np.concatenate(comm.allgather_array(ln))
+            flat = np.concatenate(comm.allgather_array(fl))
+            counters = comm.allreduce_host(np.asarray(c, dtype=np.uint64))
+        words, lst = nat.canonical_words(types_all, lens_all, flat)
+        types, lens = types_all, lens_all.astype(np.int64)
         stored = np.nonzero(types != 0)[0]
         if records is None:
             ids = _LazyIds(names, stored, int(names["n"]))
@@ -734,17 +860,11 @@ class PseudoAlignment:
             self.filtered_quality_kmers += int(counters[1])
         if mg is not None:
             self.filtered_hr_kmers += int(counters[2])
+        # a dropped read has an empty list, so the lists of the stored reads are `flat` as it is
         s_lens = lens[stored]
         list_off = np.zeros(len(stored) + 1, dtype=np.int64)
         np.cumsum(s_lens, out=list_off[1:])
-        genome_idx = np.zeros(int(list_off[-1]), dtype=np.uint32)
-        s_payload = payload[stored]
-        single = s_lens == 1
-        genome_idx[list_off[:-1][single]] = s_payload[single]
-        for j in np.nonzero(s_lens > 1)[0]:
-            genome_idx[list_off[j]:list_off[j + 1]] = lst[s_payload[j]:s_payload[j] + s_lens[j]]
-        batch = _Batch(ids, types[stored].astype(np.uint8), list_off, genome_idx, [g.identifier for g in ref.genomes],
-                       words, lst)
+        batch = _Batch(ids, types[stored].astype(np.uint8), list_off, flat, [g.identifier for g in ref.genomes], words, lst)
         self.reads.chunks.append(batch)
 
     def get_summary(self) -> Dict[str, Dict[str, Union[int, Dict[str, int]]]]:
@@ -789,15 +909,20 @@ class PseudoAlignment:
 
     # -- persistence and reporting (kmer.py:659-699) ------------------------------------------------
     def __getstate__(self):
+        # the view's chunks travel as they are: array-backed batches (with their identifiers as one blob) and the plain
+        # dict entries of reads added one at a time -- never 10^7 Python dict entries
         state = dict(self.__dict__)
-        state["reads"] = dict(self.reads.items())  # plain dict: loadable without this class's internals
+        state["reads"] = {"chunks": self.reads.chunks}
         return state
 
     def __setstate__(self, state):
         self.__dict__.update(state)
         view = _ReadsView()
-        if state["reads"]:
-            view.chunks.append(dict(state["reads"]))
+        stored = state["reads"]
+        if isinstance(stored, dict) and set(stored.keys()) == {"chunks"} and isinstance(stored["chunks"], list):
+            view.chunks = stored["chunks"]
+        elif stored:                      # files written before the array format: a plain dict of every read
+            view.chunks.append(dict(stored))
         self.reads = view
 
     def save(self, align_file: str) -> None:

@@ -11,6 +11,10 @@ itself is done by kmer.KmerReference / kmer.PseudoAlignment on the GPU.
 One deliberate difference: `-t align -g G.fa -k K --reads R.fq -a OUT.aln` without
 `-r` crashes in the reference with a TypeError (it calls save(None), main.py:372);
 here the reference database is simply not written when no `-r` path is given.
+
+Multi-GPU: launched under torchrun (`python -m torch.distributed.run --nproc-per-node N main.py ...`) every rank runs the
+same task; KmerReference builds its index partitioned over the ranks and PseudoAlignment aligns one block of the reads
+per rank (multi_gpu.init).  Rank 0 alone prints and writes files; the output is byte for byte the single-GPU output.
 """
 import argparse
 import gzip
@@ -24,6 +28,16 @@ from data_file import FASTAFile, FASTAQFile, InvalidExtensionError, NoRecordsInD
 from kmer import AddingExistingRead, KmerReference, NotValidatingUniqueMapping, PseudoAlignment
 
 BAD_FORMAT = "Error: Incorrect format of input file."
+
+
+def _is_root() -> bool:
+    """Rank 0 of a torchrun launch (or the only process): the one that prints and writes files."""
+    return int(os.environ.get("RANK", "0")) == 0
+
+
+def _emit(text: str) -> None:
+    if _is_root():
+        print(text)
 
 
 # ---------------------------------------------------------------------------
@@ -78,7 +92,9 @@ def create_reference(fasta_file: str, kmer_size: int, filter_similar: bool = Fal
 
 def create_reference_and_save_it(fasta_file: str, kmer_size: int, reference_file: str, filter_similar: bool = False,
                                  similarity_threshold: float = 0.95) -> None:
-    create_reference(fasta_file, kmer_size, filter_similar, similarity_threshold).save(reference_file)
+    reference = create_reference(fasta_file, kmer_size, filter_similar, similarity_threshold)
+    if _is_root():
+        reference.save(reference_file)
 
 
 def _load(kind, path: str):
@@ -90,7 +106,7 @@ def _load(kind, path: str):
 
 def dump_reference(kmer_reference: KmerReference) -> None:
     # the text of json.dumps(kmer_reference.get_summary(), indent=4) (main.py:127), written without the nested dicts
-    print(kmer_reference.summary_json(indent=4))
+    _emit(kmer_reference.summary_json(indent=4))
 
 
 def dump_reference_file(reference_file: str) -> None:
@@ -112,8 +128,9 @@ def create_alignment_from_reference(kmer_reference: KmerReference, reads_file: s
 
 def create_alignment_file_from_reference(kmer_reference: KmerReference, reads_file: str, align_file: str, m: int, p: int,
                                          min_read_quality, min_kmer_quality, max_genomes) -> None:
-    create_alignment_from_reference(kmer_reference, reads_file, m, p, min_read_quality, min_kmer_quality,
-                                    max_genomes).save(align_file)
+    alignment = create_alignment_from_reference(kmer_reference, reads_file, m, p, min_read_quality, min_kmer_quality, max_genomes)
+    if _is_root():
+        alignment.save(align_file)
 
 
 def create_alignment_from_reference_file(reference_file: str, reads_file: str, align_file: str, m: int, p: int,
@@ -130,14 +147,14 @@ def build_reference_and_create_alignment_file(fasta_file: str, kmer_size: int, r
 
 
 def dump_alignment_file(align_file: str) -> None:
-    print(json.dumps(_load(PseudoAlignment, align_file).get_summary(), indent=4))
+    _emit(json.dumps(_load(PseudoAlignment, align_file).get_summary(), indent=4))
 
 
 def dump_alignment_from_reference(reference_file: str, reads_file: str, m: int, p: int, min_read_quality,
                                   min_kmer_quality, max_genomes) -> None:
     alignment = create_alignment_from_reference(_load(KmerReference, reference_file), reads_file, m, p,
                                                 min_read_quality, min_kmer_quality, max_genomes)
-    print(json.dumps(alignment.get_summary(), indent=4))
+    _emit(json.dumps(alignment.get_summary(), indent=4))
 
 
 def build_reference_align_and_dump(fasta_file: str, kmer_size: int, reads_file: str, m: int, p: int, min_read_quality,
@@ -145,7 +162,7 @@ def build_reference_align_and_dump(fasta_file: str, kmer_size: int, reads_file: 
                                    similarity_threshold: float = 0.95) -> None:
     alignment = create_alignment_from_reference(create_reference(fasta_file, kmer_size, filter_similar, similarity_threshold),
                                                 reads_file, m, p, min_read_quality, min_kmer_quality, max_genomes)
-    print(json.dumps(alignment.get_summary(), indent=4))
+    _emit(json.dumps(alignment.get_summary(), indent=4))
 
 
 # ---------------------------------------------------------------------------
@@ -218,6 +235,9 @@ def main() -> None:
     args.unique_threshold = args.unique_threshold or DEFAULT_UNIQUE_THRESHOLD
     args.ambiguous_threhold = args.ambiguous_threhold or DEFAULT_AMBIGUOUS_THRESHOLD
     args.similarity_threshold = args.similarity_threshold or DEFAULT_SIMILARITY_THRESHOLD
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:   # one rank of a torchrun launch: attach to the others
+        import multi_gpu
+        multi_gpu.init()
     try:
         _run(args)
     except gzip.BadGzipFile:

@@ -192,20 +192,9 @@ def fuzz_case(seed: int, k_range=(2, 8), max_genomes: int = 6, with_n: bool = Tr
 # Canonical digest of per-read results (tools/fullsize_parity.py, bench.py's parity leg, tests/golden/fullsize_digest.json)
 # ---------------------------------------------------------------------------
 def flatten_results(words: np.ndarray, lst: np.ndarray):
-    """Result words (+ the side list) of pa_align_batch[_device] -> (types uint8[n], lens int32[n], flat genome indices
-    uint32[sum lens]) in read order: the shape the oracle returns, independent of where the list cursor put a list."""
-    words = np.ascontiguousarray(words, dtype=np.uint64)
-    types = (words >> np.uint64(62)).astype(np.uint8)
-    lens = ((words >> np.uint64(40)) & np.uint64(0x3FFFFF)).astype(np.int64)
-    payload = (words & np.uint64(0xFFFFFFFFFF)).astype(np.int64)
-    off = np.zeros(len(words) + 1, dtype=np.int64)
-    np.cumsum(lens, out=off[1:])
-    flat = np.zeros(int(off[-1]), dtype=np.uint32)
-    single = lens == 1
-    flat[off[:-1][single]] = payload[single]
-    for i in np.nonzero(lens > 1)[0]:
-        flat[off[i]:off[i + 1]] = lst[payload[i]:payload[i] + lens[i]]
-    return types, lens.astype(np.int32), flat
+    """See _native.flatten_results (kept here for the tools that import it from synth)."""
+    import _native
+    return _native.flatten_results(words, lst)
 
 
 def result_digest(types: np.ndarray, lens: np.ndarray, flat: np.ndarray) -> str:

@@ -43,7 +43,7 @@ extern "C" {
 #define PA_ERR_CAPACITY (-5)    /* an output buffer is too small; the needed size is reported */
 #define PA_ERR_UNSUPPORTED (-6) /* outside the built scope (k > 31, > 2^32-2 bases, ...) -> ValueError */
 
-#define PA_ABI_VERSION 2
+#define PA_ABI_VERSION 3
 #define PA_RANK_MISS UINT64_MAX
 
 typedef struct pa_index pa_index;
@@ -52,7 +52,7 @@ typedef struct pa_index_info {
   int32_t k;
   int32_t device;
   uint32_t n_genomes;
-  uint32_t block_bits;      /* log2(number of 512-byte blocks of the minimizer-bucketed lookup table) */
+  uint32_t blocks_per_digit; /* the lookup table has blocks_per_digit << digit_bits blocks of 512 bytes */
   uint32_t tag_bits;        /* bits of the k-mer stored in a slot (the rest is implied by the line) */
   uint32_t stash_count;     /* k-mers that overflowed their bucket chain */
   uint64_t n_keys;          /* distinct k-mers            (len(KmerReference.kmers)) */
@@ -63,6 +63,10 @@ typedef struct pa_index_info {
   uint64_t device_bytes;
   float build_encode_ms, build_sort_ms, build_rle_ms, build_table_ms; /* CUDA-event times of the last build */
   uint32_t minimizer_len;   /* m: k-mers sharing their minimizer m-mer share a table block */
+  uint32_t digit_bits;      /* top bits of the minimizer hash: ownership unit of a multi-GPU build */
+  uint64_t n_blocks;        /* blocks of the lookup table */
+  uint64_t table_bytes;     /* slots + stash + genome sets: all the alignment kernel reads */
+  uint32_t align_only;      /* 1: table-only index (no CSR, no positions): alignment and table lookups only */
   uint32_t reserved;
 } pa_index_info;
 
@@ -104,12 +108,24 @@ int32_t pa_index_info_get(pa_index* idx, pa_index_info* info);
  * keys are private encodings: decode with pa_decode_kmers.  Any pointer may be NULL to skip that array. */
 int32_t pa_index_export(pa_index* idx, uint64_t* keys, uint64_t* run_off, uint32_t* run_genome, uint64_t* pos_off,
                         uint32_t* pos, uint32_t* order, uint64_t* first_occ);
+/* Content checksum of the CSR: four sums modulo 2^64 over {k-mers, (k-mer, genome) pairs, (k-mer, genome, position)
+ * triples, k-mer count}.  Order-independent and additive over disjoint key sets: the checksums of the partitions of a
+ * multi-GPU build add up to the checksum of the single-GPU index exactly when the contents agree. */
+int32_t pa_index_checksum(pa_index* idx, uint64_t sums[4]);
 int32_t pa_decode_kmers(int32_t k, const uint64_t* keys, uint64_t n, uint8_t* ascii /* n*k bytes */);
 int32_t pa_encode_kmers(int32_t k, const uint8_t* ascii, uint64_t n, uint64_t* keys /* UINT64_MAX when not ACGT */);
 
 /* KmerReference.get_kmer_references / __getitem__ (kmer.py:284-298): rank of each k-mer (n strings of k bytes)
  * among the exported keys, PA_RANK_MISS when absent. */
 int32_t pa_index_lookup(pa_index* idx, const uint8_t* kmers_ascii, uint64_t n, uint64_t* rank);
+
+/* The CSR entries of a few k-mers (point lookups of KmerReference.__getitem__ / get_kmer_references, kmer.py:284-298,
+ * and Read.extract_kmer_references, kmer.py:410-429): ranks from pa_index_lookup (no PA_RANK_MISS).  Outputs are a small
+ * CSR of their own: run_off[n + 1] into run_genome[*run_total], pos_off[*run_total + 1] into pos[*pos_total].
+ * PA_ERR_CAPACITY (with *run_total / *pos_total set) when run_cap / pos_cap are too small or a buffer is NULL. */
+int32_t pa_index_entries(pa_index* idx, const uint64_t* ranks, uint64_t n, uint64_t* run_off, uint32_t* run_genome,
+                         uint64_t run_cap, uint64_t* pos_off, uint32_t* pos, uint64_t pos_cap, uint64_t* run_total,
+                         uint64_t* pos_total);
 
 /* ---- EXTSIM (kmer.py:152-263) ---------------------------------------------------------------------
  * group[g] = identifier class of genome g (kmer.py:162 keys everything by record.identifier).
@@ -120,56 +136,79 @@ int32_t pa_extsim_pairwise(pa_index* idx, const uint32_t* group, uint32_t n_grou
 /* _remove_filtered_genomes_from_kmers + _update_genomes_list (kmer.py:232-250); keep[g] != 0 survives */
 int32_t pa_index_drop_genomes(pa_index* idx, const uint8_t* keep);
 
-/* ---- multi-GPU build (SURVEY.md 8(e) "Build: one exchange step") ------------------------------------------
- * One process per GPU.  Rank r encodes a run of whole genomes, splits its (hashed k-mer, global position) records
- * by key range, the ranks exchange the parts with one all-to-all (torch.distributed / NCCL over NVLink, see
- * multi_gpu.py), and every rank sorts + run-length encodes the key range it owns into a CSR partition.  The align
- * index is replicated: the partitions' keys and genome runs are gathered into a replica (no positions) whose lookup
- * table every rank builds.  All buffers are caller-owned device memory; `stream` = cudaStream_t or NULL.
- *   pa_records_encode_device        K1 over genomes [g_lo, g_hi): d_bases = those genomes concatenated (16-byte
- *                                   aligned); writes one record per base (invalid windows get an all-ones key);
- *                                   genome_off = offsets of ALL genomes (positions are global)
- *   pa_records_partition_device     stable split into n_parts key ranges, invalid windows dropped; part_off[n_parts+1]
- *                                   (host) = start of every part in the output, which is the tmp pair when
- *                                   *result_in_tmp != 0
- *   pa_partition_of_key             the part a hashed key (pa_encode_kmers) belongs to
- *   pa_index_build_from_records_device   K2 + K3 over received records (sorted in place / through scratch) */
-int32_t pa_records_encode_device(const uint8_t* d_bases, const uint64_t* genome_off, uint32_t n_genomes, uint32_t g_lo,
-                                 uint32_t g_hi, int32_t k, int32_t device, uint64_t* d_keys, uint32_t* d_vals,
-                                 uint64_t* n_valid, void* stream);
-int32_t pa_records_partition_device(uint64_t* d_keys, uint32_t* d_vals, uint64_t* d_keys_tmp, uint32_t* d_vals_tmp, uint64_t n,
-                                    int32_t k, uint32_t n_parts, int32_t device, uint64_t* part_off, int32_t* result_in_tmp,
-                                    void* stream);
-int32_t pa_partition_of_key(int32_t k, uint64_t hashed_key, uint32_t n_parts, uint32_t* part);
-int32_t pa_index_build_from_records_device(uint64_t* d_keys, uint32_t* d_vals, uint64_t n, const uint64_t* genome_off,
-                                           uint32_t n_genomes, int32_t k, int32_t device, int32_t build_tables, pa_index** out);
-/* Fused partition + exchange: instead of pa_records_partition_device + all_to_all, the stable scatter pass stores every
- * record straight into the receive buffer of the rank that owns its key range -- peer memory mapped through CUDA IPC,
- * the stores travel over NVLink -- so the exchange overlaps the pass tile by tile and no send buffer is written.
- *   pa_peer_alloc / pa_peer_open / pa_peer_close / pa_peer_free   receive buffers: cudaMalloc + 64-byte IPC handle, opened
- *                                   by the other ranks (same node)
- *   pa_records_digit_counts         counts[256] of the partition digit = key bits [begin_bit, begin_bit + 8); digits
- *                                   below 2^top_bits are real (part = digit * n_parts >> top_bits), 255 = invalid windows.
- *                                   The ranks all-gather these to lay out the receive buffers (sender-major, digit-minor)
- *   pa_records_scatter_to_peers     dst_keys[d] / dst_vals[d] = where this rank's run of digit d starts (device pointers,
- *                                   possibly peer memory; NULL drops the digit).  Returns after the stores are complete;
- *                                   a barrier between the ranks then makes every receive buffer final. */
-int32_t pa_peer_alloc(uint64_t bytes, int32_t device, void** d_ptr, uint8_t* handle);
-int32_t pa_peer_open(const uint8_t* handle, int32_t device, void** d_ptr);
-int32_t pa_peer_close(void* d_ptr, int32_t device);
-int32_t pa_peer_free(void* d_ptr, int32_t device);
-int32_t pa_records_digit_counts(const uint64_t* d_keys, uint64_t n, int32_t k, int32_t device, uint64_t* counts,
-                                int32_t* begin_bit, int32_t* top_bits, void* stream);
-int32_t pa_records_scatter_to_peers(const uint64_t* d_keys, const uint32_t* d_vals, uint64_t n, int32_t k, int32_t device,
-                                    uint64_t* const* dst_keys, uint32_t* const* dst_vals, void* stream);
-/* device pointers of an index's keys[n_keys], run_off[n_keys+1], run_genome[n_runs] (for the gather / to fill a replica) */
-int32_t pa_index_csr_device(pa_index* idx, uint64_t** d_keys, uint64_t** d_run_off, uint32_t** d_run_genome);
-/* replica = align-only index: allocate, fill keys / run_off (rebased) / run_genome through pa_index_csr_device,
- * then pa_index_finish_replica builds the lookup table.  Positions stay in the partitions. */
-int32_t pa_index_alloc_replica(int32_t k, uint32_t n_genomes, const uint64_t* genome_off, uint64_t n_keys, uint64_t n_runs,
-                               uint64_t n_occ, int32_t device, pa_index** out);
-int32_t pa_index_finish_replica(pa_index* idx);
-int32_t pa_index_build_tables(pa_index* idx);
+/* ---- communicator (SURVEY.md 8(b) "multi-GPU: pa_comm_init, pa_comm_allreduce_summary, pa_build_exchange") ----------
+ * One process per GPU on one node.  The reference has no counterpart (it is single-threaded); the multi-GPU split sits
+ * behind the same two call sites as everything else: KmerReference.__init__ (kmer.py:113-133) and
+ * PseudoAlignment.align_reads_from_container (kmer.py:600-620).
+ *   pa_comm_unique_id        rank 0 creates the NCCL id; the caller hands the 128 bytes to every rank (file, socket, MPI,
+ *                            torch.distributed ... -- the library does not care)
+ *   pa_comm_init             ncclCommInitRank on `device`.  NCCL is resolved with dlopen at this call (the copy already in
+ *                            the process if there is one, else PA_NCCL_LIB, else libnccl.so.2), so the library itself
+ *                            links only the CUDA runtime
+ *   pa_comm_init_callbacks   the same communicator over a caller-supplied host all-gather instead of NCCL (tests over
+ *                            gloo, MPI bootstraps): allgather(user, in, out, bytes) fills out[r * bytes ..] with rank r's
+ *                            `bytes`, returns 0 on success; device data then travels through CUDA IPC peer memory only.
+ *                            device < 0: host-only communicator (host collectives, no CUDA device needed)
+ *   pa_comm_allreduce_summary  the ONE exchange of read-sharded alignment: SUM over d_sum[n_sum] = {stats[4],
+ *                            unique_reads[G], ambiguous_reads[G], counters[3] ...} and MIN over d_min[n_min] =
+ *                            first_seen[G] (uint64, device memory, in place; both reductions in one NCCL group on
+ *                            `stream`; with the callback transport the call returns after completion)
+ *   pa_comm_allreduce_host   SUM (op 0) or MIN (op 1) over host uint64 (EXTSIM: per-class totals and the G x G
+ *                            intersection matrix are sums over disjoint key ranges, kmer.py:152-177, 206-207) */
+typedef struct pa_comm pa_comm;
+typedef struct pa_comm_callbacks {
+  void* user;
+  int32_t (*allgather)(void* user, const void* in, void* out, uint64_t bytes_per_rank);
+} pa_comm_callbacks;
+int32_t pa_comm_unique_id(uint8_t id[128]);
+int32_t pa_comm_init(int32_t n_ranks, int32_t rank, const uint8_t id[128], int32_t device, pa_comm** out);
+int32_t pa_comm_init_callbacks(int32_t n_ranks, int32_t rank, int32_t device, const pa_comm_callbacks* cb, pa_comm** out);
+int32_t pa_comm_free(pa_comm* comm);
+int32_t pa_comm_info(pa_comm* comm, int32_t* n_ranks, int32_t* rank, int32_t* device, int32_t* has_nccl);
+int32_t pa_comm_allreduce_summary(pa_comm* comm, uint64_t* d_sum, uint64_t n_sum, uint64_t* d_min, uint64_t n_min, void* stream);
+int32_t pa_comm_allreduce_host(pa_comm* comm, uint64_t* values, uint64_t n, int32_t op);
+/* out[r * bytes_per_rank ..] = rank r's `bytes_per_rank` bytes (host memory) */
+int32_t pa_comm_allgather_host(pa_comm* comm, const void* in, void* out, uint64_t bytes_per_rank);
+int32_t pa_comm_barrier(pa_comm* comm);
+
+/* ---- partitioned / streamed index build (SURVEY.md 8(e) "Build: one exchange step"; kmer.py:135-150 across ranks) -----
+ * Rank r holds the genomes [g_lo, g_hi) (FASTA order is kept: genome indices ascend with the rank).  K1 encodes them and
+ * names the OWNER of every record: the k-mer space is partitioned by the top bits ("digit") of the k-mer's minimizer
+ * hash, which is also what the lookup table is laid out by, so the rank that owns a key range owns a contiguous slice of
+ * the table.  One stable scatter pass then stores every record straight into the owner's receive buffer -- peer memory
+ * mapped through CUDA IPC, one long coalesced run per (tile, owner), the stores travel over NVLink -- so partition and
+ * all-to-all are one kernel (pa_build_exchange); every rank sorts + run-length encodes what it received (K2, K3) into a
+ * CSR partition, inserts those k-mers into ITS slice of the (full-size) lookup table, and the slices are all-gathered
+ * in place (NCCL broadcasts, or IPC pulls): the replica every rank aligns against is the table alone.
+ *   flags  PA_BUILD_TABLE_ONLY   keep no CSR: *partition is not produced, records carry genome indices instead of
+ *                                positions (no 2^32-base limit), and the key space may be processed in several ROUNDS
+ *                                per rank (n_rounds; 0 = as many as the device memory asks for) -- config E's 2,000
+ *                                genomes build on one GPU that way
+ *          PA_BUILD_HOST_BASES   `bases` is host memory (uploaded chunk by chunk); default: device memory, 32-byte aligned
+ *   bases  the genomes [g_lo, g_hi) concatenated; genome_off[n_genomes + 1] = offsets of ALL genomes (positions and
+ *          genome indices are global).  comm == NULL: single GPU.
+ *   *partition  CSR of the key range this rank owns, with positions (pa_index_export, pa_extsim_*, pa_index_drop_genomes);
+ *   *replica    align-only index of all keys (pa_align_batch*, pa_debug_table_lookup, pa_index_info_get)
+ * pa_index_rebuild_replica: the table again from the partitions, after pa_index_drop_genomes on every partition. */
+#define PA_BUILD_TABLE_ONLY 1u
+#define PA_BUILD_HOST_BASES 2u
+int32_t pa_index_build_partitioned(pa_comm* comm, const uint8_t* bases, const uint64_t* genome_off, uint32_t n_genomes,
+                                   uint32_t g_lo, uint32_t g_hi, int32_t k, int32_t device, uint32_t flags, uint32_t n_rounds,
+                                   pa_index** partition, pa_index** replica);
+int32_t pa_index_rebuild_replica(pa_comm* comm, pa_index* partition, pa_index** replica);
+/* the genome range [*g_lo, *g_hi) of `rank`: contiguous runs of whole genomes balanced by bases */
+int32_t pa_genome_shard(const uint64_t* genome_off, uint32_t n_genomes, int32_t n_ranks, int32_t rank, uint32_t* g_lo,
+                        uint32_t* g_hi);
+/* The exchange step alone, for callers that drive the phases themselves: n records (device memory) with owner[i] = the
+ * rank record i goes to (255: dropped).  On return *recv_keys / *recv_vals (device memory owned by the communicator,
+ * valid until its next exchange) hold the *n_recv records this rank owns: sender-major, inside a sender in input order. */
+int32_t pa_build_exchange(pa_comm* comm, const uint64_t* d_keys, const uint32_t* d_vals, const uint8_t* d_owner, uint64_t n,
+                          uint64_t** recv_keys, uint32_t** recv_vals, uint64_t* n_recv, void* stream);
+/* timings (ms) of the phases of the last pa_index_build_partitioned on this rank:
+ * [0] encode + count, [1] scatter + exchange, [2] sort, [3] CSR, [4] table slice, [5] table gather, [6] total */
+int32_t pa_build_timings(pa_index* replica, float ms[8]);
+/* the owner rank of a k-mer (ASCII, k bytes) when the key space is split over n_parts */
+int32_t pa_partition_of_kmer(int32_t k, const uint8_t* kmer_ascii, uint32_t n_parts, uint32_t* part);
 
 /* ---- alignment: PseudoAlignment.align_reads_from_container (kmer.py:563-620) over a packed batch ---
  * bases/quals: concatenated read strings (quals may be NULL when no quality filter is on);
@@ -184,7 +223,8 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
                        uint64_t n_reads, const pa_align_params* params, uint64_t* out_words, uint32_t* out_list,
                        uint64_t list_cap, uint64_t* list_len, uint64_t counters[3]);
 /* device-resident variant: every pointer except params is device memory; d_state is 5 x uint64 of device
- * memory = {list cursor, overflow flag, counters[3]}, zeroed by the caller; asynchronous on `stream`. */
+ * memory = {list cursor, flag, counters[3]}, zeroed by the caller; asynchronous on `stream`.  flag: 1 = out_list too
+ * small (the cursor holds the size needed), 2 = a read was longer than max_read_len (results invalid). */
 int32_t pa_align_batch_device(pa_index* idx, const uint8_t* d_bases, const uint8_t* d_quals, const uint64_t* d_read_off,
                               uint64_t n_reads, uint64_t max_read_len, const pa_align_params* params,
                               uint64_t* d_words, uint32_t* d_list, uint64_t list_cap, uint64_t* d_state, void* stream,

@@ -26,7 +26,7 @@ def test_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in include/pa_b200.h but not exported"
     assert sorted(declared) == sorted(nat.EXPORTED_SYMBOLS)
-    assert lib.pa_abi_version() == 2
+    assert lib.pa_abi_version() == 3
 
 
 def test_encode_decode_kmers_round_trip_on_host():
@@ -199,17 +199,25 @@ for i in range(hi - lo):
         acc[4 + (0 if t == 2 else G) + int(g)] += 1
         key = ((lo + i) << 22) | j
         first[g] = key if first[g] < 0 else min(first[g], key)
-counters = torch.tensor([al.filtered_quality_reads, al.filtered_quality_kmers, al.filtered_hr_kmers], dtype=torch.int64)
-acc_t, first_t = torch.from_numpy(acc), torch.from_numpy(first)
-multi_gpu.allreduce_summary(acc_t, first_t)
-dist.all_reduce(counters)
+import _native as nat
+# the product's communicator (pa_comm, csrc/comm.cu) over a gloo all-gather: host-only, no CUDA device needed
+comm = nat.Comm.callbacks(world, rank, -1, lambda data: _allgather(data))
+def _allgather(data):
+    mine = torch.frombuffer(bytearray(data), dtype=torch.uint8)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine)
+    return [bytes(t.numpy().tobytes()) for t in out]
+counters = np.array([al.filtered_quality_reads, al.filtered_quality_kmers, al.filtered_hr_kmers], dtype=np.uint64)
+stats, uniq, amb, counters, fs = multi_gpu.reduce_summary(comm, acc[:4].astype(np.uint64), acc[4:4 + G].astype(np.uint64),
+                                                          acc[4 + G:].astype(np.uint64), counters, first.view(np.uint64))
+assert comm.allgather_bytes(bytes([rank]) * (rank + 1)) == [bytes([r]) * (r + 1) for r in range(world)]
 if rank == 0:
     flags = (pr["mrq"] is not None, pr["mkq"] is not None, pr["mg"] is not None)
-    got = multi_gpu.summary_from_accumulators(acc[:4], acc[4:4 + G], acc[4 + G:], first.astype(np.uint64),
-                                              [g[0] for g in case["genomes"]], flags, counters.tolist())
+    got = multi_gpu.summary_from_accumulators(stats, uniq, amb, fs, [g[0] for g in case["genomes"]], flags, counters.tolist())
     want = o.align(reads, pr["m"], pr["p"], pr["mrq"], pr["mkq"], pr["mg"]).get_summary()
     assert json.dumps(got) == json.dumps(want), (got, want)
     print("OK")
+comm.close()
 dist.destroy_process_group()
 '''
 
@@ -243,12 +251,13 @@ def test_shard_bounds_cover_everything_once():
 # multi-GPU build: host-side partitioning logic (the kernels are covered by tests/test_gpu_multi.py)
 # ---------------------------------------------------------------------------
 def test_genome_shards_are_contiguous_and_balanced():
-    import multi_gpu
+    import _native as nat
     rng = np.random.default_rng(5)
     for world in (1, 2, 3, 8):
         for n in (0, 1, 5, 100):
             lengths = rng.integers(1, 1000, size=n)
-            shards = multi_gpu.genome_shards(lengths, world)
+            off = np.concatenate([[0], np.cumsum(lengths)]).astype(np.uint64)
+            shards = [nat.genome_shard(off, world, r) for r in range(world)]
             assert len(shards) == world and shards[0][0] == 0 and shards[-1][1] == n
             assert all(shards[i][1] == shards[i + 1][0] for i in range(world - 1))
             if n == 100:
@@ -256,29 +265,34 @@ def test_genome_shards_are_contiguous_and_balanced():
                 assert max(loads) - min(loads) <= 2 * int(lengths.max())
 
 
-def test_partition_of_key_is_monotonic_and_balanced():
-    """pa_partition_of_key is pure host code: key ranges ascend with the part, and hashed k-mers spread evenly."""
+def test_partition_of_kmer_follows_the_minimizer_and_is_balanced():
+    """pa_partition_of_kmer is pure host code: the owner of a k-mer is a function of the top bits of its minimizer hash
+    (so k-mers sharing minimizer and table block share their owner), and the owners carry equal load although the
+    orders of minimizers crowd near zero (the hash spreads them)."""
     import ctypes
     import _native as nat
     L = nat.lib()
     rng = np.random.default_rng(9)
     for k in (4, 11, 31):
-        kmers = rng.integers(0, 4, size=(20000, k))
-        flat = np.ascontiguousarray(np.frombuffer(b"ACGT", dtype=np.uint8)[kmers].reshape(-1))
-        keys = np.zeros(20000, dtype=np.uint64)
-        nat.check(L.pa_encode_kmers(k, nat._p(flat), 20000, nat._p(keys)))
-        keys = np.unique(keys)
+        n = 20000
+        kmers = ["".join(x) for x in np.frombuffer(b"ACGT", dtype="S1")[rng.integers(0, 4, size=(n, k))].astype(str)]
+        flat = np.frombuffer("".join(kmers).encode(), dtype=np.uint8).copy()
+        mh = np.zeros(n, np.uint32); off = np.zeros(n, np.uint32)
+        assert L.pa_debug_minimizer(k, nat._p(flat), n, nat._p(mh), nat._p(off)) == 0
+        m = min(k, 16)
+        tb = min(8, 2 * m)
+        digit = mh.astype(np.uint64) >> np.uint64(2 * m - tb)
         for parts in (1, 2, 3, 8):
-            out = np.zeros(len(keys), dtype=np.uint32)
-            p = ctypes.c_uint32(0)
-            for i, key in enumerate(keys.tolist()):
-                nat.check(L.pa_partition_of_key(k, key, parts, ctypes.byref(p)))
-                out[i] = p.value
-            assert np.all(np.diff(out.astype(np.int64)) >= 0)          # keys are sorted ascending: parts must be too
-            assert out.max() == parts - 1 and out.min() == 0
+            got = np.array([nat.partition_of_kmer(k, km, parts) for km in kmers[:3000]])
+            want = (digit[:3000] * np.uint64(parts)) >> np.uint64(tb)
+            assert np.array_equal(got, want.astype(np.int64))
+            assert got.max() == parts - 1 and got.min() == 0
             if k >= 11:
-                counts = np.bincount(out, minlength=parts)
-                assert counts.max() < 1.25 * counts.mean() + 50
+                counts = np.bincount(((digit * np.uint64(parts)) >> np.uint64(tb)).astype(np.int64), minlength=parts)
+                assert counts.max() < 1.15 * counts.mean() + 50
+        if k >= 11:   # the digits themselves: no digit holds more than a few times its share
+            counts = np.bincount(digit.astype(np.int64), minlength=1 << tb)
+            assert counts.max() < 4 * counts.mean() + 20
 
 
 @pytest.mark.parametrize("scalar", ["0", "1"])
@@ -479,7 +493,9 @@ def test_native_dumpref_writer_against_json_dumps():
 def _minimizer_restated(kmer):
     """The definition in DESIGN.md §3: m = min(k,16); the m-mer x at offset j is (high plane << m) | low plane with bit i =
     base j+i; hdrop = max(0, 2m-28); order(x) = xorshift-multiply-xorshift of x >> hdrop on 2m-hdrop bits; the minimizer is the
-    leftmost m-mer of smallest order and its hash is order << hdrop | low hdrop bits of x."""
+    leftmost m-mer of smallest order and its hash is [low hdrop bits of x][order * 0x9E3779B1 mod 2^(2m-hdrop)] (the
+    multiplication spreads the orders of minimizers, which crowd near zero; the raw bits go on top so that m-mers of equal
+    order land in different table blocks)."""
     k = len(kmer)
     m = min(k, 16)
     code = {"A": 0, "C": 1, "T": 2, "G": 3}
@@ -498,7 +514,7 @@ def _minimizer_restated(kmer):
         if best is None or y < best[0]:
             best = (y, j, x)
     y, j, x = best
-    return (y << hdrop) | (x & ((1 << hdrop) - 1)), j
+    return ((x & ((1 << hdrop) - 1)) << ybits) | (((y * 0x9E3779B1) & 0xFFFFFFFF) & ymask), j
 
 
 def test_minimizer_hash_is_a_bijection_and_matches_its_definition():

@@ -95,7 +95,7 @@ def main():
         "build_s": t_build, "build_s_all": [round(t, 4) for t in builds], "build_kmers_per_s": inf.n_occ / t_build,
         "build_kernels_ms": {"encode": inf.build_encode_ms, "sort": inf.build_sort_ms, "csr": inf.build_rle_ms, "table": inf.build_table_ms},
         "extsim_stats_s": t_stats, "extsim_pairwise_s": t_pair, "greedy_host_s": t_greedy, "drop_genomes_s": t_drop,
-        "table": {"block_bits": int(inf.block_bits), "stash_count": int(inf.stash_count), "set_sectors": int(inf.n_list_sectors),
+        "table": {"table_blocks": int(inf.n_blocks), "table_bytes": int(inf.table_bytes), "stash_count": int(inf.stash_count), "set_sectors": int(inf.n_list_sectors),
                   "index_bytes": int(inf.device_bytes)},
         "genomes_filtered": int(dropped), "genomes_kept": int(inf2.n_genomes), "distinct_kmers_after": int(inf2.n_keys),
         "parity": "covered by tests/test_gpu_shim.py::test_extsim_clusters_k31_against_oracle and tests/test_gpu_abi.py::test_extsim_kernels_against_oracle"}))
