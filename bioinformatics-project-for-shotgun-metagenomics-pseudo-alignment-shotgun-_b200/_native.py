@@ -27,7 +27,7 @@ RANK_MISS = 0xFFFFFFFFFFFFFFFF
 
 EXPORTED_SYMBOLS = [
     "pa_abi_version", "pa_last_error", "pa_device_count", "pa_index_build", "pa_index_build_device", "pa_index_import",
-    "pa_index_free", "pa_index_info_get", "pa_index_export", "pa_decode_kmers", "pa_encode_kmers", "pa_index_lookup", "pa_index_entries", "pa_index_checksum",
+    "pa_index_free", "pa_index_info_get", "pa_index_export", "pa_decode_kmers", "pa_encode_kmers", "pa_index_lookup", "pa_index_entries", "pa_index_checksum", "pa_index_csr_device",
     "pa_extsim_stats", "pa_extsim_pairwise", "pa_index_drop_genomes", "pa_align_batch", "pa_align_batch_device",
     "pa_summary_reduce_device", "pa_summary_reduce", "pa_debug_sort_pairs", "pa_debug_table_lookup",
     "pa_comm_unique_id", "pa_comm_init", "pa_comm_init_callbacks", "pa_comm_free", "pa_comm_info", "pa_comm_allreduce_summary",
@@ -102,6 +102,7 @@ def lib() -> ctypes.CDLL:
         "pa_index_lookup": (i32, [vp, vp, u64, vp]),
         "pa_index_entries": (i32, [vp, vp, u64, vp, vp, u64, vp, vp, u64, vp, vp]),
         "pa_index_checksum": (i32, [vp, vp]),
+        "pa_index_csr_device": (i32, [vp, vp, vp, vp]),
         "pa_extsim_stats": (i32, [vp, vp, u32, vp, vp]),
         "pa_extsim_pairwise": (i32, [vp, vp, u32, vp]),
         "pa_index_drop_genomes": (i32, [vp, vp]),

@@ -179,11 +179,10 @@ __device__ __forceinline__ void prefetch_read(const ReadInput& in, bool valid, u
   if constexpr (PACKED) {
     p.v[0] = valid ? load_plane_words(in.planes, 2 * ((beg - in.base0) / 32 + read), (uint32_t)((L + 31) / 32), 0, lane) : 0u;
   } else {
+    const uint8_t* src = in.bases + beg + lane;
+    const uint32_t L32 = !valid ? 0u : (L > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)L);
 #pragma unroll
-    for (int c = 0; c <= AL_ROUNDS; ++c) {
-      const uint64_t bi = (uint64_t)(32 * c) + lane;
-      p.v[c] = (valid && bi < L) ? in.bases[beg + bi] : 0;
-    }
+    for (int c = 0; c <= AL_ROUNDS; ++c) p.v[c] = (32u * c + lane < L32) ? src[32 * c] : 0;
   }
 }
 
@@ -621,14 +620,95 @@ __device__ __forceinline__ void ld_set_sector(const uint32_t* p, uint32_t (&ids)
   ids[0] = a.x; ids[1] = a.y; ids[2] = a.z; ids[3] = a.w; ids[4] = b.x; ids[5] = b.y; ids[6] = b.z; ids[7] = b.w;
 }
 
+// ---------------------------------------------------------------------------
+// Stage C of the fast kernels: resolve the loaded sectors and apply the rules that need no per-genome table.
+// VAL32: a slot word splits at bit 32 -- the high word is exactly [k-mer without its minimizer : 2(k-m) = 30 bits][chain
+// distance : 2] and the low word [minimizer hash bits kept in the tag][CONT, kind, payload] (k = 31, m = 16: the case
+// this path is tuned for).  Values, kinds and payloads are then 32-bit quantities, the tag word is built without 64-bit
+// shifts, and a tag matches when the high words are equal and the low words agree above val_bits: three instructions per
+// slot instead of two 64-bit shifts and a compare.  Every other geometry runs the same code on 64-bit words.
+// ---------------------------------------------------------------------------
+// block / bucket of a window and the tag as it sits in a slot word, as two 32-bit halves
+struct SlotWord { uint32_t block, bucket, tw_lo, tw_hi; };
+template <bool VAL32>
+__device__ __forceinline__ SlotWord slot_word(const TableView& t, uint32_t lo, uint32_t hi, uint32_t mhash, uint32_t p) {
+  SlotWord a;
+  if constexpr (VAL32) {
+    const uint32_t km = t.k - t.m;
+    const uint32_t below = (1u << p) - 1;
+    const uint32_t rl = (lo & below) | ((lo >> t.m) & ~below);
+    const uint32_t rh = (hi & below) | ((hi >> t.m) & ~below);
+    a.tw_hi = ((rh << km) | rl) << CHAIN_BITS;                 // 2(k-m) + CHAIN_BITS = 32
+    a.tw_lo = (mhash & t.hmask) << t.val_bits;
+    a.block = (uint32_t)(((uint64_t)mhash * t.bpd) >> t.dshift);
+    a.bucket = (p + mhash) & (BLOCK_BUCKETS - 1);
+  } else {
+    const SlotAddr g = slot_addr(t, lo, hi, mhash, p);
+    const uint64_t tagword = g.tag << t.val_bits;
+    a.tw_lo = (uint32_t)tagword; a.tw_hi = (uint32_t)(tagword >> 32);
+    a.block = (uint32_t)g.block; a.bucket = g.bucket;
+  }
+  return a;
+}
+
+template <bool VAL32> struct ValT { using type = uint64_t; };
+template <> struct ValT<true> { using type = uint32_t; };
+
+template <bool VAL32>
+__device__ __forceinline__ typename ValT<VAL32>::type resolve_home(const TableView& t, const uint64_t (&s)[4], uint32_t tw_lo, uint32_t tw_hi, bool* cont) {
+  if constexpr (VAL32) {
+    const uint32_t lomask = t.val_bits >= 32 ? 0u : (0xFFFFFFFFu << t.val_bits);
+    uint32_t hit = 0;
+    bool found = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t lo = (uint32_t)s[i], hi = (uint32_t)(s[i] >> 32);
+      const bool m = ((((lo ^ tw_lo) & lomask) | (hi ^ tw_hi)) == 0);   // an empty slot (all ones) never equals a distance-0 tag
+      hit = m ? lo : hit;
+      found |= m;
+    }
+    const uint32_t last = (uint32_t)s[3];
+    *cont = !found && s[3] != EMPTY64 && ((last >> (t.val_bits - 1)) & 1u);
+    return found ? (hit & ((1u << (t.val_bits - 1)) - 1u)) : 0xFFFFFFFFu;
+  } else {
+    const uint64_t tagword = ((uint64_t)tw_hi << 32) | tw_lo;
+    const uint64_t tmask = ~0ULL << t.val_bits;
+    uint64_t hit = 0;
+    bool found = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool m = ((s[i] ^ tagword) & tmask) == 0;
+      hit = m ? s[i] : hit;
+      found |= m;
+    }
+    *cont = !found && s[3] != EMPTY64 && ((s[3] >> (t.val_bits - 1)) & 1);
+    return found ? (hit & (((uint64_t)1 << (t.val_bits - 1)) - 1)) : LOOKUP_MISS;
+  }
+}
+
+template <typename V> __device__ __forceinline__ bool is_miss(V v) { return v == (V)~(V)0; }
+template <typename V> __device__ __forceinline__ uint32_t vkind(const TableView& t, V v) { return (uint32_t)(v >> (t.val_bits - 3)) & 3u; }
+template <typename V> __device__ __forceinline__ V vpayload(const TableView& t, V v) { return v & ((((V)1) << (t.val_bits - 3)) - 1); }
+template <typename V>
+__device__ __forceinline__ uint32_t vinline_count(const TableView& t, V payload) {
+  const uint32_t gm = (1u << t.gbits) - 1;
+  uint32_t c = 1, prev = (uint32_t)payload & gm;
+  for (uint32_t i = 1; i < t.n_inline; ++i) {
+    const uint32_t g = (uint32_t)(payload >> (i * t.gbits)) & gm;
+    if (g == prev) break;
+    prev = g; ++c;
+  }
+  return c;
+}
 // does the genome set of a multi-genome k-mer contain genome g?
-__device__ __forceinline__ bool set_contains(const TableView& t, uint64_t val, uint32_t g) {
-  const uint64_t payload = value_payload(t, val);
-  if (value_kind(t, val) == KIND_INLINE) {
-    const uint32_t gm = (1u << t.gbits) - 1;
-    bool hit = false;
-    for (uint32_t i = 0; i < t.n_inline; ++i) hit |= ((uint32_t)(payload >> (i * t.gbits)) & gm) == g;  // padding fields repeat a member
-    return hit;
+template <typename V>
+__device__ __forceinline__ bool vset_contains(const TableView& t, V val, uint32_t g) {
+  const V payload = vpayload(t, val);
+  if (vkind(t, val) == KIND_INLINE) {
+    // is one of the n_inline fields equal to g?  All fields at once: xor with g replicated into every field, then the
+    // classic "has a zero field" test (exact for existence); padding fields repeat a member, so they cannot add a hit
+    const V x = payload ^ ((V)g * (V)t.inl_ones);
+    return ((x - (V)t.inl_ones) & ~x & (V)t.inl_highs) != 0;
   }
   for (uint64_t sector = payload;; ++sector) {
     uint32_t ids[8];
@@ -641,7 +721,78 @@ __device__ __forceinline__ bool set_contains(const TableView& t, uint64_t val, u
   }
 }
 
-template <bool QUAL, bool PACKED>
+// lo / hi / mkey: the read's planes and slid minimizer keys (to redo the address of a window whose chain goes on)
+template <bool VAL32>
+__device__ __forceinline__ void fast_stage_c(const TableView& t, const AlignParams& prm, uint32_t look,
+                                             const uint64_t (&sector)[AL_ROUNDS][4], const uint32_t (&tw_lo)[AL_ROUNDS],
+                                             const uint32_t (&tw_hi)[AL_ROUNDS],
+                                             const uint32_t (&lo)[AL_ROUNDS + 1], const uint32_t (&hi)[AL_ROUNDS + 1],
+                                             const uint32_t (&mkey)[AL_ROUNDS + 1], uint32_t lane, int k, uint32_t kmask,
+                                             uint64_t& res, bool& defer, uint32_t& read_nr) {
+  using V = typename ValT<VAL32>::type;
+  V val[AL_ROUNDS];
+  uint32_t chain = 0;   // bit r: the chain of window r goes on (rare)
+#pragma unroll
+  for (int r = 0; r < AL_ROUNDS; ++r) {
+    bool cont;
+    const V v = resolve_home<VAL32>(t, sector[r], tw_lo[r], tw_hi[r], &cont);
+    const bool on = (look >> r) & 1;
+    val[r] = on ? v : (V)~(V)0;
+    chain |= (on && cont) ? (1u << r) : 0u;
+  }
+  if (chain) {
+#pragma unroll
+    for (int r = 0; r < AL_ROUNDS; ++r)
+      if ((chain >> r) & 1) {
+        const uint32_t wl = __funnelshift_r(lo[r], lo[r + 1], lane) & kmask;
+        const uint32_t wh = __funnelshift_r(hi[r], hi[r + 1], lane) & kmask;
+        uint32_t mh, mp;
+        window_minimizer(t, mkey[r], wl, &mh, &mp);
+        val[r] = (V)lookup_chain_window(t, ((uint64_t)wh << k) | wl, mh, mp);   // LOOKUP_MISS truncates to the 32-bit miss
+      }
+  }
+  uint32_t mine = NO_GENOME, l_filtered = 0;
+  bool same = true, l_multi = false;
+#pragma unroll
+  for (int r = 0; r < AL_ROUNDS; ++r) {
+    const V v = val[r];
+    const bool hitr = !is_miss(v);
+    const uint32_t kind = vkind(t, v);
+    bool keep = hitr;
+    if (prm.has_mg) {  // max-genomes filter, per occurrence (kmer.py:425-427)
+      uint32_t c = 1;
+      if (hitr && kind == KIND_INLINE) c = vinline_count(t, vpayload(t, v));
+      else if (hitr && kind == KIND_MLIST) c = (prm.mg <= (int64_t)t.n_inline) ? t.n_inline + 1 : mlist_count(t.mlist, vpayload(t, v));
+      const bool f = hitr && (int64_t)c > prm.mg;
+      l_filtered += f;
+      keep = hitr && !f;
+    }
+    const bool spec = keep && kind == KIND_SPECIFIC;
+    const uint32_t g = (uint32_t)vpayload(t, v);
+    same &= !spec || mine == NO_GENOME || g == mine;
+    mine = (spec && mine == NO_GENOME) ? g : mine;
+    const bool multi = keep && !spec;
+    l_multi |= multi;
+    val[r] = multi ? v : (V)~(V)0;   // from here on: the kept multi-genome values of this lane
+  }
+  read_nr += l_filtered;
+  const uint32_t have = __ballot_sync(0xffffffffu, mine != NO_GENOME);
+  const bool w_multi = __any_sync(0xffffffffu, l_multi);
+  if (have == 0) {
+    res = make_word(w_multi ? 3 : 1, 0, 0);
+  } else {
+    const uint32_t g0 = __shfl_sync(0xffffffffu, mine, __ffs(have) - 1);
+    bool ok = same && (mine == NO_GENOME || mine == g0);
+    if (w_multi && prm.p >= 0) {
+#pragma unroll
+      for (int r = 0; r < AL_ROUNDS; ++r)
+        if (!is_miss(val[r])) ok = ok && vset_contains(t, val[r], g0);
+    }
+    if (__all_sync(0xffffffffu, ok)) res = make_word(2, 1, g0); else defer = true;
+  }
+}
+
+template <bool QUAL, bool PACKED, bool VAL32>
 __global__ void __launch_bounds__(FA_THREADS, PA_FAST_MINB)
 align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
                   const uint64_t* __restrict__ read_off, uint64_t n_reads, AlignParams prm, uint64_t* __restrict__ out_word,
@@ -717,7 +868,7 @@ align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
         }
       }
       // ---- minimizers ----
-      uint32_t mkey[AL_ROUNDS + 1], mh[AL_ROUNDS], mpos[AL_ROUNDS];
+      uint32_t mkey[AL_ROUNDS + 1];
 #pragma unroll
       for (int c = 0; c <= AL_ROUNDS; ++c) {
         const uint32_t nl = c < AL_ROUNDS ? lo[c + 1] : 0u, nh = c < AL_ROUNDS ? hi[c + 1] : 0u;
@@ -731,7 +882,7 @@ align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
         if (t.w > span) window_min_step(mkey, t.w - span, lane);
       }
       // ---- per window: quality filter, block / bucket / tag, one sector load ----
-      uint64_t tag[AL_ROUNDS];
+      uint32_t tw_lo[AL_ROUNDS], tw_hi[AL_ROUNDS];
       uint64_t sector[AL_ROUNDS][4];
       uint32_t look = 0;   // bit r: window r of this lane is looked up
 #pragma unroll
@@ -750,57 +901,14 @@ align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
         const uint32_t wl = __funnelshift_r(lo[r], lo[r + 1], lane) & kmask;
         const uint32_t wh = __funnelshift_r(hi[r], hi[r + 1], lane) & kmask;
         const uint32_t wi = __funnelshift_r(inv[r], inv[r + 1], lane) & kmask;
-        window_minimizer(t, mkey[r], wl, &mh[r], &mpos[r]);   // full hash and offset inside the window, 0 .. w-1
-        const SlotAddr a = slot_addr(t, wl, wh, mh[r], mpos[r]);
-        tag[r] = a.tag;
+        uint32_t mh, mpos;
+        window_minimizer(t, mkey[r], wl, &mh, &mpos);   // full hash and offset inside the window, 0 .. w-1
+        const SlotWord a = slot_word<VAL32>(t, wl, wh, mh, mpos);
+        tw_lo[r] = a.tw_lo; tw_hi[r] = a.tw_hi;         // the tag as it sits in a slot word
         if (exists && !qf && wi == 0) { look |= 1u << r; ld_sector_nc(bucket_ptr(t, a.block, a.bucket), sector[r]); }
       }
       // ---- resolve and classify ----
-      uint32_t mine = NO_GENOME, l_filtered = 0;
-      bool same = true;
-      uint64_t multi[AL_ROUNDS];   // kept multi-genome values of this lane (LOOKUP_MISS = none)
-#pragma unroll
-      for (int r = 0; r < AL_ROUNDS; ++r) {
-        multi[r] = LOOKUP_MISS;
-        if (!((look >> r) & 1)) continue;
-        bool cont;
-        uint64_t v = bucket_resolve_home(t, sector[r], tag[r], &cont);
-        if (cont) {
-          const uint32_t wl = __funnelshift_r(lo[r], lo[r + 1], lane) & kmask;
-          const uint32_t wh = __funnelshift_r(hi[r], hi[r + 1], lane) & kmask;
-          v = lookup_chain_window(t, ((uint64_t)wh << k) | wl, mh[r], mpos[r]);
-        }
-        if (v == LOOKUP_MISS) continue;
-        const uint32_t kind = value_kind(t, v);
-        if (prm.has_mg) {  // max-genomes filter, per occurrence (kmer.py:425-427)
-          uint32_t c = 1;
-          if (kind == KIND_INLINE) c = inline_count(t, value_payload(t, v));
-          else if (kind == KIND_MLIST) c = (prm.mg <= (int64_t)t.n_inline) ? t.n_inline + 1 : mlist_count(t.mlist, value_payload(t, v));
-          if ((int64_t)c > prm.mg) { ++l_filtered; continue; }
-        }
-        if (kind == KIND_SPECIFIC) {
-          const uint32_t g = (uint32_t)value_payload(t, v);
-          if (mine == NO_GENOME) mine = g; else same &= (g == mine);
-        } else {
-          multi[r] = v;
-        }
-      }
-      read_nr += l_filtered;
-      const uint32_t have = __ballot_sync(0xffffffffu, mine != NO_GENOME);
-      const bool l_multi = (multi[0] & multi[1] & multi[2] & multi[3]) != LOOKUP_MISS;
-      const bool w_multi = __any_sync(0xffffffffu, l_multi);
-      if (have == 0) {
-        res = make_word(w_multi ? 3 : 1, 0, 0);
-      } else {
-        const uint32_t g0 = __shfl_sync(0xffffffffu, mine, __ffs(have) - 1);
-        bool ok = same && (mine == NO_GENOME || mine == g0);
-        if (w_multi && prm.p >= 0) {
-#pragma unroll
-          for (int r = 0; r < AL_ROUNDS; ++r)
-            if (multi[r] != LOOKUP_MISS) ok = ok && set_contains(t, multi[r], g0);
-        }
-        if (__all_sync(0xffffffffu, ok)) res = make_word(2, 1, g0); else defer = true;
-      }
+      fast_stage_c<VAL32>(t, prm, look, sector, tw_lo, tw_hi, lo, hi, mkey, lane, k, kmask, res, defer, read_nr);
     }
     if (defer) {
       if (lane == 0) queue[atomicAdd(queue_count, 1ULL)] = (uint32_t)read;
@@ -890,7 +998,7 @@ __device__ __forceinline__ void fast_stage_a(const TableView& t, const AlignPara
   if (t.w > span) window_min_step(f.mkey, t.w - span, lane);
 }
 
-template <bool QUAL, bool PACKED>
+template <bool QUAL, bool PACKED, bool VAL32>
 __global__ void __launch_bounds__(FA_THREADS, PA_FAST_MINB)
 align_fast_split_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
                         const uint64_t* __restrict__ read_off, uint64_t n_reads, AlignParams prm, uint64_t* __restrict__ out_word,
@@ -927,7 +1035,7 @@ align_fast_split_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ q
 
   for (uint64_t read = warp_global; read < n_reads; read += n_warps) {
     // ---- stage B: per window quality filter, block / bucket / tag, one sector load ----
-    uint64_t tag[AL_ROUNDS];
+    uint32_t tw_lo[AL_ROUNDS], tw_hi[AL_ROUNDS];
     uint64_t sector[AL_ROUNDS][4];
     uint32_t look = 0;   // bit r: window r of this lane is looked up
     uint32_t read_nq = 0, read_nr = 0;
@@ -950,8 +1058,8 @@ align_fast_split_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ q
         const uint32_t wi = __funnelshift_r(cur.inv[r], cur.inv[r + 1], lane) & kmask;
         uint32_t mh, mp;
         window_minimizer(t, cur.mkey[r], wl, &mh, &mp);
-        const SlotAddr a = slot_addr(t, wl, wh, mh, mp);
-        tag[r] = a.tag;
+        const SlotWord a = slot_word<VAL32>(t, wl, wh, mh, mp);
+        tw_lo[r] = a.tw_lo; tw_hi[r] = a.tw_hi;         // the tag as it sits in a slot word
         if (exists && !qf && wi == 0) { look |= 1u << r; ld_sector_nc(bucket_ptr(t, a.block, a.bucket), sector[r]); }
       }
     }
@@ -977,55 +1085,7 @@ align_fast_split_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ q
     // ---- stage C: resolve and classify ----
     uint64_t res = cur.dropped ? 0 : make_word(1, 0, 0);   // UNMAPPED unless decided otherwise
     bool defer = cur.defer;
-    if (cur.W) {
-      uint32_t mine = NO_GENOME, l_filtered = 0;
-      bool same = true;
-      uint64_t multi[AL_ROUNDS];   // kept multi-genome values of this lane (LOOKUP_MISS = none)
-#pragma unroll
-      for (int r = 0; r < AL_ROUNDS; ++r) {
-        multi[r] = LOOKUP_MISS;
-        if (!((look >> r) & 1)) continue;
-        bool cont;
-        uint64_t v = bucket_resolve_home(t, sector[r], tag[r], &cont);
-        if (cont) {
-          const uint32_t wl = __funnelshift_r(cur.lo[r], cur.lo[r + 1], lane) & kmask;
-          const uint32_t wh = __funnelshift_r(cur.hi[r], cur.hi[r + 1], lane) & kmask;
-          uint32_t mh, mp;
-          window_minimizer(t, cur.mkey[r], wl, &mh, &mp);
-          v = lookup_chain_window(t, ((uint64_t)wh << k) | wl, mh, mp);
-        }
-        if (v == LOOKUP_MISS) continue;
-        const uint32_t kind = value_kind(t, v);
-        if (prm.has_mg) {  // max-genomes filter, per occurrence (kmer.py:425-427)
-          uint32_t c = 1;
-          if (kind == KIND_INLINE) c = inline_count(t, value_payload(t, v));
-          else if (kind == KIND_MLIST) c = (prm.mg <= (int64_t)t.n_inline) ? t.n_inline + 1 : mlist_count(t.mlist, value_payload(t, v));
-          if ((int64_t)c > prm.mg) { ++l_filtered; continue; }
-        }
-        if (kind == KIND_SPECIFIC) {
-          const uint32_t g = (uint32_t)value_payload(t, v);
-          if (mine == NO_GENOME) mine = g; else same &= (g == mine);
-        } else {
-          multi[r] = v;
-        }
-      }
-      read_nr += l_filtered;
-      const uint32_t have = __ballot_sync(0xffffffffu, mine != NO_GENOME);
-      const bool l_multi = (multi[0] & multi[1] & multi[2] & multi[3]) != LOOKUP_MISS;
-      const bool w_multi = __any_sync(0xffffffffu, l_multi);
-      if (have == 0) {
-        res = make_word(w_multi ? 3 : 1, 0, 0);
-      } else {
-        const uint32_t g0 = __shfl_sync(0xffffffffu, mine, __ffs(have) - 1);
-        bool ok = same && (mine == NO_GENOME || mine == g0);
-        if (w_multi && prm.p >= 0) {
-#pragma unroll
-          for (int r = 0; r < AL_ROUNDS; ++r)
-            if (multi[r] != LOOKUP_MISS) ok = ok && set_contains(t, multi[r], g0);
-        }
-        if (__all_sync(0xffffffffu, ok)) res = make_word(2, 1, g0); else defer = true;
-      }
-    }
+    if (cur.W) fast_stage_c<VAL32>(t, prm, look, sector, tw_lo, tw_hi, cur.lo, cur.hi, cur.mkey, lane, k, kmask, res, defer, read_nr);
     if (defer) {
       if (lane == 0) queue[atomicAdd(queue_count, 1ULL)] = (uint32_t)read;
     } else {
@@ -1151,15 +1211,20 @@ int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_q
   uint32_t* q_items = reinterpret_cast<uint32_t*>(ix.align_queue.as<unsigned char>() + 16);
   PA_CUDA(cudaMemsetAsync(q_count, 0, 8, s));
   {
-#if PA_FAST_SPLIT
     // the staggered kernel wins without quality filters (15.4 -> 15.0 ms per 10^7 reads); with them its extra state
-    // spills (20.1 -> 30.1 ms), so EXTQUALITY keeps the plain order of stages
-    auto fk = qual ? (packed ? align_fast_kernel<true, true> : align_fast_kernel<true, false>)
-                   : (packed ? align_fast_split_kernel<false, true> : align_fast_split_kernel<false, false>);
-#else
-    auto fk = qual ? (packed ? align_fast_kernel<true, true> : align_fast_kernel<true, false>)
-                   : (packed ? align_fast_kernel<false, true> : align_fast_kernel<false, false>);
-#endif
+    // spills (20.1 -> 30.1 ms), so EXTQUALITY keeps the plain order of stages.  VAL32: see fast_stage_c.
+    const bool v32 = tv.val_bits <= 32 && 2 * (tv.k - tv.m) + CHAIN_BITS == 32;
+    using FastKernel = void (*)(TableView, ReadInput, const uint8_t*, const uint64_t*, uint64_t, AlignParams, uint64_t*, unsigned long long*,
+                                uint32_t*, unsigned long long*);
+    FastKernel fk;
+    static const int qual_split = getenv("PA_QUAL_SPLIT") ? atoi(getenv("PA_QUAL_SPLIT")) : 0;   // tuning knob, see DESIGN.md section 4
+    if (qual && qual_split && v32) fk = packed ? align_fast_split_kernel<true, true, true> : align_fast_split_kernel<true, false, true>;
+    else if (qual) fk = packed ? (v32 ? align_fast_kernel<true, true, true> : align_fast_kernel<true, true, false>)
+                          : (v32 ? align_fast_kernel<true, false, true> : align_fast_kernel<true, false, false>);
+    else if (PA_FAST_SPLIT) fk = packed ? (v32 ? align_fast_split_kernel<false, true, true> : align_fast_split_kernel<false, true, false>)
+                                        : (v32 ? align_fast_split_kernel<false, false, true> : align_fast_split_kernel<false, false, false>);
+    else fk = packed ? (v32 ? align_fast_kernel<false, true, true> : align_fast_kernel<false, true, false>)
+                     : (v32 ? align_fast_kernel<false, false, true> : align_fast_kernel<false, false, false>);
     int occ = 1;
     PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fk, FA_THREADS, 0));
     if (occ < 1) occ = 1;

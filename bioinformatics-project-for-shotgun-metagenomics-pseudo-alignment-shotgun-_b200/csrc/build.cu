@@ -122,6 +122,7 @@ encode_windows(const uint8_t* __restrict__ bases, uint64_t total, uint64_t pos0,
   __shared__ uint32_t s_lo[ENC_WORDS], s_hi[ENC_WORDS], s_inv[ENC_WORDS], s_brk[ENC_WORDS];
   __shared__ uint32_t s_cnt[ENC_THREADS / 32];
   __shared__ uint32_t s_g0;
+  __shared__ uint32_t s_ord[ENC_TILE + MINIMIZER_MAX];   // order of the m-mer at every position of the tile (partitioned builds)
   const uint64_t tile_base = (uint64_t)blockIdx.x * ENC_TILE;
   const int tid = threadIdx.x;
   bool bad = false;
@@ -172,6 +173,17 @@ encode_windows(const uint8_t* __restrict__ bases, uint64_t total, uint64_t pos0,
   TableView mt;                   // only the minimizer fields are used (owner of a record = f(digit of its minimizer))
   minimizer_params(mt, k);
   const uint32_t tb = digit_bits_for_k(k);
+  if (opt.owner) {
+    // the order of every m-mer once (not once per window it is a candidate of): a window then takes the minimum over its
+    // w consecutive entries -- (order << 4 | offset) makes the leftmost candidate win ties, like kmer_minimizer
+    for (int q = tid; q < ENC_TILE + (int)mt.w - 1; q += ENC_THREADS) {
+      const uint32_t w = q >> 5, b = q & 31;
+      const uint32_t xl = __funnelshift_r(s_lo[w], s_lo[w + 1], b) & mt.mmask;
+      const uint32_t xh = __funnelshift_r(s_hi[w], s_hi[w + 1], b) & mt.mmask;
+      s_ord[q] = mmer_order((xh << mt.m) | xl, mt) << 4;
+    }
+    __syncthreads();
+  }
   uint32_t cnt = 0;
   uint32_t g_walk = (tile_base < total) ? s_g0 : 0;
 #pragma unroll 4
@@ -196,8 +208,10 @@ encode_windows(const uint8_t* __restrict__ bases, uint64_t total, uint64_t pos0,
     if (opt.owner) {
       uint32_t own = 255;
       if (valid) {
-        uint32_t mh, mp;
-        kmer_minimizer(mt, lo, hi, &mh, &mp);
+        uint32_t best = s_ord[s];
+        for (uint32_t c = 1; c < mt.w; ++c) best = min(best, s_ord[s + c] + c);
+        const uint32_t mp = best & 15u;
+        const uint32_t mh = hash_from_order(best >> 4, lo >> mp, mt);
         const uint32_t part = (uint32_t)(((uint64_t)(mh >> mt.dshift) * opt.n_parts) >> tb);
         if (part % opt.n_rounds == opt.round) own = part / opt.n_rounds;
       }

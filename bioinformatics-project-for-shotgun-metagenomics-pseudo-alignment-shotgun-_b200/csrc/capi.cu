@@ -288,6 +288,16 @@ int32_t pa_index_export(pa_index* idx, uint64_t* keys, uint64_t* run_off, uint32
   return PA_OK;
 }
 
+int32_t pa_index_csr_device(pa_index* idx, uint64_t** d_keys, uint64_t** d_run_off, uint32_t** d_run_genome) {
+  NEED(idx, "null index");
+  Index& ix = *IDX(idx);
+  NEED(!ix.align_only, "a table-only index holds no CSR");
+  if (d_keys) *d_keys = ix.ukeys.as<uint64_t>();
+  if (d_run_off) *d_run_off = ix.run_off.as<uint64_t>();
+  if (d_run_genome) *d_run_genome = ix.run_genome.as<uint32_t>();
+  return PA_OK;
+}
+
 int32_t pa_index_checksum(pa_index* idx, uint64_t sums[4]) {
   NEED(idx && sums, "null argument");
   NEED(!IDX(idx)->align_only, "a table-only index holds no CSR");

@@ -53,7 +53,9 @@ constexpr uint32_t MLIST_SECTOR = 8;                       // genome ids per 32-
 // align kernel encodes 32 windows with three ballots and three funnel shifts.
 // ---------------------------------------------------------------------------
 __host__ __device__ __forceinline__ bool is_acgt(uint32_t c) {
-  return c == 'A' || c == 'C' || c == 'G' || c == 'T';
+  // 'A' 0x41, 'C' 0x43, 'G' 0x47, 'T' 0x54: the bytes 0x40 + i with bit i of 0x0010008A set
+  const uint32_t i = c - 0x40u;
+  return i < 32u && ((0x0010008Au >> i) & 1u);
 }
 __host__ __device__ __forceinline__ uint32_t base_code(uint32_t c) { return (c >> 1) & 3u; }
 
@@ -141,6 +143,8 @@ struct TableView {
   uint32_t val_bits;   // 64 - tag_bits = CONT bit + 2 kind bits + payload
   uint32_t gbits;      // bits per genome id inside an inline list
   uint32_t n_inline;   // longest inline list (1 = inline lists unused)
+  uint64_t inl_ones;   // bit 0 of every inline field: sum of 1 << (i * gbits), i < n_inline
+  uint64_t inl_highs;  // the top bit of every inline field
   uint32_t mmask;      // 2^m - 1
   uint32_t hdrop;      // low bits of an m-mer that stay raw in its hash: max(0, 2m - 28)
   uint32_t ymask;      // 2^(2m - hdrop) - 1: the mixed part of the hash, also the minimizer order

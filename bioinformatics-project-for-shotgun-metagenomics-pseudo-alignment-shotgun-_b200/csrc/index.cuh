@@ -117,6 +117,9 @@ struct Index {
     t.val_bits = val_bits;
     t.gbits = gbits;
     t.n_inline = n_inline;
+    t.inl_ones = 0;
+    for (uint32_t i = 0; i < n_inline; ++i) t.inl_ones |= 1ULL << (i * gbits);
+    t.inl_highs = t.inl_ones << (gbits - 1);
     return t;
   }
   uint64_t n_blocks() const { return (uint64_t)bpd << digit_bits_for_k(k); }

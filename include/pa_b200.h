@@ -270,6 +270,8 @@ int32_t pa_format_kmers_json(int32_t k, uint64_t n_keys, const uint64_t* keys, c
 int32_t pa_free_text(uint8_t* p);
 
 /* ---- diagnostics used by the tests ----------------------------------------------------------------- */
+/* device pointers of an index's keys[n_keys], run_off[n_keys+1], run_genome[n_runs] (valid until the index changes) */
+int32_t pa_index_csr_device(pa_index* idx, uint64_t** d_keys, uint64_t** d_run_off, uint32_t** d_run_genome);
 /* stable LSD radix sort of (key, value) pairs on key bits [0, end_bit), host in / host out (K2) */
 int32_t pa_debug_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t n, int32_t end_bit, int32_t device);
 /* the host-side 2-bit packing of pa_align_batch (pure host code): planes needs 2 * (n_bases / 32 + n_reads + 1) words;

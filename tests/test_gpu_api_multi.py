@@ -41,10 +41,12 @@ for seed in [int(x) for x in sys.argv[1].split(",")]:
     fasta = "".join(f">{{g}}\n{{s}}\n" for g, s in case["genomes"])
     fastq = "".join(f"@{{r}}\n{{s}}\n+\n{{q}}\n" for r, s, q in case["reads"])
     try:
-        ref = kmer.KmerReference(case["k"], FASTARecordContainer(fasta), filter_similar=pr.get("filter_similar", False),
+        fc = FASTARecordContainer()
+        fc.parse_records(fasta)
+        ref = kmer.KmerReference(case["k"], fc, filter_similar=pr.get("filter_similar", False),
                                  similarity_threshold=pr.get("threshold", 0.95))
-    except Exception as e:   # the parser / the build refuse the input: every rank must refuse it the same way
-        out[seed] = ["error", type(e).__name__]
+    except ValueError as e:   # the build refuses the input (k > 31 ...): every rank must refuse it the same way
+        out[seed] = ["error", type(e).__name__, str(e)]
         continue
     assert ref._dist is not None or world == 1
     res = {{"ref": ref.summary_json(), "ref_dict": json.dumps(ref.get_summary(), indent=4), "genomes": [g.identifier for g in ref.genomes]}}
@@ -53,7 +55,8 @@ for seed in [int(x) for x in sys.argv[1].split(",")]:
     some = [km for km in list(ref.kmers)[:5]]
     res["lookups"] = [[km, sorted((g.identifier, sorted(p)) for g, p in ref.get_kmer_references(km).items())] for km in some]
     try:
-        reads = FASTAQRecordContainer(fastq)
+        reads = FASTAQRecordContainer()
+        reads.parse_records(fastq)
         al = kmer.PseudoAlignment(ref)
         al.align_reads_from_container(reads, pr["m"], pr["p"], pr["mrq"], pr["mkq"], pr["mg"])
         res["align"] = json.dumps(al.get_summary(), indent=4)
@@ -61,8 +64,8 @@ for seed in [int(x) for x in sys.argv[1].split(",")]:
         al2 = pickle.loads(pickle.dumps(al))          # .aln round trip (array-backed)
         res["align_reloaded"] = json.dumps(al2.get_summary(), indent=4)
         res["reads_reloaded"] = [[rid, d["mapping_type"].name, d["genomes_mapped_to"]] for rid, d in al2.reads.items()]
-    except Exception as e:
-        res["align_error"] = type(e).__name__
+    except (ValueError, ZeroDivisionError) as e:
+        res["align_error"] = [type(e).__name__, str(e)]
     out[seed] = res
 if rank == 0:
     with open(sys.argv[2], "w") as f:

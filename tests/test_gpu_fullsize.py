@@ -21,6 +21,21 @@ import conftest
 
 pytestmark = pytest.mark.gpu
 
+
+class _DevArray:
+    """A raw device pointer dressed as a CUDA array for torch.as_tensor (no copy)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def _as_tensor(ptr, n, typestr, dev):
+    import torch
+    dt = {"<i8": torch.int64, "<i4": torch.int32}[typestr]
+    if n == 0 or not ptr:
+        return torch.empty(0, dtype=dt, device=dev)
+    return torch.as_tensor(_DevArray(ptr, n, typestr), device=dev)
+
 G, GL, NR, RL, K = 100, 5_000_000, 10_000_000, 150, 31
 
 
@@ -69,10 +84,9 @@ def test_index_invariants_and_checksums(world):
     L = nat.lib()
     pk, po, pg = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
     nat.check(L.pa_index_csr_device(ix.handle, ctypes.byref(pk), ctypes.byref(po), ctypes.byref(pg)))
-    import multi_gpu
-    keys = multi_gpu._as_tensor(pk.value, inf.n_keys, "<i8", world["dev"])
-    run_off = multi_gpu._as_tensor(po.value, inf.n_keys + 1, "<i8", world["dev"])
-    run_genome = multi_gpu._as_tensor(pg.value, inf.n_runs, "<i4", world["dev"])
+    keys = _as_tensor(pk.value, inf.n_keys, "<i8", world["dev"])
+    run_off = _as_tensor(po.value, inf.n_keys + 1, "<i8", world["dev"])
+    run_genome = _as_tensor(pg.value, inf.n_runs, "<i4", world["dev"])
     assert bool((keys[1:] > keys[:-1]).all()) and int(keys.min()) >= 0 and int(keys.max()) < (1 << 62)
     d = run_off[1:] - run_off[:-1]
     assert bool((d >= 1).all()) and int(run_off[0]) == 0 and int(run_off[-1]) == inf.n_runs
@@ -178,3 +192,25 @@ def test_consistency_across_call_paths_and_orders(world, extq):
     assert bool(((pw >> 40) == tl[:1_000_000][perm]).all())
     s1 = (((pw >> 40) & 0x3FFFFF) == 1)
     assert bool((pw[s1] == words[:1_000_000][perm][s1]).all())
+
+
+@pytest.mark.parametrize("name,filters", [("configs[1] plain", (None, None, None)), ("configs[2] extquality", (62, 60, 3))])
+def test_all_reads_equal_the_oracle_digest(world, name, filters):
+    """Every one of the 10^7 per-read results (type + ordered genome list) equals what the C oracle produced for this exact
+    workload: tools/fullsize_parity.py ran both on the GPU box, diffed them read by read and committed the digest."""
+    import json
+    import synth
+    gold = json.load(open(os.path.join(conftest.ROOT, "tests", "golden", "fullsize_digest.json")))
+    wl = gold["workload"]
+    assert (wl["genomes"], wl["genome_len"], wl["reads"], wl["read_len"], wl["k"], wl["genome_seed"], wl["read_seed"]) == (G, GL, NR, RL, K, 1000, 2000)
+    case = gold["cases"][name]
+    assert all(case["equal_to_oracle"].values())
+    nat = world["nat"]
+    mrq, mkq, mg = filters
+    words, lst, state = _align_device(world, world["rb"], world["rq"], world["roff"], NR, nat.make_params(1, 1, mrq, mkq, mg), mrq is not None)
+    n_list = int(state[0])
+    types, lens, flat = nat.flatten_results(words.cpu().numpy().view(np.uint64), lst[:max(n_list, 1)].cpu().numpy().view(np.uint32))
+    assert synth.result_digest(types, lens, flat) == case["oracle_digest_sha256"]
+    assert [int(x) for x in state[2:5].cpu().tolist()] == case["counters"]
+    inf = world["ix"].info()
+    assert (int(inf.n_keys), int(inf.n_runs), int(inf.n_occ)) == (gold["index"]["n_keys"], gold["index"]["n_runs"], gold["index"]["n_occ"])

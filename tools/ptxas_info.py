@@ -9,7 +9,7 @@ for line in out.splitlines():
     m = re.search(r"Compiling entry function '(\S+)'", line)
     if m:
         name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
-        name = re.sub(r"\(.*", "", name).replace("pa::(anonymous namespace)::", "").replace("void ", "")
+        name = re.sub(r"\(.*", "", name.replace("pa::(anonymous namespace)::", "").replace("void ", ""))
     m = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", line)
     if m:
         stack = m.groups()
