@@ -28,7 +28,7 @@ RANK_MISS = 0xFFFFFFFFFFFFFFFF
 EXPORTED_SYMBOLS = [
     "pa_abi_version", "pa_last_error", "pa_device_count", "pa_index_build", "pa_index_build_device", "pa_index_import",
     "pa_index_free", "pa_index_info_get", "pa_index_export", "pa_decode_kmers", "pa_encode_kmers", "pa_index_lookup", "pa_index_entries", "pa_index_checksum", "pa_index_csr_device",
-    "pa_extsim_stats", "pa_extsim_pairwise", "pa_index_drop_genomes", "pa_align_batch", "pa_align_batch_device",
+    "pa_extsim_stats", "pa_extsim_pairwise", "pa_index_drop_genomes", "pa_align_batch", "pa_align_batch_device", "pa_pack_reads", "pa_align_batch_packed",
     "pa_summary_reduce_device", "pa_summary_reduce", "pa_debug_sort_pairs", "pa_debug_table_lookup",
     "pa_comm_unique_id", "pa_comm_init", "pa_comm_init_callbacks", "pa_comm_free", "pa_comm_info", "pa_comm_allreduce_summary",
     "pa_comm_allreduce_host", "pa_comm_allgather_host", "pa_comm_barrier", "pa_index_build_partitioned", "pa_index_rebuild_replica", "pa_genome_shard",
@@ -108,6 +108,8 @@ def lib() -> ctypes.CDLL:
         "pa_index_drop_genomes": (i32, [vp, vp]),
         "pa_align_batch": (i32, [vp, vp, vp, vp, u64, vp, vp, vp, u64, vp, vp]),
         "pa_align_batch_device": (i32, [vp, vp, vp, vp, u64, u64, vp, vp, vp, u64, vp, vp, vp]),
+        "pa_pack_reads": (i32, [vp, vp, u64, vp, u64, vp]),
+        "pa_align_batch_packed": (i32, [vp, vp, vp, vp, u64, vp, vp, vp, u64, vp, vp]),
         "pa_summary_reduce_device": (i32, [vp, vp, u64, u64, u32, vp, vp, vp, vp, vp]),
         "pa_summary_reduce": (i32, [vp, vp, vp, u64, u64, u64, vp, vp, vp, vp]),
         "pa_debug_sort_pairs": (i32, [vp, vp, u64, i32, i32]),
@@ -405,6 +407,27 @@ class NativeIndex:
             check(st)
             return words[:n], lst[:need.value], counters
 
+    def align_packed(self, planes: np.ndarray, quals: Optional[np.ndarray], read_off: np.ndarray, params: AlignParams):
+        """pa_align_batch_packed: reads already packed with pack_reads()."""
+        planes = np.ascontiguousarray(planes, dtype=np.uint32)
+        quals = None if quals is None else _u8(quals)
+        read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
+        n = len(read_off) - 1
+        words = np.zeros(max(n, 1), dtype=np.uint64)
+        counters = np.zeros(3, dtype=np.uint64)
+        cap = max(n // 4, 1024)
+        while True:
+            lst = np.zeros(cap, dtype=np.uint32)
+            need = ctypes.c_uint64(0)
+            st = lib().pa_align_batch_packed(self.handle, _p(planes), _p(quals), _p(read_off), n, ctypes.byref(params), _p(words),
+                                             _p(lst), cap, ctypes.byref(need), _p(counters))
+            if st == PA_ERR_CAPACITY:
+                cap = int(need.value) + 16
+                counters[:] = 0
+                continue
+            check(st)
+            return words[:n], lst[:need.value], counters
+
     def summary(self, words: np.ndarray, lst: np.ndarray, read_index_base: int = 0):
         """K8 on host buffers.  Returns (stats[4], unique_reads[G], ambiguous_reads[G], first_seen[G])."""
         G = self.info().n_genomes
@@ -602,6 +625,18 @@ def partition_of_kmer(k: int, kmer: str, n_parts: int) -> int:
     out = ctypes.c_uint32()
     check(lib().pa_partition_of_kmer(int(k), _p(b), int(n_parts), ctypes.byref(out)))
     return out.value
+
+
+def pack_reads(bases: np.ndarray, read_off: np.ndarray):
+    """pa_pack_reads: (planes uint32[...], all_acgt).  Pure host code."""
+    bases = _u8(bases)
+    read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
+    n = len(read_off) - 1
+    words = 2 * (int(read_off[-1] - read_off[0]) // 32 + n + 1)
+    planes = np.zeros(words, dtype=np.uint32)
+    ok = ctypes.c_int32(0)
+    check(lib().pa_pack_reads(_p(bases), _p(read_off), n, _p(planes), words, ctypes.byref(ok)))
+    return planes, bool(ok.value)
 
 
 def decode_kmers(k: int, keys: np.ndarray) -> List[str]:

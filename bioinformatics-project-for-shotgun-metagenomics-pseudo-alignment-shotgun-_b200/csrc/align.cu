@@ -161,6 +161,7 @@ struct ReadInput {
   const uint8_t* bases;
   const uint32_t* planes;
   uint64_t base0;
+  uint64_t read0;   // index of the kernel's read 0 inside the packed buffer (a chunk of a batch that was packed as a whole)
 };
 
 template <bool PACKED> struct Prefetch { uint32_t v[PACKED ? 1 : AL_ROUNDS + 1]; };
@@ -177,7 +178,7 @@ template <bool PACKED>
 __device__ __forceinline__ void prefetch_read(const ReadInput& in, bool valid, uint64_t read, uint64_t beg, uint64_t L,
                                               uint32_t lane, Prefetch<PACKED>& p) {
   if constexpr (PACKED) {
-    p.v[0] = valid ? load_plane_words(in.planes, 2 * ((beg - in.base0) / 32 + read), (uint32_t)((L + 31) / 32), 0, lane) : 0u;
+    p.v[0] = valid ? load_plane_words(in.planes, 2 * ((beg - in.base0) / 32 + in.read0 + read), (uint32_t)((L + 31) / 32), 0, lane) : 0u;
   } else {
     const uint8_t* src = in.bases + beg + lane;
     const uint32_t L32 = !valid ? 0u : (L > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)L);
@@ -194,7 +195,7 @@ __device__ __forceinline__ void encode_planes(const ReadInput& in, const Prefetc
   if constexpr (PACKED) {
     uint32_t w = p.v[0];
     if (wbase != 0)
-      w = load_plane_words(in.planes, 2 * ((beg - in.base0) / 32 + read), (uint32_t)((L + 31) / 32), (uint32_t)(wbase / 32), lane);
+      w = load_plane_words(in.planes, 2 * ((beg - in.base0) / 32 + in.read0 + read), (uint32_t)((L + 31) / 32), (uint32_t)(wbase / 32), lane);
 #pragma unroll
     for (int c = 0; c <= AL_ROUNDS; ++c) {
       lo[c] = __shfl_sync(0xffffffffu, w, c);
@@ -809,7 +810,7 @@ align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
   uint64_t nx_beg = 0, nx_end = 0, cur_beg = 0, cur_end = 0;
   Prefetch<PACKED> nx_ch, cur_ch;
   Prefetch<false> nx_q, cur_q;   // QUAL: the quality bytes travel through the same pipeline (one byte per lane per chunk)
-  const ReadInput qin{quals, nullptr, 0};
+  const ReadInput qin{quals, nullptr, 0, 0};
   {
     uint64_t r0 = warp_global, r1 = warp_global + n_warps;
     if (r0 < n_reads) { cur_beg = read_off[r0]; cur_end = read_off[r0 + 1]; }
@@ -1010,7 +1011,7 @@ align_fast_split_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ q
   const int k = (int)t.k;
   const uint32_t kmask = (k >= 1 && k < 32) ? ((1u << k) - 1) : 0u;
   unsigned long long c_drop = 0, c_nq = 0, c_nr = 0;  // per-lane partial counters
-  const ReadInput qin{quals, nullptr, 0};
+  const ReadInput qin{quals, nullptr, 0, 0};
 
   // input pipeline: while read i is resolved, stage A runs on read i+1 (bases requested one iteration earlier), the
   // bases of read i+2 and the offsets of read i+3 are requested
@@ -1180,7 +1181,7 @@ int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_q
                            uint64_t n_reads, uint64_t max_read_len, const AlignParams& prm_in, uint64_t* d_words,
                            uint32_t* d_list, uint64_t list_cap, unsigned long long* d_cursor /*[2]*/,
                            unsigned long long* d_counters /*[3]*/, cudaStream_t s, int32_t* launches,
-                           const uint32_t* d_planes, uint64_t planes_base0) {
+                           const uint32_t* d_planes, uint64_t planes_base0, uint64_t planes_read0) {
   if (launches) *launches = 0;
   if (n_reads == 0) return ST_OK;
   constexpr uint64_t MAX_BATCH = 1ULL << 31;   // read indices travel through the queue as uint32
@@ -1189,7 +1190,7 @@ int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_q
     for (uint64_t lo = 0; lo < n_reads; lo += MAX_BATCH) {
       int32_t l = 0;
       PA_TRY(align_batch_device(ix, d_bases, d_quals, d_read_off + lo, std::min(MAX_BATCH, n_reads - lo), max_read_len, prm_in,
-                                d_words + lo, d_list, list_cap, d_cursor, d_counters, s, &l, nullptr, 0));
+                                d_words + lo, d_list, list_cap, d_cursor, d_counters, s, &l, nullptr, 0, 0));
       if (launches) *launches += l;
     }
     return ST_OK;
@@ -1203,7 +1204,7 @@ int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_q
   PA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   TableView tv = ix.view();  // k <= 0: the kernels see no windows (kmer.py:91-92) and only apply the read-quality drop
   const bool packed = d_planes != nullptr;
-  const ReadInput in{d_bases, d_planes, planes_base0};
+  const ReadInput in{d_bases, d_planes, planes_base0, planes_read0};
 
   // ---- fast kernel over all reads; what it cannot decide goes to the queue ----
   if (ix.align_queue.bytes < 16 + n_reads * 4) PA_TRY(ix.align_queue.alloc(16 + n_reads * 4 + n_reads / 2));

@@ -23,7 +23,7 @@ int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_q
                            uint64_t n_reads, uint64_t max_read_len, const AlignParams& prm, uint64_t* d_words,
                            uint32_t* d_list, uint64_t list_cap, unsigned long long* d_cursor,
                            unsigned long long* d_counters, cudaStream_t s, int32_t* launches,
-                           const uint32_t* d_planes = nullptr, uint64_t planes_base0 = 0);
+                           const uint32_t* d_planes = nullptr, uint64_t planes_base0 = 0, uint64_t planes_read0 = 0);
 // d_planes != nullptr: the reads arrive as host-packed bit planes (see ReadInput in align.cu / hostpack.h) and
 // d_bases is not read
 

@@ -596,6 +596,93 @@ int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals
   return PA_OK;
 }
 
+int32_t pa_pack_reads(const uint8_t* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t* planes, uint64_t planes_cap,
+                      int32_t* all_acgt) {
+  NEED(read_off && planes && all_acgt, "null argument");
+  NEED(n_reads == 0 || bases, "null argument");
+  uint64_t mx = 0, mn = 0;
+  NEED(scan_offsets(read_off, 0, n_reads, &mx, &mn, host_pack_threads()), "read_off is not monotonic");
+  NEED(planes_cap >= planes_words(read_off[n_reads] - read_off[0], n_reads), "planes buffer too small");
+  *all_acgt = pack_reads_planes(bases, read_off, 0, n_reads, planes, host_pack_threads()) ? 1 : 0;
+  return PA_OK;
+}
+
+int32_t pa_align_batch_packed(pa_index* idx, const uint32_t* planes, const uint8_t* quals, const uint64_t* read_off,
+                              uint64_t n_reads, const pa_align_params* params, uint64_t* out_words, uint32_t* out_list,
+                              uint64_t list_cap, uint64_t* list_len, uint64_t counters[3]) {
+  NEED(idx && params, "null argument");
+  NEED(params->m >= 0, "m must be bigger than or equal to 0");
+  if (list_len) *list_len = 0;
+  if (n_reads == 0) return PA_OK;
+  NEED(planes && read_off && out_words && counters, "null host buffer");
+  Index& ix = *IDX(idx);
+  NEED(!ix.no_tables, "a partition holds no lookup table: align against the replica");
+  NEED(n_reads <= (1ull << 31), "packed input is limited to 2^31 reads per call");
+  PA_CUDA(cudaSetDevice(ix.device));
+  const bool need_q = params->has_min_read_quality || params->has_min_kmer_quality;
+  NEED(!need_q || quals, "quality filters requested without quality data");
+  const AlignParams prm = clamp_params(params);
+  // the pipeline of pa_align_batch without its packing stage: chunk c -> slot c % N_SLOTS: H2D(plane words, [quals], offsets) -> K4 -> D2H(words)
+  constexpr int N_SLOTS = Index::N_HOST_SLOTS;
+  for (auto& sl : ix.slot) {
+    if (!sl.stream) PA_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    if (!sl.kernel_done) PA_CUDA(cudaEventCreateWithFlags(&sl.kernel_done, cudaEventDisableTiming));
+    if (!sl.h2d_done) PA_CUDA(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+    if (!sl.copy_beg) PA_CUDA(cudaEventCreate(&sl.copy_beg));
+    if (!sl.copy_end) PA_CUDA(cudaEventCreate(&sl.copy_end));
+  }
+  PA_TRY(ensure(ix.host_list, std::max<uint64_t>(list_cap, 1) * 4));
+  PA_TRY(ensure(ix.host_state, 64));
+  PA_CUDA(cudaMemsetAsync(ix.host_state.p, 0, 40, ix.slot[0].stream));
+  PA_CUDA(cudaEventRecord(ix.slot[N_SLOTS - 1].kernel_done, ix.slot[0].stream));
+  uint64_t chunk = std::min<uint64_t>(std::max<uint64_t>(n_reads / 20, 1u << 16), 1u << 20);
+  if (const char* e = getenv("PA_CHUNK_READS")) { uint64_t v = strtoull(e, nullptr, 10); if (v) chunk = v; }
+  const uint64_t B0 = read_off[0];
+  uint64_t c = 0;
+  for (uint64_t lo = 0; lo < n_reads; lo += chunk, ++c) {
+    const uint64_t hi = std::min(n_reads, lo + chunk), n = hi - lo;
+    Index::HostSlot& sl = ix.slot[c % N_SLOTS];
+    Index::HostSlot& prev = ix.slot[(c + N_SLOTS - 1) % N_SLOTS];
+    const uint64_t b0 = read_off[lo], nb = read_off[hi] - b0;
+    uint64_t max_len = 0, min_len = 0;
+    NEED(scan_offsets(read_off, lo, hi, &max_len, &min_len, host_pack_threads()), "read_off is not monotonic");
+    // the words of reads [lo, hi) inside the batch-wide layout (hostpack.h): from w_lo up to the start of read hi
+    const uint64_t w_lo = 2 * ((b0 - B0) / 32 + lo), w_hi = 2 * ((read_off[hi] - B0) / 32 + hi);
+    PA_CUDA(cudaStreamSynchronize(sl.stream));
+    if (need_q) PA_TRY(ensure(sl.quals, nb + 64));
+    PA_TRY(ensure(sl.off, (n + 1) * 8));
+    PA_TRY(ensure(sl.words, n * 8));
+    PA_TRY(ensure(sl.planes, (w_hi - w_lo + 2) * 4));
+    PA_CUDA(cudaMemcpyAsync(sl.planes.p, planes + w_lo, (w_hi - w_lo) * 4, cudaMemcpyHostToDevice, sl.stream));
+    if (need_q && nb) PA_CUDA(cudaMemcpyAsync(sl.quals.p, quals + b0, nb, cudaMemcpyHostToDevice, sl.stream));
+    if (min_len == max_len) {
+      fill_offsets_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, sl.stream>>>(sl.off.as<uint64_t>(), n + 1, b0, max_len);
+      PA_CUDA(cudaGetLastError());
+    } else {
+      PA_CUDA(cudaMemcpyAsync(sl.off.p, read_off + lo, (n + 1) * 8, cudaMemcpyHostToDevice, sl.stream));
+    }
+    PA_CUDA(cudaStreamWaitEvent(sl.stream, prev.kernel_done, 0));
+    // the kernel finds the words of its read i at 2 ((o - B0) / 32 + lo + i) - w_lo of the slot buffer: rebase the pointer
+    PA_TRY(align_batch_device(ix, nullptr, need_q ? sl.quals.as<uint8_t>() - b0 : nullptr, sl.off.as<uint64_t>(), n, max_len, prm,
+                              sl.words.as<uint64_t>(), ix.host_list.as<uint32_t>(), list_cap, ix.host_state.as<unsigned long long>(),
+                              ix.host_state.as<unsigned long long>() + 2, sl.stream, nullptr, sl.planes.as<uint32_t>() - w_lo, B0, lo));
+    PA_CUDA(cudaEventRecord(sl.kernel_done, sl.stream));
+    PA_CUDA(cudaMemcpyAsync(out_words + lo, sl.words.p, n * 8, cudaMemcpyDeviceToHost, sl.stream));
+  }
+  for (auto& sl : ix.slot) PA_CUDA(cudaStreamSynchronize(sl.stream));
+  uint64_t h_state[5];
+  PA_CUDA(cudaMemcpy(h_state, ix.host_state.p, 40, cudaMemcpyDeviceToHost));
+  if (list_len) *list_len = h_state[0];
+  if (h_state[1] == 2) { set_error("align: a read is longer than the length the batch was sized for"); return PA_ERR_INVALID_ARG; }
+  if (h_state[0] > list_cap) { set_error("out_list too small: %llu entries needed", (unsigned long long)h_state[0]); return PA_ERR_CAPACITY; }
+  if (h_state[0]) {
+    NEED(out_list, "null out_list");
+    PA_CUDA(cudaMemcpy(out_list, ix.host_list.p, h_state[0] * 4, cudaMemcpyDeviceToHost));
+  }
+  counters[0] += h_state[2]; counters[1] += h_state[3]; counters[2] += h_state[4];
+  return PA_OK;
+}
+
 int32_t pa_summary_reduce_device(const uint64_t* d_words, const uint32_t* d_list, uint64_t n_reads,
                                  uint64_t read_index_base, uint32_t n_genomes, uint64_t* d_stats, uint64_t* d_unique_reads,
                                  uint64_t* d_ambiguous_reads, uint64_t* d_first_seen, void* stream) {

@@ -222,6 +222,20 @@ int32_t pa_partition_of_kmer(int32_t k, const uint8_t* kmer_ascii, uint32_t n_pa
 int32_t pa_align_batch(pa_index* idx, const uint8_t* bases, const uint8_t* quals, const uint64_t* read_off,
                        uint64_t n_reads, const pa_align_params* params, uint64_t* out_words, uint32_t* out_list,
                        uint64_t list_cap, uint64_t* list_len, uint64_t counters[3]);
+/* Reads that were packed once (e.g. when the FASTQ was ingested) instead of on every call: pa_pack_reads turns the
+ * concatenated ACGT read strings into the two bit planes K4's ballots would compute -- planes needs
+ * 2 * (n_bases / 32 + n_reads + 1) uint32 words; read i, starting at base offset o, owns the words from
+ * 2 * ((o - read_off[0]) / 32 + i): ceil(L / 32) low-plane words, then as many high-plane words (bit j of low word c =
+ * bit 1 of the ASCII code of base 32 c + j, high word = bit 2; A=0 C=1 T=2 G=3).  *all_acgt = 0 when a base outside ACGT
+ * was met: such a batch must go through pa_align_batch (a non-ACGT window can never match but still counts for the
+ * quality filter, kmer.py:420-422).  pa_align_batch_packed = pa_align_batch on such planes: a quarter of the bytes
+ * cross PCIe and no host core touches the reads again.  quals (may be NULL without quality filters) and read_off as in
+ * pa_align_batch (quals is indexed with the absolute offsets). */
+int32_t pa_pack_reads(const uint8_t* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t* planes, uint64_t planes_cap,
+                      int32_t* all_acgt);
+int32_t pa_align_batch_packed(pa_index* idx, const uint32_t* planes, const uint8_t* quals, const uint64_t* read_off,
+                              uint64_t n_reads, const pa_align_params* params, uint64_t* out_words, uint32_t* out_list,
+                              uint64_t list_cap, uint64_t* list_len, uint64_t counters[3]);
 /* device-resident variant: every pointer except params is device memory; d_state is 5 x uint64 of device
  * memory = {list cursor, flag, counters[3]}, zeroed by the caller; asynchronous on `stream`.  flag: 1 = out_list too
  * small (the cursor holds the size needed), 2 = a read was longer than max_read_len (results invalid). */

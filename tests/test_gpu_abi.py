@@ -192,6 +192,43 @@ def test_host_packed_reads_give_the_same_results(mode, monkeypatch):
         check_case(synth.fuzz_case(900 + seed))
 
 
+def test_prepacked_reads_through_pa_align_batch_packed(monkeypatch):
+    """pa_pack_reads once, then pa_align_batch_packed: same words, lists and counters as pa_align_batch on the ASCII reads --
+    fixed-length and ragged reads, plain and EXTQUALITY, long reads, several chunks (chunk starts that are not multiples
+    of 32 bases inside the batch-wide plane layout); a batch with a base outside ACGT is reported by pa_pack_reads."""
+    import _native as nat
+    monkeypatch.setenv("PA_CHUNK_READS", "333")
+    genomes = synth.make_genomes(6, 40_000, seed=15, cluster_size=3, shared_frac=0.35, n_every=9000, n_run=11)
+    data, goff = nat.pack_strings([s for _, s in synth.genomes_as_pairs(genomes)])
+    ix = nat.NativeIndex.build(data, goff, 31)
+    rng = np.random.default_rng(16)
+    for trial, (n, L, ragged) in enumerate([(3000, 150, False), (2500, 101, False), (1500, 150, True), (200, 700, False)]):
+        b, q, off = synth.make_reads(genomes, n, L, seed=17 + trial, sub_rate=0.02, random_frac=0.05)
+        if ragged:   # cut every read to a random length: offsets stop being an arithmetic sequence
+            lens = rng.integers(1, L + 1, size=n)
+            keep = np.concatenate([np.arange(int(o), int(o) + int(l)) for o, l in zip(off[:-1], lens)])
+            b, q = b[keep], q[keep]
+            off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        shift = 7 * trial                      # offsets need not start at 0
+        bb = np.concatenate([np.full(shift, ord("A"), np.uint8), b]); qq = np.concatenate([np.full(shift, 33, np.uint8), q])
+        off = off + np.uint64(shift)
+        planes, ok = nat.pack_reads(bb, off)
+        assert ok
+        for pr in [(None, None, None), (62, 60, 1), (None, 63, 3)]:
+            params = nat.make_params(1, 1, *pr)
+            quals = qq if (pr[0] is not None or pr[1] is not None) else None
+            w1, l1, c1 = ix.align(bb, quals, off, params)
+            w2, l2, c2 = ix.align_packed(planes, quals, off, params)
+            t1, n1, f1 = nat.flatten_results(w1, l1)
+            t2, n2, f2 = nat.flatten_results(w2, l2)
+            assert np.array_equal(t1, t2) and np.array_equal(n1, n2) and np.array_equal(f1, f2)
+            assert np.array_equal(c1, c2)
+    bad = bb.copy()
+    bad[int(off[5]) + 3] = ord("N")
+    assert nat.pack_reads(bad, off)[1] is False
+    ix.close()
+
+
 def test_long_reads_take_the_multi_round_path():
     genomes = synth.make_genomes(5, 6000, seed=9, cluster_size=5, shared_frac=0.5, n_every=2500, n_run=5)
     b, q, off = synth.make_reads(genomes, 300, 700, seed=10, sub_rate=0.03, random_frac=0.1)
