@@ -26,7 +26,7 @@ PA_ERR_UNSUPPORTED = -6
 RANK_MISS = 0xFFFFFFFFFFFFFFFF
 
 EXPORTED_SYMBOLS = [
-    "pa_abi_version", "pa_last_error", "pa_device_count", "pa_index_build", "pa_index_build_device", "pa_index_import",
+    "pa_abi_version", "pa_last_error", "pa_device_count", "pa_trim_memory", "pa_index_build", "pa_index_build_device", "pa_index_import",
     "pa_index_free", "pa_index_info_get", "pa_index_export", "pa_decode_kmers", "pa_encode_kmers", "pa_index_lookup", "pa_index_entries", "pa_index_checksum", "pa_index_csr_device",
     "pa_extsim_stats", "pa_extsim_pairwise", "pa_index_drop_genomes", "pa_align_batch", "pa_align_batch_device", "pa_pack_reads", "pa_align_batch_packed",
     "pa_summary_reduce_device", "pa_summary_reduce", "pa_debug_sort_pairs", "pa_debug_table_lookup",
@@ -91,6 +91,7 @@ def lib() -> ctypes.CDLL:
         "pa_abi_version": (i32, []),
         "pa_last_error": (i32, [ctypes.c_char_p, ctypes.c_size_t]),
         "pa_device_count": (i32, [vp]),
+        "pa_trim_memory": (i32, []),
         "pa_index_build": (i32, [vp, vp, u32, i32, i32, vp]),
         "pa_index_build_device": (i32, [vp, vp, u32, i32, i32, vp]),
         "pa_index_import": (i32, [i32, u32, vp, u64, u64, u64, vp, vp, vp, vp, vp, vp, i32, vp]),
@@ -167,6 +168,11 @@ def device_count() -> int:
     n = ctypes.c_int32(0)
     st = lib().pa_device_count(ctypes.byref(n))
     return n.value if st == PA_OK else 0
+
+
+def trim_memory() -> None:
+    """Gives the device buffers the library keeps for reuse back to the driver (pa_trim_memory)."""
+    lib().pa_trim_memory()
 
 
 def require_device() -> None:

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -37,10 +38,89 @@ AllocScope::AllocScope(cudaStream_t) : outermost(tl_scope_depth == 0) {
 AllocScope::~AllocScope() {
   --tl_scope_depth;
   if (outermost && tl_parked) {
-    for (auto& b : *tl_parked) cudaFree(b.first);
-    delete tl_parked;
+    std::vector<std::pair<void*, size_t>>* parked = tl_parked;
     tl_parked = nullptr;
+    // every public entry point synchronises its stream before it returns, so what is parked here is idle
+    for (auto& b : *parked)
+      if (!cache_put(b.first, b.second)) cudaFree(b.first);
+    delete parked;
   }
+}
+
+// ---- retired-buffer cache (see index.cuh) ----
+namespace {
+struct CacheEntry { void* p; size_t bytes; int device; };
+std::mutex g_cache_m;
+std::vector<CacheEntry> g_cache;
+constexpr size_t CACHE_MIN = 32u << 20;
+
+size_t cache_limit(int device) {
+  static double gb = getenv("PA_CACHE_GB") ? atof(getenv("PA_CACHE_GB")) : -1.0;
+  if (gb >= 0) return (size_t)(gb * 1e9);
+  static size_t quarter[64] = {0};
+  if (device < 0 || device >= 64) return 0;
+  if (!quarter[device]) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    quarter[device] = total_b / 4;
+  }
+  return quarter[device];
+}
+}  // namespace
+
+bool cache_take(size_t bytes, void** p, size_t* got) {
+  if (bytes < CACHE_MIN) return false;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  std::lock_guard<std::mutex> g(g_cache_m);
+  size_t best = SIZE_MAX; int at = -1;
+  for (int i = 0; i < (int)g_cache.size(); ++i) {
+    const CacheEntry& e = g_cache[i];
+    if (e.device == dev && e.bytes >= bytes && e.bytes <= bytes + bytes / 8 + (64u << 20) && e.bytes < best) { best = e.bytes; at = i; }
+  }
+  if (at < 0) return false;
+  *p = g_cache[at].p; *got = best;
+  g_cache.erase(g_cache.begin() + at);
+  return true;
+}
+
+bool cache_put(void* p, size_t bytes) {
+  if (bytes < CACHE_MIN) return false;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  const size_t limit = cache_limit(dev);
+  if (bytes > limit) return false;
+  std::vector<void*> evict;
+  {
+    std::lock_guard<std::mutex> g(g_cache_m);
+    size_t held = 0;
+    for (const CacheEntry& e : g_cache) if (e.device == dev) held += e.bytes;
+    for (size_t i = 0; i < g_cache.size() && held + bytes > limit;) {   // oldest first
+      if (g_cache[i].device == dev) { held -= g_cache[i].bytes; evict.push_back(g_cache[i].p); g_cache.erase(g_cache.begin() + i); }
+      else ++i;
+    }
+    g_cache.push_back({p, bytes, dev});
+  }
+  for (void* q : evict) cudaFree(q);
+  return true;
+}
+
+size_t cache_held() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  std::lock_guard<std::mutex> g(g_cache_m);
+  size_t held = 0;
+  for (const CacheEntry& e : g_cache) if (e.device == dev) held += e.bytes;
+  return held;
+}
+
+void cache_trim() {
+  std::vector<CacheEntry> all;
+  { std::lock_guard<std::mutex> g(g_cache_m); all.swap(g_cache); }
+  int cur = 0;
+  (void)cudaGetDevice(&cur);
+  for (const CacheEntry& e : all) { cudaSetDevice(e.device); cudaFree(e.p); }
+  cudaSetDevice(cur);
 }
 bool scope_take(size_t bytes, void** p, size_t* got) {
   if (!tl_parked || bytes < (1u << 20)) return false;       // small buffers are not worth the bookkeeping
@@ -151,6 +231,11 @@ int32_t pa_last_error(char* buf, size_t n) {
   size_t len = strlen(e);
   if (buf && n) { size_t c = std::min(len, n - 1); memcpy(buf, e, c); buf[c] = 0; }
   return (int32_t)len;
+}
+
+int32_t pa_trim_memory(void) {
+  cache_trim();
+  return PA_OK;
 }
 
 int32_t pa_device_count(int32_t* n) {

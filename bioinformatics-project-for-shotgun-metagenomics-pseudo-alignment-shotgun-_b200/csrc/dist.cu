@@ -396,7 +396,7 @@ int32_t DistBuild::table_round(uint32_t round) {
     if (R > 1) U_est = sums[1] ? (uint64_t)((double)sums[0] / (double)sums[1] * (double)sums[2] * 1.01) + 1024 : sums[2];
     size_t free_b = 0, total_b = 0;
     PA_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    uint64_t free_min = free_b;
+    uint64_t free_min = free_b + cache_held();   // buffers kept for reuse are memory a build may have
     PA_TRY(comm->allreduce_u64_host(&free_min, 1, true));
     const double load = table_load_factor(k, U_est, (size_t)free_min);
     uint32_t min_bpd = 1;

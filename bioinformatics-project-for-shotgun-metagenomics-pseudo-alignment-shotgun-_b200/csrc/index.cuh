@@ -22,6 +22,17 @@ struct AllocScope {
 bool scope_take(size_t bytes, void** p, size_t* got);   // a parked block of >= bytes (and not absurdly larger), if any
 bool scope_park(void* p, size_t bytes);                 // false outside a scope: the caller frees
 
+// Retired-buffer cache (process-wide, per device): what is still parked when a build ends, and the big buffers of an index
+// that is freed, are kept instead of cudaFree'd -- up to PA_CACHE_GB (default: a quarter of the device memory, 0 switches
+// it off) -- and the next build takes them over.  cudaMalloc / cudaFree of multi-GB buffers cost milliseconds each and
+// synchronise the device; a process that builds more than once (EXTSIM rebuilds, benchmarks, a server) pays them once.
+// Every cached buffer is idle: it is retired only after the stream that used it was synchronised.  cudaMalloc failures
+// trim the cache and retry; pa_trim_memory() releases everything.
+bool cache_take(size_t bytes, void** p, size_t* got);
+bool cache_put(void* p, size_t bytes);                  // false: not cached, the caller frees
+void cache_trim();
+size_t cache_held();                                    // bytes cached for the current device (memory that is free for a build)
+
 // Owns a device allocation; frees on destruction.
 struct DevBuf {
   void* p = nullptr;
@@ -31,15 +42,16 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p && !scope_park(p, bytes)) cudaFree(p);
+    if (p && !scope_park(p, bytes) && !cache_put(p, bytes)) cudaFree(p);
     p = nullptr; bytes = 0;
   }
   int32_t alloc(size_t n) {
     release();
     if (n == 0) n = 16;
     size_t got = 0;
-    if (scope_take(n, &p, &got)) { bytes = got; return ST_OK; }
+    if (scope_take(n, &p, &got) || cache_take(n, &p, &got)) { bytes = got; return ST_OK; }
     cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaErrorMemoryAllocation) { (void)cudaGetLastError(); cache_trim(); e = cudaMalloc(&p, n); }
     if (e != cudaSuccess) { p = nullptr; (void)cudaGetLastError(); set_error("cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e)); return ST_NOMEM; }
     bytes = n;
     return ST_OK;

@@ -295,6 +295,7 @@ int32_t index_build_tables(Index& ix) {
   ix.stash_cap = 0; ix.stash_count = 0; ix.n_msectors = 0;
   size_t free_b = 0, total_b = 0;
   PA_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  free_b += cache_held();   // buffers kept for reuse are memory a build may have
   const double load = table_load_factor(ix.k, U, free_b);
   const CsrView csr{ix.ukeys.as<uint64_t>(), ix.run_off.as<uint64_t>(), ix.run_genome.as<uint32_t>(), U};
   TableGeom g;

@@ -82,6 +82,10 @@ int32_t pa_abi_version(void);
 /* copies the calling thread's last error message (NUL-terminated) into buf; returns its full length */
 int32_t pa_last_error(char* buf, size_t n);
 int32_t pa_device_count(int32_t* n);
+/* The library keeps the big device buffers of finished builds / freed indexes (up to PA_CACHE_GB, default a quarter of
+ * the device memory; 0 switches the cache off) and hands them to the next build instead of paying cudaMalloc / cudaFree
+ * again; an allocation failure releases them by itself.  pa_trim_memory gives everything back now. */
+int32_t pa_trim_memory(void);
 
 /* ---- index build: KmerReference.__init__ / _build_kmer_mapping (kmer.py:113-150) ------------------
  * bases      concatenated genome strings, bytes in ACGTN (host); genome_off[G+1] offsets into it.
