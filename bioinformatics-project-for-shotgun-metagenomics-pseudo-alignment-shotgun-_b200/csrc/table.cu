@@ -174,6 +174,10 @@ double table_load_factor(int k, uint64_t U, size_t free_bytes) {
   // 0.195 / 0.25 / 0.30 (40 / 32 / 26.7 bytes of table per k-mer): fast while memory is plentiful, dense when it is not
   double load = 0.2;
   if (const char* e = getenv("PA_TABLE_LOAD")) { const double v = atof(e); if (v > 0) return v; }
+  if (const char* e = getenv("PA_TABLE_DENSE")) {   // tests: n > 0 doubles the load factor n times (chains, CONT, stash), n < 0 halves it
+    const int n = atoi(e);
+    return n >= 0 ? std::min(0.9, load * (double)(1u << std::min(n, 8))) : load / (double)(1u << std::min(-n, 8));
+  }
   // denser while the table would take more than 40 % of the free device memory (config E: 2,000 genomes)
   const double bytes_per_slot = 8.0;
   while (load < 0.42 && (double)U / load * bytes_per_slot > 0.4 * (double)free_bytes) load += 0.02;

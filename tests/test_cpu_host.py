@@ -552,3 +552,42 @@ def test_minimizer_hash_is_a_bijection_and_matches_its_definition():
         mh, off = native(kmers, k)
         for s, h, o in zip(kmers, mh, off):
             assert (int(h), int(o)) == _minimizer_restated(s), (k, s)
+
+
+def test_host_pool_serves_concurrent_callers():
+    """ctypes releases the GIL, so two Python threads (one per GPU, say) may pack and parse at the same time: the worker
+    pool must run one job at a time and every caller must get its own complete result (ADVICE r01: Pool::parallel_for)."""
+    import ctypes
+    import threading
+    import _native as nat
+    L = nat.lib()
+    rng = np.random.default_rng(21)
+    jobs = []
+    for t in range(6):
+        n = 20_000 + 1000 * t
+        off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(150))
+        bases = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n * 150)].copy()
+        want, ok = nat.pack_reads(bases, off)      # single-threaded caller: the reference result
+        assert ok
+        jobs.append((bases, off, want))
+    text = "".join(f"@r{i}\nACGTACGTAC\n+\nIIIIIIIIII\n" for i in range(30_000))
+    errors = []
+
+    def pack_worker(bases, off, want):
+        for _ in range(6):
+            got, ok = nat.pack_reads(bases, off)
+            if not ok or not np.array_equal(got, want):
+                errors.append("pack")
+
+    def parse_worker():
+        for _ in range(6):
+            pk = nat.parse_records_native(text, True)
+            if pk is None or pk["n"] != 30_000 or pk["seq"].size != 300_000:
+                errors.append("parse")
+
+    threads = [threading.Thread(target=pack_worker, args=j) for j in jobs] + [threading.Thread(target=parse_worker) for _ in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors

@@ -348,3 +348,26 @@ def test_k_above_31_is_out_of_scope():
     data, off = nat.pack_strings(["ACGT" * 20])
     with pytest.raises(ValueError):
         nat.NativeIndex.build(data, off, 32)
+
+
+def test_builds_on_two_devices_in_one_process():
+    """The > 48 KB shared-memory opt-in of the sort and scatter kernels is per device (a static flag made the
+    first build on a second device fail); the buffer cache is per device too."""
+    import ctypes
+    n = ctypes.c_int32(0)
+    nat.lib().pa_device_count(ctypes.byref(n))
+    if n.value < 2:
+        pytest.skip("needs two GPUs")
+    genomes = synth.make_genomes(4, 30_000, seed=51, cluster_size=2, shared_frac=0.3, n_every=9000, n_run=7)
+    data, goff = nat.pack_strings([s for _, s in synth.genomes_as_pairs(genomes)])
+    b, q, off = synth.make_reads(genomes, 2000, 150, seed=52, sub_rate=0.01, random_frac=0.03)
+    results = []
+    for device in (0, 1, 0, 1):
+        ix = nat.NativeIndex.build(data, goff, 31, device=device)
+        w, l, c = ix.align(b, q, off, nat.make_params(1, 1, 60, 58, 2))
+        results.append((ix.info().n_keys, nat.flatten_results(w, l), [int(x) for x in c]))
+        ix.close()
+    for r in results[1:]:
+        assert r[0] == results[0][0] and r[2] == results[0][2]
+        assert all(np.array_equal(a, b_) for a, b_ in zip(r[1], results[0][1]))
+    nat.trim_memory()
