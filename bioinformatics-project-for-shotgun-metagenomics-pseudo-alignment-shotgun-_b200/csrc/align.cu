@@ -945,7 +945,8 @@ align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
 
 template <bool QUAL>
 struct FrontState {
-  uint32_t lo[AL_ROUNDS + 1], hi[AL_ROUNDS + 1], inv[AL_ROUNDS + 1];   // bit planes of the read (warp-uniform)
+  uint32_t lo[AL_ROUNDS + 1], hi[AL_ROUNDS + 1];                       // bit planes of the read (warp-uniform)
+  uint32_t ok;                                                         // bit r: window r of this lane holds ACGT only
   uint32_t mkey[AL_ROUNDS + 1];                                        // slid minimizer keys
   uint32_t qex[QUAL ? AL_ROUNDS + 1 : 1];                              // exclusive quality prefix at this lane's base
   uint32_t W;                                                          // windows to look up (0: none)
@@ -975,7 +976,17 @@ __device__ __forceinline__ void fast_stage_a(const TableView& t, const AlignPara
   if (W > AL_SUPER) { f.defer = true; return; }   // longer than one super-round: the general kernel loops over super-rounds
   if (W == 0) return;
   f.W = (uint32_t)W;
-  encode_planes<PACKED>(in, ch, read, beg, L, 0, lane, f.lo, f.hi, f.inv);
+  {
+    // the "not ACGT" plane is needed for one test per window only: reduce it to four bits here instead of carrying five
+    // words through the pipeline (the carried state is what limits the registers of the staggered kernel)
+    uint32_t inv[AL_ROUNDS + 1];
+    encode_planes<PACKED>(in, ch, read, beg, L, 0, lane, f.lo, f.hi, inv);
+    const uint32_t kmask = (k >= 1 && k < 32) ? ((1u << k) - 1) : 0u;
+    f.ok = 0;
+#pragma unroll
+    for (int r = 0; r < AL_ROUNDS; ++r)
+      f.ok |= ((__funnelshift_r(inv[r], inv[r + 1], lane) & kmask) == 0 ? 1u : 0u) << r;
+  }
   if (QUAL && prm.has_mkq) {
     uint32_t carry = 0;
 #pragma unroll
@@ -1056,7 +1067,7 @@ align_fast_split_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ q
         }
         const uint32_t wl = __funnelshift_r(cur.lo[r], cur.lo[r + 1], lane) & kmask;
         const uint32_t wh = __funnelshift_r(cur.hi[r], cur.hi[r + 1], lane) & kmask;
-        const uint32_t wi = __funnelshift_r(cur.inv[r], cur.inv[r + 1], lane) & kmask;
+        const uint32_t wi = ((cur.ok >> r) & 1u) ^ 1u;
         uint32_t mh, mp;
         window_minimizer(t, cur.mkey[r], wl, &mh, &mp);
         const SlotWord a = slot_word<VAL32>(t, wl, wh, mh, mp);
