@@ -13,7 +13,6 @@
 #include "table.cuh"
 
 #include <algorithm>
-#include <chrono>
 #include <cstdlib>
 #include <vector>
 
@@ -674,19 +673,6 @@ float elapsed_ms(cudaEvent_t a, cudaEvent_t b) {
 // ===========================================================================
 // host orchestration
 // ===========================================================================
-namespace {
-struct PhaseTrace {   // PA_TRACE=1: host wall-clock of the build phases on stderr
-  bool on = getenv("PA_TRACE") != nullptr;
-  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-  void mark(const char* what, cudaStream_t s) {
-    if (!on) return;
-    cudaStreamSynchronize(s);
-    auto t1 = std::chrono::steady_clock::now();
-    fprintf(stderr, "[pa trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-    t0 = t1;
-  }
-};
-}  // namespace
 
 // K3 host side: CSR of the index from n_valid sorted (key, global position) records -- or (key, genome index) records,
 // which give the keys and genome runs only (no positions: table-only builds)

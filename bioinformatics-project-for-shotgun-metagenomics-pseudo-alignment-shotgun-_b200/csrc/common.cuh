@@ -368,8 +368,6 @@ __device__ __forceinline__ uint32_t inline_count(const TableView& t, uint64_t pa
 // ---------------------------------------------------------------------------
 // small device utilities
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
-
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

@@ -26,8 +26,6 @@ namespace pa {
 
 namespace {
 
-inline unsigned grid_for(uint64_t n, int threads) { return (unsigned)std::max<uint64_t>(1, (n + threads - 1) / threads); }
-
 // ===========================================================================
 // exchange kernels
 // ===========================================================================

@@ -455,11 +455,6 @@ def _check_align_args(kmer_reference, m, p, mrq, mkq, mg, debug=False) -> None:
         raise ValueError(f"m must be bigger than or equal to {M_THRESHOLD}")
 
 
-def _unpack_lists(words: np.ndarray, lst: np.ndarray):
-    types, lens, payload = nat.decode_words(words)
-    return types, lens, payload
-
-
 class Read:
     """One sequencing read (kmer.py:357-526)."""
 
