@@ -165,6 +165,62 @@ owner_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ va
   }
 }
 
+// ===========================================================================
+// Table slices on the wire.  A slice is mostly empty slots (load factor 0.2: four of five are all ones), so a rank does
+// not ship its slice but, per 512-byte block, a 64-bit occupancy bitmap plus the occupied slot words -- 110 instead of
+// 512 bytes per block at load 0.2 -- and every rank expands what it receives into its table: HBM bandwidth (cheap)
+// traded for NVLink bytes (the bound of the gather).  One warp per block, two slots per lane.
+// ===========================================================================
+constexpr int CMP_THREADS = 256;
+constexpr uint32_t BLOCK_SLOTS = BLOCK_BUCKETS * BUCKET_SLOTS;   // 64
+
+__global__ void __launch_bounds__(CMP_THREADS)
+slice_bitmaps(const uint64_t* __restrict__ slots, uint64_t b_lo, uint64_t b_hi, unsigned long long* __restrict__ bitmap,
+              uint32_t* __restrict__ cnt) {
+  const uint64_t b = b_lo + (blockIdx.x * (uint64_t)CMP_THREADS + threadIdx.x) / 32;
+  const uint32_t lane = threadIdx.x & 31;
+  if (b >= b_hi) return;
+  const uint64_t* p = slots + b * BLOCK_SLOTS;
+  const uint32_t m0 = __ballot_sync(0xffffffffu, p[lane] != EMPTY64), m1 = __ballot_sync(0xffffffffu, p[32 + lane] != EMPTY64);
+  if (lane == 0) { bitmap[b] = ((unsigned long long)m1 << 32) | m0; cnt[b - b_lo] = __popc(m0) + __popc(m1); }
+}
+
+__global__ void __launch_bounds__(CMP_THREADS)
+slice_words(const uint64_t* __restrict__ slots, uint64_t b_lo, uint64_t b_hi, const uint64_t* __restrict__ off /* per block of the slice */,
+            uint64_t* __restrict__ words) {
+  const uint64_t b = b_lo + (blockIdx.x * (uint64_t)CMP_THREADS + threadIdx.x) / 32;
+  const uint32_t lane = threadIdx.x & 31;
+  if (b >= b_hi) return;
+  const uint64_t* p = slots + b * BLOCK_SLOTS;
+  const uint64_t s0 = p[lane], s1 = p[32 + lane];
+  const uint32_t m0 = __ballot_sync(0xffffffffu, s0 != EMPTY64), m1 = __ballot_sync(0xffffffffu, s1 != EMPTY64);
+  const uint32_t lt = (1u << lane) - 1;
+  uint64_t* dst = words + off[b - b_lo];
+  if (s0 != EMPTY64) dst[__popc(m0 & lt)] = s0;
+  if (s1 != EMPTY64) dst[__popc(m0) + __popc(m1 & lt)] = s1;
+}
+
+__global__ void __launch_bounds__(CMP_THREADS)
+bitmap_counts(const unsigned long long* __restrict__ bitmap, uint64_t n_blocks, uint32_t* __restrict__ cnt) {
+  const uint64_t b = blockIdx.x * (uint64_t)CMP_THREADS + threadIdx.x;
+  if (b < n_blocks) cnt[b] = __popcll(bitmap[b]);
+}
+
+// every block outside [skip_lo, skip_hi) (this rank's own slice, already in place): bitmap + words -> 64 slots
+__global__ void __launch_bounds__(CMP_THREADS)
+slice_expand(const unsigned long long* __restrict__ bitmap, const uint64_t* __restrict__ off, const uint64_t* __restrict__ words,
+             uint64_t n_blocks, uint64_t skip_lo, uint64_t skip_hi, uint64_t* __restrict__ slots) {
+  const uint64_t b = (blockIdx.x * (uint64_t)CMP_THREADS + threadIdx.x) / 32;
+  const uint32_t lane = threadIdx.x & 31;
+  if (b >= n_blocks || (b >= skip_lo && b < skip_hi)) return;
+  const unsigned long long bm = bitmap[b];
+  const uint32_t m0 = (uint32_t)bm, m1 = (uint32_t)(bm >> 32), lt = (1u << lane) - 1;
+  const uint64_t* src = words + off[b];
+  uint64_t* p = slots + b * BLOCK_SLOTS;
+  p[lane] = ((m0 >> lane) & 1u) ? src[__popc(m0 & lt)] : EMPTY64;
+  p[32 + lane] = ((m1 >> lane) & 1u) ? src[__popc(m0) + __popc(m1 & lt)] : EMPTY64;
+}
+
 double ms_since(std::chrono::steady_clock::time_point a) {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
 }
@@ -258,6 +314,7 @@ struct DistBuild {
   int32_t run(Index** partition_out);
   int32_t table_round(uint32_t round);
   int32_t finalize();
+  int32_t gather_slices_compressed(const std::vector<uint64_t>& blk_off);
 };
 
 int32_t DistBuild::run(Index** partition_out) {
@@ -437,6 +494,54 @@ int32_t DistBuild::table_round(uint32_t round) {
   return ST_OK;
 }
 
+// All-gather of the table slices in compressed form (see slice_bitmaps): blk_off[r] .. blk_off[r + 1] = the blocks of rank r
+int32_t DistBuild::gather_slices_compressed(const std::vector<uint64_t>& blk_off) {
+  cudaStream_t s = rep->stream;
+  const uint32_t me = (uint32_t)comm->rank;
+  const uint64_t n_blocks = blk_off[W], b_lo = blk_off[me], b_hi = blk_off[me + 1], nb_me = b_hi - b_lo;
+  if (n_blocks >= 0xFFFFFFFFull / 2) { set_error("table gather: too many blocks"); return ST_UNSUPPORTED; }
+  DevBuf bitmap, cnt, off_all, tile_sums, d_total;
+  PA_TRY(bitmap.alloc((n_blocks + 1) * 8));
+  PA_TRY(cnt.alloc((n_blocks + 1) * 4));
+  PA_TRY(off_all.alloc((n_blocks + 1) * 8));
+  PA_TRY(tile_sums.alloc((scan_tiles(n_blocks) + 1) * 8));
+  PA_TRY(d_total.alloc(8));
+  const uint64_t* slots = rep->slots.as<uint64_t>();
+  auto warps_grid = [](uint64_t blocks) { return (unsigned)std::max<uint64_t>(1, (blocks * 32 + CMP_THREADS - 1) / CMP_THREADS); };
+  // ---- my slice -> bitmaps + word counts -> offsets -> words ----
+  uint64_t my_words = 0;
+  if (nb_me) {
+    slice_bitmaps<<<warps_grid(nb_me), CMP_THREADS, 0, s>>>(slots, b_lo, b_hi, bitmap.as<unsigned long long>(), cnt.as<uint32_t>());
+    PA_TRY(exclusive_scan_u32(cnt.as<uint32_t>(), off_all.as<uint64_t>(), nb_me, tile_sums.as<uint64_t>(), d_total.as<uint64_t>(), s));
+    PA_CUDA(cudaMemcpyAsync(&my_words, d_total.p, 8, cudaMemcpyDeviceToHost, s));
+    PA_CUDA(cudaStreamSynchronize(s));
+  }
+  std::vector<uint64_t> nwords(W, 0), w_off(W + 1, 0);
+  PA_TRY(comm->allgather_host(&my_words, nwords.data(), 8));
+  for (uint32_t r = 0; r < W; ++r) w_off[r + 1] = w_off[r] + nwords[r];
+  DevBuf words;
+  PA_TRY(words.alloc((w_off[W] + 1) * 8));
+  if (nb_me)
+    slice_words<<<warps_grid(nb_me), CMP_THREADS, 0, s>>>(slots, b_lo, b_hi, off_all.as<uint64_t>(), words.as<uint64_t>() + w_off[me]);
+  PA_CUDA(cudaGetLastError());
+  PA_CUDA(cudaStreamSynchronize(s));
+  // ---- all ranks' bitmaps (block order) and words (block order): two in-place all-gathers ----
+  std::vector<uint64_t> seg(W + 1, 0);
+  for (uint32_t r = 0; r <= W; ++r) seg[r] = blk_off[r] * 8;
+  PA_TRY(comm->allgatherv_device_inplace(bitmap.p, seg.data(), s));
+  for (uint32_t r = 0; r <= W; ++r) seg[r] = w_off[r] * 8;
+  PA_TRY(comm->allgatherv_device_inplace(words.p, seg.data(), s));
+  // ---- expand every other rank's blocks into my table ----
+  bitmap_counts<<<(unsigned)std::max<uint64_t>(1, (n_blocks + CMP_THREADS - 1) / CMP_THREADS), CMP_THREADS, 0, s>>>(
+      bitmap.as<unsigned long long>(), n_blocks, cnt.as<uint32_t>());
+  PA_TRY(exclusive_scan_u32(cnt.as<uint32_t>(), off_all.as<uint64_t>(), n_blocks, tile_sums.as<uint64_t>(), d_total.as<uint64_t>(), s));
+  slice_expand<<<warps_grid(n_blocks), CMP_THREADS, 0, s>>>(bitmap.as<unsigned long long>(), off_all.as<uint64_t>(), words.as<uint64_t>(),
+                                                            n_blocks, b_lo, b_hi, rep->slots.as<uint64_t>());
+  PA_CUDA(cudaGetLastError());
+  PA_CUDA(cudaStreamSynchronize(s));
+  return ST_OK;
+}
+
 // replicate: table slices in place, genome sets and stash entries through the host
 int32_t DistBuild::finalize() {
   cudaStream_t s = rep->stream;
@@ -444,9 +549,11 @@ int32_t DistBuild::finalize() {
 
   auto t0 = std::chrono::steady_clock::now();
   {
-    std::vector<uint64_t> off(W + 1, 0);
-    for (uint32_t r = 0; r <= W; ++r) off[r] = (uint64_t)first_digit(r * R) * geom.bpd * block_bytes;
-    PA_TRY(comm->allgatherv_device_inplace(rep->slots.p, off.data(), s));
+    std::vector<uint64_t> blk(W + 1, 0), off(W + 1, 0);
+    for (uint32_t r = 0; r <= W; ++r) { blk[r] = (uint64_t)first_digit(r * R) * geom.bpd; off[r] = blk[r] * block_bytes; }
+    const char* how = getenv("PA_TABLE_GATHER");   // "raw" / "ipc" / "nccl": ship the slices as they are
+    if (W > 1 && !how) PA_TRY(gather_slices_compressed(blk));
+    else PA_TRY(comm->allgatherv_device_inplace(rep->slots.p, off.data(), s));
   }
   {
     // my pieces as one blob: [n_pieces][base, n_ids][ids ...]
