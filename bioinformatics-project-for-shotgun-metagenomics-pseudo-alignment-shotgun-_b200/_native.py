@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "pa_abi_version", "pa_last_error", "pa_device_count", "pa_trim_memory", "pa_index_build", "pa_index_build_device", "pa_index_import",
     "pa_index_free", "pa_index_info_get", "pa_index_export", "pa_decode_kmers", "pa_encode_kmers", "pa_index_lookup", "pa_index_entries", "pa_index_checksum", "pa_index_csr_device",
     "pa_extsim_stats", "pa_extsim_pairwise", "pa_index_drop_genomes", "pa_align_batch", "pa_align_batch_device", "pa_pack_reads", "pa_align_batch_packed",
-    "pa_summary_reduce_device", "pa_summary_reduce", "pa_debug_sort_pairs", "pa_debug_table_lookup",
+    "pa_summary_reduce_device", "pa_summary_reduce", "pa_debug_sort_pairs", "pa_debug_sort_pairs_hashed", "pa_debug_table_lookup",
     "pa_comm_unique_id", "pa_comm_init", "pa_comm_init_callbacks", "pa_comm_free", "pa_comm_info", "pa_comm_allreduce_summary",
     "pa_comm_allreduce_host", "pa_comm_allgather_host", "pa_comm_barrier", "pa_index_build_partitioned", "pa_index_rebuild_replica", "pa_genome_shard",
     "pa_build_exchange", "pa_build_timings", "pa_partition_of_kmer",
@@ -114,6 +114,7 @@ def lib() -> ctypes.CDLL:
         "pa_summary_reduce_device": (i32, [vp, vp, u64, u64, u32, vp, vp, vp, vp, vp]),
         "pa_summary_reduce": (i32, [vp, vp, vp, u64, u64, u64, vp, vp, vp, vp]),
         "pa_debug_sort_pairs": (i32, [vp, vp, u64, i32, i32]),
+        "pa_debug_sort_pairs_hashed": (i32, [vp, vp, u64, i32, i32, i32, vp]),
         "pa_debug_table_lookup": (i32, [vp, vp, u64, vp, vp]),
         "pa_comm_unique_id": (i32, [vp]),
         "pa_comm_init": (i32, [i32, i32, vp, i32, vp]),
@@ -662,6 +663,16 @@ def debug_sort_pairs(keys: np.ndarray, vals: np.ndarray, end_bit: int = 64, devi
     vals = np.ascontiguousarray(vals, dtype=np.uint32).copy()
     check(lib().pa_debug_sort_pairs(_p(keys), _p(vals), len(keys), end_bit, device))
     return keys, vals
+
+
+def debug_sort_pairs_hashed(keys: np.ndarray, vals: np.ndarray, end_bit: int = 64, top_bits: int = 0, device: int = 0):
+    """Returns (keys, vals, fell_back): the build's top-bits sort + repair (sort.cu), see pa_debug_sort_pairs_hashed."""
+    require_device()
+    keys = np.ascontiguousarray(keys, dtype=np.uint64).copy()
+    vals = np.ascontiguousarray(vals, dtype=np.uint32).copy()
+    fb = ctypes.c_int32(0)
+    check(lib().pa_debug_sort_pairs_hashed(_p(keys), _p(vals), len(keys), end_bit, top_bits, device, ctypes.byref(fb)))
+    return keys, vals, bool(fb.value)
 
 
 def parse_records_native(raw, fastq: bool):

@@ -774,8 +774,8 @@ int32_t index_build_from_device_bases(Index& ix, const uint8_t* d_bases) {
 
   // ---- K2 ----
   int in_b = 0;
-  PA_TRY(radix_sort_pairs(keys_a.as<uint64_t>(), vals_a.as<uint32_t>(), keys_b.as<uint64_t>(), vals_b.as<uint32_t>(), total,
-                          std::min(64, 2 * k + 1), sort_tmp.p, sort_tmp.bytes, s, &in_b));
+  PA_TRY(radix_sort_pairs_hashed(keys_a.as<uint64_t>(), vals_a.as<uint32_t>(), keys_b.as<uint64_t>(), vals_b.as<uint32_t>(), total,
+                                 std::min(64, 2 * k + 1), sort_tmp.p, sort_tmp.bytes, s, &in_b));
   PA_CUDA(cudaEventRecord(ev[2], s));
   if (in_b) { keys_a.swap(keys_b); vals_a.swap(vals_b); }
   keys_b.release(); vals_b.release(); sort_tmp.release();

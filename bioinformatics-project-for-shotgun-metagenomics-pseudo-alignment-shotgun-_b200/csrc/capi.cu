@@ -830,6 +830,27 @@ int32_t pa_debug_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t n, int32_t 
   return PA_OK;
 }
 
+int32_t pa_debug_sort_pairs_hashed(uint64_t* keys, uint32_t* vals, uint64_t n, int32_t end_bit, int32_t top_bits, int32_t device,
+                                   int32_t* fell_back) {
+  NEED(n == 0 || (keys && vals), "null argument");
+  if (fell_back) *fell_back = 0;
+  if (n == 0) return PA_OK;
+  PA_CUDA(cudaSetDevice(device));
+  DevBuf ka, kb, va, vb, tmp;
+  PA_TRY(ka.alloc(n * 8)); PA_TRY(kb.alloc(n * 8)); PA_TRY(va.alloc(n * 4)); PA_TRY(vb.alloc(n * 4));
+  PA_TRY(tmp.alloc(radix_sort_temp_bytes(n)));
+  PA_CUDA(cudaMemcpy(ka.p, keys, n * 8, cudaMemcpyHostToDevice));
+  PA_CUDA(cudaMemcpy(va.p, vals, n * 4, cudaMemcpyHostToDevice));
+  int in_b = 0, fb = 0;
+  PA_TRY(radix_sort_pairs_hashed(ka.as<uint64_t>(), va.as<uint32_t>(), kb.as<uint64_t>(), vb.as<uint32_t>(), n, end_bit, tmp.p,
+                                 tmp.bytes, 0, &in_b, top_bits, &fb));
+  PA_CUDA(cudaDeviceSynchronize());
+  if (fell_back) *fell_back = fb;
+  PA_CUDA(cudaMemcpy(keys, in_b ? kb.p : ka.p, n * 8, cudaMemcpyDeviceToHost));
+  PA_CUDA(cudaMemcpy(vals, in_b ? vb.p : va.p, n * 4, cudaMemcpyDeviceToHost));
+  return PA_OK;
+}
+
 int32_t pa_debug_pack_reads(const uint8_t* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t* planes, uint64_t planes_cap,
                             int32_t n_threads, int32_t* all_acgt) {
   NEED(read_off && planes && all_acgt, "null argument");

@@ -411,8 +411,8 @@ int32_t DistBuild::run(Index** partition_out) {
         PA_TRY(keys_b.alloc(n_recv * 8)); PA_TRY(vals_b.alloc(n_recv * 4));
         PA_TRY(sort_tmp.alloc(radix_sort_temp_bytes(n_recv)));
         int in_b = 0;
-        PA_TRY(radix_sort_pairs(recv_k, recv_v, keys_b.as<uint64_t>(), vals_b.as<uint32_t>(), n_recv, std::min(64, 2 * k), sort_tmp.p,
-                                sort_tmp.bytes, s, &in_b));
+        PA_TRY(radix_sort_pairs_hashed(recv_k, recv_v, keys_b.as<uint64_t>(), vals_b.as<uint32_t>(), n_recv, std::min(64, 2 * k),
+                                       sort_tmp.p, sort_tmp.bytes, s, &in_b));
         if (in_b) { sk = keys_b.as<uint64_t>(); sv = vals_b.as<uint32_t>(); }
         PA_CUDA(cudaStreamSynchronize(s));
       }

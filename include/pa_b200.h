@@ -292,6 +292,11 @@ int32_t pa_free_text(uint8_t* p);
 int32_t pa_index_csr_device(pa_index* idx, uint64_t** d_keys, uint64_t** d_run_off, uint32_t** d_run_genome);
 /* stable LSD radix sort of (key, value) pairs on key bits [0, end_bit), host in / host out (K2) */
 int32_t pa_debug_sort_pairs(uint64_t* keys, uint32_t* vals, uint64_t n, int32_t end_bit, int32_t device);
+/* the sort the index builds use for their hashed k-mer keys: digit passes over the top `top_bits` bits only (0 = chosen
+ * from n), then a stable repair of the runs of equal top bits that hold different keys; *fell_back = 1 when the keys were
+ * not spread evenly enough and the remaining passes ran after all.  Same result as pa_debug_sort_pairs on any input. */
+int32_t pa_debug_sort_pairs_hashed(uint64_t* keys, uint32_t* vals, uint64_t n, int32_t end_bit, int32_t top_bits, int32_t device,
+                                   int32_t* fell_back);
 /* the host-side 2-bit packing of pa_align_batch (pure host code): planes needs 2 * (n_bases / 32 + n_reads + 1) words;
  * read i owns the words from 2 * ((read_off[i] - read_off[0]) / 32 + i): ceil(L / 32) low-plane words, then as many
  * high-plane words.  *all_acgt = 0 when a base outside ACGT was met. */

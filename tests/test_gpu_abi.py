@@ -121,6 +121,55 @@ def test_radix_sort_pairs(n, end_bit):
     assert np.array_equal(v2, vals[order])      # stability
 
 
+def _check_hashed_sort(keys, end_bit, top_bits, expect_fallback=None):
+    vals = np.arange(len(keys), dtype=np.uint32)
+    k2, v2, fb = nat.debug_sort_pairs_hashed(keys, vals, end_bit, top_bits)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k2, keys[order])
+    assert np.array_equal(v2, vals[order])      # stability inside equal keys
+    if expect_fallback is not None:
+        assert fb == expect_fallback
+    return fb
+
+
+@pytest.mark.parametrize("n,end_bit,top_bits", [(2, 63, 8), (1000, 63, 0), (4097, 62, 16), (100_003, 63, 24), (1_000_000, 63, 24),
+                                                 (1_000_000, 63, 0), (3_000_001, 62, 32), (2_000_000, 40, 24)])
+def test_hashed_sort_repairs_mixed_runs(n, end_bit, top_bits):
+    """Sort on the top bits + repair = the full stable sort: spread keys with duplicates (the occurrences of a k-mer)."""
+    rng = np.random.default_rng(n + end_bit + top_bits)
+    keys = rng.integers(0, 1 << (end_bit - 1), size=n, dtype=np.uint64)
+    if n > 10:
+        dup = rng.integers(0, n, size=n // 2)
+        keys[dup] = keys[rng.integers(0, n, size=n // 2)]                      # many repeated keys
+        keys[rng.integers(0, n, size=n // 50 + 1)] = np.uint64((1 << end_bit) - 1)  # the sentinel of invalid windows
+    _check_hashed_sort(keys, end_bit, top_bits)
+
+
+def test_hashed_sort_long_runs_and_fallback():
+    rng = np.random.default_rng(77)
+    end_bit, top_bits = 63, 16
+    low = end_bit - top_bits
+    # (a) a k-mer with 50,000 occurrences sharing its top bits with three strangers, interleaved: one big group
+    top = np.uint64(0x1234) << np.uint64(low)
+    a, b, c, d = (top | np.uint64(x) for x in (500, 20, 900, 7))
+    group = np.full(50_000, a, dtype=np.uint64)
+    group[[0, 17, 30_000, 49_999]] = [c, b, d, b]
+    rest = rng.integers(0, 1 << 62, size=200_000, dtype=np.uint64)
+    rest = rest[(rest >> np.uint64(low)) != np.uint64(0x1234)]
+    keys = np.concatenate([rest[:100_000], group[:25_000], rest[100_000:], group[25_000:]])
+    assert _check_hashed_sort(keys, end_bit, top_bits) in (False, True)
+    # (b) two heavy keys interleaved record by record (every position is a boundary)
+    inter = np.where(np.arange(40_000) % 2 == 0, a, b).astype(np.uint64)
+    keys = np.concatenate([rest[:50_000], inter, rest[50_000:]])
+    _check_hashed_sort(keys, end_bit, top_bits)
+    # (c) keys that are not spread at all (all in one run of top bits, thousands of distinct keys): the fallback passes
+    dense = rng.integers(0, 1 << 20, size=300_000, dtype=np.uint64)
+    _check_hashed_sort(dense, end_bit, top_bits, expect_fallback=True)
+    # (d) nothing to repair
+    spread = (np.arange(100_000, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)) & np.uint64((1 << 62) - 1)
+    _check_hashed_sort(spread, end_bit, 32, expect_fallback=False)
+
+
 @pytest.mark.parametrize("block", range(6))
 def test_fuzz_small_k_against_oracle(block):
     for seed in range(block * 100, block * 100 + 100):
