@@ -874,6 +874,30 @@ int32_t pa_debug_minimizer(int32_t k, const uint8_t* kmers_ascii, uint64_t n, ui
   return PA_OK;
 }
 
+int32_t pa_debug_slot_roundtrip(int32_t k, uint32_t n_genomes, uint64_t n_kmers_planned, double load, const uint8_t* kmers_ascii,
+                                uint64_t n, uint64_t* n_bad) {
+  NEED(k >= 1 && k <= 31, "k out of range");
+  NEED(n_bad && (n == 0 || kmers_ascii), "null argument");
+  TableGeom g;
+  PA_TRY(table_geometry(k, n_genomes, n_kmers_planned, load, 1, &g));
+  Index ix;
+  ix.k = k;
+  apply_geometry(ix, g);
+  const TableView t = ix.view();
+  const uint32_t kmask = (1u << k) - 1;
+  *n_bad = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    bool ok;
+    const uint64_t raw = encode_kmer_host(kmers_ascii + i * (uint64_t)k, k, &ok);
+    NEED(ok, "k-mer with a base outside ACGT");
+    uint32_t mh, p;
+    kmer_minimizer(t, (uint32_t)raw & kmask, (uint32_t)(raw >> k) & kmask, &mh, &p);
+    const SlotAddr a = slot_addr(t, (uint32_t)raw & kmask, (uint32_t)(raw >> k) & kmask, mh, p);
+    if (raw_from_slot(t, a.block, a.bucket, a.tag) != raw) ++*n_bad;
+  }
+  return PA_OK;
+}
+
 int32_t pa_debug_table_lookup(pa_index* idx, const uint8_t* kmers_ascii, uint64_t n, uint32_t* n_genomes,
                               uint32_t* first_genome) {
   NEED(idx, "null index");

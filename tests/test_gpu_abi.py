@@ -218,6 +218,34 @@ def test_overloaded_table_walks_chains_and_stash(dense, monkeypatch):
         check_case(dict(case, k=k))
 
 
+@pytest.mark.parametrize("shift,dense", [("0", None), ("3", None), ("6", "3"), ("2", "5"), ("19", "5")])
+def test_region_ordered_table_insert(shift, dense, monkeypatch):
+    """Large tables take their inserts grouped by table region (table.cu: region_count / region_scatter / region_insert);
+    forced on here for small cases, with tiny regions, also on overloaded tables (chains, CONT, stash entries that are
+    turned back into k-mers by raw_from_slot)."""
+    monkeypatch.setenv("PA_TABLE_REGIONS", "1")
+    monkeypatch.setenv("PA_TABLE_REGION_SHIFT", shift)
+    if dense:
+        monkeypatch.setenv("PA_TABLE_DENSE", dense)
+    genomes = synth.make_genomes(12, 30_000, seed=15, cluster_size=6, shared_frac=0.6, sub_rate=0.03, n_every=9000, n_run=11)
+    b, q, off = synth.make_reads(genomes, 3000, 150, seed=16, sub_rate=0.02, random_frac=0.05)
+    case = {"k": 31, "genomes": synth.genomes_as_pairs(genomes), "reads": synth.reads_as_triples(b, q, off),
+            "params": dict(m=1, p=1, mrq=None, mkq=None, mg=None), "seed": 2}
+    if dense == "5":
+        data, goff = nat.pack_strings([g[1] for g in case["genomes"]])
+        ix = nat.NativeIndex.build(data, goff, 31)
+        inf = ix.info()
+        ix.close()
+        assert inf.stash_count > 0, "the test is meant to reach the stash"
+    check_case(case)
+    for k in (7, 13, 20):
+        check_case(dict(case, k=k, params=dict(m=2, p=0, mrq=None, mkq=60, mg=4)))
+    for seed in range(9100, 9130):
+        check_case(synth.fuzz_case(seed))
+    for seed in range(9200, 9215):
+        check_case(synth.fuzz_case(seed, k_range=(9, 31), max_genomes=8))
+
+
 @pytest.mark.parametrize("mode", ["1", "0"])
 def test_host_packed_reads_give_the_same_results(mode, monkeypatch):
     """PA_HOST_PACK=1: every chunk of pa_align_batch is turned into 2-bit planes on the host and aligned by the packed
