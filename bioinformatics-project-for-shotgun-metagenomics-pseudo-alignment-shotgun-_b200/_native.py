@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "pa_comm_unique_id", "pa_comm_init", "pa_comm_init_callbacks", "pa_comm_free", "pa_comm_info", "pa_comm_allreduce_summary",
     "pa_comm_allreduce_host", "pa_comm_allgather_host", "pa_comm_barrier", "pa_index_build_partitioned", "pa_index_rebuild_replica", "pa_genome_shard",
     "pa_build_exchange", "pa_build_timings", "pa_partition_of_kmer",
-    "pa_debug_pack_reads", "pa_debug_minimizer", "pa_debug_slot_roundtrip",
+    "pa_debug_pack_reads", "pa_debug_minimizer",
     "pa_parse_records", "pa_parsed_copy", "pa_parsed_free",
     "pa_format_kmers_json", "pa_free_text",
 ]
@@ -133,7 +133,6 @@ def lib() -> ctypes.CDLL:
         "pa_partition_of_kmer": (i32, [i32, vp, u32, vp]),
         "pa_debug_pack_reads": (i32, [vp, vp, u64, vp, u64, i32, vp]),
         "pa_debug_minimizer": (i32, [i32, vp, u64, vp, vp]),
-        "pa_debug_slot_roundtrip": (i32, [i32, u32, u64, ctypes.c_double, vp, u64, vp]),
         "pa_parse_records": (i32, [vp, u64, i32, vp, vp, vp, vp]),
         "pa_parsed_copy": (i32, [vp, vp, vp, vp, vp, vp, vp, vp]),
         "pa_parsed_free": (i32, [vp]),

@@ -943,24 +943,107 @@ align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
 #define PA_FAST_SPLIT 1
 #endif
 
-template <bool QUAL>
+// QUAL: 0 = no quality filters, 1 = quality bytes scanned in the kernel, 2 = the filters were evaluated by
+// quality_masks_kernel beforehand (one bit per window + one "dropped" byte per read): the quality state carried from
+// stage A to stage B is then one register instead of five prefix sums, which is what made the staggered order spill.
+template <int QUAL>
 struct FrontState {
   uint32_t lo[AL_ROUNDS + 1], hi[AL_ROUNDS + 1];                       // bit planes of the read (warp-uniform)
   uint32_t ok;                                                         // bit r: window r of this lane holds ACGT only
   uint32_t mkey[AL_ROUNDS + 1];                                        // slid minimizer keys
-  uint32_t qex[QUAL ? AL_ROUNDS + 1 : 1];                              // exclusive quality prefix at this lane's base
+  uint32_t qex[QUAL == 1 ? AL_ROUNDS + 1 : 1];                         // QUAL 1: exclusive quality prefix at this lane's base
+  uint32_t qf;                                                         // QUAL 2: bit r = window r of this lane fails min-kmer-quality
   uint32_t W;                                                          // windows to look up (0: none)
   bool dropped, defer;
 };
 
-template <bool QUAL, bool PACKED>
+// Quality filters of a batch, ahead of K4 (kmer.py:394-408, 420-422, 587): per read a 128-bit mask -- bit 32 r + l = window
+// 32 r + l has sum(q[w..w+k)) < mkq * k -- and a byte: 1 = sum(q) < mrq * len (the read is dropped).  Integer tests equal to
+// the reference's float comparisons.  Reads with more than 128 windows get no mask: the general kernel
+// scans their qualities itself.  Streaming: 1 byte in per base, 17 bytes out per read.
+// One THREAD per read: a warp stages the quality bytes of its 32 reads (one contiguous span of the input) in shared memory
+// with coalesced 16-byte loads, then every thread slides the k-byte window sum along its own read -- ~50 warp instructions
+// per read where the warp-per-read scan of K4 (prefix sums by shuffles) takes ~250.
+constexpr int QM_WARP_BYTES = 32 * 160 + 32;
+__global__ void __launch_bounds__(256) quality_masks_kernel(const uint8_t* __restrict__ quals, const uint64_t* __restrict__ read_off,
+                                                            uint64_t n_reads, AlignParams prm, int k, uint4* __restrict__ masks,
+                                                            uint8_t* __restrict__ drop) {
+  __shared__ __align__(16) uint8_t sh[8][QM_WARP_BYTES];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* my = sh[warp];
+  const uint64_t n_groups = (n_reads + 31) / 32;
+  const int64_t thr = prm.mkq * (int64_t)k;                       // window filter: sum < thr, sum is a uint32
+  const bool thr_all = thr > (int64_t)0xFFFFFFFFLL;
+  const uint32_t thr32 = thr <= 0 ? 0u : (thr_all ? 0xFFFFFFFFu : (uint32_t)thr);
+  for (uint64_t grp = (uint64_t)blockIdx.x * 8 + warp; grp < n_groups; grp += (uint64_t)gridDim.x * 8) {
+    const uint64_t read = grp * 32 + lane;
+    const bool valid = read < n_reads;
+    const uint64_t beg = read_off[valid ? read : n_reads];
+    const uint64_t last = read_off[min(grp * 32 + 32, n_reads)];
+    uint64_t end = __shfl_down_sync(0xffffffffu, beg, 1);
+    if (lane == 31) end = last;
+    const uint64_t L = valid ? end - beg : 0;
+    const uint64_t span_beg = __shfl_sync(0xffffffffu, beg, 0), span = last - span_beg;
+    const uint8_t* src = quals + span_beg;
+    const uint32_t pre = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);   // the staged copy starts at the 16-byte line of the span
+    const bool staged = span + pre <= (uint64_t)QM_WARP_BYTES;
+    if (staged) {
+      const uint8_t* a0 = src - pre;
+      const uint32_t nbytes = (uint32_t)span + pre;
+      for (uint32_t i = lane * 16; i < nbytes; i += 512) {
+        if (i + 16 <= nbytes) *reinterpret_cast<uint4*>(my + i) = __ldcs(reinterpret_cast<const uint4*>(a0 + i));
+        else for (uint32_t j = i; j < nbytes; ++j) my[j] = a0[j];
+      }
+    }
+    __syncwarp();
+    const uint8_t* qp = staged ? my + pre + (beg - span_beg) : quals + beg;
+    uint32_t m[AL_ROUNDS] = {0, 0, 0, 0};
+    uint64_t total = 0;
+    const uint64_t W = (k >= 1 && L >= (uint64_t)k) ? L - k + 1 : 0;
+    if (prm.has_mkq && W > 0 && W <= AL_SUPER) {
+      uint32_t s = 0;
+      for (int i = 0; i < k; ++i) s += qp[i];
+      uint32_t tot32 = s;
+      const uint32_t Wn = (uint32_t)W;
+#pragma unroll
+      for (int r = 0; r < AL_ROUNDS; ++r) {
+        uint32_t word = 0;
+        const uint32_t w_end = min(Wn, 32u * (r + 1));
+        for (uint32_t w = 32u * r; w < w_end; ++w) {
+          word |= ((thr_all || s < thr32) ? 1u : 0u) << (w & 31);
+          if (w + 1 < Wn) { const uint32_t in = qp[w + k]; s += in - qp[w]; tot32 += in; }
+        }
+        m[r] = word;
+      }
+      total = tot32;
+    } else if (prm.has_mrq) {
+      for (uint64_t i = 0; i < L; ++i) total += qp[i];
+    }
+    __syncwarp();   // the staging buffer is rewritten by the next group
+    if (valid) {
+      masks[read] = make_uint4(m[0], m[1], m[2], m[3]);
+      drop[read] = (prm.has_mrq && (int64_t)total < prm.mrq * (int64_t)L) ? 1 : 0;
+    }
+  }
+}
+
+// the mask record of a read, through the quality slot of the input pipeline (every lane loads the same 17 bytes)
+__device__ __forceinline__ void prefetch_masks(const uint8_t* __restrict__ qm, uint64_t n_reads, bool valid, uint64_t read,
+                                               Prefetch<false>& p) {
+  uint4 m = make_uint4(0u, 0u, 0u, 0u);
+  uint32_t d = 0;
+  if (valid) { m = __ldg(reinterpret_cast<const uint4*>(qm) + read); d = __ldg(qm + 16 * n_reads + read); }
+  p.v[0] = m.x; p.v[1] = m.y; p.v[2] = m.z; p.v[3] = m.w; p.v[AL_ROUNDS] = d;
+}
+
+template <int QUAL, bool PACKED>
 __device__ __forceinline__ void fast_stage_a(const TableView& t, const AlignParams& prm, const ReadInput& in,
                                              const uint8_t* __restrict__ quals, const Prefetch<PACKED>& ch,
                                              const Prefetch<false>& q, uint64_t read, uint64_t beg, uint64_t L, uint32_t lane,
                                              FrontState<QUAL>& f, unsigned long long& c_drop) {
   const int k = (int)t.k;
-  f.dropped = false; f.defer = false; f.W = 0;
-  if (QUAL && prm.has_mrq) {  // Read.mean_quality() < min_read_quality  (kmer.py:587)
+  f.dropped = false; f.defer = false; f.W = 0; f.qf = 0;
+  if (QUAL == 1 && prm.has_mrq) {  // Read.mean_quality() < min_read_quality  (kmer.py:587)
     uint64_t s = 0;
     if (L <= 32 * (AL_ROUNDS + 1)) {   // the prefetched bytes cover the read (bytes beyond L were loaded as 0)
 #pragma unroll
@@ -971,6 +1054,11 @@ __device__ __forceinline__ void fast_stage_a(const TableView& t, const AlignPara
     }
     s = warp_sum(s);
     if ((int64_t)s < prm.mrq * (int64_t)L) { f.dropped = true; if (lane == 0) ++c_drop; }
+  }
+  if (QUAL == 2) {
+    if (q.v[AL_ROUNDS]) { f.dropped = true; if (lane == 0) ++c_drop; }
+#pragma unroll
+    for (int r = 0; r < AL_ROUNDS; ++r) f.qf |= ((q.v[r] >> lane) & 1u) << r;
   }
   const uint64_t W = (!f.dropped && k >= 1 && L >= (uint64_t)k) ? L - k + 1 : 0;  // kmer.py:91-92
   if (W > AL_SUPER) { f.defer = true; return; }   // longer than one super-round: the general kernel loops over super-rounds
@@ -987,14 +1075,14 @@ __device__ __forceinline__ void fast_stage_a(const TableView& t, const AlignPara
     for (int r = 0; r < AL_ROUNDS; ++r)
       f.ok |= ((__funnelshift_r(inv[r], inv[r + 1], lane) & kmask) == 0 ? 1u : 0u) << r;
   }
-  if (QUAL && prm.has_mkq) {
+  if (QUAL == 1 && prm.has_mkq) {
     uint32_t carry = 0;
 #pragma unroll
     for (int c = 0; c <= AL_ROUNDS; ++c) {
       uint32_t qq = q.v[c], incl = qq;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-      f.qex[QUAL ? c : 0] = carry + incl - qq;
+      f.qex[QUAL == 1 ? c : 0] = carry + incl - qq;
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
@@ -1010,7 +1098,7 @@ __device__ __forceinline__ void fast_stage_a(const TableView& t, const AlignPara
   if (t.w > span) window_min_step(f.mkey, t.w - span, lane);
 }
 
-template <bool QUAL, bool PACKED, bool VAL32>
+template <int QUAL, bool PACKED, bool VAL32>
 __global__ void __launch_bounds__(FA_THREADS, PA_FAST_MINB)
 align_fast_split_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
                         const uint64_t* __restrict__ read_off, uint64_t n_reads, AlignParams prm, uint64_t* __restrict__ out_word,
@@ -1039,9 +1127,11 @@ align_fast_split_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ q
     Prefetch<PACKED> ch0;
     Prefetch<false> q0;
     prefetch_read<PACKED>(in, r0 < n_reads, r0, beg0, end0 - beg0, lane, ch0);
-    if (QUAL) prefetch_read<false>(qin, r0 < n_reads, r0, beg0, end0 - beg0, lane, q0);
+    if (QUAL == 1) prefetch_read<false>(qin, r0 < n_reads, r0, beg0, end0 - beg0, lane, q0);
+    if (QUAL == 2) prefetch_masks(quals, n_reads, r0 < n_reads, r0, q0);
     prefetch_read<PACKED>(in, r1 < n_reads, r1, nx_beg, nx_end - nx_beg, lane, nx_ch);
-    if (QUAL) prefetch_read<false>(qin, r1 < n_reads, r1, nx_beg, nx_end - nx_beg, lane, nx_q);
+    if (QUAL == 1) prefetch_read<false>(qin, r1 < n_reads, r1, nx_beg, nx_end - nx_beg, lane, nx_q);
+    if (QUAL == 2) prefetch_masks(quals, n_reads, r1 < n_reads, r1, nx_q);
     if (r0 < n_reads) fast_stage_a<QUAL, PACKED>(t, prm, in, quals, ch0, q0, r0, beg0, end0 - beg0, lane, cur, c_drop);
   }
 
@@ -1057,14 +1147,15 @@ align_fast_split_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ q
         const uint32_t s = 32 * r + lane;
         const bool exists = s < cur.W;
         bool qf = false;
-        if (QUAL && prm.has_mkq) {  // kmer_quality(start, k) < min_kmer_quality, before the lookup (kmer.py:420-422)
+        if (QUAL == 1 && prm.has_mkq) {  // kmer_quality(start, k) < min_kmer_quality, before the lookup (kmer.py:420-422)
           const uint32_t tl = lane + k;
-          const uint32_t p_a = __shfl_sync(0xffffffffu, cur.qex[QUAL ? r : 0], tl & 31);
-          const uint32_t p_b = __shfl_sync(0xffffffffu, cur.qex[QUAL ? r + 1 : 0], tl & 31);
+          const uint32_t p_a = __shfl_sync(0xffffffffu, cur.qex[QUAL == 1 ? r : 0], tl & 31);
+          const uint32_t p_b = __shfl_sync(0xffffffffu, cur.qex[QUAL == 1 ? r + 1 : 0], tl & 31);
           const uint32_t end = tl < 32 ? p_a : p_b;
-          qf = exists && ((int64_t)(end - cur.qex[QUAL ? r : 0]) < prm.mkq * (int64_t)k);
+          qf = exists && ((int64_t)(end - cur.qex[QUAL == 1 ? r : 0]) < prm.mkq * (int64_t)k);
           read_nq += qf;
         }
+        if (QUAL == 2) { qf = exists && ((cur.qf >> r) & 1u); read_nq += qf; }
         const uint32_t wl = __funnelshift_r(cur.lo[r], cur.lo[r + 1], lane) & kmask;
         const uint32_t wh = __funnelshift_r(cur.hi[r], cur.hi[r + 1], lane) & kmask;
         const uint32_t wi = ((cur.ok >> r) & 1u) ^ 1u;
@@ -1084,12 +1175,13 @@ align_fast_split_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ q
       Prefetch<PACKED> n2_ch;
       Prefetch<false> n2_q;
       prefetch_read<PACKED>(in, r2 < n_reads, r2, n2_beg, n2_end - n2_beg, lane, n2_ch);
-      if (QUAL) prefetch_read<false>(qin, r2 < n_reads, r2, n2_beg, n2_end - n2_beg, lane, n2_q);
+      if (QUAL == 1) prefetch_read<false>(qin, r2 < n_reads, r2, n2_beg, n2_end - n2_beg, lane, n2_q);
+      if (QUAL == 2) prefetch_masks(quals, n_reads, r2 < n_reads, r2, n2_q);
       uint64_t n3_beg = 0, n3_end = 0;
       if (r3 < n_reads) { n3_beg = read_off[r3]; n3_end = read_off[r3 + 1]; }
       if (r1 < n_reads) fast_stage_a<QUAL, PACKED>(t, prm, in, quals, nx_ch, nx_q, r1, nx_beg, nx_end - nx_beg, lane, nx, c_drop);
       nx_ch = n2_ch;
-      if (QUAL) nx_q = n2_q;
+      if (QUAL != 0) nx_q = n2_q;
       nx_beg = n2_beg; nx_end = n2_end;
       n2_beg = n3_beg; n2_end = n3_end;
     }
@@ -1223,25 +1315,42 @@ int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_q
   uint32_t* q_items = reinterpret_cast<uint32_t*>(ix.align_queue.as<unsigned char>() + 16);
   PA_CUDA(cudaMemsetAsync(q_count, 0, 8, s));
   {
-    // the staggered kernel wins without quality filters (15.4 -> 15.0 ms per 10^7 reads); with them its extra state
-    // spills (20.1 -> 30.1 ms), so EXTQUALITY keeps the plain order of stages.  VAL32: see fast_stage_c.
+    // VAL32: see fast_stage_c.
     const bool v32 = tv.val_bits <= 32 && 2 * (tv.k - tv.m) + CHAIN_BITS == 32;
     using FastKernel = void (*)(TableView, ReadInput, const uint8_t*, const uint64_t*, uint64_t, AlignParams, uint64_t*, unsigned long long*,
                                 uint32_t*, unsigned long long*);
     FastKernel fk;
+    // EXTQUALITY: the filters are evaluated by quality_masks_kernel first and K4 runs in the staggered order on their bits
+    // (PA_QUAL_MASKS=0: the kernel that scans the quality bytes itself, in the plain order -- the state of that scan spills
+    // in the staggered order, PA_QUAL_SPLIT=1)
+    const char* qm_env = getenv("PA_QUAL_MASKS");
+    const bool qual_masks = qual && PA_FAST_SPLIT && !(qm_env && *qm_env == '0');
     static const int qual_split = getenv("PA_QUAL_SPLIT") ? atoi(getenv("PA_QUAL_SPLIT")) : 0;   // tuning knob, see DESIGN.md section 4
-    if (qual && qual_split && v32) fk = packed ? align_fast_split_kernel<true, true, true> : align_fast_split_kernel<true, false, true>;
+    const uint8_t* fast_quals = d_quals;
+    if (qual_masks) {
+      if (ix.align_qmasks.bytes < n_reads * 17 + 16) PA_TRY(ix.align_qmasks.alloc(n_reads * 17 + n_reads / 2 + 16));
+      uint8_t* qm = ix.align_qmasks.as<uint8_t>();
+      const uint64_t qgrid = std::min<uint64_t>((uint64_t)sms * 5, (n_reads + 255) / 256);
+      quality_masks_kernel<<<(unsigned)std::max<uint64_t>(qgrid, 1), 256, 0, s>>>(d_quals, d_read_off, n_reads, prm, k,
+                                                                                 reinterpret_cast<uint4*>(qm), qm + 16 * n_reads);
+      PA_CUDA(cudaGetLastError());
+      if (launches) ++*launches;
+      fast_quals = qm;
+      fk = packed ? (v32 ? align_fast_split_kernel<2, true, true> : align_fast_split_kernel<2, true, false>)
+                  : (v32 ? align_fast_split_kernel<2, false, true> : align_fast_split_kernel<2, false, false>);
+    }
+    else if (qual && qual_split && v32) fk = packed ? align_fast_split_kernel<1, true, true> : align_fast_split_kernel<1, false, true>;
     else if (qual) fk = packed ? (v32 ? align_fast_kernel<true, true, true> : align_fast_kernel<true, true, false>)
                           : (v32 ? align_fast_kernel<true, false, true> : align_fast_kernel<true, false, false>);
-    else if (PA_FAST_SPLIT) fk = packed ? (v32 ? align_fast_split_kernel<false, true, true> : align_fast_split_kernel<false, true, false>)
-                                        : (v32 ? align_fast_split_kernel<false, false, true> : align_fast_split_kernel<false, false, false>);
+    else if (PA_FAST_SPLIT) fk = packed ? (v32 ? align_fast_split_kernel<0, true, true> : align_fast_split_kernel<0, true, false>)
+                                        : (v32 ? align_fast_split_kernel<0, false, true> : align_fast_split_kernel<0, false, false>);
     else fk = packed ? (v32 ? align_fast_kernel<false, true, true> : align_fast_kernel<false, true, false>)
                      : (v32 ? align_fast_kernel<false, false, true> : align_fast_kernel<false, false, false>);
     int occ = 1;
     PA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fk, FA_THREADS, 0));
     if (occ < 1) occ = 1;
     uint64_t grid = std::min<uint64_t>((uint64_t)sms * occ, (n_reads + FA_WARPS - 1) / FA_WARPS);
-    fk<<<(unsigned)std::max<uint64_t>(grid, 1), FA_THREADS, 0, s>>>(tv, in, d_quals, d_read_off, n_reads, prm, d_words,
+    fk<<<(unsigned)std::max<uint64_t>(grid, 1), FA_THREADS, 0, s>>>(tv, in, fast_quals, d_read_off, n_reads, prm, d_words,
                                                                      d_counters, q_items, q_count);
     PA_CUDA(cudaGetLastError());
     if (launches) ++*launches;

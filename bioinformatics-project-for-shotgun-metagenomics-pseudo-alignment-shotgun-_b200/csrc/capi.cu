@@ -105,6 +105,11 @@ bool cache_put(void* p, size_t bytes) {
   return true;
 }
 
+void alloc_miss(size_t bytes) {
+  static const bool on = getenv("PA_TRACE_ALLOC") != nullptr;
+  if (on && bytes >= (1u << 20)) fprintf(stderr, "[pa alloc] cudaMalloc of %.1f MB (no parked or cached buffer fits)\n", (double)bytes / 1e6);
+}
+
 size_t cache_held() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
@@ -870,30 +875,6 @@ int32_t pa_debug_minimizer(int32_t k, const uint8_t* kmers_ascii, uint64_t n, ui
     const uint64_t raw = encode_kmer_host(kmers_ascii + i * (uint64_t)k, k, &ok);
     NEED(ok, "k-mer with a base outside ACGT");
     kmer_minimizer(t, (uint32_t)raw & kmask, (uint32_t)(raw >> k) & kmask, &mhash[i], &offset[i]);
-  }
-  return PA_OK;
-}
-
-int32_t pa_debug_slot_roundtrip(int32_t k, uint32_t n_genomes, uint64_t n_kmers_planned, double load, const uint8_t* kmers_ascii,
-                                uint64_t n, uint64_t* n_bad) {
-  NEED(k >= 1 && k <= 31, "k out of range");
-  NEED(n_bad && (n == 0 || kmers_ascii), "null argument");
-  TableGeom g;
-  PA_TRY(table_geometry(k, n_genomes, n_kmers_planned, load, 1, &g));
-  Index ix;
-  ix.k = k;
-  apply_geometry(ix, g);
-  const TableView t = ix.view();
-  const uint32_t kmask = (1u << k) - 1;
-  *n_bad = 0;
-  for (uint64_t i = 0; i < n; ++i) {
-    bool ok;
-    const uint64_t raw = encode_kmer_host(kmers_ascii + i * (uint64_t)k, k, &ok);
-    NEED(ok, "k-mer with a base outside ACGT");
-    uint32_t mh, p;
-    kmer_minimizer(t, (uint32_t)raw & kmask, (uint32_t)(raw >> k) & kmask, &mh, &p);
-    const SlotAddr a = slot_addr(t, (uint32_t)raw & kmask, (uint32_t)(raw >> k) & kmask, mh, p);
-    if (raw_from_slot(t, a.block, a.bucket, a.tag) != raw) ++*n_bad;
   }
   return PA_OK;
 }

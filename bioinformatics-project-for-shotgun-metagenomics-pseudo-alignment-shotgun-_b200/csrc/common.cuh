@@ -231,36 +231,6 @@ __host__ __device__ __forceinline__ void kmer_minimizer(const TableView& t, uint
   *p = bp;
 }
 
-// multiplicative inverse of an odd number modulo 2^32 (Newton: five doublings of the 3 correct bits of x = a)
-__host__ __device__ constexpr uint32_t inv_odd_u32(uint32_t a) {
-  uint32_t x = a;
-  for (int i = 0; i < 5; ++i) x *= 2u - a * x;
-  return x;
-}
-
-// The k-mer (raw planes key) that a slot holds, from where it lives and its tag at chain distance 0: block -> the
-// hashes of the block are consecutive integers and the tag keeps their low bits -> minimizer hash -> (both mixes are
-// invertible) the minimizer's bases; bucket -> its offset p; tag -> the remaining bases.  Inverse of kmer_minimizer +
-// slot_addr; the region-ordered table build uses it for the rare k-mer that ends in the stash.
-__host__ __device__ inline uint64_t raw_from_slot(const TableView& t, uint64_t block, uint32_t bucket, uint64_t tag0) {
-  const uint32_t low = (uint32_t)tag0 & t.hmask;
-  const uint32_t rest = (uint32_t)(tag0 >> (CHAIN_BITS + t.hi_bits));
-  const uint64_t h0 = ((block << t.dshift) + t.bpd - 1) / t.bpd;          // smallest hash that maps to the block
-  const uint32_t mhash = (uint32_t)h0 + ((low - (uint32_t)h0) & t.hmask);
-  const uint32_t p = (bucket - mhash) & (BLOCK_BUCKETS - 1);
-  uint32_t y = ((mhash & t.ymask) * inv_odd_u32(MMER_SPREAD)) & t.ymask;  // the order (hash_from_order undone)
-  y ^= y >> t.yshift;                                                     // mmer_order undone: the xorshift is an involution
-  y = (y * inv_odd_u32(0x7FEB352DU)) & t.ymask;
-  y ^= y >> t.yshift;
-  const uint32_t x = (y << t.hdrop) | (mhash >> (2 * t.m - t.hdrop));     // the m-mer: [high plane : m][low plane : m]
-  const uint32_t lo_m = x & t.mmask, hi_m = (x >> t.m) & t.mmask;
-  const uint32_t km = t.k - t.m, below = (1u << p) - 1;
-  const uint32_t rl = rest & ((1u << km) - 1), rh = rest >> km;
-  const uint32_t lo = (rl & below) | (lo_m << p) | ((rl & ~below) << t.m);
-  const uint32_t hi = (rh & below) | (hi_m << p) | ((rh & ~below) << t.m);
-  return ((uint64_t)hi << t.k) | lo;
-}
-
 // inverse of mix_key (decoding exported keys back into k-mer strings; the table build un-hashes the CSR keys)
 __host__ __device__ inline uint64_t unmix_key(uint64_t x, const MixParams& p) {
   // inverses of the two odd multipliers modulo 2^64 (valid modulo every 2^n)

@@ -32,6 +32,7 @@ bool cache_take(size_t bytes, void** p, size_t* got);
 bool cache_put(void* p, size_t bytes);                  // false: not cached, the caller frees
 void cache_trim();
 size_t cache_held();                                    // bytes cached for the current device (memory that is free for a build)
+void alloc_miss(size_t bytes);                          // PA_TRACE_ALLOC=1: reports every allocation that had to call cudaMalloc
 
 // Owns a device allocation; frees on destruction.
 struct DevBuf {
@@ -50,6 +51,7 @@ struct DevBuf {
     if (n == 0) n = 16;
     size_t got = 0;
     if (scope_take(n, &p, &got) || cache_take(n, &p, &got)) { bytes = got; return ST_OK; }
+    alloc_miss(n);
     cudaError_t e = cudaMalloc(&p, n);
     if (e == cudaErrorMemoryAllocation) { (void)cudaGetLastError(); cache_trim(); e = cudaMalloc(&p, n); }
     if (e != cudaSuccess) { p = nullptr; (void)cudaGetLastError(); set_error("cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e)); return ST_NOMEM; }
@@ -95,6 +97,7 @@ struct Index {
   // per-warp scratch of the align kernel (allocated on first use)
   DevBuf align_scratch;
   DevBuf align_queue;   // {count u64, pad, uint32 read indices}: reads the fast kernel hands to the general kernel
+  DevBuf align_qmasks;  // EXTQUALITY: per read a 128-bit window mask, then per read a "dropped" byte (quality_masks_kernel)
   uint64_t align_scratch_warps = 0, align_scratch_stride = 0;
   // host-buffer alignment path (pa_align_batch): chunk slots so that packing / the H2D copy of later chunks overlaps the
   // kernel of chunk i; buffers grow on demand and are kept for the next call
@@ -137,11 +140,11 @@ struct Index {
   uint64_t n_blocks() const { return (uint64_t)bpd << digit_bits_for_k(k); }
   size_t device_bytes() const {
     return ukeys.bytes + run_off.bytes + run_genome.bytes + pos_off.bytes + pos.bytes + genome_off.bytes + first_occ.bytes +
-           slots.bytes + stash.bytes + mlist.bytes + align_scratch.bytes + align_queue.bytes;
+           slots.bytes + stash.bytes + mlist.bytes + align_scratch.bytes + align_queue.bytes + align_qmasks.bytes;
   }
   ~Index() {
     for (DevBuf* b : {&ukeys, &run_off, &run_genome, &pos_off, &pos, &genome_off, &first_occ, &slots, &stash, &mlist,
-                      &align_scratch, &align_queue, &host_list, &host_state})
+                      &align_scratch, &align_queue, &align_qmasks, &host_list, &host_state})
       b->release();
     if (stream) cudaStreamSynchronize(stream);
     for (auto& sl : slot) { if (sl.stream) cudaStreamDestroy(sl.stream); if (sl.kernel_done) cudaEventDestroy(sl.kernel_done); if (sl.h2d_done) cudaEventDestroy(sl.h2d_done); if (sl.copy_beg) cudaEventDestroy(sl.copy_beg); if (sl.copy_end) cudaEventDestroy(sl.copy_end); if (sl.h_planes) cudaFreeHost(sl.h_planes); }

@@ -16,26 +16,56 @@ inline unsigned grid_for(uint64_t n, int threads) { return (unsigned)std::max<ui
 // Related genomes share long runs of k-mers, so the number of DISTINCT genome sets is tiny next to the number of
 // k-mers carrying them (config B: a few hundred sets for 10^7 k-mers).  Storing each set once keeps mlist inside
 // L1/L2 and keeps the slot payload (a sector index) short.
-//   long_flags    flag[u] = 1 when k-mer u has more than n_inline genomes
-//   set_hash_keys (hash of the genome list, u) for every flagged k-mer, compacted by the scan of the flags
+//   long_count    number of k-mers with more than n_inline genomes
+//   long_collect  (hash of the genome list, u) for each of them, appended in any order
 //   [radix sort by hash]
 //   set_heads     an entry opens a new set unless its list equals its sorted predecessor's (hash AND content)
 //   set_assign    msec_off[u] = first sector of the k-mer's set; heads write their list into mlist
-__global__ void long_flags(const uint64_t* __restrict__ run_off, uint64_t U, uint32_t n_inline, uint32_t* __restrict__ flag) {
-  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (u >= U) return;
-  flag[u] = (run_off[u + 1] - run_off[u]) > n_inline ? 1u : 0u;
+__global__ void __launch_bounds__(256) long_count(const uint64_t* __restrict__ run_off, uint64_t U, uint32_t n_inline,
+                                                  unsigned long long* __restrict__ total) {
+  const uint64_t stride = (uint64_t)gridDim.x * 256;
+  uint32_t mine = 0;
+  for (uint64_t u = blockIdx.x * 256ull + threadIdx.x; u < U; u += stride) mine += (run_off[u + 1] - run_off[u]) > n_inline ? 1u : 0u;
+  mine = warp_sum(mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(total, (unsigned long long)mine);
 }
 
-__global__ void set_hash_keys(const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome, uint64_t U,
-                              const uint32_t* __restrict__ flag, const uint64_t* __restrict__ rank,
-                              uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (u >= U || !flag[u]) return;
-  uint64_t h = 0xCBF29CE484222325ULL;
-  for (uint64_t r = run_off[u]; r < run_off[u + 1]; ++r) { h ^= run_genome[r]; h *= 0x100000001B3ULL; h ^= h >> 29; }
-  keys[rank[u]] = h;
-  vals[rank[u]] = (uint32_t)u;
+// (hash of the genome list, u) for every k-mer with a long list, appended through a cursor that a block advances once per
+// tile of 4,096 k-mers (one atomic per warp on a single address was the whole cost of this kernel: 7.9 ms); the order of
+// the entries is arbitrary (they are sorted by hash next; which k-mer of a set becomes its head does not matter)
+constexpr int LC_ITEMS = 16;
+constexpr int LC_TILE = 256 * LC_ITEMS;
+__global__ void __launch_bounds__(256) long_collect(const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome, uint64_t U,
+                                                    uint32_t n_inline, unsigned long long* __restrict__ cursor,
+                                                    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  __shared__ uint32_t scratch[256 / 32];
+  __shared__ unsigned long long s_base;
+  const uint64_t tiles = (U + LC_TILE - 1) / LC_TILE;
+  for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const uint64_t u0 = tile * LC_TILE + threadIdx.x;
+    uint32_t flags = 0;
+#pragma unroll
+    for (int r = 0; r < LC_ITEMS; ++r) {
+      const uint64_t u = u0 + (uint64_t)r * 256;
+      if (u < U && run_off[u + 1] - run_off[u] > n_inline) flags |= 1u << r;
+    }
+    uint32_t total;
+    const uint32_t excl = block_exclusive_scan<256, uint32_t>((uint32_t)__popc(flags), total, scratch);
+    if (threadIdx.x == 0) s_base = total ? atomicAdd(cursor, (unsigned long long)total) : 0ULL;
+    __syncthreads();
+    uint64_t at = s_base + excl;
+    while (flags) {
+      const int r = __ffs(flags) - 1;
+      flags &= flags - 1;
+      const uint64_t u = u0 + (uint64_t)r * 256;
+      uint64_t h = 0xCBF29CE484222325ULL;
+      for (uint64_t q = run_off[u], q1 = run_off[u + 1]; q < q1; ++q) { h ^= run_genome[q]; h *= 0x100000001B3ULL; h ^= h >> 29; }
+      keys[at] = h;
+      vals[at] = (uint32_t)u;
+      ++at;
+    }
+    __syncthreads();   // s_base is rewritten by the next tile
+  }
 }
 
 __global__ void set_heads(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t n,
@@ -114,164 +144,6 @@ __global__ void table_insert(const uint64_t* __restrict__ ukeys, const uint64_t*
   }
   uint32_t at = atomicAdd(ovf_count, 1u);
   if (at < ovf_cap) { ovf_pairs[2 * (size_t)at] = raw; ovf_pairs[2 * (size_t)at + 1] = value; }
-}
-
-// ---------------------------------------------------------------------------
-// Region-ordered insertion (large tables).
-//
-// table_insert above visits the k-mers in CSR order (ascending hashed key), i.e. the table in random order: every
-// insert is a read-modify-write of a line that DRAM has to fetch and write back (profiles/r01_table_insert_ncu.json:
-// 138 bytes of DRAM traffic per 8-byte slot).  Here the inserts are first brought into TABLE order, coarsely: the
-// table is cut into regions of 2^rshift buckets (16 MB by default -- a few of them fit the L2 together), and
-//   region_count    histogram of the k-mers' home regions (un-hash, minimizer, block: the same arithmetic as the insert)
-//   region_scan     start of every region's records
-//   region_scatter  per tile of 4,096 k-mers: {slot word at chain distance 0, home bucket} records, grouped by region
-//                   in shared memory, appended to their regions (any order inside a region: inserts commute)
-//   region_insert   the records in region order: the CAS traffic of a region stays in the L2, DRAM sees each table
-//                   line once on its way in and once on its way out
-// A record that overflows its chain is turned back into {raw k-mer, value} for the stash by raw_from_slot.
-// ---------------------------------------------------------------------------
-constexpr int REG_THREADS = 256;
-constexpr int REG_ITEMS = 16;
-constexpr int REG_TILE = REG_THREADS * REG_ITEMS;
-constexpr uint32_t REG_MAX = 1024;
-
-__device__ __forceinline__ uint32_t home_bucket_index(const TableView& t, const MixParams& mix, uint64_t ukey, uint64_t* tag0) {
-  const uint64_t raw = unmix_key(ukey, mix);
-  const uint32_t kmask = (t.k >= 32) ? 0xFFFFFFFFu : ((1u << t.k) - 1);
-  const uint32_t lo = (uint32_t)raw & kmask, hi = (uint32_t)(raw >> t.k) & kmask;
-  uint32_t mh, p;
-  kmer_minimizer(t, lo, hi, &mh, &p);
-  const SlotAddr a = slot_addr(t, lo, hi, mh, p);
-  *tag0 = a.tag;
-  return (uint32_t)(a.block * BLOCK_BUCKETS + a.bucket);   // the caller made sure the table has < 2^32 buckets
-}
-
-__global__ void __launch_bounds__(REG_THREADS) region_count(const uint64_t* __restrict__ ukeys, uint64_t U, TableView t, MixParams mix,
-                                                            uint32_t rshift, uint32_t n_regions, uint32_t* __restrict__ counts) {
-  __shared__ uint32_t sh[REG_MAX];
-  for (uint32_t i = threadIdx.x; i < n_regions; i += REG_THREADS) sh[i] = 0;
-  __syncthreads();
-  const uint64_t stride = (uint64_t)gridDim.x * REG_THREADS;
-  for (uint64_t u = blockIdx.x * (uint64_t)REG_THREADS + threadIdx.x; u < U; u += stride) {
-    uint64_t tag0;
-    atomicAdd(&sh[home_bucket_index(t, mix, ukeys[u], &tag0) >> rshift], 1u);
-  }
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < n_regions; i += REG_THREADS)
-    if (sh[i]) atomicAdd(&counts[i], sh[i]);
-}
-
-// one block: cursor[r] = exclusive scan of counts (n_regions <= REG_MAX = 4 per thread)
-__global__ void __launch_bounds__(REG_THREADS) region_scan(const uint32_t* __restrict__ counts, uint32_t n_regions,
-                                                           uint32_t* __restrict__ cursor) {
-  __shared__ uint32_t scratch[REG_THREADS / 32];
-  constexpr uint32_t PER = REG_MAX / REG_THREADS;
-  uint32_t v[PER], sum = 0;
-#pragma unroll
-  for (uint32_t j = 0; j < PER; ++j) { const uint32_t r = threadIdx.x * PER + j; v[j] = r < n_regions ? counts[r] : 0u; sum += v[j]; }
-  uint32_t total;
-  uint32_t base = block_exclusive_scan<REG_THREADS, uint32_t>(sum, total, scratch);
-#pragma unroll
-  for (uint32_t j = 0; j < PER; ++j) { const uint32_t r = threadIdx.x * PER + j; if (r < n_regions) cursor[r] = base; base += v[j]; }
-}
-
-struct RegionSmem {
-  uint64_t word[REG_TILE];      // records as computed (thread order) ...
-  uint64_t sorted_word[REG_TILE];   // ... and grouped by region
-  uint32_t bidx[REG_TILE];
-  uint32_t sorted_bidx[REG_TILE];
-  uint16_t rank[REG_TILE];
-  uint32_t cnt[REG_MAX], loff[REG_MAX], gbase[REG_MAX];
-  uint32_t scratch[REG_THREADS / 32];
-};
-
-__global__ void __launch_bounds__(REG_THREADS)
-region_scatter(const uint64_t* __restrict__ ukeys, const uint64_t* __restrict__ run_off, const uint32_t* __restrict__ run_genome,
-               const uint64_t* __restrict__ msec_off, uint64_t msec_base, uint64_t U, TableView t, MixParams mix, uint32_t rshift,
-               uint32_t n_regions, uint32_t* __restrict__ cursor, uint64_t* __restrict__ rec_word, uint32_t* __restrict__ rec_bidx) {
-  extern __shared__ __align__(16) unsigned char region_smem_raw[];
-  RegionSmem& sm = *reinterpret_cast<RegionSmem*>(region_smem_raw);
-  const int tid = threadIdx.x;
-  const uint64_t tile_start = (uint64_t)blockIdx.x * REG_TILE;
-  const uint32_t tile_n = (uint32_t)min((uint64_t)REG_TILE, U - tile_start);
-  for (uint32_t i = tid; i < n_regions; i += REG_THREADS) sm.cnt[i] = 0;
-  __syncthreads();
-  for (uint32_t li = tid; li < tile_n; li += REG_THREADS) {
-    const uint64_t u = tile_start + li;
-    uint64_t tag0;
-    const uint32_t b = home_bucket_index(t, mix, ukeys[u], &tag0);
-    const uint64_t r0 = run_off[u], c = run_off[u + 1] - r0;
-    const uint64_t value = entry_value(t, c, run_genome + r0, c > t.n_inline ? msec_off[u] + msec_base : 0);
-    sm.word[li] = (tag0 << t.val_bits) | value;
-    sm.bidx[li] = b;
-    sm.rank[li] = (uint16_t)atomicAdd(&sm.cnt[b >> rshift], 1u);
-  }
-  __syncthreads();
-  {  // offsets of the regions inside the tile; room in the regions' record ranges
-    constexpr uint32_t PER = REG_MAX / REG_THREADS;
-    uint32_t v[PER], sum = 0;
-#pragma unroll
-    for (uint32_t j = 0; j < PER; ++j) { const uint32_t r = tid * PER + j; v[j] = r < n_regions ? sm.cnt[r] : 0u; sum += v[j]; }
-    uint32_t total;
-    uint32_t base = block_exclusive_scan<REG_THREADS, uint32_t>(sum, total, sm.scratch);
-#pragma unroll
-    for (uint32_t j = 0; j < PER; ++j) {
-      const uint32_t r = tid * PER + j;
-      if (r < n_regions) {
-        sm.loff[r] = base;
-        if (v[j]) sm.gbase[r] = atomicAdd(&cursor[r], v[j]);
-      }
-      base += v[j];
-    }
-  }
-  __syncthreads();
-  for (uint32_t li = tid; li < tile_n; li += REG_THREADS) {
-    const uint32_t b = sm.bidx[li];
-    const uint32_t at = sm.loff[b >> rshift] + sm.rank[li];
-    sm.sorted_word[at] = sm.word[li];
-    sm.sorted_bidx[at] = b;
-  }
-  __syncthreads();
-  for (uint32_t i = tid; i < tile_n; i += REG_THREADS) {
-    const uint32_t b = sm.sorted_bidx[i], r = b >> rshift;
-    const uint32_t dst = sm.gbase[r] + (i - sm.loff[r]);
-    rec_word[dst] = sm.sorted_word[i];
-    rec_bidx[dst] = b;
-  }
-}
-
-__global__ void __launch_bounds__(REG_THREADS)
-region_insert(const uint64_t* __restrict__ rec_word, const uint32_t* __restrict__ rec_bidx, uint64_t U, TableView t,
-              unsigned long long* __restrict__ slots, unsigned int* __restrict__ ovf_count,
-              unsigned long long* __restrict__ ovf_pairs, uint32_t ovf_cap) {
-  const uint64_t i = blockIdx.x * (uint64_t)REG_THREADS + threadIdx.x;
-  if (i >= U) return;
-  const unsigned long long word0 = __ldcs(reinterpret_cast<const unsigned long long*>(rec_word) + i);
-  const uint32_t bidx = __ldcs(rec_bidx + i);
-  unsigned long long* b = slots + (uint64_t)bidx * BUCKET_SLOTS;
-#pragma unroll
-  for (uint32_t j = 0; j < BUCKET_SLOTS; ++j)
-    if (atomicCAS(b + j, (unsigned long long)EMPTY64, word0) == EMPTY64) return;
-  // home bucket full: the chain (rare), as in table_insert
-  const unsigned long long cont_bit = 1ULL << (t.val_bits - 1);
-  atomicOr(b + BUCKET_SLOTS - 1, cont_bit);
-  const uint64_t block = bidx / BLOCK_BUCKETS, first = (block / t.bpd) * t.bpd;
-  const uint32_t bucket = bidx % BLOCK_BUCKETS;
-  for (uint32_t d = 1; d < CHAIN_LEN; ++d) {
-    uint64_t local = block - first + d;
-    while (local >= t.bpd) local -= t.bpd;
-    b = slots + ((first + local) * BLOCK_BUCKETS + bucket) * BUCKET_SLOTS;
-    const unsigned long long word = word0 + ((unsigned long long)d << (t.hi_bits + t.val_bits));   // chain field was 00
-    for (uint32_t j = 0; j < BUCKET_SLOTS; ++j)
-      if (atomicCAS(b + j, (unsigned long long)EMPTY64, word) == EMPTY64) return;
-    atomicOr(b + BUCKET_SLOTS - 1, cont_bit);
-  }
-  const uint32_t at = atomicAdd(ovf_count, 1u);
-  if (at < ovf_cap) {
-    ovf_pairs[2 * (size_t)at] = raw_from_slot(t, block, bucket, word0 >> t.val_bits);
-    ovf_pairs[2 * (size_t)at + 1] = word0 & ((1ULL << t.val_bits) - 1);
-  }
 }
 
 __global__ void stash_insert(const unsigned long long* __restrict__ pairs, uint32_t n, unsigned long long* __restrict__ stash /* {raw key, value} */,
@@ -356,16 +228,17 @@ int32_t build_genome_sets(cudaStream_t s, const CsrView& c, uint32_t n_inline, G
   const uint64_t U = c.U;
   out->n_msec = 0;
   out->msec_off.release(); out->mlist.release();
-  DevBuf flag, lrank, tile_sums, d_total, set_ka, set_kb, set_va, set_vb, set_tmp, head_secs, sec_off;
-  PA_TRY(d_total.alloc(8));
+  DevBuf tile_sums, d_total, set_ka, set_kb, set_va, set_vb, set_tmp, head_secs, sec_off;
+  PA_TRY(d_total.alloc(16));
   uint64_t n_msec = 0, n_long = 0;
   uint32_t* set_vals = nullptr;   // k-mers with long lists, sorted by set
+  int dev = 0, sms = 148;
+  PA_CUDA(cudaGetDevice(&dev));
+  PA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const unsigned ugrid = (unsigned)std::min<uint64_t>(grid_for(U, 256), (uint64_t)sms * 16);
   if (U) {
-    PA_TRY(flag.alloc((U + 1) * 4));
-    PA_TRY(lrank.alloc((U + 1) * 8));
-    PA_TRY(tile_sums.alloc((scan_tiles(U) + 1) * 8));
-    long_flags<<<grid_for(U, 256), 256, 0, s>>>(c.run_off, U, n_inline, flag.as<uint32_t>());
-    PA_TRY(exclusive_scan_u32(flag.as<uint32_t>(), lrank.as<uint64_t>(), U, tile_sums.as<uint64_t>(), d_total.as<uint64_t>(), s));
+    PA_CUDA(cudaMemsetAsync(d_total.p, 0, 16, s));
+    long_count<<<ugrid, 256, 0, s>>>(c.run_off, U, n_inline, d_total.as<unsigned long long>());
     PA_CUDA(cudaMemcpyAsync(&n_long, d_total.p, 8, cudaMemcpyDeviceToHost, s));
     PA_CUDA(cudaStreamSynchronize(s));
   }
@@ -375,15 +248,15 @@ int32_t build_genome_sets(cudaStream_t s, const CsrView& c, uint32_t n_inline, G
     PA_TRY(set_ka.alloc(n_long * 8)); PA_TRY(set_kb.alloc(n_long * 8)); PA_TRY(set_va.alloc(n_long * 4)); PA_TRY(set_vb.alloc(n_long * 4));
     PA_TRY(set_tmp.alloc(radix_sort_temp_bytes(n_long)));
     PA_TRY(head_secs.alloc(n_long * 4)); PA_TRY(sec_off.alloc(n_long * 8));
-    set_hash_keys<<<grid_for(U, 256), 256, 0, s>>>(c.run_off, c.run_genome, U, flag.as<uint32_t>(), lrank.as<uint64_t>(),
-                                                    set_ka.as<uint64_t>(), set_va.as<uint32_t>());
+    PA_TRY(tile_sums.alloc((scan_tiles(n_long) + 1) * 8));
+    long_collect<<<ugrid, 256, 0, s>>>(c.run_off, c.run_genome, U, n_inline, d_total.as<unsigned long long>() + 1,
+                                       set_ka.as<uint64_t>(), set_va.as<uint32_t>());
     int in_b = 0;
-    PA_TRY(radix_sort_pairs(set_ka.as<uint64_t>(), set_va.as<uint32_t>(), set_kb.as<uint64_t>(), set_vb.as<uint32_t>(), n_long, 64,
-                            set_tmp.p, set_tmp.bytes, s, &in_b));
+    PA_TRY(radix_sort_pairs_hashed(set_ka.as<uint64_t>(), set_va.as<uint32_t>(), set_kb.as<uint64_t>(), set_vb.as<uint32_t>(), n_long, 64,
+                                   set_tmp.p, set_tmp.bytes, s, &in_b));
     const uint64_t* skeys = in_b ? set_kb.as<uint64_t>() : set_ka.as<uint64_t>();
     set_vals = in_b ? set_vb.as<uint32_t>() : set_va.as<uint32_t>();
     set_heads<<<grid_for(n_long, 256), 256, 0, s>>>(skeys, set_vals, n_long, c.run_off, c.run_genome, head_secs.as<uint32_t>());
-    if (scan_tiles(n_long) > scan_tiles(U)) PA_TRY(tile_sums.alloc((scan_tiles(n_long) + 1) * 8));
     PA_TRY(exclusive_scan_u32(head_secs.as<uint32_t>(), sec_off.as<uint64_t>(), n_long, tile_sums.as<uint64_t>(), d_total.as<uint64_t>(), s));
     PA_CUDA(cudaMemcpyAsync(&n_msec, d_total.p, 8, cudaMemcpyDeviceToHost, s));
     PA_CUDA(cudaStreamSynchronize(s));
@@ -410,45 +283,10 @@ int32_t table_insert_csr(Index& ix, const CsrView& c, const GenomeSets& sets, ui
   const uint32_t ovf_cap = (uint32_t)std::min<uint64_t>(c.U / 64 + 65536, 0x0FFFFFF0ull);
   PA_TRY(ovf_pairs.alloc((size_t)ovf_cap * 16));
   PA_CUDA(cudaMemsetAsync(ovf_count.p, 0, 4, s));
-  // Large tables take the inserts in table order (see region_count); PA_TABLE_REGIONS=0 / 1 switches that off / forces it,
-  // PA_TABLE_REGION_SHIFT sets log2(buckets per region) (default: 16 MB regions, coarser when that gives more than 1,024).
-  const uint64_t n_buckets = ix.n_blocks() * BLOCK_BUCKETS;
-  bool by_region = c.U >= (1u << 22);
-  if (const char* e = getenv("PA_TABLE_REGIONS")) by_region = *e == '1';
-  if (n_buckets >= 0xFFFFFFFFull || c.U >= 0xFFFFFFFFull) by_region = false;
-  if (by_region) {
-    uint32_t rshift = 19;
-    if (const char* e = getenv("PA_TABLE_REGION_SHIFT")) rshift = (uint32_t)std::min(30, std::max(0, atoi(e)));
-    while (((n_buckets - 1) >> rshift) + 1 > REG_MAX) ++rshift;
-    const uint32_t n_regions = (uint32_t)(((n_buckets - 1) >> rshift) + 1);
-    DevBuf counts, rec_word, rec_bidx;
-    PA_TRY(counts.alloc((size_t)REG_MAX * 8));
-    PA_TRY(rec_word.alloc(c.U * 8)); PA_TRY(rec_bidx.alloc(c.U * 4));
-    uint32_t* d_counts = counts.as<uint32_t>();
-    uint32_t* d_cursor = d_counts + REG_MAX;
-    PA_CUDA(cudaMemsetAsync(counts.p, 0, (size_t)REG_MAX * 8, s));
-    int dev = 0, sms = 148;
-    PA_CUDA(cudaGetDevice(&dev));
-    PA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const TableView tv = ix.view();
-    region_count<<<(unsigned)std::min<uint64_t>(grid_for(c.U, REG_THREADS), (uint64_t)sms * 8), REG_THREADS, 0, s>>>(
-        c.ukeys, c.U, tv, ix.mix, rshift, n_regions, d_counts);
-    region_scan<<<1, REG_THREADS, 0, s>>>(d_counts, n_regions, d_cursor);
-    PA_CUDA(cudaFuncSetAttribute(region_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem)));
-    region_scatter<<<grid_for(c.U, REG_TILE), REG_THREADS, sizeof(RegionSmem), s>>>(
-        c.ukeys, c.run_off, c.run_genome, sets.msec_off.as<uint64_t>(), msec_base, c.U, tv, ix.mix, rshift, n_regions, d_cursor,
-        rec_word.as<uint64_t>(), rec_bidx.as<uint32_t>());
-    region_insert<<<grid_for(c.U, REG_THREADS), REG_THREADS, 0, s>>>(rec_word.as<uint64_t>(), rec_bidx.as<uint32_t>(), c.U, tv,
-                                                                      ix.slots.as<unsigned long long>(), ovf_count.as<unsigned int>(),
-                                                                      ovf_pairs.as<unsigned long long>(), ovf_cap);
-    PA_CUDA(cudaGetLastError());
-    PA_CUDA(cudaStreamSynchronize(s));   // the record buffers are released when this scope ends
-  } else {
-    table_insert<<<grid_for(c.U, 256), 256, 0, s>>>(c.ukeys, c.run_off, c.run_genome, sets.msec_off.as<uint64_t>(), msec_base, c.U,
-                                                    ix.view(), ix.mix, ix.slots.as<unsigned long long>(), ovf_count.as<unsigned int>(),
-                                                    ovf_pairs.as<unsigned long long>(), ovf_cap);
-    PA_CUDA(cudaGetLastError());
-  }
+  table_insert<<<grid_for(c.U, 256), 256, 0, s>>>(c.ukeys, c.run_off, c.run_genome, sets.msec_off.as<uint64_t>(), msec_base, c.U,
+                                                  ix.view(), ix.mix, ix.slots.as<unsigned long long>(), ovf_count.as<unsigned int>(),
+                                                  ovf_pairs.as<unsigned long long>(), ovf_cap);
+  PA_CUDA(cudaGetLastError());
   uint32_t n_ovf = 0;
   PA_CUDA(cudaMemcpyAsync(&n_ovf, ovf_count.p, 4, cudaMemcpyDeviceToHost, s));
   PA_CUDA(cudaStreamSynchronize(s));

@@ -305,11 +305,6 @@ int32_t pa_debug_pack_reads(const uint8_t* bases, const uint64_t* read_off, uint
 /* minimizer of each k-mer (pure host code, the function the table build and K4 share): mhash = bijective hash of its m-mer,
  * m = min(k, 16); offset = position of that m-mer inside the k-mer (leftmost among equal orders) */
 int32_t pa_debug_minimizer(int32_t k, const uint8_t* kmers_ascii, uint64_t n, uint32_t* mhash, uint32_t* offset);
-/* pure host code: for each k-mer, slot address (block, bucket, tag) under the table geometry planned for n_kmers_planned
- * k-mers of n_genomes genomes at the given load factor, and back again (raw_from_slot, what the region-ordered table build
- * uses for stash entries); *n_bad = k-mers that did not come back */
-int32_t pa_debug_slot_roundtrip(int32_t k, uint32_t n_genomes, uint64_t n_kmers_planned, double load, const uint8_t* kmers_ascii,
-                                uint64_t n, uint64_t* n_bad);
 /* direct table lookups (K4's lookup step): n_genomes[i] = number of genomes of k-mer i (0 = miss),
  * first_genome[i] = its smallest genome index */
 int32_t pa_debug_table_lookup(pa_index* idx, const uint8_t* kmers_ascii, uint64_t n, uint32_t* n_genomes,

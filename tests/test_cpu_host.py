@@ -592,25 +592,3 @@ def test_host_pool_serves_concurrent_callers():
         th.join()
     assert not errors, errors
 
-
-def test_slot_address_is_invertible():
-    """raw_from_slot (common.cuh) undoes kmer_minimizer + slot_addr: block, bucket and tag identify the k-mer exactly.  The
-    region-ordered table build relies on it for the k-mers that end in the stash."""
-    import ctypes
-    import _native as nat
-    L = nat.lib()
-    rng = np.random.default_rng(23)
-    for k in (1, 2, 5, 8, 13, 14, 15, 16, 17, 20, 24, 30, 31):
-        n = 4 ** k if k <= 5 else 20_000
-        if k <= 5:
-            import itertools
-            kmers = ["".join(p) for p in itertools.product("ACGT", repeat=k)]
-        else:
-            kmers = ["".join(x) for x in np.frombuffer(b"ACGT", dtype="S1")[rng.integers(0, 4, size=(n, k))].astype(str)]
-            kmers[:4] = ["A" * k, "T" * k, "AC" * (k // 2) + "G" * (k % 2), "G" * (k - 1) + "C"]
-        flat = np.frombuffer("".join(kmers).encode(), dtype=np.uint8).copy()
-        for n_genomes, planned, load in ((3, 1000, 0.2), (100, 418_000_000, 0.2), (2000, 3_350_000_000, 0.42), (7, 50_000, 0.9)):
-            bad = ctypes.c_uint64(123)
-            rc = L.pa_debug_slot_roundtrip(k, n_genomes, planned, load, nat._p(flat), len(kmers), ctypes.byref(bad))
-            assert rc == 0, nat.last_error() if hasattr(nat, "last_error") else rc
-            assert bad.value == 0, (k, n_genomes, planned, load, bad.value)

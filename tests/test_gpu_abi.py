@@ -197,6 +197,23 @@ def test_k31_moderate():
                     "params": pr, "seed": 1})
 
 
+@pytest.mark.parametrize("masks", ["1", "0"])
+def test_quality_filters_by_masks_and_in_kernel(masks, monkeypatch):
+    """EXTQUALITY has two implementations: quality_masks_kernel + the staggered K4 reading one bit per window (default), and
+    the K4 variant that scans the quality bytes itself (PA_QUAL_MASKS=0).  Both against the oracle: read drop, window filter
+    counted per occurrence, together with max-genomes, on reads shorter than k, of ragged lengths and longer than 128 windows."""
+    monkeypatch.setenv("PA_QUAL_MASKS", masks)
+    genomes = synth.make_genomes(6, 40_000, seed=5, cluster_size=3, shared_frac=0.35, n_every=9000, n_run=11)
+    for read_len, n in ((150, 3000), (40, 500), (31, 200), (20, 50), (158, 400), (159, 400), (300, 300)):
+        b, q, off = synth.make_reads(genomes, n, read_len, seed=60 + read_len, sub_rate=0.02, random_frac=0.05)
+        for pr in [dict(m=1, p=1, mrq=62, mkq=60, mg=1), dict(m=0, p=0, mrq=None, mkq=63, mg=3),
+                   dict(m=2, p=-1, mrq=61, mkq=None, mg=None), dict(m=1, p=1, mrq=90, mkq=10, mg=None)]:
+            check_case({"k": 31, "genomes": synth.genomes_as_pairs(genomes), "reads": synth.reads_as_triples(b, q, off),
+                        "params": pr, "seed": 1})
+    for seed in range(9300, 9360):   # small k, ragged reads, random thresholds
+        check_case(synth.fuzz_case(seed))
+
+
 @pytest.mark.parametrize("dense", ["2", "3", "5"])
 def test_overloaded_table_walks_chains_and_stash(dense, monkeypatch):
     """PA_TABLE_DENSE doubles the load factor per step: buckets overflow into the next blocks (CONT) and into the stash,
@@ -216,34 +233,6 @@ def test_overloaded_table_walks_chains_and_stash(dense, monkeypatch):
     check_case(dict(case, params=dict(m=2, p=0, mrq=None, mkq=60, mg=4)))
     for k in (7, 13, 20):   # w = 1 (k <= 16) and w = 5: short minimizer windows
         check_case(dict(case, k=k))
-
-
-@pytest.mark.parametrize("shift,dense", [("0", None), ("3", None), ("6", "3"), ("2", "5"), ("19", "5")])
-def test_region_ordered_table_insert(shift, dense, monkeypatch):
-    """Large tables take their inserts grouped by table region (table.cu: region_count / region_scatter / region_insert);
-    forced on here for small cases, with tiny regions, also on overloaded tables (chains, CONT, stash entries that are
-    turned back into k-mers by raw_from_slot)."""
-    monkeypatch.setenv("PA_TABLE_REGIONS", "1")
-    monkeypatch.setenv("PA_TABLE_REGION_SHIFT", shift)
-    if dense:
-        monkeypatch.setenv("PA_TABLE_DENSE", dense)
-    genomes = synth.make_genomes(12, 30_000, seed=15, cluster_size=6, shared_frac=0.6, sub_rate=0.03, n_every=9000, n_run=11)
-    b, q, off = synth.make_reads(genomes, 3000, 150, seed=16, sub_rate=0.02, random_frac=0.05)
-    case = {"k": 31, "genomes": synth.genomes_as_pairs(genomes), "reads": synth.reads_as_triples(b, q, off),
-            "params": dict(m=1, p=1, mrq=None, mkq=None, mg=None), "seed": 2}
-    if dense == "5":
-        data, goff = nat.pack_strings([g[1] for g in case["genomes"]])
-        ix = nat.NativeIndex.build(data, goff, 31)
-        inf = ix.info()
-        ix.close()
-        assert inf.stash_count > 0, "the test is meant to reach the stash"
-    check_case(case)
-    for k in (7, 13, 20):
-        check_case(dict(case, k=k, params=dict(m=2, p=0, mrq=None, mkq=60, mg=4)))
-    for seed in range(9100, 9130):
-        check_case(synth.fuzz_case(seed))
-    for seed in range(9200, 9215):
-        check_case(synth.fuzz_case(seed, k_range=(9, 31), max_genomes=8))
 
 
 @pytest.mark.parametrize("mode", ["1", "0"])

@@ -1,5 +1,5 @@
 #!/bin/bash
-# K4 timings of the current build: plain and EXTQUALITY (both stage orders); one JSON line each into gpurun_out/k4_variants.jsonl
+# K4 timings of the current build: plain and EXTQUALITY (mask pre-kernel + staggered K4, and the in-kernel quality scan); one JSON line each into gpurun_out/k4_variants.jsonl
 mkdir -p gpurun_out
 : > gpurun_out/k4_variants.jsonl
 run() {
@@ -11,6 +11,6 @@ print(json.dumps({'variant': '$label', 'k4_ms': d['roofline']['kernel_ms'], 'ms_
 " >> gpurun_out/k4_variants.jsonl
 }
 EXTRA="" run plain PA_X=0
-EXTRA="--extquality" run extq PA_QUAL_SPLIT=0
-EXTRA="--extquality" run extq_split PA_QUAL_SPLIT=1
+EXTRA="--extquality" run extq_masks PA_QUAL_MASKS=1
+EXTRA="--extquality" run extq_in_kernel PA_QUAL_MASKS=0
 cat gpurun_out/k4_variants.jsonl
