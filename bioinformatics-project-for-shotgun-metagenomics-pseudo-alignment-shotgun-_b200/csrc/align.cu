@@ -143,10 +143,10 @@ __device__ __forceinline__ void window_minimizer(const TableView& t, uint32_t ke
 
 // rare continuation of a lookup whose home bucket was full, without a match, and has CONT set (kept out of line:
 // the fast path only carries the tag)
-__device__ __noinline__ uint64_t lookup_chain_window(const TableView& t, uint64_t raw, uint32_t mhash, uint32_t p) {
+__device__ __noinline__ uint64_t lookup_chain_window(const TableView& t, uint64_t raw, uint32_t mhash, uint32_t p, uint32_t d0 = 1) {
   const uint32_t kmask = (t.k >= 32) ? 0xFFFFFFFFu : ((1u << t.k) - 1);
   const SlotAddr a = slot_addr(t, (uint32_t)raw & kmask, (uint32_t)(raw >> t.k) & kmask, mhash, p);
-  return lookup_chain(t, a, mhash, raw);
+  return lookup_chain(t, a, mhash, raw, d0);
 }
 
 
@@ -742,6 +742,8 @@ __device__ __forceinline__ void fast_stage_c(const TableView& t, const AlignPara
     chain |= (on && cont) ? (1u << r) : 0u;
   }
   if (chain) {
+    // (requesting the distance-1 sectors of all such windows first -- L2 prefetches, or loads held in registers -- was
+    // measured slower: 13.28 -> 13.46 ms, the latter spills)
 #pragma unroll
     for (int r = 0; r < AL_ROUNDS; ++r)
       if ((chain >> r) & 1) {

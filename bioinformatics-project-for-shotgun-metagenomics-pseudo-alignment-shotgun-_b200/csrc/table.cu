@@ -200,16 +200,19 @@ int32_t table_geometry(int k_in, uint32_t G, uint64_t U, double load, uint32_t m
 }
 
 double table_load_factor(int k, uint64_t U, size_t free_bytes) {
-  // measured on config B (profiles/r02_load_sweep.jsonl): K4 takes 14.7 / 15.7 / 17.0 ms per 10^7 reads at load
-  // 0.195 / 0.25 / 0.30 (40 / 32 / 26.7 bytes of table per k-mer): fast while memory is plentiful, dense when it is not
-  double load = 0.2;
+  // measured on config B (profiles/r02_load_sweep.jsonl): K4 takes 12.3 / 12.8 / 13.3 / 15.7 / 17.0 ms per 10^7 reads at load
+  // 0.10 / 0.15 / 0.20 / 0.25 / 0.30 (80 / 53 / 40 / 32 / 26.7 bytes of table per k-mer): sparse while memory is plentiful,
+  // dense when it is not
   if (const char* e = getenv("PA_TABLE_LOAD")) { const double v = atof(e); if (v > 0) return v; }
-  if (const char* e = getenv("PA_TABLE_DENSE")) {   // tests: n > 0 doubles the load factor n times (chains, CONT, stash), n < 0 halves it
+  if (const char* e = getenv("PA_TABLE_DENSE")) {   // tests: n > 0 doubles the load factor 0.2 n times (chains, CONT, stash), n < 0 halves it
     const int n = atoi(e);
-    return n >= 0 ? std::min(0.9, load * (double)(1u << std::min(n, 8))) : load / (double)(1u << std::min(-n, 8));
+    return n >= 0 ? std::min(0.9, 0.2 * (double)(1u << std::min(n, 8))) : 0.2 / (double)(1u << std::min(-n, 8));
   }
-  // denser while the table would take more than 40 % of the free device memory (config E: 2,000 genomes)
   const double bytes_per_slot = 8.0;
+  double load = 0.10;
+  // up to a quarter of the free device memory for a sparse table, up to 40 % before it gets denser than 1/5 (config E: 2,000
+  // genomes end at 0.42)
+  while (load < 0.199 && (double)U / load * bytes_per_slot > 0.25 * (double)free_bytes) load += 0.02;
   while (load < 0.42 && (double)U / load * bytes_per_slot > 0.4 * (double)free_bytes) load += 0.02;
   (void)k;
   return load;
