@@ -275,6 +275,21 @@ int32_t Comm::allgatherv_device_inplace(void* base, const uint64_t* off, cudaStr
   return ST_OK;
 }
 
+int32_t Comm::allgather_device_strided(void* base, uint64_t stride, cudaStream_t s) {
+  if (single() || stride == 0) return ST_OK;
+  const char* force = getenv("PA_TABLE_GATHER");
+  if (nccl && !(force && strcmp(force, "ipc") == 0)) {
+    PA_CUDA(cudaSetDevice(device));
+    NcclApi* api = nccl_api();
+    PA_NCCL(api->AllGather(static_cast<char*>(base) + (size_t)rank * stride, base, stride, ncclUint8, reinterpret_cast<ncclComm_t>(nccl), s));
+    PA_CUDA(cudaStreamSynchronize(s));
+    return ST_OK;
+  }
+  std::vector<uint64_t> off((size_t)n_ranks + 1);
+  for (int r = 0; r <= n_ranks; ++r) off[r] = (uint64_t)r * stride;
+  return allgatherv_device_inplace(base, off.data(), s);
+}
+
 void Comm::release_exchange() {
   for (int r = 0; r < (int)ex.peer_k.size(); ++r) {
     if (r == rank) continue;

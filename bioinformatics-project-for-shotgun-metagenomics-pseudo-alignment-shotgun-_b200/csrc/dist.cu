@@ -174,30 +174,54 @@ owner_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ va
 constexpr int CMP_THREADS = 256;
 constexpr uint32_t BLOCK_SLOTS = BLOCK_BUCKETS * BUCKET_SLOTS;   // 64
 
+// A warp takes CMP_BLOCKS consecutive blocks and has all their loads in flight before it looks at the first.
+constexpr int CMP_BLOCKS = 8;
 __global__ void __launch_bounds__(CMP_THREADS)
 slice_bitmaps(const uint64_t* __restrict__ slots, uint64_t b_lo, uint64_t b_hi, unsigned long long* __restrict__ bitmap,
               uint32_t* __restrict__ cnt) {
-  const uint64_t b = b_lo + (blockIdx.x * (uint64_t)CMP_THREADS + threadIdx.x) / 32;
+  const uint64_t b0 = b_lo + ((blockIdx.x * (uint64_t)CMP_THREADS + threadIdx.x) / 32) * CMP_BLOCKS;
   const uint32_t lane = threadIdx.x & 31;
-  if (b >= b_hi) return;
-  const uint64_t* p = slots + b * BLOCK_SLOTS;
-  const uint32_t m0 = __ballot_sync(0xffffffffu, p[lane] != EMPTY64), m1 = __ballot_sync(0xffffffffu, p[32 + lane] != EMPTY64);
-  if (lane == 0) { bitmap[b] = ((unsigned long long)m1 << 32) | m0; cnt[b - b_lo] = __popc(m0) + __popc(m1); }
+  if (b0 >= b_hi) return;
+  uint64_t s0[CMP_BLOCKS], s1[CMP_BLOCKS];
+#pragma unroll
+  for (int j = 0; j < CMP_BLOCKS; ++j) {
+    const bool ok = b0 + j < b_hi;
+    const uint64_t* p = slots + (b0 + j) * BLOCK_SLOTS;
+    s0[j] = ok ? p[lane] : EMPTY64;
+    s1[j] = ok ? p[32 + lane] : EMPTY64;
+  }
+  unsigned long long mine = 0;
+#pragma unroll
+  for (int j = 0; j < CMP_BLOCKS; ++j) {
+    const uint32_t m0 = __ballot_sync(0xffffffffu, s0[j] != EMPTY64), m1 = __ballot_sync(0xffffffffu, s1[j] != EMPTY64);
+    if (lane == (uint32_t)j) mine = ((unsigned long long)m1 << 32) | m0;
+  }
+  if (lane < CMP_BLOCKS && b0 + lane < b_hi) { bitmap[b0 + lane] = mine; cnt[b0 + lane - b_lo] = __popcll(mine); }
 }
 
 __global__ void __launch_bounds__(CMP_THREADS)
 slice_words(const uint64_t* __restrict__ slots, uint64_t b_lo, uint64_t b_hi, const uint64_t* __restrict__ off /* per block of the slice */,
             uint64_t* __restrict__ words) {
-  const uint64_t b = b_lo + (blockIdx.x * (uint64_t)CMP_THREADS + threadIdx.x) / 32;
+  const uint64_t b0 = b_lo + ((blockIdx.x * (uint64_t)CMP_THREADS + threadIdx.x) / 32) * CMP_BLOCKS;
   const uint32_t lane = threadIdx.x & 31;
-  if (b >= b_hi) return;
-  const uint64_t* p = slots + b * BLOCK_SLOTS;
-  const uint64_t s0 = p[lane], s1 = p[32 + lane];
-  const uint32_t m0 = __ballot_sync(0xffffffffu, s0 != EMPTY64), m1 = __ballot_sync(0xffffffffu, s1 != EMPTY64);
+  if (b0 >= b_hi) return;
+  uint64_t s0[CMP_BLOCKS], s1[CMP_BLOCKS];
+#pragma unroll
+  for (int j = 0; j < CMP_BLOCKS; ++j) {
+    const bool ok = b0 + j < b_hi;
+    const uint64_t* p = slots + (b0 + j) * BLOCK_SLOTS;
+    s0[j] = ok ? p[lane] : EMPTY64;
+    s1[j] = ok ? p[32 + lane] : EMPTY64;
+  }
+  const uint64_t my_off = (lane < CMP_BLOCKS && b0 + lane < b_hi) ? off[b0 + lane - b_lo] : 0;
   const uint32_t lt = (1u << lane) - 1;
-  uint64_t* dst = words + off[b - b_lo];
-  if (s0 != EMPTY64) dst[__popc(m0 & lt)] = s0;
-  if (s1 != EMPTY64) dst[__popc(m0) + __popc(m1 & lt)] = s1;
+#pragma unroll
+  for (int j = 0; j < CMP_BLOCKS; ++j) {
+    const uint32_t m0 = __ballot_sync(0xffffffffu, s0[j] != EMPTY64), m1 = __ballot_sync(0xffffffffu, s1[j] != EMPTY64);
+    uint64_t* dst = words + __shfl_sync(0xffffffffu, my_off, j);
+    if (s0[j] != EMPTY64) dst[__popc(m0 & lt)] = s0[j];
+    if (s1[j] != EMPTY64) dst[__popc(m0) + __popc(m1 & lt)] = s1[j];
+  }
 }
 
 __global__ void __launch_bounds__(CMP_THREADS)
@@ -206,19 +230,36 @@ bitmap_counts(const unsigned long long* __restrict__ bitmap, uint64_t n_blocks, 
   if (b < n_blocks) cnt[b] = __popcll(bitmap[b]);
 }
 
-// every block outside [skip_lo, skip_hi) (this rank's own slice, already in place): bitmap + words -> 64 slots
+// the blocks [b_lo, b_hi) of one source rank: bitmap + words -> 64 slots each.  A warp expands EXP_BLOCKS consecutive
+// blocks and has all their word loads in flight before the first store (one block per warp left the kernel at 2.3 TB/s:
+// four dependent loads in front of every 512 bytes written).  off = offsets of the blocks' words in the dense global
+// order, delta = where this rank's words really start minus where they would start in that order.
+constexpr int EXP_BLOCKS = 8;
 __global__ void __launch_bounds__(CMP_THREADS)
 slice_expand(const unsigned long long* __restrict__ bitmap, const uint64_t* __restrict__ off, const uint64_t* __restrict__ words,
-             uint64_t n_blocks, uint64_t skip_lo, uint64_t skip_hi, uint64_t* __restrict__ slots) {
-  const uint64_t b = (blockIdx.x * (uint64_t)CMP_THREADS + threadIdx.x) / 32;
+             uint64_t b_lo, uint64_t b_hi, long long delta, uint64_t* __restrict__ slots) {
+  const uint64_t b0 = b_lo + ((blockIdx.x * (uint64_t)CMP_THREADS + threadIdx.x) / 32) * EXP_BLOCKS;
   const uint32_t lane = threadIdx.x & 31;
-  if (b >= n_blocks || (b >= skip_lo && b < skip_hi)) return;
-  const unsigned long long bm = bitmap[b];
-  const uint32_t m0 = (uint32_t)bm, m1 = (uint32_t)(bm >> 32), lt = (1u << lane) - 1;
-  const uint64_t* src = words + off[b];
-  uint64_t* p = slots + b * BLOCK_SLOTS;
-  p[lane] = ((m0 >> lane) & 1u) ? src[__popc(m0 & lt)] : EMPTY64;
-  p[32 + lane] = ((m1 >> lane) & 1u) ? src[__popc(m0) + __popc(m1 & lt)] : EMPTY64;
+  if (b0 >= b_hi) return;
+  unsigned long long my_bm = 0, my_off = 0;
+  if (lane < EXP_BLOCKS && b0 + lane < b_hi) { my_bm = bitmap[b0 + lane]; my_off = (unsigned long long)((long long)off[b0 + lane] + delta); }
+  const uint32_t lt = (1u << lane) - 1;
+  uint64_t v0[EXP_BLOCKS], v1[EXP_BLOCKS];
+#pragma unroll
+  for (int j = 0; j < EXP_BLOCKS; ++j) {
+    const unsigned long long bm = __shfl_sync(0xffffffffu, my_bm, j), of = __shfl_sync(0xffffffffu, my_off, j);
+    const uint32_t m0 = (uint32_t)bm, m1 = (uint32_t)(bm >> 32);
+    const uint64_t* src = words + of;
+    v0[j] = ((m0 >> lane) & 1u) ? __ldcs(src + __popc(m0 & lt)) : EMPTY64;
+    v1[j] = ((m1 >> lane) & 1u) ? __ldcs(src + __popc(m0) + __popc(m1 & lt)) : EMPTY64;
+  }
+#pragma unroll
+  for (int j = 0; j < EXP_BLOCKS; ++j)
+    if (b0 + j < b_hi) {
+      uint64_t* p = slots + (b0 + j) * BLOCK_SLOTS;
+      __stcs(p + lane, v0[j]);
+      __stcs(p + 32 + lane, v1[j]);
+    }
 }
 
 double ms_since(std::chrono::steady_clock::time_point a) {
@@ -507,11 +548,14 @@ int32_t DistBuild::gather_slices_compressed(const std::vector<uint64_t>& blk_off
   PA_TRY(tile_sums.alloc((scan_tiles(n_blocks) + 1) * 8));
   PA_TRY(d_total.alloc(8));
   const uint64_t* slots = rep->slots.as<uint64_t>();
+  const bool trace = getenv("PA_TRACE") != nullptr;
+  auto tp = std::chrono::steady_clock::now();
+  double t_compress = 0, t_bitmaps = 0, t_words = 0, t_expand = 0;
   auto warps_grid = [](uint64_t blocks) { return (unsigned)std::max<uint64_t>(1, (blocks * 32 + CMP_THREADS - 1) / CMP_THREADS); };
   // ---- my slice -> bitmaps + word counts -> offsets -> words ----
   uint64_t my_words = 0;
   if (nb_me) {
-    slice_bitmaps<<<warps_grid(nb_me), CMP_THREADS, 0, s>>>(slots, b_lo, b_hi, bitmap.as<unsigned long long>(), cnt.as<uint32_t>());
+    slice_bitmaps<<<warps_grid((nb_me + CMP_BLOCKS - 1) / CMP_BLOCKS), CMP_THREADS, 0, s>>>(slots, b_lo, b_hi, bitmap.as<unsigned long long>(), cnt.as<uint32_t>());
     PA_TRY(exclusive_scan_u32(cnt.as<uint32_t>(), off_all.as<uint64_t>(), nb_me, tile_sums.as<uint64_t>(), d_total.as<uint64_t>(), s));
     PA_CUDA(cudaMemcpyAsync(&my_words, d_total.p, 8, cudaMemcpyDeviceToHost, s));
     PA_CUDA(cudaStreamSynchronize(s));
@@ -519,26 +563,41 @@ int32_t DistBuild::gather_slices_compressed(const std::vector<uint64_t>& blk_off
   std::vector<uint64_t> nwords(W, 0), w_off(W + 1, 0);
   PA_TRY(comm->allgather_host(&my_words, nwords.data(), 8));
   for (uint32_t r = 0; r < W; ++r) w_off[r + 1] = w_off[r] + nwords[r];
+  // every rank's words at r * stride: equal segments, so that the words travel in one ncclAllGather
+  uint64_t stride = 0;
+  for (uint32_t r = 0; r < W; ++r) stride = std::max(stride, nwords[r]);
+  stride = (stride + 15) & ~15ull;
   DevBuf words;
-  PA_TRY(words.alloc((w_off[W] + 1) * 8));
+  PA_TRY(words.alloc((stride * W + 1) * 8));
   if (nb_me)
-    slice_words<<<warps_grid(nb_me), CMP_THREADS, 0, s>>>(slots, b_lo, b_hi, off_all.as<uint64_t>(), words.as<uint64_t>() + w_off[me]);
+    slice_words<<<warps_grid((nb_me + CMP_BLOCKS - 1) / CMP_BLOCKS), CMP_THREADS, 0, s>>>(slots, b_lo, b_hi, off_all.as<uint64_t>(), words.as<uint64_t>() + (size_t)me * stride);
   PA_CUDA(cudaGetLastError());
   PA_CUDA(cudaStreamSynchronize(s));
-  // ---- all ranks' bitmaps (block order) and words (block order): two in-place all-gathers ----
+  t_compress = ms_since(tp); tp = std::chrono::steady_clock::now();
+  // ---- all ranks' bitmaps (block order) and words: two in-place all-gathers ----
   std::vector<uint64_t> seg(W + 1, 0);
   for (uint32_t r = 0; r <= W; ++r) seg[r] = blk_off[r] * 8;
   PA_TRY(comm->allgatherv_device_inplace(bitmap.p, seg.data(), s));
-  for (uint32_t r = 0; r <= W; ++r) seg[r] = w_off[r] * 8;
-  PA_TRY(comm->allgatherv_device_inplace(words.p, seg.data(), s));
+  if (trace) { PA_CUDA(cudaStreamSynchronize(s)); t_bitmaps = ms_since(tp); tp = std::chrono::steady_clock::now(); }
+  PA_TRY(comm->allgather_device_strided(words.p, stride * 8, s));
+  if (trace) { PA_CUDA(cudaStreamSynchronize(s)); t_words = ms_since(tp); tp = std::chrono::steady_clock::now(); }
   // ---- expand every other rank's blocks into my table ----
   bitmap_counts<<<(unsigned)std::max<uint64_t>(1, (n_blocks + CMP_THREADS - 1) / CMP_THREADS), CMP_THREADS, 0, s>>>(
       bitmap.as<unsigned long long>(), n_blocks, cnt.as<uint32_t>());
   PA_TRY(exclusive_scan_u32(cnt.as<uint32_t>(), off_all.as<uint64_t>(), n_blocks, tile_sums.as<uint64_t>(), d_total.as<uint64_t>(), s));
-  slice_expand<<<warps_grid(n_blocks), CMP_THREADS, 0, s>>>(bitmap.as<unsigned long long>(), off_all.as<uint64_t>(), words.as<uint64_t>(),
-                                                            n_blocks, b_lo, b_hi, rep->slots.as<uint64_t>());
+  for (uint32_t r = 0; r < W; ++r) {
+    if (r == me || blk_off[r + 1] == blk_off[r]) continue;
+    const uint64_t nb = blk_off[r + 1] - blk_off[r];
+    slice_expand<<<warps_grid((nb + EXP_BLOCKS - 1) / EXP_BLOCKS), CMP_THREADS, 0, s>>>(
+        bitmap.as<unsigned long long>(), off_all.as<uint64_t>(), words.as<uint64_t>(), blk_off[r], blk_off[r + 1],
+        (long long)((uint64_t)r * stride) - (long long)w_off[r], rep->slots.as<uint64_t>());
+  }
   PA_CUDA(cudaGetLastError());
   PA_CUDA(cudaStreamSynchronize(s));
+  t_expand = ms_since(tp);
+  if (trace)
+    fprintf(stderr, "[pa gather] rank %u: compress %.2f ms (%.2f GB of words), bitmaps %.2f ms, words %.2f ms, expand %.2f ms\n", me,
+            t_compress, (double)my_words * 8 / 1e9, t_bitmaps, t_words, t_expand);
   return ST_OK;
 }
 
