@@ -57,14 +57,16 @@ constexpr size_t CACHE_MIN = 32u << 20;
 size_t cache_limit(int device) {
   static double gb = getenv("PA_CACHE_GB") ? atof(getenv("PA_CACHE_GB")) : -1.0;
   if (gb >= 0) return (size_t)(gb * 1e9);
-  static size_t quarter[64] = {0};
+  // default: 45 % of the device memory -- the buffers of one whole configs[1] build (index with the load-0.1 table 49 GB +
+  // the sort's double buffers) fit, so a rebuild finds every buffer it needs (a quarter held the round-1 index only)
+  static size_t share[64] = {0};
   if (device < 0 || device >= 64) return 0;
-  if (!quarter[device]) {
+  if (!share[device]) {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
-    quarter[device] = total_b / 4;
+    share[device] = total_b / 20 * 9;
   }
-  return quarter[device];
+  return share[device];
 }
 }  // namespace
 

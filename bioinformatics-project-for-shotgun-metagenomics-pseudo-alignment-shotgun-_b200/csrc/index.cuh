@@ -23,7 +23,7 @@ bool scope_take(size_t bytes, void** p, size_t* got);   // a parked block of >= 
 bool scope_park(void* p, size_t bytes);                 // false outside a scope: the caller frees
 
 // Retired-buffer cache (process-wide, per device): what is still parked when a build ends, and the big buffers of an index
-// that is freed, are kept instead of cudaFree'd -- up to PA_CACHE_GB (default: a quarter of the device memory, 0 switches
+// that is freed, are kept instead of cudaFree'd -- up to PA_CACHE_GB (default: 45 % of the device memory, 0 switches
 // it off) -- and the next build takes them over.  cudaMalloc / cudaFree of multi-GB buffers cost milliseconds each and
 // synchronise the device; a process that builds more than once (EXTSIM rebuilds, benchmarks, a server) pays them once.
 // Every cached buffer is idle: it is retired only after the stream that used it was synchronised.  cudaMalloc failures
