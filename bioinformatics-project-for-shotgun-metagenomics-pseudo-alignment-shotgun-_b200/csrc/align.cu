@@ -143,10 +143,10 @@ __device__ __forceinline__ void window_minimizer(const TableView& t, uint32_t ke
 
 // rare continuation of a lookup whose home bucket was full, without a match, and has CONT set (kept out of line:
 // the fast path only carries the tag)
-__device__ __noinline__ uint64_t lookup_chain_window(const TableView& t, uint64_t raw, uint32_t mhash, uint32_t p, uint32_t d0 = 1) {
+__device__ __noinline__ uint64_t lookup_chain_window(const TableView& t, uint64_t raw, uint32_t mhash, uint32_t p) {
   const uint32_t kmask = (t.k >= 32) ? 0xFFFFFFFFu : ((1u << t.k) - 1);
   const SlotAddr a = slot_addr(t, (uint32_t)raw & kmask, (uint32_t)(raw >> t.k) & kmask, mhash, p);
-  return lookup_chain(t, a, mhash, raw, d0);
+  return lookup_chain(t, a, mhash, raw);
 }
 
 
@@ -764,7 +764,8 @@ __device__ __forceinline__ void fast_stage_c(const TableView& t, const AlignPara
     bool keep = hitr;
     if (prm.has_mg) {  // max-genomes filter, per occurrence (kmer.py:425-427)
       uint32_t c = 1;
-      if (hitr && kind == KIND_INLINE) c = vinline_count(t, vpayload(t, v));
+      // an inline list holds at most n_inline genomes: it is only counted when max_genomes is smaller than that
+      if (hitr && kind == KIND_INLINE) c = (prm.mg >= (int64_t)t.n_inline) ? 2u : vinline_count(t, vpayload(t, v));
       else if (hitr && kind == KIND_MLIST) c = (prm.mg <= (int64_t)t.n_inline) ? t.n_inline + 1 : mlist_count(t.mlist, vpayload(t, v));
       const bool f = hitr && (int64_t)c > prm.mg;
       l_filtered += f;
@@ -945,15 +946,15 @@ align_fast_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ quals,
 #define PA_FAST_SPLIT 1
 #endif
 
-// QUAL: 0 = no quality filters, 1 = quality bytes scanned in the kernel, 2 = the filters were evaluated by
-// quality_masks_kernel beforehand (one bit per window + one "dropped" byte per read): the quality state carried from
-// stage A to stage B is then one register instead of five prefix sums, which is what made the staggered order spill.
+// QUAL: 0 = no quality filters, 2 = the filters were evaluated by quality_masks_kernel beforehand (one bit per window +
+// one "dropped" byte per read): the quality state carried from stage A to stage B is one register.  (1 = quality bytes
+// scanned in the kernel exists in the plain stage order only, align_fast_kernel: its five prefix sums per lane made the
+// staggered order spill 108 bytes -- 26.6 ms against 17.5.)
 template <int QUAL>
 struct FrontState {
   uint32_t lo[AL_ROUNDS + 1], hi[AL_ROUNDS + 1];                       // bit planes of the read (warp-uniform)
   uint32_t ok;                                                         // bit r: window r of this lane holds ACGT only
   uint32_t mkey[AL_ROUNDS + 1];                                        // slid minimizer keys
-  uint32_t qex[QUAL == 1 ? AL_ROUNDS + 1 : 1];                         // QUAL 1: exclusive quality prefix at this lane's base
   uint32_t qf;                                                         // QUAL 2: bit r = window r of this lane fails min-kmer-quality
   uint32_t W;                                                          // windows to look up (0: none)
   bool dropped, defer;
@@ -1045,18 +1046,6 @@ __device__ __forceinline__ void fast_stage_a(const TableView& t, const AlignPara
                                              FrontState<QUAL>& f, unsigned long long& c_drop) {
   const int k = (int)t.k;
   f.dropped = false; f.defer = false; f.W = 0; f.qf = 0;
-  if (QUAL == 1 && prm.has_mrq) {  // Read.mean_quality() < min_read_quality  (kmer.py:587)
-    uint64_t s = 0;
-    if (L <= 32 * (AL_ROUNDS + 1)) {   // the prefetched bytes cover the read (bytes beyond L were loaded as 0)
-#pragma unroll
-      for (int c = 0; c <= AL_ROUNDS; ++c) s += q.v[c];
-    } else {
-      const uint8_t* rq = quals + beg;
-      for (uint64_t i = lane; i < L; i += 32) s += rq[i];
-    }
-    s = warp_sum(s);
-    if ((int64_t)s < prm.mrq * (int64_t)L) { f.dropped = true; if (lane == 0) ++c_drop; }
-  }
   if (QUAL == 2) {
     if (q.v[AL_ROUNDS]) { f.dropped = true; if (lane == 0) ++c_drop; }
 #pragma unroll
@@ -1076,17 +1065,6 @@ __device__ __forceinline__ void fast_stage_a(const TableView& t, const AlignPara
 #pragma unroll
     for (int r = 0; r < AL_ROUNDS; ++r)
       f.ok |= ((__funnelshift_r(inv[r], inv[r + 1], lane) & kmask) == 0 ? 1u : 0u) << r;
-  }
-  if (QUAL == 1 && prm.has_mkq) {
-    uint32_t carry = 0;
-#pragma unroll
-    for (int c = 0; c <= AL_ROUNDS; ++c) {
-      uint32_t qq = q.v[c], incl = qq;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-      f.qex[QUAL == 1 ? c : 0] = carry + incl - qq;
-      carry += __shfl_sync(0xffffffffu, incl, 31);
-    }
   }
 #pragma unroll
   for (int c = 0; c <= AL_ROUNDS; ++c) {
@@ -1112,7 +1090,6 @@ align_fast_split_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ q
   const int k = (int)t.k;
   const uint32_t kmask = (k >= 1 && k < 32) ? ((1u << k) - 1) : 0u;
   unsigned long long c_drop = 0, c_nq = 0, c_nr = 0;  // per-lane partial counters
-  const ReadInput qin{quals, nullptr, 0, 0};
 
   // input pipeline: while read i is resolved, stage A runs on read i+1 (bases requested one iteration earlier), the
   // bases of read i+2 and the offsets of read i+3 are requested
@@ -1129,10 +1106,8 @@ align_fast_split_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ q
     Prefetch<PACKED> ch0;
     Prefetch<false> q0;
     prefetch_read<PACKED>(in, r0 < n_reads, r0, beg0, end0 - beg0, lane, ch0);
-    if (QUAL == 1) prefetch_read<false>(qin, r0 < n_reads, r0, beg0, end0 - beg0, lane, q0);
     if (QUAL == 2) prefetch_masks(quals, n_reads, r0 < n_reads, r0, q0);
     prefetch_read<PACKED>(in, r1 < n_reads, r1, nx_beg, nx_end - nx_beg, lane, nx_ch);
-    if (QUAL == 1) prefetch_read<false>(qin, r1 < n_reads, r1, nx_beg, nx_end - nx_beg, lane, nx_q);
     if (QUAL == 2) prefetch_masks(quals, n_reads, r1 < n_reads, r1, nx_q);
     if (r0 < n_reads) fast_stage_a<QUAL, PACKED>(t, prm, in, quals, ch0, q0, r0, beg0, end0 - beg0, lane, cur, c_drop);
   }
@@ -1149,14 +1124,7 @@ align_fast_split_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ q
         const uint32_t s = 32 * r + lane;
         const bool exists = s < cur.W;
         bool qf = false;
-        if (QUAL == 1 && prm.has_mkq) {  // kmer_quality(start, k) < min_kmer_quality, before the lookup (kmer.py:420-422)
-          const uint32_t tl = lane + k;
-          const uint32_t p_a = __shfl_sync(0xffffffffu, cur.qex[QUAL == 1 ? r : 0], tl & 31);
-          const uint32_t p_b = __shfl_sync(0xffffffffu, cur.qex[QUAL == 1 ? r + 1 : 0], tl & 31);
-          const uint32_t end = tl < 32 ? p_a : p_b;
-          qf = exists && ((int64_t)(end - cur.qex[QUAL == 1 ? r : 0]) < prm.mkq * (int64_t)k);
-          read_nq += qf;
-        }
+        // kmer_quality(start, k) < min_kmer_quality, before the lookup (kmer.py:420-422): bit r of the read's mask
         if (QUAL == 2) { qf = exists && ((cur.qf >> r) & 1u); read_nq += qf; }
         const uint32_t wl = __funnelshift_r(cur.lo[r], cur.lo[r + 1], lane) & kmask;
         const uint32_t wh = __funnelshift_r(cur.hi[r], cur.hi[r + 1], lane) & kmask;
@@ -1177,7 +1145,6 @@ align_fast_split_kernel(TableView t, ReadInput in, const uint8_t* __restrict__ q
       Prefetch<PACKED> n2_ch;
       Prefetch<false> n2_q;
       prefetch_read<PACKED>(in, r2 < n_reads, r2, n2_beg, n2_end - n2_beg, lane, n2_ch);
-      if (QUAL == 1) prefetch_read<false>(qin, r2 < n_reads, r2, n2_beg, n2_end - n2_beg, lane, n2_q);
       if (QUAL == 2) prefetch_masks(quals, n_reads, r2 < n_reads, r2, n2_q);
       uint64_t n3_beg = 0, n3_end = 0;
       if (r3 < n_reads) { n3_beg = read_off[r3]; n3_end = read_off[r3 + 1]; }
@@ -1323,11 +1290,9 @@ int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_q
                                 uint32_t*, unsigned long long*);
     FastKernel fk;
     // EXTQUALITY: the filters are evaluated by quality_masks_kernel first and K4 runs in the staggered order on their bits
-    // (PA_QUAL_MASKS=0: the kernel that scans the quality bytes itself, in the plain order -- the state of that scan spills
-    // in the staggered order, PA_QUAL_SPLIT=1)
+    // (PA_QUAL_MASKS=0: the kernel that scans the quality bytes itself, in the plain stage order)
     const char* qm_env = getenv("PA_QUAL_MASKS");
     const bool qual_masks = qual && PA_FAST_SPLIT && !(qm_env && *qm_env == '0');
-    static const int qual_split = getenv("PA_QUAL_SPLIT") ? atoi(getenv("PA_QUAL_SPLIT")) : 0;   // tuning knob, see DESIGN.md section 4
     const uint8_t* fast_quals = d_quals;
     if (qual_masks) {
       if (ix.align_qmasks.bytes < n_reads * 17 + 16) PA_TRY(ix.align_qmasks.alloc(n_reads * 17 + n_reads / 2 + 16));
@@ -1341,7 +1306,6 @@ int32_t align_batch_device(Index& ix, const uint8_t* d_bases, const uint8_t* d_q
       fk = packed ? (v32 ? align_fast_split_kernel<2, true, true> : align_fast_split_kernel<2, true, false>)
                   : (v32 ? align_fast_split_kernel<2, false, true> : align_fast_split_kernel<2, false, false>);
     }
-    else if (qual && qual_split && v32) fk = packed ? align_fast_split_kernel<1, true, true> : align_fast_split_kernel<1, false, true>;
     else if (qual) fk = packed ? (v32 ? align_fast_kernel<true, true, true> : align_fast_kernel<true, true, false>)
                           : (v32 ? align_fast_kernel<true, false, true> : align_fast_kernel<true, false, false>);
     else if (PA_FAST_SPLIT) fk = packed ? (v32 ? align_fast_split_kernel<0, true, true> : align_fast_split_kernel<0, true, false>)

@@ -52,7 +52,8 @@ namespace {
 struct CacheEntry { void* p; size_t bytes; int device; };
 std::mutex g_cache_m;
 std::vector<CacheEntry> g_cache;
-constexpr size_t CACHE_MIN = 32u << 20;
+constexpr size_t CACHE_MIN = 1u << 20;   // megabyte-sized scratch (tile counters, genome map) is worth keeping too: a cudaMalloc costs
+                                         // milliseconds on a process that holds tens of GB, whatever its size
 
 size_t cache_limit(int device) {
   static double gb = getenv("PA_CACHE_GB") ? atof(getenv("PA_CACHE_GB")) : -1.0;
@@ -78,7 +79,7 @@ bool cache_take(size_t bytes, void** p, size_t* got) {
   size_t best = SIZE_MAX; int at = -1;
   for (int i = 0; i < (int)g_cache.size(); ++i) {
     const CacheEntry& e = g_cache[i];
-    if (e.device == dev && e.bytes >= bytes && e.bytes <= bytes + bytes / 8 + (64u << 20) && e.bytes < best) { best = e.bytes; at = i; }
+    if (e.device == dev && e.bytes >= bytes && e.bytes <= bytes + bytes / 8 + std::min<size_t>(64u << 20, bytes) && e.bytes < best) { best = e.bytes; at = i; }
   }
   if (at < 0) return false;
   *p = g_cache[at].p; *got = best;

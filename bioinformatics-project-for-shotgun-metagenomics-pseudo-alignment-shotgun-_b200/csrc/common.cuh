@@ -324,9 +324,8 @@ __host__ __device__ __forceinline__ uint64_t chain_block(const TableView& t, uin
   return first + local;
 }
 
-static __device__ __noinline__ uint64_t lookup_chain(const TableView& t, const SlotAddr& a, uint32_t mhash, uint64_t raw_key,
-                                                     uint32_t d0 = 1) {
-  for (uint32_t d = d0; d < CHAIN_LEN; ++d) {
+static __device__ __noinline__ uint64_t lookup_chain(const TableView& t, const SlotAddr& a, uint32_t mhash, uint64_t raw_key) {
+  for (uint32_t d = 1; d < CHAIN_LEN; ++d) {
     uint64_t s[4];
     ld_sector_nc(bucket_ptr(t, chain_block(t, a.block, d, mhash), a.bucket), s);
     bool cont;
