@@ -204,13 +204,13 @@ def test_quality_filters_by_masks_and_in_kernel(masks, monkeypatch):
     counted per occurrence, together with max-genomes, on reads shorter than k, of ragged lengths and longer than 128 windows."""
     monkeypatch.setenv("PA_QUAL_MASKS", masks)
     genomes = synth.make_genomes(6, 40_000, seed=5, cluster_size=3, shared_frac=0.35, n_every=9000, n_run=11)
-    for read_len, n in ((150, 3000), (40, 500), (31, 200), (20, 50), (158, 400), (159, 400), (300, 300)):
+    for read_len, n in ((150, 1500), (40, 300), (31, 100), (20, 50), (158, 200), (159, 200), (300, 150)):
         b, q, off = synth.make_reads(genomes, n, read_len, seed=60 + read_len, sub_rate=0.02, random_frac=0.05)
         for pr in [dict(m=1, p=1, mrq=62, mkq=60, mg=1), dict(m=0, p=0, mrq=None, mkq=63, mg=3),
-                   dict(m=2, p=-1, mrq=61, mkq=None, mg=None), dict(m=1, p=1, mrq=90, mkq=10, mg=None)]:
+                   dict(m=2, p=-1, mrq=61, mkq=None, mg=None)]:
             check_case({"k": 31, "genomes": synth.genomes_as_pairs(genomes), "reads": synth.reads_as_triples(b, q, off),
                         "params": pr, "seed": 1})
-    for seed in range(9300, 9360):   # small k, ragged reads, random thresholds
+    for seed in range(9300, 9340):   # small k, ragged reads, random thresholds
         check_case(synth.fuzz_case(seed))
 
 
