@@ -210,10 +210,10 @@ double table_load_factor(int k, uint64_t U, size_t free_bytes) {
   }
   const double bytes_per_slot = 8.0;
   double load = 0.10;
-  // up to a quarter of the free device memory for a sparse table, up to 40 % before it gets denser than 1/5 (config E: 2,000
-  // genomes end at 0.42)
+  // up to a quarter of the free device memory for a sparse table, up to half of it before the table gets denser than 1/5
+  // (config E: 3.35e9 k-mers end at 0.32 = 84 GB on a 180-GB device; 0.42 is the densest the chains stay short at)
   while (load < 0.199 && (double)U / load * bytes_per_slot > 0.25 * (double)free_bytes) load += 0.02;
-  while (load < 0.42 && (double)U / load * bytes_per_slot > 0.4 * (double)free_bytes) load += 0.02;
+  while (load < 0.42 && (double)U / load * bytes_per_slot > 0.5 * (double)free_bytes) load += 0.02;
   (void)k;
   return load;
 }
