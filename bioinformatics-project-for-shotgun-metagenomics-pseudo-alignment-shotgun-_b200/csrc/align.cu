@@ -1,5 +1,6 @@
-// align.cu -- K4 (warp-per-read pseudo-alignment with the EXTQUALITY filters
-// fused in) and K8 (summary reduction).
+// align.cu -- K4 (warp-per-read pseudo-alignment), quality_masks_kernel (the
+// EXTQUALITY filters of a batch, evaluated ahead of K4: one bit per window, one
+// byte per read) and K8 (summary reduction).
 //
 // Reference being replaced, per read: Read.mean_quality / kmer_quality /
 // extract_kmer_references / generate_genome_counts / try_to_align_specific /
